@@ -1,0 +1,324 @@
+"""ctypes binding of libcfl_b200.so (the C ABI declared in include/cfl_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a ``CflNativeError`` is
+raised.  torch is used only for device memory, streams and (elsewhere) torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libcfl_b200.so")
+
+MODES = {"pcd": 0, "monomer": 1, "siamese": 2}
+ACTS = {None: 0, "linear": 0, "tanh": 1, "sigmoid": 2, "relu": 3, "lrelu": 4}
+MAX_K, MAX_D, MAX_TOPK = 8, 256, 128
+
+
+class CflNativeError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+_i64, _int, _f32, _sz, _vp = C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/cfl_b200.h one to one
+SIGNATURES = {
+    "cfl_last_error": (C.c_char_p, []),
+    "cfl_version": (_int, []),
+    "cfl_device_info": (_int, [C.POINTER(_int)] * 3),
+    "cfl_project_fwd_workspace_bytes": (_sz, [_i64, _int, _int]),
+    "cfl_project_fwd": (_int, [_vp, _i64, _int, _i64, _vp, _int, _i64, _vp, _vp, _int, _f32, _int,
+                               _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "cfl_project_bwd_workspace_bytes": (_sz, [_i64, _int, _int]),
+    "cfl_project_bwd": (_int, [_vp, _i64, _int, _i64, _vp, _int, _i64, _vp, _vp, _int, _f32, _int,
+                               _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _int, _f32, _vp, _sz, _vp]),
+    "cfl_pair_workspace_bytes": (_sz, [_i64]),
+    "cfl_pair_loss_fwd": (_int, [_int, _vp, _i64, _vp, _i64, _vp, _i64, _int, _int, _vp, _int, _f32,
+                                 _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cfl_pair_loss_bwd": (_int, [_int, _vp, _i64, _vp, _i64, _vp, _i64, _int, _int, _vp, _int, _f32,
+                                 _f32, _f32, _f32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "cfl_score_topk_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
+    "cfl_score_topk": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _i64, _i64, _vp, _int, _i64,
+                              _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cfl_topk_merge": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
+    "cfl_col_mean_workspace_bytes": (_sz, [_i64, _int]),
+    "cfl_col_mean": (_int, [_vp, _i64, _int, _i64, _vp, _vp, _sz, _vp]),
+    "cfl_auc_workspace_bytes": (_sz, [_i64, _i64]),
+    "cfl_auc": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "cfl_adam_step": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "cfl_selftest_umma": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
+}
+
+
+def lib():
+    """Loads the library once; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise CflNativeError(
+                    f"{LIB_PATH} not found: build it with "
+                    "`python compatibility-family-learning_b200/build.py` (there is no CPU fallback)")
+            l = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(l, name)          # AttributeError if the .so lacks a declared symbol
+                fn.restype, fn.argtypes = res, args
+            _lib = l
+    return _lib
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        msg = lib().cfl_last_error().decode("utf-8", "replace")
+        raise CflNativeError(f"{what} failed (status {status}): {msg}")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CflNativeError(f"{name} must be a CUDA tensor (no CPU path)")
+    if t.dtype != torch.float32:
+        raise CflNativeError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def _rows(t, name):
+    """2-D view with unit inner stride; returns (tensor, leading dimension)."""
+    t = _f32c(t, name)
+    if t.dim() != 2 or t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+class _WorkspaceCache:
+    """One growing byte buffer per (device, stream) -- the C ABI never allocates."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        b = self.bufs.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+            self.bufs[key] = b
+        return b
+
+
+_ws = _WorkspaceCache()
+
+
+def device_info():
+    a, b, c = _int(), _int(), _int()
+    _check(lib().cfl_device_info(C.byref(a), C.byref(b), C.byref(c)), "cfl_device_info")
+    return a.value, b.value, c.value
+
+
+# ------------------------------------------------------------------------------------------
+# Stage 1
+# ------------------------------------------------------------------------------------------
+def project_fwd(x, V, g=None, bias=None, weight_norm=True, in_scale=1.0, act=None,
+                want_pre=False, want_z=False):
+    """y = act((in_scale*x @ V) * g/|V_col| + bias)  -- cfl/layers.py:80-94."""
+    x, ldx = _rows(x, "x")
+    V, ldV = _rows(V, "V")
+    B, F = x.shape
+    N = V.shape[1]
+    if V.shape[0] != F:
+        raise CflNativeError(f"project_fwd: x is [*, {F}] but V is {tuple(V.shape)}")
+    y = torch.empty(B, N, dtype=torch.float32, device=x.device)
+    pre = torch.empty_like(y) if want_pre else None
+    z = torch.empty_like(y) if want_z else None
+    g = _f32c(g, "g")
+    bias = _f32c(bias, "bias")
+    nws = lib().cfl_project_fwd_workspace_bytes(B, F, N)
+    ws = _ws.get(nws, x.device)
+    _check(lib().cfl_project_fwd(_ptr(x), B, F, ldx, _ptr(V), N, ldV, _ptr(g), _ptr(bias),
+                                 1 if weight_norm else 0, float(in_scale), ACTS[act], _ptr(y), N,
+                                 _ptr(pre), _ptr(z), _ptr(ws), ws.numel(), _stream()), "cfl_project_fwd")
+    return y, pre, z
+
+
+def project_bwd(x, V, g, bias, weight_norm, in_scale, act, y, z, dy, dV=None, dg=None, dbias=None,
+                accumulate=False, reg_c=0.0, want_dg=True, want_dbias=True):
+    x, ldx = _rows(x, "x")
+    V, ldV = _rows(V, "V")
+    dy, lddy = _rows(dy, "dy")
+    B, F = x.shape
+    N = V.shape[1]
+    # y and z share one leading dimension in the C ABI: pass both dense
+    y = None if y is None else _f32c(y, "y").contiguous()
+    z = None if z is None else _f32c(z, "z").contiguous()
+    ldy = N
+    dev = x.device
+    if dV is None:
+        dV = torch.empty(F, N, dtype=torch.float32, device=dev)
+        accumulate = False
+    if dg is None and want_dg and weight_norm and g is not None:
+        dg = torch.empty(N, dtype=torch.float32, device=dev)
+    if dbias is None and want_dbias:
+        dbias = torch.empty(N, dtype=torch.float32, device=dev)
+    nws = lib().cfl_project_bwd_workspace_bytes(B, F, N)
+    ws = _ws.get(nws, dev)
+    _check(lib().cfl_project_bwd(_ptr(x), B, F, ldx, _ptr(V), N, ldV, _ptr(g), _ptr(bias),
+                                 1 if weight_norm else 0, float(in_scale), ACTS[act], _ptr(y), ldy,
+                                 _ptr(z), _ptr(dy), lddy, _ptr(dV), _ptr(dg), _ptr(dbias),
+                                 1 if accumulate else 0, float(reg_c), _ptr(ws), ws.numel(), _stream()),
+           "cfl_project_bwd")
+    return dV, dg, dbias
+
+
+# ------------------------------------------------------------------------------------------
+# Stage 2, paired
+# ------------------------------------------------------------------------------------------
+def _pair_views(a, P, K, d):
+    a, lda = _rows(a, "a")
+    P = _f32c(P, "P")
+    B = a.shape[0]
+    P2 = P.reshape(B, K * d)
+    P2, ldP = _rows(P2, "P")
+    return a, lda, P2, ldP, B
+
+
+def pair_loss_fwd(mode, a, P, w=None, theta=None, label=-1, margin=0.0, want_dist=True,
+                  want_score=False, want_s=False, want_stats=False):
+    """dist / score / softmax weights / batch statistics of paired rows."""
+    K = P.shape[1] if P.dim() == 3 else 1
+    d = a.shape[1]
+    a, lda, P2, ldP, B = _pair_views(a, P, K, d)
+    dev = a.device
+    dist = torch.empty(B, dtype=torch.float32, device=dev) if want_dist else None
+    score = torch.empty(B, dtype=torch.float32, device=dev) if want_score else None
+    s = torch.empty(B, K, dtype=torch.float32, device=dev) if want_s else None
+    stats = torch.empty(8, dtype=torch.float64, device=dev) if want_stats else None
+    w = None if w is None else _f32c(w, "w").contiguous()
+    ws = _ws.get(lib().cfl_pair_workspace_bytes(B), dev)
+    _check(lib().cfl_pair_loss_fwd(MODES[mode], _ptr(a), lda, _ptr(P2), ldP, _ptr(w), B, K, d,
+                                   _ptr(theta), int(label), float(margin), _ptr(dist), _ptr(score),
+                                   _ptr(s), _ptr(stats), _ptr(ws), ws.numel(), _stream()),
+           "cfl_pair_loss_fwd")
+    return dist, score, s, stats
+
+
+def pair_loss_bwd(mode, a, P, w=None, theta=None, label=1, margin=0.0, c_ce=0.0, c_lin=0.0,
+                  c_margin=0.0, ddist=None, want_dtheta=False, da=None, dP=None):
+    K = P.shape[1] if P.dim() == 3 else 1
+    d = a.shape[1]
+    a, lda, P2, ldP, B = _pair_views(a, P, K, d)
+    dev = a.device
+    if da is None:
+        da = torch.empty(B, d, dtype=torch.float32, device=dev)
+    if dP is None:
+        dP = torch.empty(B, K * d, dtype=torch.float32, device=dev)
+    da2, ldda = _rows(da, "da")
+    dP2, lddP = _rows(dP.reshape(B, K * d), "dP")
+    dw = torch.empty(B, K, dtype=torch.float32, device=dev) if mode == "monomer" else None
+    dth = torch.empty(1, dtype=torch.float64, device=dev) if want_dtheta else None
+    w = None if w is None else _f32c(w, "w").contiguous()
+    ddist = None if ddist is None else _f32c(ddist, "ddist").contiguous()
+    ws = _ws.get(lib().cfl_pair_workspace_bytes(B), dev)
+    _check(lib().cfl_pair_loss_bwd(MODES[mode], _ptr(a), lda, _ptr(P2), ldP, _ptr(w), B, K, d,
+                                   _ptr(theta), int(label), float(margin), float(c_ce), float(c_lin),
+                                   float(c_margin), _ptr(ddist), _ptr(da2), ldda, _ptr(dP2), lddP,
+                                   _ptr(dw), _ptr(dth), _ptr(ws), ws.numel(), _stream()),
+           "cfl_pair_loss_bwd")
+    return da, dP.reshape(B, K, d) if dP.dim() == 2 else dP, dw, dth
+
+
+# ------------------------------------------------------------------------------------------
+# Stage 2, all pairs
+# ------------------------------------------------------------------------------------------
+def col_mean(E):
+    E, lde = _rows(E, "E")
+    N, d = E.shape
+    mu = torch.empty(d, dtype=torch.float32, device=E.device)
+    ws = _ws.get(lib().cfl_col_mean_workspace_bytes(N, d), E.device)
+    _check(lib().cfl_col_mean(_ptr(E), N, d, lde, _ptr(mu), _ptr(ws), ws.numel(), _stream()),
+           "cfl_col_mean")
+    return mu
+
+
+def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False):
+    """Top-k candidates of every query by soft-min distance; exact (rescored) values."""
+    Pq = _f32c(Pq, "Pq")
+    if Pq.dim() == 2:
+        Pq = Pq[:, None, :]
+    Q, K, d = Pq.shape
+    Pq2, ldq = _rows(Pq.reshape(Q, K * d), "Pq")
+    E, lde = _rows(E, "E")
+    N = E.shape[0]
+    if E.shape[1] != d:
+        raise CflNativeError(f"score_topk: Pq has d={d} but E is {tuple(E.shape)}")
+    dev = E.device
+    top_val = torch.empty(Q, k, dtype=torch.float32, device=dev)
+    top_idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    dense = torch.empty(Q, N, dtype=torch.float32, device=dev) if want_dense else None
+    mu = None if mu is None else _f32c(mu, "mu").contiguous()
+    ws = _ws.get(lib().cfl_score_topk_workspace_bytes(Q, K, d, N, k), dev)
+    _check(lib().cfl_score_topk(MODES[mode], _ptr(Pq2), Q, K, d, ldq, _ptr(E), N, lde, _ptr(mu),
+                                int(k), int(idx_base), _ptr(top_val), _ptr(top_idx), _ptr(dense),
+                                _ptr(ws), ws.numel(), _stream()), "cfl_score_topk")
+    return (top_val, top_idx, dense) if want_dense else (top_val, top_idx)
+
+
+def topk_merge(vals, idx):
+    """vals/idx: [R,Q,k] sorted per (r,q) -> merged [Q,k]."""
+    vals = _f32c(vals, "vals").contiguous()
+    idx = idx.contiguous()
+    if idx.dtype != torch.int64:
+        raise CflNativeError("topk_merge: idx must be int64")
+    R, Q, k = vals.shape
+    tv = torch.empty(Q, k, dtype=torch.float32, device=vals.device)
+    ti = torch.empty(Q, k, dtype=torch.int64, device=vals.device)
+    _check(lib().cfl_topk_merge(_ptr(vals), _ptr(idx), R, Q, k, _ptr(tv), _ptr(ti), _stream()),
+           "cfl_topk_merge")
+    return tv, ti
+
+
+def auc_counts(pos_scores, neg_scores):
+    """-> int64[4] device tensor: twoU, n_pos, n_neg, correct@0 (cfl/utils.py:247-268)."""
+    pos = _f32c(pos_scores, "pos_scores").reshape(-1).contiguous()
+    neg = _f32c(neg_scores, "neg_scores").reshape(-1).contiguous()
+    out = torch.empty(4, dtype=torch.int64, device=pos.device)
+    ws = _ws.get(lib().cfl_auc_workspace_bytes(pos.numel(), neg.numel()), pos.device)
+    _check(lib().cfl_auc(_ptr(pos), pos.numel(), _ptr(neg), neg.numel(), _ptr(out), _ptr(ws),
+                         ws.numel(), _stream()), "cfl_auc")
+    return out
+
+
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _f32c(t, n)
+        if not t.is_contiguous():
+            raise CflNativeError(f"adam_step: {n} must be contiguous")
+    _check(lib().cfl_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), int(step), float(lr),
+                               float(beta1), float(beta2), float(eps), float(grad_scale), _stream()),
+           "cfl_adam_step")
+
+
+def selftest_umma(A, Bm):
+    """D[128,N] = A[128,Kd] @ Bm[N,Kd]^T through the tcgen05 3xTF32 core (test only)."""
+    A = _f32c(A, "A").contiguous()
+    Bm = _f32c(Bm, "Bm").contiguous()
+    N, Kd = Bm.shape
+    D = torch.empty(128, N, dtype=torch.float32, device=A.device)
+    _check(lib().cfl_selftest_umma(_ptr(A), _ptr(Bm), _ptr(D), N, Kd, _stream()), "cfl_selftest_umma")
+    return D

@@ -1,0 +1,341 @@
+// Stage 1: projection of item features onto the e0 / prototype heads, forward + backward.
+// Replaces fully_connected_weight_norm (cfl/layers.py:80-94) and the plain FC of
+// FCEncoder (cfl/models/dist.py:45-65).
+//
+// Forward:  the GEMM runs on tcgen05 tensor cores as error-compensated 3xTF32
+//           (project_umma.cu) whenever the shape fits its tiling (F % 8 == 0, 16-byte aligned
+//           rows, N <= 256); the fp32 CUDA-core tile kernel below covers the remaining shapes
+//           (tiny / odd F) and is the reference point for the tensor-core kernel's parity test.
+// Backward: dV = x^T dpre with the weight-norm column terms, fp32 CUDA cores,
+//           batch split into slabs and reduced in a fixed order (deterministic).
+#include "common.cuh"
+
+namespace cfl {
+
+int project_fwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float* V, int N,
+                     int64_t ldV, const float* scaler, const float* bias, float in_scale, int act,
+                     float* y, int64_t ldy, float* pre, float* z, void* ws, size_t ws_bytes,
+                     cudaStream_t st);                       // project_umma.cu
+size_t project_fwd_umma_workspace(int64_t B, int F, int N);  // project_umma.cu
+bool project_fwd_umma_supported(const float* x, int64_t B, int F, int64_t ldx, int N);
+
+// ---- column scaler s_j = g_j / |V_:j| ----------------------------------------------------
+// one block per 32 columns, 8 row slices per block, fixed-order reduction over the slices.
+__global__ void colnorm_kernel(const float* __restrict__ V, int F, int N, int64_t ldV,
+                               const float* __restrict__ g, float* __restrict__ scaler,
+                               float* __restrict__ norm_out) {
+  __shared__ float sm[8][33];
+  int j = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.0f;
+  if (j < N)
+    for (int i = threadIdx.y; i < F; i += 8) { float v = V[(int64_t)i * ldV + j]; acc = fmaf(v, v, acc); }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sm[r][threadIdx.x];
+    float n = sqrtf(t);                                   // no epsilon: layers.py:81
+    if (norm_out) norm_out[j] = n;
+    scaler[j] = (g ? g[j] : 1.0f) / n;
+  }
+}
+
+// ---- fp32 tile GEMM (64x64x16, 4x4 per thread) with the fused epilogue -------------------
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <bool TRANS_A>
+__device__ __forceinline__ void tile_mainloop(const float* __restrict__ A, int64_t lda,
+                                              const float* __restrict__ Bm, int64_t ldb, int64_t M,
+                                              int N, int64_t k0, int64_t k1, int64_t m0, int n0,
+                                              float (&acc)[4][4]) {
+  // C[m,n] = sum_k A(m,k) * B(k,n);  TRANS_A: A(m,k) stored at A[k*lda + m]
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  for (int64_t kk = k0; kk < k1; kk += TK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * 256;
+      if (TRANS_A) {
+        int k = e / TM, m = e % TM;
+        int64_t gk = kk + k, gm = m0 + m;
+        As[k][m] = (gk < k1 && gm < M) ? A[gk * lda + gm] : 0.0f;
+      } else {
+        int m = e / TK, k = e % TK;
+        int64_t gk = kk + k, gm = m0 + m;
+        As[k][m] = (gk < k1 && gm < M) ? A[gm * lda + gk] : 0.0f;
+      }
+      int k = e / TN, n = e % TN;
+      int64_t gk = kk + k;
+      int gn = n0 + n;
+      Bs[k][n] = (gk < k1 && gn < N) ? Bm[gk * ldb + gn] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+project_fwd_simt(const float* __restrict__ x, int64_t B, int F, int64_t ldx,
+                 const float* __restrict__ V, int N, int64_t ldV,
+                 const float* __restrict__ scaler, const float* __restrict__ bias, float in_scale,
+                 int act, float* __restrict__ y, int64_t ldy, float* __restrict__ pre,
+                 float* __restrict__ z) {
+  float acc[4][4] = {};
+  int64_t m0 = (int64_t)blockIdx.y * TM;
+  int n0 = blockIdx.x * TN;
+  tile_mainloop<false>(x, ldx, V, ldV, B, N, 0, F, m0, n0, acc);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t b = m0 + ty * 4 + i;
+    if (b >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float zz = acc[i][j] * in_scale;
+      float p = zz * (scaler ? scaler[n] : 1.0f) + (bias ? bias[n] : 0.0f);
+      if (z) z[b * ldy + n] = zz;
+      if (pre) pre[b * ldy + n] = p;
+      y[b * ldy + n] = apply_act(p, act);
+    }
+  }
+}
+
+// ---- backward ----------------------------------------------------------------------------
+__device__ __forceinline__ float dpre_of(const float* __restrict__ dy, int64_t lddy,
+                                         const float* __restrict__ y, int64_t ldy, int act,
+                                         int64_t b, int n) {
+  float g = dy[b * lddy + n];
+  if (act != CFL_ACT_LINEAR) g *= act_grad_from_y(y[b * ldy + n], act);
+  return g;
+}
+
+// column statistics per batch slab: q_j = sum_b dpre*z, db_j = sum_b dpre  (double partials)
+__global__ void colstats_kernel(const float* __restrict__ dy, int64_t lddy,
+                                const float* __restrict__ y, int64_t ldy,
+                                const float* __restrict__ z, int act, int64_t B, int N,
+                                int64_t rows_per_slab, double* __restrict__ part) {
+  __shared__ double sq[8][33], sb[8][33];
+  int j = blockIdx.x * 32 + threadIdx.x;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
+  int64_t r1 = r0 + rows_per_slab; if (r1 > B) r1 = B;
+  double q = 0.0, db = 0.0;
+  if (j < N)
+    for (int64_t b = r0 + threadIdx.y; b < r1; b += 8) {
+      float g = dpre_of(dy, lddy, y, ldy, act, b, j);
+      db += (double)g;
+      if (z) q += (double)g * (double)z[b * ldy + j];
+    }
+  sq[threadIdx.y][threadIdx.x] = q; sb[threadIdx.y][threadIdx.x] = db;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < N) {
+    double tq = 0.0, tb = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { tq += sq[r][threadIdx.x]; tb += sb[r][threadIdx.x]; }
+    part[((int64_t)blockIdx.y * N + j) * 2 + 0] = tq;
+    part[((int64_t)blockIdx.y * N + j) * 2 + 1] = tb;
+  }
+}
+
+__global__ void colstats_final(const double* __restrict__ part, int slabs, int N,
+                               const float* __restrict__ norm, const float* __restrict__ bias,
+                               int weight_norm, int accumulate, float reg_c,
+                               float* __restrict__ qn3, float* __restrict__ dg,
+                               float* __restrict__ dbias, const float* __restrict__ g) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  double q = 0.0, db = 0.0;
+  for (int s = 0; s < slabs; ++s) { q += part[((int64_t)s * N + j) * 2]; db += part[((int64_t)s * N + j) * 2 + 1]; }
+  if (weight_norm) {
+    float n = norm[j];
+    float gg = g ? g[j] : 1.0f;
+    qn3[j] = (float)(gg * q / ((double)n * n * n));        // g q / n^3
+    if (dg) dg[j] = (accumulate ? dg[j] : 0.0f) + (float)(q / n);
+  }
+  if (dbias) dbias[j] = (accumulate ? dbias[j] : 0.0f) + (float)db + (bias ? reg_c * bias[j] : 0.0f);
+}
+
+// partial dV over one batch slab: C[f,n] = sum_{b in slab} x[b,f] * dpre[b,n]
+__global__ void __launch_bounds__(256)
+project_bwd_gemm(const float* __restrict__ x, int64_t B, int F, int64_t ldx,
+                 const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y,
+                 int64_t ldy, int act, int N, int64_t rows_per_slab, float* __restrict__ Cpart) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  float acc[4][4] = {};
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  int64_t f0 = (int64_t)blockIdx.y * TM;
+  int n0 = blockIdx.x * TN;
+  int64_t k0 = (int64_t)blockIdx.z * rows_per_slab;
+  int64_t k1 = k0 + rows_per_slab; if (k1 > B) k1 = B;
+  for (int64_t kk = k0; kk < k1; kk += TK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * 256;
+      int k = e / TM, m = e % TM;
+      int64_t gb = kk + k, gf = f0 + m;
+      As[k][m] = (gb < k1 && gf < F) ? x[gb * ldx + gf] : 0.0f;
+      int n = e % TN;
+      int gn = n0 + n;
+      Bs[k][n] = (gb < k1 && gn < N) ? dpre_of(dy, lddy, y, ldy, act, gb, gn) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* C = Cpart + (int64_t)blockIdx.z * F * N;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t f = f0 + ty * 4 + i;
+    if (f >= F) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < N) C[f * N + n] = acc[i][j];
+    }
+  }
+}
+
+// dV[f,n] (+)= in_scale*s_n*sum_slabs C - V[f,n]*qn3[n] + reg_c*V[f,n]
+__global__ void project_bwd_final(const float* __restrict__ Cpart, int slabs, int F, int N,
+                                  const float* __restrict__ V, int64_t ldV,
+                                  const float* __restrict__ scaler, const float* __restrict__ qn3,
+                                  float in_scale, float reg_c, int accumulate,
+                                  float* __restrict__ dV) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)F * N;
+  if (i >= total) return;
+  int64_t f = i / N; int n = (int)(i % N);
+  float c = 0.0f;
+  for (int s = 0; s < slabs; ++s) c += Cpart[(int64_t)s * total + i];
+  float v = V[f * ldV + n];
+  float r = c * in_scale * (scaler ? scaler[n] : 1.0f) - (qn3 ? v * qn3[n] : 0.0f) + reg_c * v;
+  dV[i] = (accumulate ? dV[i] : 0.0f) + r;
+}
+
+static int bwd_slabs(int64_t B) {
+  int64_t s = (B + 2047) / 2048;
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  return (int)s;
+}
+
+}  // namespace cfl
+
+using namespace cfl;
+
+extern "C" {
+
+size_t cfl_project_fwd_workspace_bytes(int64_t B, int F, int N) {
+  return align_up((size_t)N * 2 * sizeof(float), 256) + project_fwd_umma_workspace(B, F, N) + 512;
+}
+
+int cfl_project_fwd(const float* x, int64_t B, int F, int64_t ldx, const float* V, int N,
+                    int64_t ldV, const float* g, const float* bias, int weight_norm,
+                    float in_scale, int act, float* y, int64_t ldy, float* pre, float* z,
+                    void* ws, size_t ws_bytes, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(x && V && y && B >= 0 && F > 0 && N > 0, CFL_ERR_INVALID, "project_fwd: bad arguments");
+  CFL_REQUIRE(ldx >= F && ldV >= N && ldy >= N, CFL_ERR_INVALID, "project_fwd: leading dimension too small");
+  CFL_REQUIRE(act >= CFL_ACT_LINEAR && act <= CFL_ACT_LRELU, CFL_ERR_INVALID, "project_fwd: bad act %d", act);
+  CFL_REQUIRE(ws && ws_bytes >= cfl_project_fwd_workspace_bytes(B, F, N), CFL_ERR_WORKSPACE,
+              "project_fwd: workspace too small");
+  if (B == 0) return CFL_OK;
+  cudaStream_t cs = (cudaStream_t)stream;
+  Workspace W(ws, ws_bytes);
+  float* scaler = nullptr;
+  if (weight_norm) {
+    scaler = W.take<float>(N);
+    colnorm_kernel<<<(N + 31) / 32, dim3(32, 8), 0, cs>>>(V, F, N, ldV, g, scaler, nullptr);
+    CFL_LAUNCH_CHECK();
+  }
+  if (project_fwd_umma_supported(x, B, F, ldx, N)) {
+    W.off = align_up(W.off, 256);
+    return project_fwd_umma(x, B, F, ldx, V, N, ldV, scaler, bias, in_scale, act, y, ldy, pre, z,
+                            W.base + W.off, W.size - W.off, cs);
+  }
+  dim3 grid((N + TN - 1) / TN, (unsigned)((B + TM - 1) / TM));
+  project_fwd_simt<<<grid, 256, 0, cs>>>(x, B, F, ldx, V, N, ldV, scaler, bias, in_scale, act, y,
+                                         ldy, pre, z);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+size_t cfl_project_bwd_workspace_bytes(int64_t B, int F, int N) {
+  int slabs = bwd_slabs(B);
+  return align_up((size_t)N * 3 * sizeof(float), 256) +
+         align_up((size_t)slabs * N * 2 * sizeof(double), 256) +
+         align_up((size_t)slabs * F * N * sizeof(float), 256) + 1024;
+}
+
+int cfl_project_bwd(const float* x, int64_t B, int F, int64_t ldx, const float* V, int N,
+                    int64_t ldV, const float* g, const float* bias, int weight_norm,
+                    float in_scale, int act, const float* y, int64_t ldy, const float* z,
+                    const float* dy, int64_t lddy, float* dV, float* dg, float* dbias,
+                    int accumulate, float reg_c, void* ws, size_t ws_bytes, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(x && V && dy && dV && B >= 0 && F > 0 && N > 0, CFL_ERR_INVALID, "project_bwd: bad arguments");
+  CFL_REQUIRE(act == CFL_ACT_LINEAR || y, CFL_ERR_INVALID, "project_bwd: non-linear act needs y");
+  CFL_REQUIRE(!weight_norm || z, CFL_ERR_INVALID, "project_bwd: weight_norm needs the saved z");
+  CFL_REQUIRE(ldx >= F && ldV >= N && lddy >= N && (!y || ldy >= N), CFL_ERR_INVALID,
+              "project_bwd: leading dimension too small");
+  CFL_REQUIRE(ws && ws_bytes >= cfl_project_bwd_workspace_bytes(B, F, N), CFL_ERR_WORKSPACE,
+              "project_bwd: workspace too small");
+  cudaStream_t cs = (cudaStream_t)stream;
+  Workspace W(ws, ws_bytes);
+  int slabs = bwd_slabs(B);
+  float* scaler = W.take<float>(N);
+  float* norm = W.take<float>(N);
+  float* qn3 = W.take<float>(N);
+  double* part = W.take<double>((size_t)slabs * N * 2);
+  float* Cpart = W.take<float>((size_t)slabs * F * N);
+  int64_t rps = (B + slabs - 1) / slabs;
+  rps = (rps + TK - 1) / TK * TK;
+  if (rps < TK) rps = TK;
+  if (weight_norm) {
+    colnorm_kernel<<<(N + 31) / 32, dim3(32, 8), 0, cs>>>(V, F, N, ldV, g, scaler, norm);
+    CFL_LAUNCH_CHECK();
+  }
+  colstats_kernel<<<dim3((N + 31) / 32, slabs), dim3(32, 8), 0, cs>>>(
+      dy, lddy, y, ldy, weight_norm ? z : nullptr, act, B, N, rps, part);
+  CFL_LAUNCH_CHECK();
+  colstats_final<<<(N + 127) / 128, 128, 0, cs>>>(part, slabs, N, norm, bias, weight_norm,
+                                                 accumulate, reg_c, qn3, dg, dbias, g);
+  CFL_LAUNCH_CHECK();
+  dim3 grid((N + TN - 1) / TN, (F + TM - 1) / TM, slabs);
+  project_bwd_gemm<<<grid, 256, 0, cs>>>(x, B, F, ldx, dy, lddy, y, ldy, act, N, rps, Cpart);
+  CFL_LAUNCH_CHECK();
+  int64_t total = (int64_t)F * N;
+  project_bwd_final<<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(
+      Cpart, slabs, F, N, V, ldV, weight_norm ? scaler : nullptr, weight_norm ? qn3 : nullptr,
+      in_scale, reg_c, accumulate, dV);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// Stage 2 on the Q x N cross product: query prep, the CUDA-core scoring
+// kernel, the part merge + direct-form rescoring kernel, the cross-rank merge kernel and the
+// cfl_score_topk / cfl_topk_merge entry points.  The tensor-core scoring kernel lives in
+// score_umma.cu and is used whenever its tiling supports the shape (see score_umma_supported);
+// both kernels share the soft-min epilogue (score.cuh) and the top-k machinery (topk.cuh).
+#include "score.cuh"
+
+namespace cfl {
+
+// ---- plan --------------------------------------------------------------------------------
+constexpr int SIMT_QT = 16;        // queries per CTA tile, CUDA-core kernel
+constexpr int SIMT_THREADS = 128;  // one thread per candidate of a 128-row tile
+
+static int choose_kk(int k) {
+  int kk = k + 28;                 // slack so Gram-form near-ties cannot change the exact top-k
+  if (kk > CFL_MAX_TOPK) kk = CFL_MAX_TOPK;
+  if (kk < k) kk = k;
+  return kk;
+}
+
+ScorePlan make_score_plan(int64_t Q, int K, int d, int64_t N, int k, bool umma_ok) {
+  ScorePlan p;
+  p.impl = umma_ok ? 1 : 0;
+  p.qt = umma_ok ? score_umma_qt(K, d) : SIMT_QT;
+  p.nqt = (int)((Q + p.qt - 1) / p.qt);
+  p.tiles = (N + 127) / 128;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int target = umma_ok ? sms : 2 * sms;
+  int64_t parts = p.nqt > 0 ? target / p.nqt : 1;
+  if (parts < 1) parts = 1;
+  if (parts > p.tiles) parts = p.tiles;
+  if (parts < 1) parts = 1;
+  p.parts = (int)parts;
+  p.kk = choose_kk(k);
+  p.dpad = (d + 7) / 8 * 8;
+  return p;
+}
+
+// ---- query prep: centre, |p_k|^2, p_k.p_l --------------------------------------------------
+__global__ void prep_queries_kernel(const float* __restrict__ Pq, int64_t Q, int K, int d,
+                                    int64_t ldq, const float* __restrict__ mu,
+                                    float* __restrict__ Pc, float* __restrict__ qpar) {
+  int64_t q = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  int lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  const float* src = Pq + q * ldq;
+  float* dst = Pc + q * (int64_t)K * d;
+  for (int i = lane; i < K * d; i += 32) {
+    int j = i % d;
+    dst[i] = src[i] - (mu ? mu[j] : 0.0f);
+  }
+  __syncwarp();
+  float* qp = qpar + q * (int64_t)(K + K * K);
+  for (int k = 0; k < K; ++k)
+    for (int l = k; l < K; ++l) {
+      float acc = 0.0f;
+      for (int j = lane; j < d; j += 32) acc = fmaf(dst[k * d + j], dst[l * d + j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        qp[K + k * K + l] = acc;
+        qp[K + l * K + k] = acc;
+        if (k == l) qp[k] = acc;
+      }
+    }
+}
+
+// ---- CUDA-core scoring kernel ---------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(SIMT_THREADS)
+score_simt_kernel(ScoreArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int d = A.d;
+  const int ldt = d + 1;
+  tkey_t* scratch = (tkey_t*)smem_raw;                                  // [4][512]
+  float* et = (float*)(scratch + (SIMT_THREADS / 32) * TOPK_CAP);      // [128][d+1]
+  float* pc = et + 128 * ldt;                                         // [QT][K][d]
+  float* qp = pc + SIMT_QT * K * d;                                   // [QT][K+K*K]
+  float* thr = qp + SIMT_QT * (K + K * K);                            // [QT]
+  int* cnt = (int*)(thr + SIMT_QT);                                   // [QT]
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int part = blockIdx.x;
+  const int64_t q0 = (int64_t)blockIdx.y * SIMT_QT;
+  const int nq = (int)((A.Q - q0 < SIMT_QT) ? (A.Q - q0) : SIMT_QT);
+  for (int i = tid; i < nq * K * d; i += SIMT_THREADS) pc[i] = A.Pc[q0 * K * d + i];
+  for (int i = tid; i < nq * (K + K * K); i += SIMT_THREADS) qp[i] = A.qpar[q0 * (K + K * K) + i];
+  if (tid < SIMT_QT) { thr[tid] = __int_as_float(0x7f800000); cnt[tid] = 0; }
+  const int64_t t0 = A.plan.tiles * part / A.plan.parts;
+  const int64_t t1 = A.plan.tiles * (part + 1) / A.plan.parts;
+  tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_CAP;
+  __syncthreads();
+
+  for (int64_t tile = t0; tile < t1; ++tile) {
+    const int64_t r0 = tile * 128;
+    for (int i = tid; i < 128 * d; i += SIMT_THREADS) {
+      int r = i / d, j = i % d;
+      int64_t row = r0 + r;
+      float v = 0.0f;
+      if (row < A.N) v = A.E[row * A.lde + j] - (A.mu ? A.mu[j] : 0.0f);
+      et[r * ldt + j] = v;
+    }
+    __syncthreads();
+    const int64_t row = r0 + tid;
+    const float* er = et + tid * ldt;
+    float e2 = 0.0f;
+    for (int j = 0; j < d; ++j) e2 = fmaf(er[j], er[j], e2);
+    for (int ql = 0; ql < nq; ++ql) {
+      float g[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) g[k] = 0.0f;
+      const float* pq = pc + ql * K * d;
+      for (int j = 0; j < d; ++j) {
+        float e = er[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) g[k] = fmaf(e, pq[k * d + j], g[k]);
+      }
+      float dist = softmin_from_gram<K>(g, e2, qp + ql * (K + K * K));
+      if (row < A.N) {
+        if (A.dist_out) A.dist_out[(q0 + ql) * A.N + row] = dist;
+        if (dist < thr[ql]) {
+          int slot = atomicAdd(&cnt[ql], 1);
+          kbase[(int64_t)ql * TOPK_CAP + slot] = pack_key(dist, (uint32_t)row);
+        }
+      }
+    }
+    __syncthreads();
+    for (int ql = wid; ql < nq; ql += SIMT_THREADS / 32) {
+      int n = cnt[ql];
+      if (n > TOPK_TRIGGER) {
+        int nk = warp_compact(kbase + (int64_t)ql * TOPK_CAP, n, A.plan.kk,
+                              scratch + wid * TOPK_CAP, lane, &thr[ql]);
+        if (lane == 0) cnt[ql] = nk;
+      }
+    }
+    __syncthreads();
+  }
+  for (int ql = wid; ql < nq; ql += SIMT_THREADS / 32) {
+    int nk = warp_compact(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk,
+                          scratch + wid * TOPK_CAP, lane, nullptr);
+    if (lane == 0) A.counts[(int64_t)part * A.Q + q0 + ql] = nk;
+  }
+}
+
+static size_t simt_smem_bytes(int K, int d) {
+  return (size_t)(SIMT_THREADS / 32) * TOPK_CAP * sizeof(tkey_t) + (size_t)128 * (d + 1) * 4 +
+         (size_t)SIMT_QT * K * d * 4 + (size_t)SIMT_QT * (K + K * K) * 4 + SIMT_QT * 8 + 64;
+}
+
+template <int K>
+static int launch_simt(const ScoreArgs& a, cudaStream_t st) {
+  size_t smem = simt_smem_bytes(K, a.d);
+  CFL_CUDA(cudaFuncSetAttribute(score_simt_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  dim3 grid(a.plan.parts, a.plan.nqt);
+  score_simt_kernel<K><<<grid, SIMT_THREADS, smem, st>>>(a);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+// ---- merge of the catalog parts + direct-form rescoring + final sort ---------------------
+// One warp per query.  Exact distance of the kk survivors in direct-difference form
+// (cfl/models/base.py:129-138 arithmetic), then (value, index) order, best k written out.
+__global__ void __launch_bounds__(32)
+merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __restrict__ counts,
+                     int parts, int64_t Q, int kk, int k, const float* __restrict__ Pq,
+                     int64_t ldq, int K, int d, const float* __restrict__ E, int64_t lde,
+                     int64_t idx_base, float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
+  __shared__ tkey_t s[TOPK_CAP];
+  const int lane = threadIdx.x;
+  const int64_t q = blockIdx.x;
+  int fill = 0;
+  for (int p = 0; p < parts; ++p) {
+    int c = counts[(int64_t)p * Q + q];
+    if (fill + c > TOPK_CAP) {
+      for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
+      __syncwarp();
+      warp_sort512(s, lane);
+      fill = fill < kk ? fill : kk;
+    }
+    const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_CAP;
+    for (int i = lane; i < c; i += 32) s[fill + i] = src[i];
+    fill += c;
+    __syncwarp();
+  }
+  for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
+  __syncwarp();
+  warp_sort512(s, lane);
+  fill = fill < kk ? fill : kk;
+  // rescoring in direct form on the raw (uncentred) rows
+  const float* pq = Pq + q * ldq;
+  for (int i = lane; i < fill; i += 32) {
+    uint32_t idx = (uint32_t)(s[i] & 0xffffffffu);
+    const float* e = E + (int64_t)idx * lde;
+    float dk[CFL_MAX_K];
+    float mn = 3.0e38f;
+    for (int kq = 0; kq < K; ++kq) {
+      float acc = 0.0f;
+      for (int j = 0; j < d; ++j) { float df = e[j] - pq[kq * d + j]; acc = fmaf(df, df, acc); }
+      dk[kq] = acc;
+      mn = fminf(mn, acc);
+    }
+    float dist;
+    if (K == 1) {
+      dist = dk[0];
+    } else {
+      float sum = 0.0f;
+      for (int kq = 0; kq < K; ++kq) { dk[kq] = expf(mn - dk[kq]); sum += dk[kq]; }
+      float inv = 1.0f / sum;
+      dist = 0.0f;
+      for (int j = 0; j < d; ++j) {
+        float m = 0.0f;
+        for (int kq = 0; kq < K; ++kq) m = fmaf(dk[kq] * inv, pq[kq * d + j], m);
+        float r = e[j] - m;
+        dist = fmaf(r, r, dist);
+      }
+    }
+    s[i] = pack_key(dist, idx);
+  }
+  __syncwarp();
+  for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
+  __syncwarp();
+  warp_sort512(s, lane);
+  for (int i = lane; i < k; i += 32) {
+    if (i < fill) {
+      top_val[q * k + i] = ord2f((uint32_t)(s[i] >> 32));
+      top_idx[q * k + i] = idx_base + (int64_t)(uint32_t)(s[i] & 0xffffffffu);
+    } else {
+      top_val[q * k + i] = __int_as_float(0x7f800000);
+      top_idx[q * k + i] = -1;
+    }
+  }
+}
+
+// ---- cross-rank merge: rank-based merge of R sorted lists --------------------------------
+__device__ __forceinline__ bool lex_less(float va, int64_t ia, float vb, int64_t ib) {
+  return va < vb || (va == vb && (uint64_t)ia < (uint64_t)ib);
+}
+
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx, int R,
+                  int64_t Q, int k, float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
+  const int64_t q = blockIdx.x;
+  for (int e = threadIdx.x; e < R * k; e += blockDim.x) {
+    int r = e / k, j = e % k;
+    float v = vals[((int64_t)r * Q + q) * k + j];
+    int64_t id = idx[((int64_t)r * Q + q) * k + j];
+    int rank = j;
+    for (int r2 = 0; r2 < R; ++r2) {
+      if (r2 == r) continue;
+      const float* lv = vals + ((int64_t)r2 * Q + q) * k;
+      const int64_t* li = idx + ((int64_t)r2 * Q + q) * k;
+      // r2 < r: count elements <= e ; r2 > r: count elements < e   (stable merge rank)
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        bool before = (r2 < r) ? !lex_less(v, id, lv[mid], li[mid]) : lex_less(lv[mid], li[mid], v, id);
+        if (before) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) { top_val[q * k + rank] = v; top_idx[q * k + rank] = id; }
+  }
+}
+
+}  // namespace cfl
+
+using namespace cfl;
+
+static size_t score_ws_layout(int64_t Q, int K, int d, const ScorePlan& p, size_t* o_pc,
+                              size_t* o_qpar, size_t* o_qimg, size_t* o_keys, size_t* o_cnt) {
+  size_t off = 0;
+  *o_pc = off;   off = align_up(off + (size_t)Q * K * d * 4, 256);
+  *o_qpar = off; off = align_up(off + (size_t)Q * (K + K * K) * 4, 256);
+  *o_qimg = off; off = align_up(off + (p.impl ? score_umma_qimg_bytes(p, K) : 0), 1024);
+  *o_keys = off; off = align_up(off + (size_t)p.parts * Q * TOPK_CAP * sizeof(tkey_t), 256);
+  *o_cnt = off;  off = align_up(off + (size_t)p.parts * Q * sizeof(int), 256);
+  return off + 1024;
+}
+
+extern "C" {
+
+size_t cfl_score_topk_workspace_bytes(int64_t Q, int K, int d, int64_t N, int k) {
+  if (Q <= 0 || N <= 0) return 1024;
+  // the plan (hence the size) may differ between the two kernels: take the larger
+  size_t a, b, c, e, f;
+  ScorePlan p0 = make_score_plan(Q, K, d, N, k, false);
+  size_t s0 = score_ws_layout(Q, K, d, p0, &a, &b, &c, &e, &f);
+  size_t s1 = 0;
+  if (score_umma_qt(K, d) > 0) {
+    ScorePlan p1 = make_score_plan(Q, K, d, N, k, true);
+    s1 = score_ws_layout(Q, K, d, p1, &a, &b, &c, &e, &f);
+  }
+  return (s0 > s1 ? s0 : s1) + 1024;
+}
+
+int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq,
+                   const float* E, int64_t N, int64_t lde, const float* mu, int k,
+                   int64_t idx_base, float* top_val, int64_t* top_idx, float* dist_out, void* ws,
+                   size_t ws_bytes, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(mode == CFL_PCD || mode == CFL_SIAMESE, CFL_ERR_UNSUPPORTED,
+              "score_topk: mode %d not supported on the cross product (pcd, siamese)", mode);
+  CFL_REQUIRE(mode != CFL_SIAMESE || K == 1, CFL_ERR_INVALID, "score_topk: siamese needs K=1");
+  CFL_REQUIRE(K >= 1 && K <= CFL_MAX_K, CFL_ERR_UNSUPPORTED, "score_topk: K=%d outside [1,%d]", K, CFL_MAX_K);
+  CFL_REQUIRE(d >= 1 && d <= 128, CFL_ERR_UNSUPPORTED, "score_topk: d=%d outside [1,128]", d);
+  CFL_REQUIRE(k >= 1 && k <= CFL_MAX_TOPK, CFL_ERR_UNSUPPORTED, "score_topk: k=%d outside [1,%d]", k, CFL_MAX_TOPK);
+  CFL_REQUIRE(Q >= 0 && N >= 0 && N < ((int64_t)1 << 32), CFL_ERR_INVALID, "score_topk: bad Q/N");
+  CFL_REQUIRE(ldq >= (int64_t)K * d && lde >= d, CFL_ERR_INVALID, "score_topk: leading dimension too small");
+  if (Q == 0) return CFL_OK;
+  CFL_REQUIRE(Pq && top_val && top_idx, CFL_ERR_INVALID, "score_topk: NULL argument");
+  CFL_REQUIRE(N == 0 || E, CFL_ERR_INVALID, "score_topk: NULL catalog");
+  cudaStream_t cs = (cudaStream_t)stream;
+  bool umma_ok = N > 0 && score_umma_supported(K, d, E, lde);
+  ScorePlan plan = make_score_plan(Q, K, d, N > 0 ? N : 1, k, umma_ok);
+  size_t o_pc, o_qpar, o_qimg, o_keys, o_cnt;
+  size_t need = score_ws_layout(Q, K, d, plan, &o_pc, &o_qpar, &o_qimg, &o_keys, &o_cnt);
+  CFL_REQUIRE(ws && ws_bytes >= need, CFL_ERR_WORKSPACE, "score_topk: workspace too small (%zu < %zu)",
+              ws_bytes, need);
+  char* base = (char*)ws;
+  ScoreArgs a;
+  a.mode = mode; a.K = K; a.d = d; a.Q = Q; a.N = N; a.lde = lde; a.E = E; a.mu = mu;
+  a.Pc = (float*)(base + o_pc); a.qpar = (float*)(base + o_qpar); a.qimg = base + o_qimg;
+  a.keys = (tkey_t*)(base + o_keys); a.counts = (int*)(base + o_cnt); a.dist_out = dist_out;
+  a.plan = plan;
+  if (N == 0) {
+    CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
+  } else {
+    prep_queries_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, cs>>>(Pq, Q, K, d, ldq, mu,
+                                                                (float*)a.Pc, (float*)a.qpar);
+    CFL_LAUNCH_CHECK();
+    if (plan.impl == 1) {
+      st = score_umma_pack_queries(a, base + o_qimg, cs);
+      if (st != CFL_OK) return st;
+      st = score_umma_launch(a, cs);
+      if (st != CFL_OK) return st;
+    } else {
+      switch (K) {
+        case 1: st = launch_simt<1>(a, cs); break;
+        case 2: st = launch_simt<2>(a, cs); break;
+        case 3: st = launch_simt<3>(a, cs); break;
+        case 4: st = launch_simt<4>(a, cs); break;
+        case 5: st = launch_simt<5>(a, cs); break;
+        case 6: st = launch_simt<6>(a, cs); break;
+        case 7: st = launch_simt<7>(a, cs); break;
+        default: st = launch_simt<8>(a, cs); break;
+      }
+      if (st != CFL_OK) return st;
+    }
+  }
+  merge_rescore_kernel<<<(unsigned)Q, 32, 0, cs>>>(mode, a.keys, a.counts, plan.parts, Q, plan.kk, k,
+                                                  Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+int cfl_topk_merge(const float* vals, const int64_t* idx, int R, int64_t Q, int k, float* top_val,
+                   int64_t* top_idx, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(vals && idx && top_val && top_idx && R >= 1 && Q >= 0 && k >= 1, CFL_ERR_INVALID,
+              "topk_merge: bad arguments");
+  if (Q == 0) return CFL_OK;
+  topk_merge_kernel<<<(unsigned)Q, 128, 0, (cudaStream_t)stream>>>(vals, idx, R, Q, k, top_val, top_idx);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// All-pairs scoring: shared declarations (plan, argument block, soft-min epilogue).
+#pragma once
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace cfl {
+
+// Work decomposition of one cfl_score_topk call.  The catalog is cut into `parts`
+// contiguous ranges of 128-candidate tiles, the queries into tiles of `qt` queries; CTA
+// (part, qtile) keeps its query tile resident and streams its catalog range.
+struct ScorePlan {
+  int impl;        // 1 = tcgen05 (score_umma.cu), 0 = CUDA-core kernel (score.cu)
+  int qt;          // queries per query tile
+  int nqt;         // number of query tiles
+  int parts;       // catalog parts
+  int64_t tiles;   // 128-candidate tiles in the catalog
+  int kk;          // internal list length: k + slack (<= 128)
+  int dpad;        // d rounded up to 8 (MMA K granularity for tf32)
+};
+
+struct ScoreArgs {
+  int mode, K, d;
+  int64_t Q, N, lde;
+  const float* E;        // raw catalog [N, lde]
+  const float* mu;       // centring vector or NULL
+  const float* Pc;       // centred query prototypes [Q,K,d] (dense)
+  const float* qpar;     // per query: p2[K] then pp[K*K]
+  const void* qimg;      // tcgen05 B-operand image per query tile (score_umma.cu)
+  tkey_t* keys;           // [parts, Q, TOPK_CAP]
+  int* counts;           // [parts, Q]
+  float* dist_out;       // optional dense [Q,N]
+  ScorePlan plan;
+};
+
+ScorePlan make_score_plan(int64_t Q, int K, int d, int64_t N, int k, bool umma_ok);
+bool score_umma_supported(int K, int d, const float* E, int64_t lde);
+size_t score_umma_qimg_bytes(const ScorePlan& p, int K);
+int score_umma_pack_queries(const ScoreArgs& a, void* qimg, cudaStream_t st);
+int score_umma_launch(const ScoreArgs& a, cudaStream_t st);
+int score_umma_qt(int K, int d);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Soft-min distance of one (candidate, query) pair from the Gram values g_k = p_k.e
+// (SURVEY App. A.3):  s = softmax_k(2 g_k - |p_k|^2)   [the |e|^2 term cancels],
+//   dist = |e|^2 - 2 sum_k s_k g_k + sum_kl s_k s_l (p_k.p_l).
+// qp -> p2[K] followed by pp[K*K] (shared memory, warp-uniform address => broadcast).
+template <int K>
+__device__ __forceinline__ float softmin_from_gram(const float (&g)[K], float e2,
+                                                   const float* __restrict__ qp) {
+  if (K == 1) return fmaf(-2.0f, g[0], e2 + qp[0]);
+  float a[K];
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { a[k] = fmaf(2.0f, g[k], -qp[k]); mx = fmaxf(mx, a[k]); }
+  float sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    a[k] = fast_ex2((a[k] - mx) * 1.4426950408889634f);
+    sum += a[k];
+  }
+  float inv = fast_rcp(sum);
+  float t1 = 0.0f, t2 = 0.0f;
+  const float* pp = qp + K;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    t1 = fmaf(a[k], g[k], t1);
+    float row = 0.5f * pp[k * K + k] * a[k];
+#pragma unroll
+    for (int l = k + 1; l < K; ++l) row = fmaf(pp[k * K + l], a[l], row);
+    t2 = fmaf(a[k], row, t2);                 // half of sum_kl a_k a_l pp_kl
+  }
+  // dist = e2 + inv * (-2 t1 + inv * 2 t2)
+  return fmaf(inv, 2.0f * fmaf(inv, t2, -t1), e2);
+}
+#endif
+
+}  // namespace cfl

@@ -1,0 +1,56 @@
+// Running per-query top-k machinery shared by the all-pairs kernels.
+//
+// A (distance, candidate) pair is one u64 key = (orderable(dist) << 32) | local_index, so the
+// ranking order "ascending distance, ties -> lower index" is plain u64 '<'.
+//
+// Each CTA owns, for every query of its query tile, an append buffer of TOPK_CAP keys in the
+// caller's workspace (L2 resident) plus a count and a threshold in shared memory.  Candidates
+// are visited in increasing index order, so a candidate may be dropped iff dist >= thr where
+// thr = the kk-th best value at the last compaction (strictly-less test keeps the tie rule
+// exact).  A tile adds at most TOPK_TILE keys per query; whenever a count exceeds
+// TOPK_CAP - TOPK_TILE - ... at a tile boundary, one warp sorts the buffer (bitonic network in
+// a 4 KB shared scratch), keeps the best kk and tightens thr.
+#pragma once
+#include "common.cuh"
+
+namespace cfl {
+
+constexpr int TOPK_CAP = 512;     // keys per (part, query) buffer
+constexpr int TOPK_TILE = 128;    // max appends per query between two compaction points
+constexpr int TOPK_TRIGGER = TOPK_CAP - TOPK_TILE;   // compact when cnt > 384 at a tile end
+
+typedef unsigned long long tkey_t;
+
+// Sorts 512 keys in shared memory ascending; one warp.
+__device__ __forceinline__ void warp_sort512(tkey_t* s, int lane) {
+  for (int size = 2; size <= TOPK_CAP; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll 4
+      for (int t = lane; t < TOPK_CAP / 2; t += 32) {
+        int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        int j = i | stride;
+        bool asc = (i & size) == 0;
+        tkey_t a = s[i], b = s[j];
+        if ((a > b) == asc) { s[i] = b; s[j] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// One warp: keep the best kk of the n keys in buf (global), sorted; returns new count and
+// writes the tightened threshold.
+__device__ __forceinline__ int warp_compact(tkey_t* __restrict__ buf, int n, int kk,
+                                            tkey_t* scratch, int lane, float* thr_out) {
+  for (int i = lane; i < TOPK_CAP; i += 32) scratch[i] = (i < n) ? buf[i] : CFL_KEY_INF;
+  __syncwarp();
+  warp_sort512(scratch, lane);
+  int nk = n < kk ? n : kk;
+  for (int i = lane; i < nk; i += 32) buf[i] = scratch[i];
+  if (lane == 0 && thr_out)
+    *thr_out = (n >= kk) ? ord2f((uint32_t)(scratch[kk - 1] >> 32)) : __int_as_float(0x7f800000);
+  __syncwarp();
+  return nk;
+}
+
+}  // namespace cfl

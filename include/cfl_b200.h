@@ -1,0 +1,171 @@
+/* cfl_b200.h -- C ABI of the B200-native CFL compatibility-scoring hot path.
+ *
+ * The reference (appier/compatibility-family-learning) has no FFI: the path is reached
+ * through Python constructors that emit stock TensorFlow ops.  Each entry point below
+ * replaces the TF op sequence of one reference call site (cited per function, paths
+ * relative to the reference root); the Python mirror in
+ * compatibility-family-learning_b200/cfl/ binds them with ctypes (INTEGRATION.md shows
+ * the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in
+ *     _host; fp32 row-major; `ld*` are leading dimensions in ELEMENTS;
+ *   - nothing is allocated inside: cfl_*_workspace_bytes() tells the caller what to pass;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and
+ *     re-entrant per stream; no global mutable state except a per-device immutable
+ *     property cache;
+ *   - return value: CFL_OK (0) or a negative cfl_status; cfl_last_error() returns a
+ *     thread-local message.  There is NO CPU fallback: without an sm_100 device every
+ *     compute call returns CFL_ERR_DEVICE.
+ */
+#ifndef CFL_B200_H_
+#define CFL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CFL_OK = 0,
+  CFL_ERR_INVALID = -1,     /* bad argument (shape, NULL, alignment)          */
+  CFL_ERR_CUDA = -2,        /* a CUDA runtime call / launch failed            */
+  CFL_ERR_UNSUPPORTED = -3, /* shape outside the compiled range               */
+  CFL_ERR_WORKSPACE = -4,   /* workspace too small                            */
+  CFL_ERR_DEVICE = -5       /* no sm_100 device                               */
+} cfl_status;
+
+/* dist_type -- cfl/models/base.py:109 (monomer), :119 (siamese), :125 (pcd*) */
+typedef enum { CFL_PCD = 0, CFL_MONOMER = 1, CFL_SIAMESE = 2 } cfl_mode;
+/* act_type -- cfl/models/cfl.py:579-586 (+ lrelu, cfl/ops.py:10, for hidden layers) */
+typedef enum { CFL_ACT_LINEAR = 0, CFL_ACT_TANH = 1, CFL_ACT_SIGMOID = 2, CFL_ACT_RELU = 3,
+               CFL_ACT_LRELU = 4 } cfl_act;
+
+#define CFL_MAX_K 8        /* num_components                                   */
+#define CFL_MAX_D 256      /* latent_size (paired kernels); all-pairs: <= 128  */
+#define CFL_MAX_TOPK 128   /* k of the all-pairs ranking                       */
+#define CFL_PAIR_STATS 8   /* doubles written by cfl_pair_loss_fwd             */
+
+const char* cfl_last_error(void);
+int cfl_version(void);
+/* Fills SM count and compute capability of the current device. */
+int cfl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage 1 -- projection.  Replaces fully_connected_weight_norm (cfl/layers.py:80-94:
+ * tf.matmul, g/sqrt(reduce_sum(square(V))), bias_add, activation) and, with
+ * weight_norm = 0, tf.contrib.layers.fully_connected (cfl/models/dist.py:45-65).  The
+ * input normaliser x/scale (cfl/ops.py:198-199; normalize_v2 with a single norm,
+ * cfl/ops.py:107-110) is folded in as in_scale.
+ *   y[b,j]  = act( (sum_i in_scale*x[b,i]*V[i,j]) * s_j + bias[j] ),  s_j = g_j/|V_:j| (or 1)
+ *   z[b,j]  = sum_i in_scale*x[b,i]*V[i,j]          (optional, saved for the backward)
+ *   pre[b,j]= value before the activation          (optional)
+ * Arithmetic: 3xTF32 error-compensated tcgen05 MMA, fp32 accumulate (fp32-equivalent).
+ * ------------------------------------------------------------------------------------- */
+size_t cfl_project_fwd_workspace_bytes(int64_t B, int F, int N);
+int cfl_project_fwd(const float* x, int64_t B, int F, int64_t ldx,
+                    const float* V, int N, int64_t ldV,
+                    const float* g, const float* bias, int weight_norm,
+                    float in_scale, int act,
+                    float* y, int64_t ldy, float* pre, float* z,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of the above w.r.t. (V, g, bias) -- the tf.gradients the reference gets
+ * implicitly from AdamOptimizer.minimize (cfl/models/cfl.py:1083-1085,
+ * cfl/models/dist.py:291-293).  dy is dL/dy (post-activation); y the saved output.
+ *   accumulate != 0 adds into dV/dg/dbias (pos and neg batches share one encoder).
+ *   reg_c adds the l2_regularizer gradient c*V and c*bias (cfl/models/cfl.py:870-874). */
+size_t cfl_project_bwd_workspace_bytes(int64_t B, int F, int N);
+int cfl_project_bwd(const float* x, int64_t B, int F, int64_t ldx,
+                    const float* V, int N, int64_t ldV,
+                    const float* g, const float* bias, int weight_norm, float in_scale, int act,
+                    const float* y, int64_t ldy, const float* z, const float* dy, int64_t lddy,
+                    float* dV, float* dg, float* dbias, int accumulate, float reg_c,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage 2, paired rows -- DistBase.build_dist (cfl/models/base.py:107-146, identical copy
+ * cfl/models/dist.py:70-89) + Thresholder (cfl/models/blocks.py:21-22) + the per-batch
+ * reductions of _build_dist_losses (cfl/models/cfl.py:879-902,932-937).
+ *   pcd:     a = v (target e0) [B,d];  P = source prototypes [B,K,d]
+ *   monomer: a = source e0;  P = TARGET prototypes;  w = source gate softmax [B,K]
+ *   siamese: a, P = the two e0 rows (K = 1)
+ *   label: 1 positive pairs, 0 negative pairs, -1 no loss statistics
+ * Outputs (each optional): dist[B], score[B] = max(theta,1e-6) - dist, s[B,K] softmax,
+ * stats[8] doubles = { sum softplus(-/+score), #correct, sum dist, sum sqrt(dist+1e-7),
+ *                      sum max(0,margin-dist), B, 0, 0 } reduced in a fixed order.
+ * Direct-difference form, fp32.
+ * ------------------------------------------------------------------------------------- */
+size_t cfl_pair_workspace_bytes(int64_t B);
+int cfl_pair_loss_fwd(int mode, const float* a, int64_t lda, const float* P, int64_t ldP,
+                      const float* w, int64_t B, int K, int d,
+                      const float* theta, int label, float margin,
+                      float* dist, float* score, float* s, double* stats,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of the paired distance + loss (its own kernel; recomputes dist/softmax).
+ * Upstream: ddist_in[B] if non-NULL, else the fused loss gradient
+ *   label 1:  c_ce*sigmoid(dist-theta+) + c_lin        (cfl.py:879-882, 912-929)
+ *   label 0: -c_ce*sigmoid(theta+-dist) - c_margin*[dist<margin]
+ * dtheta_sum (double, optional) = -sum of the sigmoid-CE part (apply the theta>=1e-6
+ * mask on the host, cfl/models/blocks.py:21).  Outputs da[B,d], dP[B,K,d], dw[B,K]. */
+int cfl_pair_loss_bwd(int mode, const float* a, int64_t lda, const float* P, int64_t ldP,
+                      const float* w, int64_t B, int K, int d,
+                      const float* theta, int label, float margin,
+                      float c_ce, float c_lin, float c_margin, const float* ddist_in,
+                      float* da, int64_t ldda, float* dP, int64_t lddP, float* dw,
+                      double* dtheta_sum, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage 2, all pairs (extension, SURVEY App. A.6: the pair scorer on the QxN cross
+ * product; no reference call site).  pcd (K>=1) and siamese (K=1).
+ *   Pq[Q,K,d] query prototypes, E[N,d] catalog embeddings, mu[d] optional centring vector
+ *   (distance is translation invariant; centring keeps the Gram form accurate).
+ * Gram form d_k = |e|^2+|p_k|^2-2 p_k.e on tensor cores (3xTF32), soft-min epilogue and a
+ * running per-query top-(k+slack) fused behind the MMA; the slack winners are rescored in
+ * direct-difference form and the best k returned:
+ *   top_val[Q,k] ascending exact distances, top_idx[Q,k] = idx_base + row (int64);
+ *   ties -> lower index.  dist_out[Q,N] (optional, parity/debug) = un-rescored Gram values.
+ * ------------------------------------------------------------------------------------- */
+size_t cfl_score_topk_workspace_bytes(int64_t Q, int K, int d, int64_t N, int k);
+int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq,
+                   const float* E, int64_t N, int64_t lde, const float* mu,
+                   int k, int64_t idx_base,
+                   float* top_val, int64_t* top_idx, float* dist_out,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* Merge R sorted lists per query (the per-rank results after ncclAllGather) into one:
+ * vals[R,Q,k], idx[R,Q,k] -> top_val[Q,k], top_idx[Q,k]; order (value, index). */
+int cfl_topk_merge(const float* vals, const int64_t* idx, int R, int64_t Q, int k,
+                   float* top_val, int64_t* top_idx, void* stream);
+
+/* Column mean of a catalog E[N,d] (the centring vector mu). */
+int cfl_col_mean(const float* E, int64_t N, int d, int64_t lde, float* mu,
+                 void* ws, size_t ws_bytes, void* stream);
+size_t cfl_col_mean_workspace_bytes(int64_t N, int d);
+
+/* ---------------------------------------------------------------------------------------
+ * AUC -- replaces sklearn.metrics.roc_auc_score at cfl/utils.py:267-268 and the accuracy
+ * counts at cfl/utils.py:247,264.  Exact integers: out[0] = 2*#{s+>s-} + #{s+==s-},
+ * out[1] = n_pos, out[2] = n_neg, out[3] = #{s+>0} + #{s-<=0}.  AUC = out[0]/(2 n+ n-).
+ * Radix sort of the negatives + rank/count of every positive.
+ * ------------------------------------------------------------------------------------- */
+size_t cfl_auc_workspace_bytes(int64_t n_pos, int64_t n_neg);
+int cfl_auc(const float* pos_scores, int64_t n_pos, const float* neg_scores, int64_t n_neg,
+            int64_t* out4, void* ws, size_t ws_bytes, void* stream);
+
+/* TF-1.x Adam (cfl/models/cfl.py:1083-1085): lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+ * p -= lr_t*m/(sqrt(v)+eps).  grad_scale multiplies g first (1/world for DP averaging). */
+int cfl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step,
+                  float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* Self-test of the tcgen05 3xTF32 GEMM core on one tile: D[128,N] = A[128,Kd] * B[N,Kd]^T.
+ * Test-only; used by tests/ to validate descriptors and layouts in isolation. */
+int cfl_selftest_umma(const float* A, const float* Bm, float* D, int N, int Kd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFL_B200_H_ */

@@ -1,0 +1,66 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds/loads and exports every
+symbol include/cfl_b200.h declares, the ctypes table matches the header, and compute calls
+fail loudly (no fallback) without an sm_100 device."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cfl_b200.h")
+
+
+def _declared():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cfl_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cfl import _native
+    lib = _native.lib()
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in cfl_b200.h but not exported"
+    assert set(names) == set(_native.SIGNATURES), "ctypes table and header disagree"
+    assert lib.cfl_version() >= 100
+
+
+def test_workspace_queries_do_not_need_a_gpu():
+    from cfl import _native
+    lib = _native.lib()
+    assert lib.cfl_pair_workspace_bytes(1000) > 0
+    assert lib.cfl_project_bwd_workspace_bytes(100, 4096, 80) >= 4096 * 80 * 4
+    assert lib.cfl_auc_workspace_bytes(10, 1 << 20) >= 2 * 4 * (1 << 20)
+    assert lib.cfl_score_topk_workspace_bytes(1024, 3, 64, 1 << 20, 100) > 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_calls_fail_loudly_without_a_gpu():
+    from cfl import _native
+    lib = _native.lib()
+    st = lib.cfl_adam_step(None, None, None, None, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 1.0, None)
+    assert st == -5                                    # CFL_ERR_DEVICE
+    assert b"device" in lib.cfl_last_error().lower()
+    with pytest.raises(_native.CflNativeError):
+        _native.project_fwd(torch.zeros(2, 4), torch.zeros(4, 3))   # CPU tensors are rejected
+
+
+def test_missing_library_is_an_error_not_a_fallback(monkeypatch):
+    from cfl import _native
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", "/nonexistent/libcfl_b200.so")
+    with pytest.raises(_native.CflNativeError):
+        _native.lib()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "compatibility-family-learning_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

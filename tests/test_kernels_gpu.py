@@ -1,0 +1,324 @@
+"""GPU parity tests: every C-ABI kernel against the fp64 oracle on the same seeded inputs.
+
+Bars: fp32 distances / losses / gradients within 1e-4 relative of the fp64
+oracle; integer work (top-k indices, AUC counts) bit-exact apart from documented near-ties.
+All calls go through the C ABI (cfl._native -> libcfl_b200.so)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cfl_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-4
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def assert_close(got, want, rtol=RTOL, atol=0.0, msg=""):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = np.maximum(np.abs(want), atol / rtol if rtol else 0)
+    err = np.abs(got - want)
+    bad = err > rtol * scale + atol
+    assert not bad.any(), f"{msg} max rel err {np.max(err / np.maximum(np.abs(want), 1e-30)):.3e} at {np.argmax(bad)}"
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from cfl import _native
+    _native.lib()
+    sms, major, _ = _native.device_info()
+    assert major == 10, "these tests need a B200 (sm_100)"
+    return _native
+
+
+# ---------------------------------------------------------------------------- paired fwd/bwd
+def test_pair_pcd_golden(nat):
+    g = np.load(os.path.join(GOLD, "pair_pcd.npz"))
+    n = len([k for k in g.files if k.endswith("_v")])
+    for i in range(n):
+        v, P, up = g[f"c{i}_v"], g[f"c{i}_P"], g[f"c{i}_up"]
+        dist, _, s, _ = nat.pair_loss_fwd("pcd", dev(v), dev(P), want_s=True)
+        # near-duplicate cases: the oracle distance is tiny next to |v|^2; the direct form keeps
+        # relative accuracy, so the same 1e-4 bar applies
+        assert_close(host(dist), g[f"c{i}_dist"], msg=f"case {i} dist")
+        assert_close(host(s), g[f"c{i}_s"], rtol=1e-4, atol=1e-6, msg=f"case {i} softmax")
+        da, dP, _, _ = nat.pair_loss_bwd("pcd", dev(v), dev(P), ddist=dev(up))
+        sc = np.abs(g[f"c{i}_dv"]).max()
+        assert_close(host(da), g[f"c{i}_dv"], atol=2e-5 * sc, msg=f"case {i} dv")
+        assert_close(host(dP), g[f"c{i}_dP"], atol=2e-5 * sc, msg=f"case {i} dP")
+
+
+def test_pair_monomer_siamese_golden(nat):
+    g = np.load(os.path.join(GOLD, "pair_modes.npz"))
+    a, b, Pt, w, up = (g[k] for k in ("a", "b", "Pt", "w", "up"))
+    dist, *_ = nat.pair_loss_fwd("monomer", dev(a), dev(Pt), w=dev(w))
+    assert_close(host(dist), g["monomer"], msg="monomer")
+    da, dPt, dw, _ = nat.pair_loss_bwd("monomer", dev(a), dev(Pt), w=dev(w), ddist=dev(up))
+    assert_close(host(da), g["da"], atol=1e-5 * np.abs(g["da"]).max())
+    assert_close(host(dPt), g["dPt"], atol=1e-5 * np.abs(g["dPt"]).max())
+    assert_close(host(dw), g["dw"], atol=1e-5 * np.abs(g["dw"]).max())
+    dist, *_ = nat.pair_loss_fwd("siamese", dev(a), dev(b)[:, None, :])
+    assert_close(host(dist), g["siamese"], msg="siamese")
+
+
+@pytest.mark.parametrize("B,K,d", [(1, 1, 1), (5, 2, 3), (257, 3, 64), (1000, 4, 20), (300, 8, 128),
+                                   (64, 5, 12), (77, 2, 200), (4096, 4, 10)])
+def test_pair_random_shapes(nat, B, K, d):
+    rng = np.random.default_rng(B * 7 + K * 3 + d)
+    v = rng.normal(size=(B, d)).astype(np.float32)
+    P = (v[:, None, :] + rng.normal(size=(B, K, d))).astype(np.float32)
+    up = rng.normal(size=B).astype(np.float32)
+    dist, *_ = nat.pair_loss_fwd("pcd", dev(v), dev(P))
+    assert_close(host(dist), O.pcd_dist(v.astype(np.float64), P.astype(np.float64)))
+    da, dP, _, _ = nat.pair_loss_bwd("pcd", dev(v), dev(P), ddist=dev(up))
+    dv_o, dP_o = O.pcd_dist_bwd(v.astype(np.float64), P.astype(np.float64), up.astype(np.float64))
+    assert_close(host(da), dv_o, atol=2e-5 * np.abs(dv_o).max())
+    assert_close(host(dP), dP_o, atol=2e-5 * np.abs(dP_o).max())
+
+
+def test_pair_empty_batch(nat):
+    v = torch.zeros(0, 8, device="cuda")
+    P = torch.zeros(0, 2, 8, device="cuda")
+    th = torch.tensor([0.5], device="cuda")
+    dist, _, _, stats = nat.pair_loss_fwd("pcd", v, P, theta=th, label=1, want_stats=True)
+    assert dist.numel() == 0 and float(stats.abs().sum()) == 0.0
+
+
+def test_fused_loss_stats_and_gradient_golden(nat):
+    """Fused loss statistics + the fused upstream gradient (cfl/models/cfl.py:868-937)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    LOSS_OPTS = mg.LOSS_OPTS
+    g = np.load(os.path.join(GOLD, "loss.npz"))
+    dp, dn = g["d_pos"], g["d_neg"]
+    # build pairs whose distance is exactly the golden d: K=1, d=1, v=sqrt(dist), P=0
+    vp, vn = np.sqrt(dp)[:, None], np.sqrt(dn)[:, None]
+    Pp, Pn = np.zeros((len(dp), 1, 1), np.float32), np.zeros((len(dn), 1, 1), np.float32)
+    for i, o in enumerate(LOSS_OPTS):
+        o = dict(o)
+        th = dev(np.array([o.pop("theta")], dtype=np.float32))
+        pw = o.get("pos_weight") or 1.0
+        margin = o.get("caffe_margin") or 0.0
+        _, sp, _, st_p = nat.pair_loss_fwd("pcd", dev(vp), dev(Pp), theta=th, label=1, margin=margin,
+                                           want_score=True, want_stats=True)
+        _, sn, _, st_n = nat.pair_loss_fwd("pcd", dev(vn), dev(Pn), theta=th, label=0, margin=margin,
+                                           want_score=True, want_stats=True)
+        st_p, st_n = host(st_p), host(st_n)
+        Bp, Bn = len(dp), len(dn)
+        assert_close(st_p[0] / Bp, g[f"o{i}_p_loss_pos"], msg=f"opt {i} L+")
+        assert_close(st_n[0] / Bn, g[f"o{i}_p_loss_neg"], msg=f"opt {i} L-")
+        assert_close(0.5 * (st_p[1] / Bp + st_n[1] / Bn), g[f"o{i}_accuracy"], rtol=1e-12)
+        assert_close(st_p[3] / Bp, g[f"o{i}_pos_dists_adapt"], msg="sqrt+")
+        assert_close(host(sp), g[f"o{i}_score_pos"], atol=1e-6)
+        if o.get("caffe_margin"):
+            cd = 0.5 * (pw * st_p[2] / Bp + st_n[4] / Bn)
+            assert_close(cd, g[f"o{i}_cd_loss"], msg="caffe margin term")
+        # fused gradient: d total / d dist, via K=1,d=1 pairs: d dist / d v = 2 v
+        use_th = o.get("use_threshold", True)
+        c_ce_p = (pw / Bp) if use_th else 0.0
+        c_ce_n = (1.0 / Bn) if use_th else 0.0
+        c_lin = (0.5 * pw / Bp) if o.get("caffe_margin") else ((o.get("lambda_m") or 0.0) * pw / Bp)
+        c_mar = (0.5 / Bn) if o.get("caffe_margin") else 0.0
+        da_p, _, _, dth_p = nat.pair_loss_bwd("pcd", dev(vp), dev(Pp), theta=th, label=1, margin=margin,
+                                              c_ce=c_ce_p, c_lin=c_lin, want_dtheta=True)
+        da_n, _, _, dth_n = nat.pair_loss_bwd("pcd", dev(vn), dev(Pn), theta=th, label=0, margin=margin,
+                                              c_ce=c_ce_n, c_margin=c_mar, want_dtheta=True)
+        assert_close(host(da_p)[:, 0], g[f"o{i}_gpos"] * 2 * vp[:, 0], atol=1e-7, msg=f"opt {i} g+")
+        assert_close(host(da_n)[:, 0], g[f"o{i}_gneg"] * 2 * vn[:, 0], atol=1e-7, msg=f"opt {i} g-")
+        gth = float(host(dth_p)[0] + host(dth_n)[0]) * (float(th.item()) >= 1e-6)
+        assert_close(gth, g[f"o{i}_gtheta"], atol=1e-7, msg=f"opt {i} dtheta")
+
+
+# ---------------------------------------------------------------------------- projection
+def test_project_golden(nat):
+    g = np.load(os.path.join(GOLD, "project.npz"))
+    x, V0, Vp, g0, gp, b0, bp = (dev(g[k]) for k in ("x", "V0", "Vp", "g0", "gp", "b0", "bp"))
+    sc = float(g["in_scale"])
+    for act in ("linear", "tanh", "sigmoid", "relu"):
+        e, _, _ = nat.project_fwd(x, V0, g0, b0, True, sc, act)
+        P, _, _ = nat.project_fwd(x, Vp, gp, bp, True, sc, act)
+        assert_close(host(e), g[f"e_{act}"], atol=1e-5, msg=f"e0 {act}")
+        assert_close(host(P).reshape(g[f"P_{act}"].shape), g[f"P_{act}"], atol=1e-5, msg=f"P {act}")
+    e, _, _ = nat.project_fwd(x, V0, None, b0, False, sc, None)
+    assert_close(host(e), g["plain_e"], atol=1e-5, msg="plain FC")
+    y, pre, z = nat.project_fwd(x, Vp, gp, bp, True, sc, None, want_pre=True, want_z=True)
+    dV, dg, db = nat.project_bwd(x, Vp, gp, bp, True, sc, None, y, z, dev(g["dy"]))
+    assert_close(host(dV), g["dVp"], atol=2e-5 * np.abs(g["dVp"]).max(), msg="dV")
+    assert_close(host(dg), g["dgp"], atol=2e-5 * np.abs(g["dgp"]).max(), msg="dg")
+    assert_close(host(db), g["dbp"], atol=2e-5 * np.abs(g["dbp"]).max(), msg="db")
+
+
+@pytest.mark.parametrize("B,F,N", [(100, 4096, 80), (500, 1024, 192), (1000, 2048, 20), (3, 7, 5),
+                                   (4097, 1024, 64), (256, 784, 60), (128, 6272, 45)])
+def test_project_fwd_shapes(nat, B, F, N):
+    rng = np.random.default_rng(B + F + N)
+    x = np.maximum(rng.normal(size=(B, F)), 0).astype(np.float32)
+    V = O.xavier_uniform(rng, F, N)
+    gg = rng.uniform(0.5, 1.5, N).astype(np.float32)
+    b = (0.1 * rng.normal(size=N)).astype(np.float32)
+    y, _, _ = nat.project_fwd(dev(x), dev(V), dev(gg), dev(b), True, 0.5, "tanh")
+    want = O.fc_weight_norm(0.5 * x.astype(np.float64), V.astype(np.float64), gg.astype(np.float64),
+                            b.astype(np.float64), "tanh")
+    assert_close(host(y), want, atol=2e-6, msg="project fwd")
+
+
+@pytest.mark.parametrize("B,F,N,wn,act", [(100, 512, 80, True, "linear"), (3000, 256, 33, True, "tanh"),
+                                          (64, 100, 20, False, "relu"), (5000, 128, 192, False, None)])
+def test_project_bwd_shapes(nat, B, F, N, wn, act):
+    rng = np.random.default_rng(B + F + N)
+    x = rng.normal(size=(B, F)).astype(np.float32)
+    V = O.xavier_uniform(rng, F, N)
+    gg = rng.uniform(0.5, 1.5, N).astype(np.float32) if wn else None
+    b = (0.1 * rng.normal(size=N)).astype(np.float32)
+    dy = rng.normal(size=(B, N)).astype(np.float32)
+    y, pre, z = nat.project_fwd(dev(x), dev(V), None if gg is None else dev(gg), dev(b), wn, 1.0, act,
+                                want_pre=True, want_z=True)
+    dV, dg, db = nat.project_bwd(dev(x), dev(V), None if gg is None else dev(gg), dev(b), wn, 1.0, act,
+                                 y, z, dev(dy), reg_c=0.01)
+    x6, V6, dy6 = x.astype(np.float64), V.astype(np.float64), dy.astype(np.float64)
+    if wn:
+        yo, preo, zo = O.fc_weight_norm(x6, V6, gg.astype(np.float64), b.astype(np.float64), act, return_pre=True)
+    else:
+        preo = x6 @ V6 + b
+        yo, zo = O.activation(preo, act), x6 @ V6
+    dpre = dy6 * O.activation_grad(yo, preo, act)
+    if wn:
+        dVo, dgo, dbo = O.fc_weight_norm_bwd(x6, V6, gg.astype(np.float64), zo, dpre)
+        assert_close(host(dg), dgo, atol=3e-5 * np.abs(dgo).max(), msg="dg")
+    else:
+        dVo, dbo = x6.T @ dpre, dpre.sum(0)
+    dVo = dVo + 0.01 * V6
+    dbo = dbo + 0.01 * b
+    assert_close(host(dV), dVo, atol=3e-5 * np.abs(dVo).max(), msg="dV")
+    assert_close(host(db), dbo, atol=3e-5 * np.abs(dbo).max(), msg="db")
+
+
+# ---------------------------------------------------------------------------- all pairs
+def _check_topk(nat, Pq, E, k, mu=None, dense_tol=True):
+    Q, K, d = Pq.shape
+    D = O.all_pairs_dist(Pq.astype(np.float64), E.astype(np.float64))
+    tv, ti, dense = nat.score_topk(dev(Pq), dev(E), k, mu=None if mu is None else dev(mu), want_dense=True)
+    tv, ti, dense = host(tv), ti.cpu().numpy(), host(dense)
+    # (1) un-rescored Gram values: 1e-4*dist + 8 eps32 (|v|^2 + max|p_k|^2), centred norms
+    c = np.zeros(d) if mu is None else mu.astype(np.float64)
+    e2 = ((E - c) ** 2).sum(-1)
+    p2 = ((Pq - c) ** 2).sum(-1).max(-1)
+    tol = 1e-4 * D + 8 * np.finfo(np.float32).eps * (e2[None, :] + p2[:, None])
+    assert (np.abs(dense - D) <= tol).all(), f"gram-form error {np.max(np.abs(dense - D) / tol):.2f}x tolerance"
+    # (2) reported distances are the exact (rescored) ones
+    kk = min(k, E.shape[0])
+    want_v, want_i = O.rank_topk(D, kk)
+    assert_close(tv[:, :kk], np.take_along_axis(D, ti[:, :kk], 1), msg="rescored values")
+    # (3) index sets equal, except candidates within tolerance of the k-th distance
+    for q in range(Q):
+        if (ti[q, :kk] == want_i[q]).all():
+            continue
+        kth = want_v[q, -1]
+        sym = set(ti[q, :kk].tolist()) ^ set(want_i[q].tolist())
+        for c_ in sym:
+            assert abs(D[q, c_] - kth) <= 2e-6 * max(kth, 1.0) + 1e-7, f"q={q} cand {c_} is not a near-tie"
+        # order must be ascending in the oracle's distance up to fp32 rounding
+        assert (np.diff(D[q, ti[q, :kk]]) >= -2e-6 * max(kth, 1.0)).all()
+    if kk < k:
+        assert (ti[:, kk:] == -1).all() and np.isinf(tv[:, kk:]).all()
+    return tv, ti
+
+
+def test_score_topk_golden_with_exact_ties(nat):
+    g = np.load(os.path.join(GOLD, "rank.npz"))
+    k = int(g["k"])
+    tv, ti = _check_topk(nat, g["Pq"], g["E"], k)
+    # rows 7, 100, 650 of E are identical: wherever one of them is ranked, ties -> lower index
+    for q in range(ti.shape[0]):
+        pos = {c: int(np.where(ti[q] == c)[0][0]) for c in (7, 100, 650) if c in ti[q]}
+        if len(pos) == 3:
+            assert pos[7] < pos[100] < pos[650]
+    assert (ti == g["top_idx"]).mean() > 0.999
+
+
+@pytest.mark.parametrize("Q,K,d,N,k", [(1, 1, 8, 300, 10), (7, 2, 10, 1000, 100), (33, 3, 64, 5000, 100),
+                                       (64, 4, 20, 20000, 100), (5, 8, 128, 3000, 50), (20, 5, 12, 129, 128),
+                                       (3, 4, 15, 50, 100), (130, 3, 64, 2500, 20)])
+def test_score_topk_shapes(nat, Q, K, d, N, k):
+    rng = np.random.default_rng(Q + K + d + N)
+    E = rng.normal(size=(N, d)).astype(np.float32)
+    Pq = (E[rng.integers(0, N, Q)][:, None, :] + 0.5 * rng.normal(size=(Q, K, d))).astype(np.float32)
+    _check_topk(nat, Pq, E, k)
+
+
+def test_score_topk_adversarial_offset_needs_centring(nat):
+    """+10 common offset, 25% near-duplicate (query, candidate) pairs."""
+    rng = np.random.default_rng(99)
+    Q, K, d, N, k = 16, 4, 64, 4000, 100
+    E = (rng.normal(size=(N, d)) + 10).astype(np.float32)
+    Pq = (E[rng.integers(0, N, Q)][:, None, :] + 0.5 * rng.normal(size=(Q, K, d))).astype(np.float32)
+    Pq[::4, 0, :] = E[rng.integers(0, N, len(Pq[::4]))] + 1e-3 * rng.normal(size=(len(Pq[::4]), d)).astype(np.float32)
+    mu = host(nat.col_mean(dev(E))).astype(np.float32)
+    np.testing.assert_allclose(mu, E.astype(np.float64).mean(0), rtol=1e-6)
+    _check_topk(nat, Pq, E, k, mu=mu)
+
+
+def test_score_topk_deterministic(nat):
+    rng = np.random.default_rng(5)
+    E = dev(rng.normal(size=(30000, 20)).astype(np.float32))
+    Pq = dev(rng.normal(size=(40, 4, 20)).astype(np.float32))
+    a = nat.score_topk(Pq, E, 100)
+    b = nat.score_topk(Pq, E, 100)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_topk_merge_equals_single_list(nat):
+    """Catalog sharding: merging per-shard top-k == top-k of the whole catalog, bit for bit."""
+    rng = np.random.default_rng(6)
+    N, d, Q, K, k, R = 8000, 20, 24, 4, 100, 4
+    E = dev(rng.normal(size=(N, d)).astype(np.float32))
+    Pq = dev(rng.normal(size=(Q, K, d)).astype(np.float32))
+    mu = nat.col_mean(E)
+    full_v, full_i = nat.score_topk(Pq, E, k, mu=mu)
+    vs, is_ = [], []
+    for r in range(R):
+        lo, hi = r * N // R, (r + 1) * N // R
+        v, i = nat.score_topk(Pq, E[lo:hi], k, mu=mu, idx_base=lo)
+        vs.append(v); is_.append(i)
+    mv, mi = nat.topk_merge(torch.stack(vs), torch.stack(is_))
+    assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
+
+
+# ---------------------------------------------------------------------------- AUC / Adam
+def test_auc_golden_and_random(nat):
+    g = np.load(os.path.join(GOLD, "auc.npz"))
+    s, l = g["scores"], g["labels"].astype(bool)
+    out = nat.auc_counts(dev(s[l]), dev(s[~l])).cpu().numpy()
+    assert out.tolist() == [int(g["two_u"]), int(g["n_pos"]), int(g["n_neg"]), int(g["correct"])]
+    rng = np.random.default_rng(8)
+    for n_pos, n_neg in [(1, 1), (10, 5000), (3000, 2049), (50000, 300000), (7, 0), (0, 9)]:
+        p = np.round(rng.normal(size=n_pos) + 0.3, 3).astype(np.float32)
+        n = np.round(rng.normal(size=n_neg), 3).astype(np.float32)
+        out = nat.auc_counts(dev(p), dev(n)).cpu().numpy()
+        two_u, _, _ = O.auc_exact(np.concatenate([p, n]), np.concatenate([np.ones(n_pos), np.zeros(n_neg)]))
+        assert out[0] == two_u and out[1] == n_pos and out[2] == n_neg
+        assert out[3] == int((p > 0).sum()) + int((n <= 0).sum())
+
+
+def test_adam_matches_tf_formula(nat):
+    rng = np.random.default_rng(9)
+    p, g = rng.normal(size=1000).astype(np.float32), rng.normal(size=1000).astype(np.float32)
+    m, v = np.zeros(1000, np.float32), np.zeros(1000, np.float32)
+    tp, tm, tv = dev(p), dev(m), dev(v)
+    po, mo, vo = p.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    for step in range(1, 4):
+        nat.adam_step(tp, dev(g), tm, tv, step, 1e-3)
+        po, mo, vo = O.adam_tf(po, g.astype(np.float64), mo, vo, step, 1e-3)
+    assert_close(host(tp), po, rtol=1e-6, atol=1e-7)
