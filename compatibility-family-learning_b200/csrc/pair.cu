@@ -326,7 +326,7 @@ static int launch_bwd(int maxe, int nb, cudaStream_t st, int mode, const float* 
 static int check_pair_args(int mode, const float* a, const float* P, const float* w, int64_t B,
                            int K, int d, int64_t lda, int64_t ldP) {
   CFL_REQUIRE(mode >= CFL_PCD && mode <= CFL_SIAMESE, CFL_ERR_INVALID, "pair: bad mode %d", mode);
-  CFL_REQUIRE(a && P && B >= 0, CFL_ERR_INVALID, "pair: NULL input");
+  CFL_REQUIRE(B >= 0 && ((a && P) || B == 0), CFL_ERR_INVALID, "pair: NULL input");
   CFL_REQUIRE(K >= 1 && K <= CFL_MAX_K, CFL_ERR_UNSUPPORTED, "pair: K=%d outside [1,%d]", K, CFL_MAX_K);
   CFL_REQUIRE(d >= 1 && d <= CFL_MAX_D, CFL_ERR_UNSUPPORTED, "pair: d=%d outside [1,%d]", d, CFL_MAX_D);
   CFL_REQUIRE(lda >= d && ldP >= (int64_t)K * d, CFL_ERR_INVALID, "pair: leading dimension too small");
