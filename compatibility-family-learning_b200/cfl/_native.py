@@ -53,6 +53,7 @@ SIGNATURES = {
     "cfl_auc_workspace_bytes": (_sz, [_i64, _i64]),
     "cfl_auc": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "cfl_adam_step": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "cfl_set_kernel_timer": (_int, [_vp, _vp]),
     "cfl_selftest_umma": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
 }
 
@@ -312,6 +313,18 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale
     _check(lib().cfl_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), int(step), float(lr),
                                float(beta1), float(beta2), float(eps), float(grad_scale), _stream()),
            "cfl_adam_step")
+
+
+def set_kernel_timer(start_event=None, stop_event=None):
+    """Records the two torch.cuda.Event objects around the dominant scoring kernel of every
+    following score_topk call on this thread (bench.py's roofline timing); None clears."""
+    if start_event is None or stop_event is None:
+        _check(lib().cfl_set_kernel_timer(None, None), "cfl_set_kernel_timer")
+        return
+    for ev in (start_event, stop_event):
+        ev.record()                      # forces creation of the underlying cudaEvent_t
+    _check(lib().cfl_set_kernel_timer(C.c_void_p(start_event.cuda_event), C.c_void_p(stop_event.cuda_event)),
+           "cfl_set_kernel_timer")
 
 
 def selftest_umma(A, Bm):

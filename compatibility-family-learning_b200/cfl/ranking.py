@@ -1,0 +1,127 @@
+"""All-candidates ranking with the CFL compatibility score.
+
+The reference only scores labelled pairs (cfl/utils.py:227-274); ranking a catalog is the
+pair scorer (DistBase.build_dist, cfl/models/base.py:125-146; Thresholder,
+cfl/models/blocks.py:21-22) applied to the query x catalog cross product, followed by a stable
+sort.  ``CatalogIndex`` keeps one shard of projected catalog embeddings resident in HBM and
+answers ``rank(query_features, k)``; with ``torch.distributed`` initialised every rank holds
+one contiguous shard, ranks locally, all-gathers the [Q,k] lists (NCCL) and merges them with
+``cfl_topk_merge`` -- the result is independent of the number of ranks.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _native as nat
+
+
+@dataclass
+class EncoderWeights:
+    """Weights of one encoder head pair, names as in the reference's variable scopes
+    (``outputs/fully_connected/{V,g,biases}``, ``prototype_outputs/...``; for the Dist model
+    ``latent_outputs/...``, ``pcd_outputs/...`` with ``weight_norm=False``)."""
+    V0: torch.Tensor                      # [F, d]
+    Vp: torch.Tensor                      # [F, K*d]
+    g0: Optional[torch.Tensor] = None
+    gp: Optional[torch.Tensor] = None
+    b0: Optional[torch.Tensor] = None
+    bp: Optional[torch.Tensor] = None
+    weight_norm: bool = True
+    in_scale: float = 1.0                 # 1/normalize_value (cfl/ops.py:198) or 1/data_norm
+    act: Optional[str] = None             # --act-type
+
+    @property
+    def d(self):
+        return self.V0.shape[1]
+
+    @property
+    def K(self):
+        return self.Vp.shape[1] // self.V0.shape[1]
+
+
+def shard_bounds(n_total: int, world: int, rank: int):
+    """Contiguous catalog rows [lo, hi) of ``rank``."""
+    return n_total * rank // world, n_total * (rank + 1) // world
+
+
+class CatalogIndex:
+    """One catalog shard of e0 embeddings, resident on the GPU."""
+
+    def __init__(self, weights: EncoderWeights, embeddings: torch.Tensor, idx_base: int = 0,
+                 n_total: Optional[int] = None, mu: Optional[torch.Tensor] = None,
+                 theta: float = 1e-6, group=None):
+        if not embeddings.is_cuda:
+            raise nat.CflNativeError("CatalogIndex needs CUDA embeddings (there is no CPU path)")
+        self.w = weights
+        self.E = embeddings
+        self.idx_base = int(idx_base)
+        self.n_total = int(n_total if n_total is not None else embeddings.shape[0])
+        self.group = group
+        self.theta = float(theta)
+        self.mu = mu if mu is not None else self._global_mean()
+
+    # -- construction -------------------------------------------------------------------
+    @classmethod
+    def from_features(cls, weights: EncoderWeights, features: torch.Tensor, idx_base: int = 0,
+                      n_total: Optional[int] = None, chunk: int = 1 << 16, **kw):
+        """Projects this rank's catalog rows (host or device features) through the e0 head in
+        chunks (stage 1 over the catalog shards by rows with no communication)."""
+        dev = weights.V0.device
+        n = features.shape[0]
+        E = torch.empty(n, weights.d, dtype=torch.float32, device=dev)
+        for lo in range(0, n, chunk):
+            xb = features[lo:lo + chunk]
+            if not xb.is_cuda:
+                xb = xb.to(dev, non_blocking=True)
+            y, _, _ = nat.project_fwd(xb, weights.V0, weights.g0, weights.b0, weights.weight_norm,
+                                      weights.in_scale, weights.act)
+            E[lo:lo + chunk] = y
+        return cls(weights, E, idx_base=idx_base, n_total=n_total, **kw)
+
+    def _global_mean(self):
+        """Centring vector = mean of the WHOLE catalog (sum over shards), so every rank uses
+        the same mu and per-candidate values do not depend on the sharding."""
+        mu = nat.col_mean(self.E) if self.E.shape[0] else torch.zeros(self.w.d, device=self.E.device)
+        if self._world() > 1:
+            s = mu.double() * self.E.shape[0]
+            torch.distributed.all_reduce(s, group=self.group)
+            mu = (s / self.n_total).float()
+        return mu
+
+    def _world(self):
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_world_size(self.group)
+        return 1
+
+    # -- queries ------------------------------------------------------------------------
+    def project_queries(self, xq: torch.Tensor) -> torch.Tensor:
+        """Query side of pcd = the K prototypes of the source item (base.py:126-131)."""
+        if not xq.is_cuda:
+            xq = xq.to(self.E.device, non_blocking=True)
+        P, _, _ = nat.project_fwd(xq, self.w.Vp, self.w.gp, self.w.bp, self.w.weight_norm,
+                                  self.w.in_scale, self.w.act)
+        return P.view(xq.shape[0], self.w.K, self.w.d)
+
+    def rank_local(self, Pq: torch.Tensor, k: int):
+        return nat.score_topk(Pq, self.E, k, mu=self.mu, mode="pcd", idx_base=self.idx_base)
+
+    def rank(self, xq: torch.Tensor, k: int = 100):
+        """-> (dist [Q,k] ascending, index [Q,k] int64 global).  score = theta+ - dist."""
+        Pq = self.project_queries(xq)
+        tv, ti = self.rank_local(Pq, k)
+        world = self._world()
+        if world == 1:
+            return tv, ti
+        Q = tv.shape[0]
+        gv = torch.empty(world, Q, k, dtype=tv.dtype, device=tv.device)
+        gi = torch.empty(world, Q, k, dtype=ti.dtype, device=ti.device)
+        torch.distributed.all_gather_into_tensor(gv, tv, group=self.group)
+        torch.distributed.all_gather_into_tensor(gi, ti, group=self.group)
+        return nat.topk_merge(gv, gi)
+
+    def scores(self, dist: torch.Tensor) -> torch.Tensor:
+        """Thresholder (blocks.py:21-22): max(theta, 1e-6) - dist."""
+        return max(self.theta, 1e-6) - dist

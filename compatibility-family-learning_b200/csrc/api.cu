@@ -12,6 +12,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local cudaEvent_t g_timer[2] = {nullptr, nullptr};
+void timer_record(int which, cudaStream_t st) {
+  if (g_timer[0] && g_timer[1]) (void)cudaEventRecord(g_timer[which], st);
+}
+
 struct DevProps { int valid; int sms; int major; int minor; };
 static DevProps g_props[64];
 
@@ -109,6 +114,12 @@ int cfl_device_info(int* sms, int* mj, int* mn) {
   if (sms) *sms = g_props[dev].sms;
   if (mj) *mj = g_props[dev].major;
   if (mn) *mn = g_props[dev].minor;
+  return CFL_OK;
+}
+
+int cfl_set_kernel_timer(void* start_event, void* stop_event) {
+  g_timer[0] = (cudaEvent_t)start_event;
+  g_timer[1] = (cudaEvent_t)stop_event;
   return CFL_OK;
 }
 

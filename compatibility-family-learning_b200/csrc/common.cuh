@@ -13,6 +13,7 @@ namespace cfl {
 void set_error(const char* fmt, ...);          // api.cu
 int  device_check();                           // api.cu: CFL_OK iff current device is sm_100
 int  sm_count();                               // api.cu (cached per device)
+void timer_record(int which, cudaStream_t st);  // api.cu: 0 = start, 1 = stop (no-op if unset)
 
 #define CFL_REQUIRE(cond, status, ...)                                                    \
   do {                                                                                    \

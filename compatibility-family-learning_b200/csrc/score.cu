@@ -333,9 +333,12 @@ int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t l
     if (plan.impl == 1) {
       st = score_umma_pack_queries(a, base + o_qimg, cs);
       if (st != CFL_OK) return st;
+      timer_record(0, cs);
       st = score_umma_launch(a, cs);
+      timer_record(1, cs);
       if (st != CFL_OK) return st;
     } else {
+      timer_record(0, cs);
       switch (K) {
         case 1: st = launch_simt<1>(a, cs); break;
         case 2: st = launch_simt<2>(a, cs); break;
@@ -346,6 +349,7 @@ int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t l
         case 7: st = launch_simt<7>(a, cs); break;
         default: st = launch_simt<8>(a, cs); break;
       }
+      timer_record(1, cs);
       if (st != CFL_OK) return st;
     }
   }

@@ -161,6 +161,11 @@ int cfl_auc(const float* pos_scores, int64_t n_pos, const float* neg_scores, int
 int cfl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step,
                   float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* Measurement hook: when both events are non-NULL, cfl_score_topk records them (cudaEventRecord
+ * on the call's stream) immediately before and after its dominant scoring kernel, so bench.py can
+ * time that kernel alone inside the timed region.  Thread-local; pass NULLs to clear. */
+int cfl_set_kernel_timer(void* start_event, void* stop_event);
+
 /* Self-test of the tcgen05 3xTF32 GEMM core on one tile: D[128,N] = A[128,Kd] * B[N,Kd]^T.
  * Test-only; used by tests/ to validate descriptors and layouts in isolation. */
 int cfl_selftest_umma(const float* A, const float* Bm, float* D, int N, int Kd, void* stream);
