@@ -51,18 +51,28 @@ __global__ void prep_queries_kernel(const float* __restrict__ Pq, int64_t Q, int
     dst[i] = src[i] - (mu ? mu[j] : 0.0f);
   }
   __syncwarp();
-  float* qp = qpar + q * (int64_t)(K + K * K);
+  float* qp = qpar + q * (int64_t)qpar_stride(K);
+  float dmax = 0.0f, pmax = 0.0f;
   for (int k = 0; k < K; ++k)
     for (int l = k; l < K; ++l) {
-      float acc = 0.0f;
-      for (int j = lane; j < d; j += 32) acc = fmaf(dst[k * d + j], dst[l * d + j], acc);
+      float acc = 0.0f, dkl = 0.0f;
+      for (int j = lane; j < d; j += 32) {
+        float a = dst[k * d + j], b = dst[l * d + j];
+        acc = fmaf(a, b, acc);
+        dkl = fmaf(a - b, a - b, dkl);
+      }
       acc = warp_sum(acc);
+      dkl = warp_sum(dkl);
+      dmax = fmaxf(dmax, dkl);
+      if (k == l) pmax = fmaxf(pmax, acc);
       if (lane == 0) {
         qp[K + k * K + l] = acc;
         qp[K + l * K + k] = acc;
         if (k == l) qp[k] = acc;
       }
     }
+  // slack of the lower bound, padded against fp32 rounding of the Gram form
+  if (lane == 0) qp[K + K * K] = 0.5f * (1.0f - 1.0f / K) * dmax * 1.0001f + 1e-5f * pmax;
 }
 
 // ---- CUDA-core scoring kernel ---------------------------------------------------------------
@@ -76,7 +86,7 @@ score_simt_kernel(ScoreArgs A) {
   float* et = (float*)(scratch + (SIMT_THREADS / 32) * TOPK_CAP);      // [128][d+1]
   float* pc = et + 128 * ldt;                                         // [QT][K][d]
   float* qp = pc + SIMT_QT * K * d;                                   // [QT][K+K*K]
-  float* thr = qp + SIMT_QT * (K + K * K);                            // [QT]
+  float* thr = qp + SIMT_QT * qpar_stride(K);                          // [QT]
   int* cnt = (int*)(thr + SIMT_QT);                                   // [QT]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -84,7 +94,7 @@ score_simt_kernel(ScoreArgs A) {
   const int64_t q0 = (int64_t)blockIdx.y * SIMT_QT;
   const int nq = (int)((A.Q - q0 < SIMT_QT) ? (A.Q - q0) : SIMT_QT);
   for (int i = tid; i < nq * K * d; i += SIMT_THREADS) pc[i] = A.Pc[q0 * K * d + i];
-  for (int i = tid; i < nq * (K + K * K); i += SIMT_THREADS) qp[i] = A.qpar[q0 * (K + K * K) + i];
+  for (int i = tid; i < nq * qpar_stride(K); i += SIMT_THREADS) qp[i] = A.qpar[q0 * qpar_stride(K) + i];
   if (tid < SIMT_QT) { thr[tid] = __int_as_float(0x7f800000); cnt[tid] = 0; }
   const int64_t t0 = A.plan.tiles * part / A.plan.parts;
   const int64_t t1 = A.plan.tiles * (part + 1) / A.plan.parts;
@@ -115,7 +125,7 @@ score_simt_kernel(ScoreArgs A) {
 #pragma unroll
         for (int k = 0; k < K; ++k) g[k] = fmaf(e, pq[k * d + j], g[k]);
       }
-      float dist = softmin_from_gram<K>(g, e2, qp + ql * (K + K * K));
+      float dist = softmin_from_gram<K>(g, e2, qp + ql * qpar_stride(K));
       if (row < A.N) {
         if (A.dist_out) A.dist_out[(q0 + ql) * A.N + row] = dist;
         if (dist < thr[ql]) {
@@ -144,7 +154,7 @@ score_simt_kernel(ScoreArgs A) {
 
 static size_t simt_smem_bytes(int K, int d) {
   return (size_t)(SIMT_THREADS / 32) * TOPK_CAP * sizeof(tkey_t) + (size_t)128 * (d + 1) * 4 +
-         (size_t)SIMT_QT * K * d * 4 + (size_t)SIMT_QT * (K + K * K) * 4 + SIMT_QT * 8 + 64;
+         (size_t)SIMT_QT * K * d * 4 + (size_t)SIMT_QT * qpar_stride(K) * 4 + SIMT_QT * 8 + 64;
 }
 
 template <int K>
@@ -271,7 +281,7 @@ static size_t score_ws_layout(int64_t Q, int K, int d, const ScorePlan& p, size_
                               size_t* o_qpar, size_t* o_qimg, size_t* o_keys, size_t* o_cnt) {
   size_t off = 0;
   *o_pc = off;   off = align_up(off + (size_t)Q * K * d * 4, 256);
-  *o_qpar = off; off = align_up(off + (size_t)Q * (K + K * K) * 4, 256);
+  *o_qpar = off; off = align_up(off + (size_t)Q * qpar_stride(K) * 4, 256);
   *o_qimg = off; off = align_up(off + (p.impl ? score_umma_qimg_bytes(p, K) : 0), 1024);
   *o_keys = off; off = align_up(off + (size_t)p.parts * Q * TOPK_CAP * sizeof(tkey_t), 256);
   *o_cnt = off;  off = align_up(off + (size_t)p.parts * Q * sizeof(int), 256);

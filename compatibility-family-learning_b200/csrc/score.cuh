@@ -32,6 +32,10 @@ struct ScoreArgs {
   ScorePlan plan;
 };
 
+// per-query parameter block: p2[K], pp[K*K], cq  (cq = slack of the soft-min lower bound
+// dist >= min_k d_k - cq,  cq = (1-1/K)/2 * max_kl |p_k-p_l|^2)
+__host__ __device__ inline int qpar_stride(int K) { return K + K * K + 1; }
+
 ScorePlan make_score_plan(int64_t Q, int K, int d, int64_t N, int k, bool umma_ok);
 bool score_umma_supported(int K, int d, const float* E, int64_t lde);
 size_t score_umma_qimg_bytes(const ScorePlan& p, int K);

@@ -1,9 +1,367 @@
-// placeholder until the tcgen05 kernel lands (replaced in the next commit)
+// Fused all-pairs scoring kernel for sm_100a: Gram-form GEMM on tcgen05 tensor cores (3xTF32,
+// fp32 accumulators in TMEM), soft-min epilogue and running per-query top-k behind the MMA; the
+// Q x N score matrix never reaches HBM.
+//
+//   D[c, k*QT + q] = e_c . p_{q,k}        M = 128 catalog rows (TMEM lanes), N = K*QT columns,
+//                                         MMA-K = the embedding dimension d (8 per K-step)
+//
+// CTA (part, qtile): the query tile's B operand (pre-split hi/lo image, <= 96 KB) is loaded once
+// by the bulk-copy (TMA) engine and stays resident in shared memory; the CTA then streams its
+// contiguous range of 128-row catalog tiles.  13 warps, warp-specialised:
+//   warps 8-11  producers: thread r owns catalog row r of the tile: LDG (8 K-steps of register
+//               prefetch) -> centre -> |e|^2 -> hi/lo split -> canonical smem layout -> full[stage]
+//   warp  12    allocates TMEM, loads the B image, and one lane issues tcgen05.mma
+//               (3 per K-step), tcgen05.commit -> empty[stage] / tmem_full[buf]
+//   warps 0-7   epilogue: tcgen05.ld of the K Gram values of 16 (8) queries at a time for the
+//               thread's row, soft-min distance (score.cuh), threshold test, warp-aggregated push
+//               into the per-query buffers (topk.cuh); accumulators are double-buffered in TMEM
+//               so the epilogue of tile t overlaps the MMAs of tile t+1.
+// Work per score: 2*K*d flops (x3 MMAs); bytes per catalog row: 4*d (read once per query tile).
 #include "score.cuh"
+#include "umma.cuh"
+
 namespace cfl {
-bool score_umma_supported(int, int, const float*, int64_t) { return false; }
-size_t score_umma_qimg_bytes(const ScorePlan&, int) { return 0; }
-int score_umma_pack_queries(const ScoreArgs&, void*, cudaStream_t) { return CFL_ERR_UNSUPPORTED; }
-int score_umma_launch(const ScoreArgs&, cudaStream_t) { return CFL_ERR_UNSUPPORTED; }
-int score_umma_qt(int, int) { return 0; }
+
+using namespace umma;
+
+constexpr int SU_THREADS = 416;
+constexpr int SU_NSTAGE = 10;
+constexpr uint32_t SU_ASTAGE = 4u * 128u * 16u;     // [hl][chunk][128 rows][16 B] = 8 KB
+constexpr int SU_PF = 8;                            // K-steps of register prefetch per producer
+constexpr size_t SU_B_BUDGET = 96 * 1024;
+
+int score_umma_qt(int K, int d) {
+  if (K < 1 || K > CFL_MAX_K || d < 1 || d > 128) return 0;
+  const int dpad = (d + 7) / 8 * 8;
+  const int gq = K <= 4 ? 16 : 8;
+  const int cand[] = {128, 64, 48, 32, 16, 8};
+  for (int qt : cand) {
+    int nc = K * qt;
+    if (nc > 256 || nc % 16 != 0 || qt % gq != 0) continue;
+    if ((size_t)dpad * nc * 8 > SU_B_BUDGET) continue;
+    return qt;
+  }
+  return 0;
 }
+
+bool score_umma_supported(int K, int d, const float* E, int64_t lde) {
+  if (getenv("CFL_FORCE_SIMT")) return false;
+  if (score_umma_qt(K, d) == 0) return false;
+  // float4 row loads: 16-byte aligned rows
+  return (lde % 4 == 0) && (((uintptr_t)E & 15u) == 0);
+}
+
+size_t score_umma_qimg_bytes(const ScorePlan& p, int K) {
+  return (size_t)p.nqt * p.dpad * 8 * (size_t)(K * p.qt);
+}
+
+struct SuLayout {
+  uint32_t b_img, a_ring, scratch, e2s, qpar, thr, cnt, mu, bars, tmem_slot, total;
+};
+__host__ __device__ inline SuLayout su_layout(int K, int qt, int dpad) {
+  SuLayout L;
+  uint32_t off = 0;
+  L.b_img = off;   off += (uint32_t)dpad * 8u * (uint32_t)(K * qt);   off = (off + 1023u) & ~1023u;
+  L.a_ring = off;  off += SU_NSTAGE * SU_ASTAGE;
+  L.scratch = off; off += 8u * TOPK_CAP * 8u;
+  L.e2s = off;     off += 4u * 128u * 4u;
+  L.qpar = off;    off += (uint32_t)qt * (uint32_t)qpar_stride(K) * 4u;  off = (off + 15u) & ~15u;
+  L.thr = off;     off += (uint32_t)qt * 4u;
+  L.cnt = off;     off += (uint32_t)qt * 4u;
+  L.mu = off;      off += (uint32_t)dpad * 4u;                        off = (off + 15u) & ~15u;
+  L.bars = off;    off += (2u * SU_NSTAGE + 5u) * 8u;
+  L.tmem_slot = off; off += 16u;
+  L.total = off;
+  return L;
+}
+
+// ---- B-operand image: [qtile][kstep][hl][chunk][row n = k*QT + ql][4 floats] ------------------
+__global__ void pack_queries_kernel(const float* __restrict__ Pc, int64_t Q, int K, int d, int qt,
+                                    int dpad, float* __restrict__ img) {
+  const int nc = K * qt;
+  const int nks = dpad / 8;
+  const int qtile = blockIdx.x;
+  float* base = img + (size_t)qtile * dpad * 2 * nc;        // floats: dpad*8*nc bytes / 4
+  for (int e = threadIdx.x; e < nks * 2 * nc; e += blockDim.x) {
+    int n = e % nc;
+    int c = (e / nc) % 2;
+    int ks = e / (2 * nc);
+    int k = n / qt, ql = n % qt;
+    int64_t q = (int64_t)qtile * qt + ql;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* xp = &x.x;
+    if (q < Q) {
+      const float* src = Pc + (q * K + k) * (int64_t)d;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int j = ks * 8 + c * 4 + i;
+        if (j < d) xp[i] = src[j];
+      }
+    }
+    float4 hi, lo;
+    split_tf32x4(x, hi, lo);
+    size_t step = (size_t)ks * 4 * nc;                       // float4 units per K-step: 4*nc
+    ((float4*)base)[step + (size_t)(0 * 2 + c) * nc + n] = hi;
+    ((float4*)base)[step + (size_t)(1 * 2 + c) * nc + n] = lo;
+  }
+}
+
+int score_umma_pack_queries(const ScoreArgs& a, void* qimg, cudaStream_t st) {
+  pack_queries_kernel<<<a.plan.nqt, 256, 0, st>>>(a.Pc, a.Q, a.K, a.d, a.plan.qt, a.plan.dpad, (float*)qimg);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- the kernel ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(SU_THREADS, 1)
+score_umma_kernel(ScoreArgs A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int GQ = K <= 4 ? 16 : 8;
+  const int QT = A.plan.qt;
+  const int NC = K * QT;
+  const int dpad = A.plan.dpad;
+  const int nks = dpad / 8;
+  const int d = A.d;
+  const SuLayout L = su_layout(K, QT, dpad);
+  unsigned char* b_img = smem + L.b_img;
+  unsigned char* a_ring = smem + L.a_ring;
+  tkey_t* scratch = (tkey_t*)(smem + L.scratch);
+  float* e2s = (float*)(smem + L.e2s);
+  float* qpar = (float*)(smem + L.qpar);
+  float* thr = (float*)(smem + L.thr);
+  int* cnt = (int*)(smem + L.cnt);
+  float* mus = (float*)(smem + L.mu);
+  uint64_t* full = (uint64_t*)(smem + L.bars);
+  uint64_t* empty = full + SU_NSTAGE;
+  uint64_t* tfull = empty + SU_NSTAGE;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(smem + L.tmem_slot);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int part = blockIdx.x, qtile = blockIdx.y;
+  const int64_t q0 = (int64_t)qtile * QT;
+  const int nq = (int)((A.Q - q0 < QT) ? (A.Q - q0) : QT);
+  const int64_t t0 = A.plan.tiles * part / A.plan.parts;
+  const int64_t t1 = A.plan.tiles * (part + 1) / A.plan.parts;
+  const int ntiles = (int)(t1 - t0);
+  const int qps = qpar_stride(K);
+
+  // ---- one-time setup ----
+  uint32_t ncols = 32;
+  while ((int)ncols < 2 * NC) ncols <<= 1;
+  if (warp == 12) {
+    if (lane == 0) {
+      for (int s = 0; s < SU_NSTAGE; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+      mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+      mbar_init(&tempty[0], 256); mbar_init(&tempty[1], 256);
+      mbar_init(bfull, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, ncols);
+  }
+  for (int i = tid; i < nq * qps; i += SU_THREADS) qpar[i] = A.qpar[q0 * qps + i];
+  for (int i = tid; i < QT; i += SU_THREADS) { thr[i] = __int_as_float(0x7f800000); cnt[i] = 0; }
+  for (int i = tid; i < dpad; i += SU_THREADS) mus[i] = (A.mu && i < d) ? A.mu[i] : 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 12) {
+    // =========================== B loader + MMA issuer (one lane) ===========================
+    if (lane == 0) {
+      const uint32_t bbytes = (uint32_t)dpad * 8u * (uint32_t)NC;
+      const unsigned char* src = (const unsigned char*)A.qimg + (size_t)qtile * bbytes;
+      mbar_arrive_expect_tx(bfull, bbytes);
+      for (uint32_t o = 0; o < bbytes; o += 32768u) {
+        uint32_t n = bbytes - o < 32768u ? bbytes - o : 32768u;
+        bulk_g2s(b_img + o, src + o, n, bfull);
+      }
+      mbar_wait(bfull, 0);
+      const uint32_t idesc = make_idesc_tf32(128, (uint32_t)NC);
+      const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_img);
+      const uint32_t b_step = 4u * (uint32_t)NC * 16u;
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&tempty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
+        for (int ks = 0; ks < nks; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          mma_step_3xtf32(d_tmem, a_base + stage * SU_ASTAGE, b_base + ks * b_step, (uint32_t)NC, idesc, ks == 0);
+          mma_commit(&empty[stage]);
+          if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 8) {
+    // ======================================= producers =======================================
+    const int r = tid - 256;                                 // catalog row of the tile
+    const int total = ntiles * nks;
+    float4 qa[SU_PF], qb[SU_PF];
+    int lt = 0, lks = 0;                                     // (tile, kstep) of the next load
+    auto load_item = [&](float4& xa, float4& xb) {
+      xa = make_float4(0.f, 0.f, 0.f, 0.f); xb = xa;
+      const int64_t row = (t0 + lt) * 128 + r;
+      if (row < A.N) {
+        const float* p = A.E + row * A.lde + lks * 8;
+        if (lks * 8 < d) xa = __ldg((const float4*)p);
+        if (lks * 8 + 4 < d) xb = __ldg((const float4*)(p + 4));
+      }
+      if (++lks == nks) { lks = 0; ++lt; }
+    };
+#pragma unroll
+    for (int u = 0; u < SU_PF; ++u) { if (u < total) load_item(qa[u], qb[u]); }
+    int stage = 0; uint32_t phase = 0;
+    int pt = 0, pks = 0;
+    float e2 = 0.0f;
+    for (int base = 0; base < total; base += SU_PF) {
+#pragma unroll
+      for (int u = 0; u < SU_PF; ++u) {
+        const int i = base + u;
+        if (i < total) {
+          float4 xa = qa[u], xb = qb[u];
+          if (i + SU_PF < total) load_item(qa[u], qb[u]);
+          // centre + mask the padding columns
+          const int j0 = pks * 8;
+          const float4 ma = *(const float4*)(mus + j0), mb = *(const float4*)(mus + j0 + 4);
+          float v[8] = {xa.x - ma.x, xa.y - ma.y, xa.z - ma.z, xa.w - ma.w,
+                        xb.x - mb.x, xb.y - mb.y, xb.z - mb.z, xb.w - mb.w};
+          const bool rowok = ((t0 + pt) * 128 + r) < A.N;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            if (!rowok || j0 + jj >= d) v[jj] = 0.0f;
+            e2 = fmaf(v[jj], v[jj], e2);
+          }
+          if (pks == nks - 1) { e2s[(pt & 3) * 128 + r] = e2; e2 = 0.0f; }
+          float4 h0, l0, h1, l1;
+          split_tf32x4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+          split_tf32x4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+          mbar_wait(&empty[stage], phase ^ 1u);
+          unsigned char* st = a_ring + stage * SU_ASTAGE;
+          *(float4*)(st + ((0 * 2 + 0) * 128 + r) * 16) = h0;
+          *(float4*)(st + ((0 * 2 + 1) * 128 + r) * 16) = h1;
+          *(float4*)(st + ((1 * 2 + 0) * 128 + r) * 16) = l0;
+          *(float4*)(st + ((1 * 2 + 1) * 128 + r) * 16) = l1;
+          fence_proxy_async();
+          mbar_arrive(&full[stage]);
+          if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
+          if (++pks == nks) { pks = 0; ++pt; }
+        }
+      }
+    }
+  } else {
+    // ======================================= epilogue ========================================
+    const int lq = warp & 3, half = warp >> 2;
+    const int lrow = lq * 32 + lane;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_CAP;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const int64_t row = (t0 + t) * 128 + lrow;
+      const bool valid = row < A.N;
+      const float e2 = e2s[(t & 3) * 128 + lrow];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
+      for (int g = half; g * GQ < nq; g += 2) {
+        float gk[K][GQ];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if constexpr (GQ == 16) tmem_ld16(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
+          else                    tmem_ld8(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < GQ; ++i) {
+          const int ql = g * GQ + i;
+          if (ql < nq) {                                       // warp-uniform
+            const float* qp = qpar + ql * qps;
+            const float th = thr[ql];
+            float gv[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) gv[k] = gk[k][i];
+            // cheap lower bound first: dist >= |e|^2 - max_k(2 g_k - |p_k|^2) - cq
+            float mx = fmaf(2.0f, gv[0], -qp[0]);
+#pragma unroll
+            for (int k = 1; k < K; ++k) mx = fmaxf(mx, fmaf(2.0f, gv[k], -qp[k]));
+            const float lower = (K == 1) ? (e2 - mx) : (e2 - mx - qp[K + K * K]);
+            bool maybe = valid && (lower < th);
+            if (A.dist_out != nullptr) maybe = valid;
+            if (__any_sync(0xffffffffu, maybe)) {
+              float dist = (K == 1) ? lower : softmin_from_gram<K>(gv, e2, qp);
+              if (A.dist_out != nullptr && valid) A.dist_out[(q0 + ql) * A.N + row] = dist;
+              const bool pass = maybe && (dist < th);
+              const uint32_t m = __ballot_sync(0xffffffffu, pass);
+              if (m) {
+                const int leader = __ffs(m) - 1;
+                int basei = 0;
+                if (lane == leader) basei = atomicAdd(&cnt[ql], __popc(m));
+                basei = __shfl_sync(0xffffffffu, basei, leader);
+                if (pass) kbase[(int64_t)ql * TOPK_CAP + basei + __popc(m & lane_lt)] = pack_key(dist, (uint32_t)row);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+      // ---- compaction point (all 8 epilogue warps) ----
+      named_bar_sync(1, 256);
+      for (int ql = warp; ql < nq; ql += 8) {
+        const int n = cnt[ql];
+        if (n > TOPK_TRIGGER) {
+          int nk = warp_compact(kbase + (int64_t)ql * TOPK_CAP, n, A.plan.kk, scratch + warp * TOPK_CAP, lane, &thr[ql]);
+          if (lane == 0) cnt[ql] = nk;
+        }
+      }
+      named_bar_sync(1, 256);
+    }
+    for (int ql = warp; ql < nq; ql += 8) {
+      int nk = warp_compact(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch + warp * TOPK_CAP, lane, nullptr);
+      if (lane == 0) A.counts[(int64_t)part * A.Q + q0 + ql] = nk;
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem_base, ncols);
+}
+
+template <int K>
+static int launch_umma(const ScoreArgs& a, cudaStream_t st) {
+  SuLayout L = su_layout(K, a.plan.qt, a.plan.dpad);
+  size_t smem = L.total + 1024;      // slack for the 1024-byte alignment of the dynamic segment
+  CFL_CUDA(cudaFuncSetAttribute(score_umma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(a.plan.parts, a.plan.nqt);
+  score_umma_kernel<K><<<grid, SU_THREADS, smem, st>>>(a);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+int score_umma_launch(const ScoreArgs& a, cudaStream_t st) {
+  switch (a.K) {
+    case 1: return launch_umma<1>(a, st);
+    case 2: return launch_umma<2>(a, st);
+    case 3: return launch_umma<3>(a, st);
+    case 4: return launch_umma<4>(a, st);
+    case 5: return launch_umma<5>(a, st);
+    case 6: return launch_umma<6>(a, st);
+    case 7: return launch_umma<7>(a, st);
+    case 8: return launch_umma<8>(a, st);
+  }
+  set_error("score_umma: K=%d unsupported", a.K);
+  return CFL_ERR_UNSUPPORTED;
+}
+
+}  // namespace cfl

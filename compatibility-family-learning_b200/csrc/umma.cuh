@@ -148,9 +148,15 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ---- 3xTF32 split ----------------------------------------------------------------------------
+// round-to-nearest tf32 (low 13 mantissa bits zero): |x-hi| <= 2^-11|x|, |x-hi-lo| <= 2^-22|x|
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
+  hi = to_tf32(x);
+  lo = to_tf32(x - hi);
 }
 __device__ __forceinline__ void split_tf32x4(const float4& x, float4& hi, float4& lo) {
   split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
