@@ -53,7 +53,8 @@ __global__ void prep_queries_kernel(const float* __restrict__ Pq, int64_t Q, int
   __syncwarp();
   float* qp = qpar + q * (int64_t)qpar_stride(K);
   float dmax = 0.0f, pmax = 0.0f;
-  for (int k = 0; k < K; ++k)
+  int o = K;
+  for (int k = 0; k < K; ++k) {
     for (int l = k; l < K; ++l) {
       float acc = 0.0f, dkl = 0.0f;
       for (int j = lane; j < d; j += 32) {
@@ -66,13 +67,17 @@ __global__ void prep_queries_kernel(const float* __restrict__ Pq, int64_t Q, int
       dmax = fmaxf(dmax, dkl);
       if (k == l) pmax = fmaxf(pmax, acc);
       if (lane == 0) {
-        qp[K + k * K + l] = acc;
-        qp[K + l * K + k] = acc;
-        if (k == l) qp[k] = acc;
+        if (k == l) { qp[k] = CFL_LOG2E * acc; qp[o] = 0.5f * acc; }
+        else qp[o + l - k] = acc;
       }
     }
+    o += K - k;
+  }
   // slack of the lower bound, padded against fp32 rounding of the Gram form
-  if (lane == 0) qp[K + K * K] = 0.5f * (1.0f - 1.0f / K) * dmax * 1.0001f + 1e-5f * pmax;
+  if (lane == 0) {
+    qp[K + qpar_tri(K)] = 0.5f * (1.0f - 1.0f / K) * dmax * 1.0001f + 1e-5f * pmax;
+    for (int i = K + qpar_tri(K) + 1; i < qpar_stride(K); ++i) qp[i] = 0.0f;
+  }
 }
 
 // ---- CUDA-core scoring kernel ---------------------------------------------------------------

@@ -32,9 +32,13 @@ struct ScoreArgs {
   ScorePlan plan;
 };
 
-// per-query parameter block: p2[K], pp[K*K], cq  (cq = slack of the soft-min lower bound
-// dist >= min_k d_k - cq,  cq = (1-1/K)/2 * max_kl |p_k-p_l|^2)
-__host__ __device__ inline int qpar_stride(int K) { return K + K * K + 1; }
+// Per-query parameter block (floats), padded to a multiple of 4 so it loads as float4:
+//   [0,K)        log2(e) * |p_k|^2
+//   [K,K+T)      upper triangle of p_k.p_l, row-major (k,l>=k), DIAGONAL PRE-HALVED; T=K(K+1)/2
+//   [K+T]        cq = slack of the soft-min lower bound dist >= min_k d_k - cq,
+//                cq = (1-1/K)/2 * max_kl |p_k-p_l|^2, padded for fp32 rounding
+__host__ __device__ constexpr int qpar_tri(int K) { return K * (K + 1) / 2; }
+__host__ __device__ constexpr int qpar_stride(int K) { return (K + qpar_tri(K) + 1 + 3) / 4 * 4; }
 
 ScorePlan make_score_plan(int64_t Q, int K, int d, int64_t N, int k, bool umma_ok);
 bool score_umma_supported(int K, int d, const float* E, int64_t lde);
@@ -55,37 +59,49 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return y;
 }
 
+constexpr float CFL_LOG2E = 1.4426950408889634f;
+constexpr float CFL_LN2 = 0.6931471805599453f;
+
 // Soft-min distance of one (candidate, query) pair from the Gram values g_k = p_k.e
 // (SURVEY App. A.3):  s = softmax_k(2 g_k - |p_k|^2)   [the |e|^2 term cancels],
 //   dist = |e|^2 - 2 sum_k s_k g_k + sum_kl s_k s_l (p_k.p_l).
-// qp -> p2[K] followed by pp[K*K] (shared memory, warp-uniform address => broadcast).
+// qp = the per-query parameter block above (registers or shared memory).
+// Also returns mx2 = log2e * max_k(2 g_k - |p_k|^2), so that min_k d_k = |e|^2 - ln2 * mx2.
+template <int K>
+__device__ __forceinline__ float softmin_max2(const float (&g)[K], const float* __restrict__ qp) {
+  float mx = fmaf(2.0f * CFL_LOG2E, g[0], -qp[0]);
+#pragma unroll
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, fmaf(2.0f * CFL_LOG2E, g[k], -qp[k]));
+  return mx;
+}
+
 template <int K>
 __device__ __forceinline__ float softmin_from_gram(const float (&g)[K], float e2,
                                                    const float* __restrict__ qp) {
-  if (K == 1) return fmaf(-2.0f, g[0], e2 + qp[0]);
+  if (K == 1) return fmaf(-CFL_LN2, fmaf(2.0f * CFL_LOG2E, g[0], -qp[0]), e2);
   float a[K];
-  float mx = -3.0e38f;
 #pragma unroll
-  for (int k = 0; k < K; ++k) { a[k] = fmaf(2.0f, g[k], -qp[k]); mx = fmaxf(mx, a[k]); }
+  for (int k = 0; k < K; ++k) a[k] = fmaf(2.0f * CFL_LOG2E, g[k], -qp[k]);
+  float mx = a[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, a[k]);
   float sum = 0.0f;
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    a[k] = fast_ex2((a[k] - mx) * 1.4426950408889634f);
-    sum += a[k];
-  }
-  float inv = fast_rcp(sum);
+  for (int k = 0; k < K; ++k) { a[k] = fast_ex2(a[k] - mx); sum += a[k]; }
+  const float inv = fast_rcp(sum);
   float t1 = 0.0f, t2 = 0.0f;
-  const float* pp = qp + K;
+  int o = K;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     t1 = fmaf(a[k], g[k], t1);
-    float row = 0.5f * pp[k * K + k] * a[k];
+    float row = qp[o] * a[k];                  // diagonal is stored pre-halved
 #pragma unroll
-    for (int l = k + 1; l < K; ++l) row = fmaf(pp[k * K + l], a[l], row);
-    t2 = fmaf(a[k], row, t2);                 // half of sum_kl a_k a_l pp_kl
+    for (int l = k + 1; l < K; ++l) row = fmaf(qp[o + l - k], a[l], row);
+    o += K - k;
+    t2 = fmaf(a[k], row, t2);                  // half of sum_kl a_k a_l pp_kl
   }
   // dist = e2 + inv * (-2 t1 + inv * 2 t2)
-  return fmaf(inv, 2.0f * fmaf(inv, t2, -t1), e2);
+  return fmaf(inv + inv, fmaf(inv, t2, -t1), e2);
 }
 #endif
 

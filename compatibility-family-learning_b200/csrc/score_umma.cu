@@ -33,7 +33,7 @@ constexpr size_t SU_B_BUDGET = 96 * 1024;
 int score_umma_qt(int K, int d) {
   if (K < 1 || K > CFL_MAX_K || d < 1 || d > 128) return 0;
   const int dpad = (d + 7) / 8 * 8;
-  const int gq = K <= 4 ? 16 : 8;
+  const int gq = K <= 2 ? 16 : 8;
   const int cand[] = {128, 64, 48, 32, 16, 8};
   for (int qt : cand) {
     int nc = K * qt;
@@ -121,7 +121,7 @@ template <int K>
 __global__ void __launch_bounds__(SU_THREADS, 1)
 score_umma_kernel(ScoreArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int GQ = K <= 4 ? 16 : 8;
+  constexpr int GQ = K <= 2 ? 16 : 8;
   const int QT = A.plan.qt;
   const int NC = K * QT;
   const int dpad = A.plan.dpad;
@@ -166,8 +166,12 @@ score_umma_kernel(ScoreArgs A) {
     __syncwarp();
     tmem_alloc(tmem_slot, ncols);
   }
-  for (int i = tid; i < nq * qps; i += SU_THREADS) qpar[i] = A.qpar[q0 * qps + i];
-  for (int i = tid; i < QT; i += SU_THREADS) { thr[i] = __int_as_float(0x7f800000); cnt[i] = 0; }
+  for (int i = tid; i < QT * qps; i += SU_THREADS) qpar[i] = (i < nq * qps) ? A.qpar[q0 * qps + i] : 0.0f;
+  // padding queries of the last tile get thr = -inf: they can never be pushed
+  for (int i = tid; i < QT; i += SU_THREADS) {
+    thr[i] = __int_as_float(i < nq ? 0x7f800000 : 0xff800000);
+    cnt[i] = 0;
+  }
   for (int i = tid; i < dpad; i += SU_THREADS) mus[i] = (A.mu && i < d) ? A.mu[i] : 0.0f;
   tc_fence_before();
   __syncthreads();
@@ -208,6 +212,7 @@ score_umma_kernel(ScoreArgs A) {
     // ======================================= producers =======================================
     const int r = tid - 256;                                 // catalog row of the tile
     const int total = ntiles * nks;
+    const bool need_mask = (d & 7) != 0;
     float4 qa[SU_PF], qb[SU_PF];
     int lt = 0, lks = 0;                                     // (tile, kstep) of the next load
     auto load_item = [&](float4& xa, float4& xb) {
@@ -237,12 +242,16 @@ score_umma_kernel(ScoreArgs A) {
           const float4 ma = *(const float4*)(mus + j0), mb = *(const float4*)(mus + j0 + 4);
           float v[8] = {xa.x - ma.x, xa.y - ma.y, xa.z - ma.z, xa.w - ma.w,
                         xb.x - mb.x, xb.y - mb.y, xb.z - mb.z, xb.w - mb.w};
-          const bool rowok = ((t0 + pt) * 128 + r) < A.N;
+          if (need_mask && pks == nks - 1) {                   // padding columns of the last K-step
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            if (!rowok || j0 + jj >= d) v[jj] = 0.0f;
-            e2 = fmaf(v[jj], v[jj], e2);
+            for (int jj = 0; jj < 8; ++jj) if (j0 + jj >= d) v[jj] = 0.0f;
           }
+          if (((t0 + pt) * 128 + r) >= A.N) {                  // rows past the catalog end (last tile)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) v[jj] = 0.0f;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) e2 = fmaf(v[jj], v[jj], e2);
           if (pks == nks - 1) { e2s[(pt & 3) * 128 + r] = e2; e2 = 0.0f; }
           float4 h0, l0, h1, l1;
           split_tf32x4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
@@ -262,10 +271,19 @@ score_umma_kernel(ScoreArgs A) {
     }
   } else {
     // ======================================= epilogue ========================================
+    constexpr int QPS = qpar_stride(K);
+    constexpr int CQ = K + qpar_tri(K);
     const int lq = warp & 3, half = warp >> 2;
     const int lrow = lq * 32 + lane;
     const uint32_t lane_lt = (1u << lane) - 1u;
+    const bool dense = A.dist_out != nullptr;
     tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_CAP;
+    // The lower bound dist >= min_k d_k - cq lets a whole 16-query group skip the soft-min when
+    // no lane can beat its threshold.  It only pays when the prototypes of a query are close
+    // together relative to the spread of distances, so each warp measures its hit rate over the
+    // first tiles and switches the test off when it rarely fires.
+    bool bound_on = (K > 1) && !dense;
+    int grp_seen = 0, grp_skipped = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
@@ -282,38 +300,66 @@ score_umma_kernel(ScoreArgs A) {
           else                    tmem_ld8(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
         }
         tmem_ld_wait();
+        const float* qg = qpar + g * GQ * QPS;
+        float tg[GQ];
 #pragma unroll
-        for (int i = 0; i < GQ; ++i) {
-          const int ql = g * GQ + i;
-          if (ql < nq) {                                       // warp-uniform
-            const float* qp = qpar + ql * qps;
-            const float th = thr[ql];
+        for (int i = 0; i < GQ; i += 4) {
+          const float4 t4 = *(const float4*)(thr + g * GQ + i);
+          tg[i] = t4.x; tg[i + 1] = t4.y; tg[i + 2] = t4.z; tg[i + 3] = t4.w;
+        }
+        if (bound_on) {
+          bool need = false;
+#pragma unroll
+          for (int i = 0; i < GQ; ++i) {
             float gv[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) gv[k] = gk[k][i];
-            // cheap lower bound first: dist >= |e|^2 - max_k(2 g_k - |p_k|^2) - cq
-            float mx = fmaf(2.0f, gv[0], -qp[0]);
+            const float lower = fmaf(-CFL_LN2, softmin_max2<K>(gv, qg + i * QPS), e2) - qg[i * QPS + CQ];
+            need |= lower < tg[i];
+          }
+          ++grp_seen;
+          if (!__any_sync(0xffffffffu, need && valid)) { ++grp_skipped; continue; }
+        }
+        float dist[GQ];
 #pragma unroll
-            for (int k = 1; k < K; ++k) mx = fmaxf(mx, fmaf(2.0f, gv[k], -qp[k]));
-            const float lower = (K == 1) ? (e2 - mx) : (e2 - mx - qp[K + K * K]);
-            bool maybe = valid && (lower < th);
-            if (A.dist_out != nullptr) maybe = valid;
-            if (__any_sync(0xffffffffu, maybe)) {
-              float dist = (K == 1) ? lower : softmin_from_gram<K>(gv, e2, qp);
-              if (A.dist_out != nullptr && valid) A.dist_out[(q0 + ql) * A.N + row] = dist;
-              const bool pass = maybe && (dist < th);
-              const uint32_t m = __ballot_sync(0xffffffffu, pass);
-              if (m) {
-                const int leader = __ffs(m) - 1;
-                int basei = 0;
-                if (lane == leader) basei = atomicAdd(&cnt[ql], __popc(m));
-                basei = __shfl_sync(0xffffffffu, basei, leader);
-                if (pass) kbase[(int64_t)ql * TOPK_CAP + basei + __popc(m & lane_lt)] = pack_key(dist, (uint32_t)row);
-              }
+        for (int i = 0; i < GQ; ++i) {
+          float qv[QPS];
+#pragma unroll
+          for (int j = 0; j < QPS; j += 4) {
+            const float4 q4 = *(const float4*)(qg + i * QPS + j);
+            qv[j] = q4.x; qv[j + 1] = q4.y; qv[j + 2] = q4.z; qv[j + 3] = q4.w;
+          }
+          float gv[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) gv[k] = gk[k][i];
+          dist[i] = softmin_from_gram<K>(gv, e2, qv);
+        }
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < GQ; ++i) bits |= (dist[i] < tg[i]) ? (1u << i) : 0u;
+        if (!valid) bits = 0;
+        if (dense && valid) {
+#pragma unroll
+          for (int i = 0; i < GQ; ++i)
+            if (g * GQ + i < nq) A.dist_out[(q0 + g * GQ + i) * A.N + row] = dist[i];
+        }
+        if (__any_sync(0xffffffffu, bits != 0)) {             // rare once the thresholds are tight
+#pragma unroll
+          for (int i = 0; i < GQ; ++i) {
+            const bool pass = (bits >> i) & 1u;
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+              const int ql = g * GQ + i;
+              const int leader = __ffs(m) - 1;
+              int basei = 0;
+              if (lane == leader) basei = atomicAdd(&cnt[ql], __popc(m));
+              basei = __shfl_sync(0xffffffffu, basei, leader);
+              if (pass) kbase[(int64_t)ql * TOPK_CAP + basei + __popc(m & lane_lt)] = pack_key(dist[i], (uint32_t)row);
             }
           }
         }
       }
+      if (t == 15 && bound_on && grp_skipped * 2 < grp_seen) bound_on = false;
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
       // ---- compaction point (all 8 epilogue warps) ----

@@ -49,6 +49,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 28); ++spin)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
