@@ -25,7 +25,7 @@ namespace cfl {
 using namespace umma;
 
 constexpr int SU_THREADS = 416;
-constexpr int SU_NSTAGE = 10;
+constexpr int SU_NSTAGE = 12;
 constexpr uint32_t SU_ASTAGE = 4u * 128u * 16u;     // [hl][chunk][128 rows][16 B] = 8 KB
 constexpr int SU_PF = 8;                            // K-steps of register prefetch per producer
 constexpr size_t SU_B_BUDGET = 96 * 1024;
@@ -63,7 +63,7 @@ __host__ __device__ inline SuLayout su_layout(int K, int qt, int dpad) {
   uint32_t off = 0;
   L.b_img = off;   off += (uint32_t)dpad * 8u * (uint32_t)(K * qt);   off = (off + 1023u) & ~1023u;
   L.a_ring = off;  off += SU_NSTAGE * SU_ASTAGE;
-  L.scratch = off; off += 8u * TOPK_CAP * 8u;
+  L.scratch = off; off += TOPK_CAP * 8u;
   L.e2s = off;     off += 4u * 128u * 4u;
   L.qpar = off;    off += (uint32_t)qt * (uint32_t)qpar_stride(K) * 4u;  off = (off + 15u) & ~15u;
   L.thr = off;     off += (uint32_t)qt * 4u;
@@ -362,20 +362,24 @@ score_umma_kernel(ScoreArgs A) {
       if (t == 15 && bound_on && grp_skipped * 2 < grp_seen) bound_on = false;
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
-      // ---- compaction point (all 8 epilogue warps) ----
+      // ---- compaction point: all 8 epilogue warps sort one over-full buffer together ----
       named_bar_sync(1, 256);
-      for (int ql = warp; ql < nq; ql += 8) {
-        const int n = cnt[ql];
-        if (n > TOPK_TRIGGER) {
-          int nk = warp_compact(kbase + (int64_t)ql * TOPK_CAP, n, A.plan.kk, scratch + warp * TOPK_CAP, lane, &thr[ql]);
-          if (lane == 0) cnt[ql] = nk;
+      {
+        const int et = tid;                                   // 0..255
+        for (int qb = 0; qb < nq; qb += 32) {
+          const int ql0 = qb + lane;
+          const uint32_t over = __ballot_sync(0xffffffffu, ql0 < nq && cnt[ql0] > TOPK_TRIGGER);
+          for (uint32_t m = over; m; m &= m - 1) {            // identical in every warp
+            const int ql = qb + __ffs(m) - 1;
+            coop_compact(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch, et, 1, &cnt[ql], &thr[ql]);
+          }
         }
       }
       named_bar_sync(1, 256);
     }
-    for (int ql = warp; ql < nq; ql += 8) {
-      int nk = warp_compact(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch + warp * TOPK_CAP, lane, nullptr);
-      if (lane == 0) A.counts[(int64_t)part * A.Q + q0 + ql] = nk;
+    for (int ql = 0; ql < nq; ++ql) {
+      coop_compact(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch, tid, 1, &cnt[ql], nullptr);
+      if (tid == 0) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
     }
   }
   // ---- teardown ----
