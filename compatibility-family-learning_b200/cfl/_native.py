@@ -47,6 +47,11 @@ SIGNATURES = {
     "cfl_score_topk_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
     "cfl_score_topk": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _i64, _i64, _vp, _int, _i64,
                               _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cfl_catalog_pack_bytes": (_sz, [_i64, _int, _int]),
+    "cfl_catalog_pack": (_int, [_vp, _i64, _int, _int, _i64, _vp, _vp, _sz, _vp]),
+    "cfl_score_topk_packed_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
+    "cfl_score_topk_packed": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _i64,
+                                     _vp, _vp, _vp, _vp, _sz, _vp]),
     "cfl_topk_merge": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
     "cfl_col_mean_workspace_bytes": (_sz, [_i64, _int]),
     "cfl_col_mean": (_int, [_vp, _i64, _int, _i64, _vp, _vp, _sz, _vp]),
@@ -257,8 +262,26 @@ def col_mean(E):
     return mu
 
 
-def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False):
-    """Top-k candidates of every query by soft-min distance; exact (rescored) values."""
+def catalog_pack(E, K, mu=None):
+    """Builds the tensor-core operand image of a catalog once (None when (K, d) has no tcgen05
+    tiling -- score_topk then uses the CUDA-core kernel on the raw rows)."""
+    E, lde = _rows(E, "E")
+    N, d = E.shape
+    nbytes = lib().cfl_catalog_pack_bytes(N, K, d)
+    if nbytes == 0:
+        return None
+    img = torch.empty(nbytes + 1024, dtype=torch.uint8, device=E.device)
+    off = (-img.data_ptr()) % 1024
+    img = img[off:off + nbytes]
+    mu = None if mu is None else _f32c(mu, "mu").contiguous()
+    _check(lib().cfl_catalog_pack(_ptr(E), N, K, d, lde, _ptr(mu), _ptr(img), nbytes, _stream()),
+           "cfl_catalog_pack")
+    return img
+
+
+def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False, image=None):
+    """Top-k candidates of every query by soft-min distance; exact (rescored) values.
+    ``image`` = catalog_pack(E, K, mu) skips the per-call packing of the catalog."""
     Pq = _f32c(Pq, "Pq")
     if Pq.dim() == 2:
         Pq = Pq[:, None, :]
@@ -273,10 +296,16 @@ def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False):
     top_idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
     dense = torch.empty(Q, N, dtype=torch.float32, device=dev) if want_dense else None
     mu = None if mu is None else _f32c(mu, "mu").contiguous()
-    ws = _ws.get(lib().cfl_score_topk_workspace_bytes(Q, K, d, N, k), dev)
-    _check(lib().cfl_score_topk(MODES[mode], _ptr(Pq2), Q, K, d, ldq, _ptr(E), N, lde, _ptr(mu),
-                                int(k), int(idx_base), _ptr(top_val), _ptr(top_idx), _ptr(dense),
-                                _ptr(ws), ws.numel(), _stream()), "cfl_score_topk")
+    if image is not None:
+        ws = _ws.get(lib().cfl_score_topk_packed_workspace_bytes(Q, K, d, N, k), dev)
+        _check(lib().cfl_score_topk_packed(MODES[mode], _ptr(Pq2), Q, K, d, ldq, _ptr(image), _ptr(E), N, lde,
+                                           _ptr(mu), int(k), int(idx_base), _ptr(top_val), _ptr(top_idx),
+                                           _ptr(dense), _ptr(ws), ws.numel(), _stream()), "cfl_score_topk_packed")
+    else:
+        ws = _ws.get(lib().cfl_score_topk_workspace_bytes(Q, K, d, N, k), dev)
+        _check(lib().cfl_score_topk(MODES[mode], _ptr(Pq2), Q, K, d, ldq, _ptr(E), N, lde, _ptr(mu),
+                                    int(k), int(idx_base), _ptr(top_val), _ptr(top_idx), _ptr(dense),
+                                    _ptr(ws), ws.numel(), _stream()), "cfl_score_topk")
     return (top_val, top_idx, dense) if want_dense else (top_val, top_idx)
 
 

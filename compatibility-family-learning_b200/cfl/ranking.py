@@ -62,6 +62,8 @@ class CatalogIndex:
         self.group = group
         self.theta = float(theta)
         self.mu = mu if mu is not None else self._global_mean()
+        # tensor-core operand image of the (static) catalog, built once
+        self.image = nat.catalog_pack(self.E, self.w.K, self.mu) if self.E.shape[0] else None
 
     # -- construction -------------------------------------------------------------------
     @classmethod
@@ -106,7 +108,8 @@ class CatalogIndex:
         return P.view(xq.shape[0], self.w.K, self.w.d)
 
     def rank_local(self, Pq: torch.Tensor, k: int):
-        return nat.score_topk(Pq, self.E, k, mu=self.mu, mode="pcd", idx_base=self.idx_base)
+        return nat.score_topk(Pq, self.E, k, mu=self.mu, mode="pcd", idx_base=self.idx_base,
+                              image=self.image)
 
     def rank(self, xq: torch.Tensor, k: int = 100):
         """-> (dist [Q,k] ascending, index [Q,k] int64 global).  score = theta+ - dist."""

@@ -282,37 +282,39 @@ topk_merge_kernel(const float* __restrict__ vals, const int64_t* __restrict__ id
 
 using namespace cfl;
 
-static size_t score_ws_layout(int64_t Q, int K, int d, const ScorePlan& p, size_t* o_pc,
-                              size_t* o_qpar, size_t* o_qimg, size_t* o_keys, size_t* o_cnt) {
+static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePlan& p, bool own_image,
+                              size_t* o_pc, size_t* o_qpar, size_t* o_qimg, size_t* o_keys, size_t* o_cnt,
+                              size_t* o_cimg) {
   size_t off = 0;
   *o_pc = off;   off = align_up(off + (size_t)Q * K * d * 4, 256);
   *o_qpar = off; off = align_up(off + (size_t)Q * qpar_stride(K) * 4, 256);
   *o_qimg = off; off = align_up(off + (p.impl ? score_umma_qimg_bytes(p, K) : 0), 1024);
   *o_keys = off; off = align_up(off + (size_t)p.parts * Q * TOPK_CAP * sizeof(tkey_t), 256);
-  *o_cnt = off;  off = align_up(off + (size_t)p.parts * Q * sizeof(int), 256);
+  *o_cnt = off;  off = align_up(off + (size_t)p.parts * Q * sizeof(int), 1024);
+  *o_cimg = off; off = align_up(off + ((p.impl && own_image) ? catalog_image_bytes(N, d) : 0), 1024);
   return off + 1024;
 }
 
-extern "C" {
-
-size_t cfl_score_topk_workspace_bytes(int64_t Q, int K, int d, int64_t N, int k) {
-  if (Q <= 0 || N <= 0) return 1024;
-  // the plan (hence the size) may differ between the two kernels: take the larger
-  size_t a, b, c, e, f;
+static size_t score_ws_bytes(int64_t Q, int K, int d, int64_t N, int k, bool own_image) {
+  if (Q <= 0 || N <= 0) return 4096;
+  // the plan (hence the size) differs between the two kernels: take the larger
+  size_t a, b, c, e, f, g;
   ScorePlan p0 = make_score_plan(Q, K, d, N, k, false);
-  size_t s0 = score_ws_layout(Q, K, d, p0, &a, &b, &c, &e, &f);
+  size_t s0 = score_ws_layout(Q, K, d, N, p0, own_image, &a, &b, &c, &e, &f, &g);
   size_t s1 = 0;
   if (score_umma_qt(K, d) > 0) {
     ScorePlan p1 = make_score_plan(Q, K, d, N, k, true);
-    s1 = score_ws_layout(Q, K, d, p1, &a, &b, &c, &e, &f);
+    s1 = score_ws_layout(Q, K, d, N, p1, own_image, &a, &b, &c, &e, &f, &g);
   }
   return (s0 > s1 ? s0 : s1) + 1024;
 }
 
-int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq,
-                   const float* E, int64_t N, int64_t lde, const float* mu, int k,
-                   int64_t idx_base, float* top_val, int64_t* top_idx, float* dist_out, void* ws,
-                   size_t ws_bytes, void* stream) {
+// Shared body of cfl_score_topk (image == NULL: packed into the workspace on every call) and
+// cfl_score_topk_packed (image built once by cfl_catalog_pack).
+static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq,
+                           const float* E, const void* image, int64_t N, int64_t lde, const float* mu,
+                           int k, int64_t idx_base, float* top_val, int64_t* top_idx, float* dist_out,
+                           void* ws, size_t ws_bytes, cudaStream_t cs) {
   int st = device_check();
   if (st != CFL_OK) return st;
   CFL_REQUIRE(mode == CFL_PCD || mode == CFL_SIAMESE, CFL_ERR_UNSUPPORTED,
@@ -326,11 +328,11 @@ int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t l
   if (Q == 0) return CFL_OK;
   CFL_REQUIRE(Pq && top_val && top_idx, CFL_ERR_INVALID, "score_topk: NULL argument");
   CFL_REQUIRE(N == 0 || E, CFL_ERR_INVALID, "score_topk: NULL catalog");
-  cudaStream_t cs = (cudaStream_t)stream;
-  bool umma_ok = N > 0 && score_umma_supported(K, d, E, lde);
+  bool umma_ok = N > 0 && score_umma_supported(K, d);
+  CFL_REQUIRE(!image || umma_ok, CFL_ERR_UNSUPPORTED, "score_topk_packed: shape K=%d d=%d has no tcgen05 tiling", K, d);
   ScorePlan plan = make_score_plan(Q, K, d, N > 0 ? N : 1, k, umma_ok);
-  size_t o_pc, o_qpar, o_qimg, o_keys, o_cnt;
-  size_t need = score_ws_layout(Q, K, d, plan, &o_pc, &o_qpar, &o_qimg, &o_keys, &o_cnt);
+  size_t o_pc, o_qpar, o_qimg, o_keys, o_cnt, o_cimg;
+  size_t need = score_ws_layout(Q, K, d, N, plan, image == nullptr, &o_pc, &o_qpar, &o_qimg, &o_keys, &o_cnt, &o_cimg);
   CFL_REQUIRE(ws && ws_bytes >= need, CFL_ERR_WORKSPACE, "score_topk: workspace too small (%zu < %zu)",
               ws_bytes, need);
   char* base = (char*)ws;
@@ -338,6 +340,7 @@ int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t l
   a.mode = mode; a.K = K; a.d = d; a.Q = Q; a.N = N; a.lde = lde; a.E = E; a.mu = mu;
   a.Pc = (float*)(base + o_pc); a.qpar = (float*)(base + o_qpar); a.qimg = base + o_qimg;
   a.keys = (tkey_t*)(base + o_keys); a.counts = (int*)(base + o_cnt); a.dist_out = dist_out;
+  a.cimg = nullptr; a.e2 = nullptr;
   a.plan = plan;
   if (N == 0) {
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
@@ -346,6 +349,13 @@ int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t l
                                                                 (float*)a.Pc, (float*)a.qpar);
     CFL_LAUNCH_CHECK();
     if (plan.impl == 1) {
+      if (!image) {
+        st = catalog_pack_launch(E, N, d, lde, mu, base + o_cimg, cs);
+        if (st != CFL_OK) return st;
+        image = base + o_cimg;
+      }
+      a.cimg = image;
+      a.e2 = (const float*)((const char*)image + (size_t)plan.tiles * (plan.dpad / 8) * 8192);
       st = score_umma_pack_queries(a, base + o_qimg, cs);
       if (st != CFL_OK) return st;
       timer_record(0, cs);
@@ -372,6 +382,48 @@ int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t l
                                                   Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
+}
+
+extern "C" {
+
+size_t cfl_score_topk_workspace_bytes(int64_t Q, int K, int d, int64_t N, int k) {
+  return score_ws_bytes(Q, K, d, N, k, true);
+}
+size_t cfl_score_topk_packed_workspace_bytes(int64_t Q, int K, int d, int64_t N, int k) {
+  return score_ws_bytes(Q, K, d, N, k, false);
+}
+
+size_t cfl_catalog_pack_bytes(int64_t N, int K, int d) {
+  if (N <= 0 || score_umma_qt(K, d) == 0) return 0;
+  return catalog_image_bytes(N, d);
+}
+
+int cfl_catalog_pack(const float* E, int64_t N, int K, int d, int64_t lde, const float* mu, void* image,
+                     size_t image_bytes, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(E && image && N > 0 && lde >= d, CFL_ERR_INVALID, "catalog_pack: bad arguments");
+  CFL_REQUIRE(score_umma_supported(K, d), CFL_ERR_UNSUPPORTED, "catalog_pack: shape K=%d d=%d has no tcgen05 tiling", K, d);
+  CFL_REQUIRE(image_bytes >= catalog_image_bytes(N, d), CFL_ERR_WORKSPACE, "catalog_pack: image buffer too small");
+  CFL_REQUIRE(((uintptr_t)image & 1023u) == 0, CFL_ERR_INVALID, "catalog_pack: image must be 1024-byte aligned");
+  return catalog_pack_launch(E, N, d, lde, mu, image, (cudaStream_t)stream);
+}
+
+int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq,
+                   const float* E, int64_t N, int64_t lde, const float* mu, int k,
+                   int64_t idx_base, float* top_val, int64_t* top_idx, float* dist_out, void* ws,
+                   size_t ws_bytes, void* stream) {
+  return score_topk_impl(mode, Pq, Q, K, d, ldq, E, nullptr, N, lde, mu, k, idx_base, top_val, top_idx,
+                         dist_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int cfl_score_topk_packed(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq,
+                          const void* image, const float* E, int64_t N, int64_t lde, const float* mu, int k,
+                          int64_t idx_base, float* top_val, int64_t* top_idx, float* dist_out, void* ws,
+                          size_t ws_bytes, void* stream) {
+  CFL_REQUIRE(image, CFL_ERR_INVALID, "score_topk_packed: NULL image");
+  return score_topk_impl(mode, Pq, Q, K, d, ldq, E, image, N, lde, mu, k, idx_base, top_val, top_idx,
+                         dist_out, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int cfl_topk_merge(const float* vals, const int64_t* idx, int R, int64_t Q, int k, float* top_val,

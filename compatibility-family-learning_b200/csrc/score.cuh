@@ -26,6 +26,8 @@ struct ScoreArgs {
   const float* Pc;       // centred query prototypes [Q,K,d] (dense)
   const float* qpar;     // per query: p2[K] then pp[K*K]
   const void* qimg;      // tcgen05 B-operand image per query tile (score_umma.cu)
+  const void* cimg;      // tcgen05 A-operand image of the catalog (cfl_catalog_pack)
+  const float* e2;       // |e - mu|^2 per catalog row, padded to whole tiles (part of the image)
   tkey_t* keys;           // [parts, Q, TOPK_CAP]
   int* counts;           // [parts, Q]
   float* dist_out;       // optional dense [Q,N]
@@ -41,7 +43,10 @@ __host__ __device__ constexpr int qpar_tri(int K) { return K * (K + 1) / 2; }
 __host__ __device__ constexpr int qpar_stride(int K) { return (K + qpar_tri(K) + 1 + 3) / 4 * 4; }
 
 ScorePlan make_score_plan(int64_t Q, int K, int d, int64_t N, int k, bool umma_ok);
-bool score_umma_supported(int K, int d, const float* E, int64_t lde);
+bool score_umma_supported(int K, int d);
+size_t catalog_image_bytes(int64_t N, int d);
+int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const float* mu, void* image,
+                        cudaStream_t st);
 size_t score_umma_qimg_bytes(const ScorePlan& p, int K);
 int score_umma_pack_queries(const ScoreArgs& a, void* qimg, cudaStream_t st);
 int score_umma_launch(const ScoreArgs& a, cudaStream_t st);

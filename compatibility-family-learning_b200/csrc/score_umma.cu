@@ -5,18 +5,22 @@
 //   D[c, k*QT + q] = e_c . p_{q,k}        M = 128 catalog rows (TMEM lanes), N = K*QT columns,
 //                                         MMA-K = the embedding dimension d (8 per K-step)
 //
-// CTA (part, qtile): the query tile's B operand (pre-split hi/lo image, <= 96 KB) is loaded once
-// by the bulk-copy (TMA) engine and stays resident in shared memory; the CTA then streams its
-// contiguous range of 128-row catalog tiles.  13 warps, warp-specialised:
-//   warps 8-11  producers: thread r owns catalog row r of the tile: LDG (8 K-steps of register
-//               prefetch) -> centre -> |e|^2 -> hi/lo split -> canonical smem layout -> full[stage]
-//   warp  12    allocates TMEM, loads the B image, and one lane issues tcgen05.mma
-//               (3 per K-step), tcgen05.commit -> empty[stage] / tmem_full[buf]
-//   warps 0-7   epilogue: tcgen05.ld of the K Gram values of 16 (8) queries at a time for the
-//               thread's row, soft-min distance (score.cuh), threshold test, warp-aggregated push
-//               into the per-query buffers (topk.cuh); accumulators are double-buffered in TMEM
-//               so the epilogue of tile t overlaps the MMAs of tile t+1.
-// Work per score: 2*K*d flops (x3 MMAs); bytes per catalog row: 4*d (read once per query tile).
+// Both operands are consumed as pre-split (hi, lo) tf32 images in the canonical K-major
+// SWIZZLE_NONE layout (umma.cuh):
+//   * the CATALOG image is built once per catalog by cfl_catalog_pack (centred on mu, split,
+//     one 8 KB block per (tile, K-step), plus |e|^2 per row) -- the catalog is static across
+//     query batches, so no per-query work is spent on it;
+//   * the QUERY image of the CTA's query tile (<= 96 KB) is packed per call and stays resident
+//     in shared memory for the whole kernel.
+// CTA (part, qtile) streams its contiguous range of 128-row catalog tiles.  Warp-specialised:
+//   warp  NEPI    one lane issues tcgen05.mma (3 per K-step) and tcgen05.commit
+//   warp  NEPI+1  one lane drives the TMA engine: cp.async.bulk of the query image, then one
+//                 8 KB catalog block per ring stage (mbarrier expect_tx / complete_tx)
+//   warps 0..NEPI-1  epilogue: tcgen05.ld of the K Gram values of 8 (16) queries for the thread's
+//                 catalog row, soft-min distance (score.cuh), threshold test, warp-aggregated push
+//                 into the per-query buffers (topk.cuh).  Accumulators are double-buffered in
+//                 TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
+// Work per score: 2*K*d flops (x3 MMAs); catalog bytes per row per query tile: 8*dpad + 4.
 #include "score.cuh"
 #include "umma.cuh"
 
@@ -24,10 +28,11 @@ namespace cfl {
 
 using namespace umma;
 
-constexpr int SU_THREADS = 416;
+constexpr int SU_NEPI = 12;                         // epilogue warps (3 per TMEM lane quarter)
+constexpr int SU_THREADS = (SU_NEPI + 2) * 32;
+constexpr int SU_EPI_THREADS = SU_NEPI * 32;
 constexpr int SU_NSTAGE = 12;
 constexpr uint32_t SU_ASTAGE = 4u * 128u * 16u;     // [hl][chunk][128 rows][16 B] = 8 KB
-constexpr int SU_PF = 8;                            // K-steps of register prefetch per producer
 constexpr size_t SU_B_BUDGET = 96 * 1024;
 
 int score_umma_qt(int K, int d) {
@@ -44,19 +49,64 @@ int score_umma_qt(int K, int d) {
   return 0;
 }
 
-bool score_umma_supported(int K, int d, const float* E, int64_t lde) {
+bool score_umma_supported(int K, int d) {
   if (getenv("CFL_FORCE_SIMT")) return false;
-  if (score_umma_qt(K, d) == 0) return false;
-  // float4 row loads: 16-byte aligned rows
-  return (lde % 4 == 0) && (((uintptr_t)E & 15u) == 0);
+  return score_umma_qt(K, d) != 0;
 }
 
 size_t score_umma_qimg_bytes(const ScorePlan& p, int K) {
   return (size_t)p.nqt * p.dpad * 8 * (size_t)(K * p.qt);
 }
 
+// ---- catalog image ----------------------------------------------------------------------------
+// [tile][kstep][hl][chunk][row 0..127][4 floats]  (8 KB per (tile,kstep)), then e2[tiles*128].
+size_t catalog_image_bytes(int64_t N, int d) {
+  const int64_t tiles = (N + 127) / 128;
+  const int nks = (d + 7) / 8;
+  return (size_t)tiles * nks * SU_ASTAGE + (size_t)tiles * 128 * sizeof(float);
+}
+
+__global__ void __launch_bounds__(128)
+pack_catalog_kernel(const float* __restrict__ E, int64_t N, int d, int64_t lde,
+                    const float* __restrict__ mu, unsigned char* __restrict__ img, float* __restrict__ e2g) {
+  const int64_t tile = blockIdx.x;
+  const int r = threadIdx.x;
+  const int64_t row = tile * 128 + r;
+  const int nks = (d + 7) / 8;
+  float e2 = 0.0f;
+  for (int ks = 0; ks < nks; ++ks) {
+    float v[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = ks * 8 + jj;
+      v[jj] = (row < N && j < d) ? E[row * lde + j] - (mu ? mu[j] : 0.0f) : 0.0f;
+      e2 = fmaf(v[jj], v[jj], e2);
+    }
+    float4 h0, l0, h1, l1;
+    split_tf32x4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+    split_tf32x4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+    unsigned char* st = img + ((size_t)tile * nks + ks) * SU_ASTAGE;
+    *(float4*)(st + ((0 * 2 + 0) * 128 + r) * 16) = h0;
+    *(float4*)(st + ((0 * 2 + 1) * 128 + r) * 16) = h1;
+    *(float4*)(st + ((1 * 2 + 0) * 128 + r) * 16) = l0;
+    *(float4*)(st + ((1 * 2 + 1) * 128 + r) * 16) = l1;
+  }
+  e2g[row] = e2;
+}
+
+int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const float* mu, void* image,
+                        cudaStream_t st) {
+  const int64_t tiles = (N + 127) / 128;
+  const int nks = (d + 7) / 8;
+  unsigned char* img = (unsigned char*)image;
+  float* e2g = (float*)(img + (size_t)tiles * nks * SU_ASTAGE);
+  pack_catalog_kernel<<<(unsigned)tiles, 128, 0, st>>>(E, N, d, lde, mu, img, e2g);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
 struct SuLayout {
-  uint32_t b_img, a_ring, scratch, e2s, qpar, thr, cnt, mu, bars, tmem_slot, total;
+  uint32_t b_img, a_ring, scratch, qpar, thr, cnt, bars, tmem_slot, total;
 };
 __host__ __device__ inline SuLayout su_layout(int K, int qt, int dpad) {
   SuLayout L;
@@ -64,18 +114,16 @@ __host__ __device__ inline SuLayout su_layout(int K, int qt, int dpad) {
   L.b_img = off;   off += (uint32_t)dpad * 8u * (uint32_t)(K * qt);   off = (off + 1023u) & ~1023u;
   L.a_ring = off;  off += SU_NSTAGE * SU_ASTAGE;
   L.scratch = off; off += TOPK_CAP * 8u;
-  L.e2s = off;     off += 4u * 128u * 4u;
   L.qpar = off;    off += (uint32_t)qt * (uint32_t)qpar_stride(K) * 4u;  off = (off + 15u) & ~15u;
   L.thr = off;     off += (uint32_t)qt * 4u;
-  L.cnt = off;     off += (uint32_t)qt * 4u;
-  L.mu = off;      off += (uint32_t)dpad * 4u;                        off = (off + 15u) & ~15u;
+  L.cnt = off;     off += (uint32_t)qt * 4u;                          off = (off + 15u) & ~15u;
   L.bars = off;    off += (2u * SU_NSTAGE + 5u) * 8u;
   L.tmem_slot = off; off += 16u;
   L.total = off;
   return L;
 }
 
-// ---- B-operand image: [qtile][kstep][hl][chunk][row n = k*QT + ql][4 floats] ------------------
+// ---- query (B operand) image: [qtile][kstep][hl][chunk][row n = k*QT + ql][4 floats] -----------
 __global__ void pack_queries_kernel(const float* __restrict__ Pc, int64_t Q, int K, int d, int qt,
                                     int dpad, float* __restrict__ img) {
   const int nc = K * qt;
@@ -112,8 +160,8 @@ int score_umma_pack_queries(const ScoreArgs& a, void* qimg, cudaStream_t st) {
   return CFL_OK;
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(SU_EPI_THREADS) : "memory");
 }
 
 // ---- the kernel ---------------------------------------------------------------------------
@@ -126,16 +174,13 @@ score_umma_kernel(ScoreArgs A) {
   const int NC = K * QT;
   const int dpad = A.plan.dpad;
   const int nks = dpad / 8;
-  const int d = A.d;
   const SuLayout L = su_layout(K, QT, dpad);
   unsigned char* b_img = smem + L.b_img;
   unsigned char* a_ring = smem + L.a_ring;
   tkey_t* scratch = (tkey_t*)(smem + L.scratch);
-  float* e2s = (float*)(smem + L.e2s);
   float* qpar = (float*)(smem + L.qpar);
   float* thr = (float*)(smem + L.thr);
   int* cnt = (int*)(smem + L.cnt);
-  float* mus = (float*)(smem + L.mu);
   uint64_t* full = (uint64_t*)(smem + L.bars);
   uint64_t* empty = full + SU_NSTAGE;
   uint64_t* tfull = empty + SU_NSTAGE;
@@ -155,11 +200,11 @@ score_umma_kernel(ScoreArgs A) {
   // ---- one-time setup ----
   uint32_t ncols = 32;
   while ((int)ncols < 2 * NC) ncols <<= 1;
-  if (warp == 12) {
+  if (warp == SU_NEPI) {
     if (lane == 0) {
-      for (int s = 0; s < SU_NSTAGE; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < SU_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-      mbar_init(&tempty[0], 256); mbar_init(&tempty[1], 256);
+      mbar_init(&tempty[0], SU_EPI_THREADS); mbar_init(&tempty[1], SU_EPI_THREADS);
       mbar_init(bfull, 1);
       fence_barrier_init();
     }
@@ -172,22 +217,14 @@ score_umma_kernel(ScoreArgs A) {
     thr[i] = __int_as_float(i < nq ? 0x7f800000 : 0xff800000);
     cnt[i] = 0;
   }
-  for (int i = tid; i < dpad; i += SU_THREADS) mus[i] = (A.mu && i < d) ? A.mu[i] : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 12) {
-    // =========================== B loader + MMA issuer (one lane) ===========================
+  if (warp == SU_NEPI) {
+    // ================================ MMA issuer (one lane) =================================
     if (lane == 0) {
-      const uint32_t bbytes = (uint32_t)dpad * 8u * (uint32_t)NC;
-      const unsigned char* src = (const unsigned char*)A.qimg + (size_t)qtile * bbytes;
-      mbar_arrive_expect_tx(bfull, bbytes);
-      for (uint32_t o = 0; o < bbytes; o += 32768u) {
-        uint32_t n = bbytes - o < 32768u ? bbytes - o : 32768u;
-        bulk_g2s(b_img + o, src + o, n, bfull);
-      }
       mbar_wait(bfull, 0);
       const uint32_t idesc = make_idesc_tf32(128, (uint32_t)NC);
       const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_img);
@@ -208,91 +245,51 @@ score_umma_kernel(ScoreArgs A) {
         mma_commit(&tfull[buf]);
       }
     }
-  } else if (warp >= 8) {
-    // ======================================= producers =======================================
-    const int r = tid - 256;                                 // catalog row of the tile
-    const int total = ntiles * nks;
-    const bool need_mask = (d & 7) != 0;
-    float4 qa[SU_PF], qb[SU_PF];
-    int lt = 0, lks = 0;                                     // (tile, kstep) of the next load
-    auto load_item = [&](float4& xa, float4& xb) {
-      xa = make_float4(0.f, 0.f, 0.f, 0.f); xb = xa;
-      const int64_t row = (t0 + lt) * 128 + r;
-      if (row < A.N) {
-        const float* p = A.E + row * A.lde + lks * 8;
-        if (lks * 8 < d) xa = __ldg((const float4*)p);
-        if (lks * 8 + 4 < d) xb = __ldg((const float4*)(p + 4));
+  } else if (warp == SU_NEPI + 1) {
+    // ================================ TMA producer (one lane) ===============================
+    if (lane == 0) {
+      const uint32_t bbytes = (uint32_t)dpad * 8u * (uint32_t)NC;
+      const unsigned char* qsrc = (const unsigned char*)A.qimg + (size_t)qtile * bbytes;
+      mbar_arrive_expect_tx(bfull, bbytes);
+      for (uint32_t o = 0; o < bbytes; o += 32768u) {
+        uint32_t n = bbytes - o < 32768u ? bbytes - o : 32768u;
+        bulk_g2s(b_img + o, qsrc + o, n, bfull);
       }
-      if (++lks == nks) { lks = 0; ++lt; }
-    };
-#pragma unroll
-    for (int u = 0; u < SU_PF; ++u) { if (u < total) load_item(qa[u], qb[u]); }
-    int stage = 0; uint32_t phase = 0;
-    int pt = 0, pks = 0;
-    float e2 = 0.0f;
-    for (int base = 0; base < total; base += SU_PF) {
-#pragma unroll
-      for (int u = 0; u < SU_PF; ++u) {
-        const int i = base + u;
-        if (i < total) {
-          float4 xa = qa[u], xb = qb[u];
-          if (i + SU_PF < total) load_item(qa[u], qb[u]);
-          // centre + mask the padding columns
-          const int j0 = pks * 8;
-          const float4 ma = *(const float4*)(mus + j0), mb = *(const float4*)(mus + j0 + 4);
-          float v[8] = {xa.x - ma.x, xa.y - ma.y, xa.z - ma.z, xa.w - ma.w,
-                        xb.x - mb.x, xb.y - mb.y, xb.z - mb.z, xb.w - mb.w};
-          if (need_mask && pks == nks - 1) {                   // padding columns of the last K-step
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) if (j0 + jj >= d) v[jj] = 0.0f;
-          }
-          if (((t0 + pt) * 128 + r) >= A.N) {                  // rows past the catalog end (last tile)
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) v[jj] = 0.0f;
-          }
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) e2 = fmaf(v[jj], v[jj], e2);
-          if (pks == nks - 1) { e2s[(pt & 3) * 128 + r] = e2; e2 = 0.0f; }
-          float4 h0, l0, h1, l1;
-          split_tf32x4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
-          split_tf32x4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
-          mbar_wait(&empty[stage], phase ^ 1u);
-          unsigned char* st = a_ring + stage * SU_ASTAGE;
-          *(float4*)(st + ((0 * 2 + 0) * 128 + r) * 16) = h0;
-          *(float4*)(st + ((0 * 2 + 1) * 128 + r) * 16) = h1;
-          *(float4*)(st + ((1 * 2 + 0) * 128 + r) * 16) = l0;
-          *(float4*)(st + ((1 * 2 + 1) * 128 + r) * 16) = l1;
-          fence_proxy_async();
-          mbar_arrive(&full[stage]);
-          if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
-          if (++pks == nks) { pks = 0; ++pt; }
-        }
+      const unsigned char* src = (const unsigned char*)A.cimg + (size_t)t0 * nks * SU_ASTAGE;
+      const int total = ntiles * nks;
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < total; ++i) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full[stage], SU_ASTAGE);
+        bulk_g2s(a_ring + stage * SU_ASTAGE, src + (size_t)i * SU_ASTAGE, SU_ASTAGE, &full[stage]);
+        if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
     // ======================================= epilogue ========================================
     constexpr int QPS = qpar_stride(K);
     constexpr int CQ = K + qpar_tri(K);
-    const int lq = warp & 3, half = warp >> 2;
+    constexpr int WPQ = SU_NEPI / 4;                         // warps per TMEM lane quarter
+    const int lq = warp & 3, sub = warp >> 2;
     const int lrow = lq * 32 + lane;
     const uint32_t lane_lt = (1u << lane) - 1u;
     const bool dense = A.dist_out != nullptr;
     tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_CAP;
-    // The lower bound dist >= min_k d_k - cq lets a whole 16-query group skip the soft-min when
-    // no lane can beat its threshold.  It only pays when the prototypes of a query are close
+    // The lower bound dist >= min_k d_k - cq lets a whole query group skip the soft-min when no
+    // lane can beat its threshold.  It only pays when the prototypes of a query are close
     // together relative to the spread of distances, so each warp measures its hit rate over the
     // first tiles and switches the test off when it rarely fires.
     bool bound_on = (K > 1) && !dense;
     int grp_seen = 0, grp_skipped = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
-      mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
-      tc_fence_after();
       const int64_t row = (t0 + t) * 128 + lrow;
       const bool valid = row < A.N;
-      const float e2 = e2s[(t & 3) * 128 + lrow];
+      const float e2 = __ldg(A.e2 + row);                    // padded to whole tiles
+      mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
-      for (int g = half; g * GQ < nq; g += 2) {
+      for (int g = sub; g * GQ < nq; g += WPQ) {
         float gk[K][GQ];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -343,12 +340,14 @@ score_umma_kernel(ScoreArgs A) {
           for (int i = 0; i < GQ; ++i)
             if (g * GQ + i < nq) A.dist_out[(q0 + g * GQ + i) * A.N + row] = dist[i];
         }
-        if (__any_sync(0xffffffffu, bits != 0)) {             // rare once the thresholds are tight
+        // which queries of the group have at least one passing lane (usually 0-2 of them)
+        const uint32_t anyq = __reduce_or_sync(0xffffffffu, bits);
+        if (anyq) {
 #pragma unroll
           for (int i = 0; i < GQ; ++i) {
-            const bool pass = (bits >> i) & 1u;
-            const uint32_t m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
+            if (anyq & (1u << i)) {                            // warp-uniform
+              const bool pass = (bits >> i) & 1u;
+              const uint32_t m = __ballot_sync(0xffffffffu, pass);
               const int ql = g * GQ + i;
               const int leader = __ffs(m) - 1;
               int basei = 0;
@@ -362,36 +361,33 @@ score_umma_kernel(ScoreArgs A) {
       if (t == 15 && bound_on && grp_skipped * 2 < grp_seen) bound_on = false;
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
-      // ---- compaction point: all 8 epilogue warps sort one over-full buffer together ----
-      named_bar_sync(1, 256);
-      {
-        const int et = tid;                                   // 0..255
-        for (int qb = 0; qb < nq; qb += 32) {
-          const int ql0 = qb + lane;
-          const uint32_t over = __ballot_sync(0xffffffffu, ql0 < nq && cnt[ql0] > TOPK_TRIGGER);
-          for (uint32_t m = over; m; m &= m - 1) {            // identical in every warp
-            const int ql = qb + __ffs(m) - 1;
-            coop_compact(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch, et, 1, &cnt[ql], &thr[ql]);
-          }
+      // ---- compaction point: all epilogue warps sort one over-full buffer together ----
+      epi_bar_sync();
+      for (int qb = 0; qb < nq; qb += 32) {
+        const int ql0 = qb + lane;
+        const uint32_t over = __ballot_sync(0xffffffffu, ql0 < nq && cnt[ql0] > TOPK_TRIGGER);
+        for (uint32_t m = over; m; m &= m - 1) {              // identical in every warp
+          const int ql = qb + __ffs(m) - 1;
+          coop_compact<SU_EPI_THREADS>(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch, tid, &cnt[ql], &thr[ql]);
         }
       }
-      named_bar_sync(1, 256);
+      epi_bar_sync();
     }
     for (int ql = 0; ql < nq; ++ql) {
-      coop_compact(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch, tid, 1, &cnt[ql], nullptr);
+      coop_compact<SU_EPI_THREADS>(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch, tid, &cnt[ql], nullptr);
       if (tid == 0) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
     }
   }
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem_base, ncols);
+  if (warp == SU_NEPI) tmem_dealloc(tmem_base, ncols);
 }
 
 template <int K>
 static int launch_umma(const ScoreArgs& a, cudaStream_t st) {
   SuLayout L = su_layout(K, a.plan.qt, a.plan.dpad);
-  size_t smem = L.total + 1024;      // slack for the 1024-byte alignment of the dynamic segment
+  size_t smem = L.total + 1024;      // slack for the alignment of the dynamic segment
   CFL_CUDA(cudaFuncSetAttribute(score_umma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(a.plan.parts, a.plan.nqt);
   score_umma_kernel<K><<<grid, SU_THREADS, smem, st>>>(a);

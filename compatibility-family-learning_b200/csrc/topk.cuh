@@ -53,42 +53,46 @@ __device__ __forceinline__ int warp_compact(tkey_t* __restrict__ buf, int n, int
   return nk;
 }
 
-// ---- cooperative variant: 256 threads (8 warps) sort the 512 keys together -----------------
+// ---- cooperative variant: NT threads (>= 256) sort the 512 keys together ----------------------
 // Comparator t (0..255) of a stage touches elements i(t) and i(t)|stride.  Warp w owns
-// comparators 32w..32w+31, i.e. elements [64w, 64w+64) whenever stride <= 32, so those 39 of
-// the 45 stages only need __syncwarp; the 6 stages with stride >= 64 need the named barrier.
-__device__ __forceinline__ void coop_bar(int bar_id) {
-  asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+// comparators 32w..32w+31, i.e. elements [64w, 64w+64) whenever stride <= 32, so those stages
+// only need __syncwarp; a named barrier (id 1, NT threads) is needed only where the next stage
+// reads keys written by another warp.  Threads t >= 256 just take part in the barriers.
+template <int NT>
+__device__ __forceinline__ void coop_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
 }
-__device__ __forceinline__ void coop_sort512(tkey_t* s, int t, int bar_id) {
+template <int NT>
+__device__ __forceinline__ void coop_sort512(tkey_t* s, int t) {
   for (int size = 2; size <= TOPK_CAP; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
-      const int j = i | stride;
-      const bool asc = (i & size) == 0;
-      const tkey_t a = s[i], b = s[j];
-      if ((a > b) == asc) { s[i] = b; s[j] = a; }
-      if (stride >= 64 || (stride == 1 && size >= 64)) coop_bar(bar_id);   // next stage crosses warps
+      if (t < TOPK_CAP / 2) {
+        const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int j = i | stride;
+        const bool asc = (i & size) == 0;
+        const tkey_t a = s[i], b = s[j];
+        if ((a > b) == asc) { s[i] = b; s[j] = a; }
+      }
+      if (stride >= 64 || (stride == 1 && size >= 64)) coop_bar<NT>();   // next stage crosses warps
       else __syncwarp();
     }
   }
 }
-// 256 threads: keep the best kk of buf[0..n) (global), sorted ascending; thread 0 publishes the
+// NT threads: keep the best kk of buf[0..n) (global), sorted ascending; thread 0 publishes the
 // new count and threshold.  Ends with a barrier so `scratch` can be reused immediately.
+template <int NT>
 __device__ __forceinline__ void coop_compact(tkey_t* __restrict__ buf, int n, int kk, tkey_t* scratch,
-                                             int t, int bar_id, int* cnt_out, float* thr_out) {
-  scratch[t] = (t < n) ? buf[t] : CFL_KEY_INF;
-  scratch[t + 256] = (t + 256 < n) ? buf[t + 256] : CFL_KEY_INF;
-  __syncwarp();                                   // first stages stay inside the warp's 64-key chunk?
-  coop_bar(bar_id);                               // no: keys t and t+256 belong to different chunks
-  coop_sort512(scratch, t, bar_id);
+                                             int t, int* cnt_out, float* thr_out) {
+  for (int i = t; i < TOPK_CAP; i += NT) scratch[i] = (i < n) ? buf[i] : CFL_KEY_INF;
+  coop_bar<NT>();
+  coop_sort512<NT>(scratch, t);
   const int nk = n < kk ? n : kk;
   if (t < nk) buf[t] = scratch[t];
   if (t == 0) {
     *cnt_out = nk;
     if (thr_out) *thr_out = (n >= kk) ? ord2f((uint32_t)(scratch[kk - 1] >> 32)) : __int_as_float(0x7f800000);
   }
-  coop_bar(bar_id);
+  coop_bar<NT>();
 }
 
 }  // namespace cfl

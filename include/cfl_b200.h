@@ -136,6 +136,22 @@ int cfl_score_topk(int mode, const float* Pq, int64_t Q, int K, int d, int64_t l
                    float* top_val, int64_t* top_idx, float* dist_out,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* Catalog image for the tensor-core kernel: the catalog is static across query batches, so its MMA
+ * operand form (centred on mu, hi/lo tf32 split, canonical shared-memory layout, |e-mu|^2 per row)
+ * is built once.  cfl_catalog_pack_bytes returns 0 when (K, d) has no tcgen05 tiling (use
+ * cfl_score_topk then).  `image` must be 1024-byte aligned; mu must be the same vector later passed
+ * to cfl_score_topk_packed, which is cfl_score_topk minus the per-call packing (E is still needed
+ * for the direct-form rescoring of the winners). */
+size_t cfl_catalog_pack_bytes(int64_t N, int K, int d);
+int cfl_catalog_pack(const float* E, int64_t N, int K, int d, int64_t lde, const float* mu,
+                     void* image, size_t image_bytes, void* stream);
+size_t cfl_score_topk_packed_workspace_bytes(int64_t Q, int K, int d, int64_t N, int k);
+int cfl_score_topk_packed(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq,
+                          const void* image, const float* E, int64_t N, int64_t lde, const float* mu,
+                          int k, int64_t idx_base,
+                          float* top_val, int64_t* top_idx, float* dist_out,
+                          void* ws, size_t ws_bytes, void* stream);
+
 /* Merge R sorted lists per query (the per-rank results after ncclAllGather) into one:
  * vals[R,Q,k], idx[R,Q,k] -> top_val[Q,k], top_idx[Q,k]; order (value, index). */
 int cfl_topk_merge(const float* vals, const int64_t* idx, int R, int64_t Q, int k,
