@@ -3,6 +3,7 @@
 // cfl_score_topk / cfl_topk_merge entry points.  The tensor-core scoring kernel lives in
 // score_umma.cu and is used whenever its tiling supports the shape (see score_umma_supported);
 // both kernels share the soft-min epilogue (score.cuh) and the top-k machinery (topk.cuh).
+#include <stdlib.h>
 #include "score.cuh"
 
 namespace cfl {
@@ -103,7 +104,7 @@ score_simt_kernel(ScoreArgs A) {
   if (tid < SIMT_QT) { thr[tid] = __int_as_float(0x7f800000); cnt[tid] = 0; }
   const int64_t t0 = A.plan.tiles * part / A.plan.parts;
   const int64_t t1 = A.plan.tiles * (part + 1) / A.plan.parts;
-  tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_CAP;
+  tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
   __syncthreads();
 
   for (int64_t tile = t0; tile < t1; ++tile) {
@@ -135,7 +136,7 @@ score_simt_kernel(ScoreArgs A) {
         if (A.dist_out) A.dist_out[(q0 + ql) * A.N + row] = dist;
         if (dist < thr[ql]) {
           int slot = atomicAdd(&cnt[ql], 1);
-          kbase[(int64_t)ql * TOPK_CAP + slot] = pack_key(dist, (uint32_t)row);
+          kbase[(int64_t)ql * TOPK_STRIDE + slot] = pack_key(dist, (uint32_t)row);
         }
       }
     }
@@ -143,7 +144,7 @@ score_simt_kernel(ScoreArgs A) {
     for (int ql = wid; ql < nq; ql += SIMT_THREADS / 32) {
       int n = cnt[ql];
       if (n > TOPK_TRIGGER) {
-        int nk = warp_compact(kbase + (int64_t)ql * TOPK_CAP, n, A.plan.kk,
+        int nk = warp_compact(kbase + (int64_t)ql * TOPK_STRIDE, n, A.plan.kk,
                               scratch + wid * TOPK_CAP, lane, &thr[ql]);
         if (lane == 0) cnt[ql] = nk;
       }
@@ -151,7 +152,7 @@ score_simt_kernel(ScoreArgs A) {
     __syncthreads();
   }
   for (int ql = wid; ql < nq; ql += SIMT_THREADS / 32) {
-    int nk = warp_compact(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk,
+    int nk = warp_compact(kbase + (int64_t)ql * TOPK_STRIDE, cnt[ql], A.plan.kk,
                           scratch + wid * TOPK_CAP, lane, nullptr);
     if (lane == 0) A.counts[(int64_t)part * A.Q + q0 + ql] = nk;
   }
@@ -186,17 +187,21 @@ merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __res
   const int64_t q = blockIdx.x;
   int fill = 0;
   for (int p = 0; p < parts; ++p) {
-    int c = counts[(int64_t)p * Q + q];
-    if (fill + c > TOPK_CAP) {
-      for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
+    int c = counts[(int64_t)p * Q + q];               // sorted (<= kk) or unsorted (<= TOPK_STRIDE)
+    const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
+    while (c > 0) {
+      if (fill == TOPK_CAP || (fill > kk && fill + c > TOPK_CAP)) {
+        for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
+        __syncwarp();
+        warp_sort512(s, lane);
+        fill = fill < kk ? fill : kk;
+      }
+      int take = TOPK_CAP - fill;
+      if (take > c) take = c;
+      for (int i = lane; i < take; i += 32) s[fill + i] = src[i];
+      fill += take; src += take; c -= take;
       __syncwarp();
-      warp_sort512(s, lane);
-      fill = fill < kk ? fill : kk;
     }
-    const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_CAP;
-    for (int i = lane; i < c; i += 32) s[fill + i] = src[i];
-    fill += c;
-    __syncwarp();
   }
   for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
   __syncwarp();
@@ -247,6 +252,36 @@ merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __res
   }
 }
 
+// ---- thresholds from the sample pass ------------------------------------------------------
+// tau[q] = kk-th smallest distance among the sampled candidates of ALL parts (sorted lists of
+// <= kk keys per part).  Any subset's kk-th best is an upper bound of the catalog's kk-th best,
+// so every member of the final top-kk satisfies dist <= tau[q].
+__global__ void __launch_bounds__(32)
+sample_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ counts, int parts,
+                        int64_t Q, int kk, float* __restrict__ tau) {
+  __shared__ tkey_t s[TOPK_CAP];
+  const int lane = threadIdx.x;
+  const int64_t q = blockIdx.x;
+  int fill = 0;
+  for (int p = 0; p < parts; ++p) {
+    const int c = counts[(int64_t)p * Q + q];
+    if (fill + c > TOPK_CAP) {
+      for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
+      __syncwarp();
+      warp_sort512(s, lane);
+      fill = fill < kk ? fill : kk;
+    }
+    const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
+    for (int i = lane; i < c; i += 32) s[fill + i] = src[i];
+    fill += c;
+    __syncwarp();
+  }
+  for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
+  __syncwarp();
+  warp_sort512(s, lane);
+  if (lane == 0) tau[q] = (fill >= kk) ? ord2f((uint32_t)(s[kk - 1] >> 32)) : __int_as_float(0x7f800000);
+}
+
 // ---- cross-rank merge: rank-based merge of R sorted lists --------------------------------
 __device__ __forceinline__ bool lex_less(float va, int64_t ia, float vb, int64_t ib) {
   return va < vb || (va == vb && (uint64_t)ia < (uint64_t)ib);
@@ -289,9 +324,10 @@ static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePla
   *o_pc = off;   off = align_up(off + (size_t)Q * K * d * 4, 256);
   *o_qpar = off; off = align_up(off + (size_t)Q * qpar_stride(K) * 4, 256);
   *o_qimg = off; off = align_up(off + (p.impl ? score_umma_qimg_bytes(p, K) : 0), 1024);
-  *o_keys = off; off = align_up(off + (size_t)p.parts * Q * TOPK_CAP * sizeof(tkey_t), 256);
+  *o_keys = off; off = align_up(off + (size_t)p.parts * Q * TOPK_STRIDE * sizeof(tkey_t), 256);
   *o_cnt = off;  off = align_up(off + (size_t)p.parts * Q * sizeof(int), 1024);
   *o_cimg = off; off = align_up(off + ((p.impl && own_image) ? catalog_image_bytes(N, d) : 0), 1024);
+  off = align_up(off + (size_t)Q * sizeof(float), 256);      // tau[Q] lives right after (see o_tau)
   return off + 1024;
 }
 
@@ -341,6 +377,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   a.Pc = (float*)(base + o_pc); a.qpar = (float*)(base + o_qpar); a.qimg = base + o_qimg;
   a.keys = (tkey_t*)(base + o_keys); a.counts = (int*)(base + o_cnt); a.dist_out = dist_out;
   a.cimg = nullptr; a.e2 = nullptr;
+  a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
   a.plan = plan;
   if (N == 0) {
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
@@ -358,8 +395,28 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       a.e2 = (const float*)((const char*)image + (size_t)plan.tiles * (plan.dpad / 8) * 8192);
       st = score_umma_pack_queries(a, base + o_qimg, cs);
       if (st != CFL_OK) return st;
+      // Long catalog ranges are scored in two passes: a sparse sample pass (every S-th tile,
+      // running thresholds) whose merged kk-th best distance bounds the final threshold, then the
+      // full pass that only filters against that fixed bound (no barriers, no compaction).
+      const char* es = getenv("CFL_SCORE_SAMPLE_STRIDE");
+      const char* em = getenv("CFL_SCORE_MIN_TILES");
+      const int sstride = es ? atoi(es) : 32;
+      const int64_t min_tiles = em ? atoll(em) : 128;
+      const bool two_pass = sstride > 1 && !dist_out && plan.tiles / plan.parts >= min_tiles;
+      float* tau = (float*)(base + align_up(o_cimg + ((image == (const void*)(base + o_cimg)) ? catalog_image_bytes(N, d) : 0), 1024));
       timer_record(0, cs);
-      st = score_umma_launch(a, cs);
+      if (two_pass) {
+        a.phase = 1; a.tile_stride = sstride; a.thr_init = nullptr;
+        st = score_umma_launch(a, cs);
+        if (st != CFL_OK) return st;
+        sample_threshold_kernel<<<(unsigned)Q, 32, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau);
+        CFL_LAUNCH_CHECK();
+        a.phase = 2; a.tile_stride = 1; a.thr_init = tau;
+        st = score_umma_launch(a, cs);
+      } else {
+        a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
+        st = score_umma_launch(a, cs);
+      }
       timer_record(1, cs);
       if (st != CFL_OK) return st;
     } else {

@@ -31,6 +31,11 @@ struct ScoreArgs {
   tkey_t* keys;           // [parts, Q, TOPK_CAP]
   int* counts;           // [parts, Q]
   float* dist_out;       // optional dense [Q,N]
+  // tcgen05 kernel pass control: phase 0 = single adaptive pass (running thresholds);
+  // phase 1 = adaptive pass over every tile_stride-th tile (the sample that yields thr_init);
+  // phase 2 = full pass filtering against the fixed per-query thresholds thr_init (dist <= thr).
+  int phase, tile_stride;
+  const float* thr_init; // [Q], phase 2
   ScorePlan plan;
 };
 

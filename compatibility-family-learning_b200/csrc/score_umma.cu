@@ -106,17 +106,18 @@ int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const flo
 }
 
 struct SuLayout {
-  uint32_t b_img, a_ring, scratch, qpar, thr, cnt, bars, tmem_slot, total;
+  uint32_t b_img, a_ring, scratch, qpar, thr, cnt, need, bars, tmem_slot, total;
 };
 __host__ __device__ inline SuLayout su_layout(int K, int qt, int dpad) {
   SuLayout L;
   uint32_t off = 0;
   L.b_img = off;   off += (uint32_t)dpad * 8u * (uint32_t)(K * qt);   off = (off + 1023u) & ~1023u;
   L.a_ring = off;  off += SU_NSTAGE * SU_ASTAGE;
-  L.scratch = off; off += TOPK_CAP * 8u;
+  L.scratch = off; off += TOPK_STRIDE * 8u;
   L.qpar = off;    off += (uint32_t)qt * (uint32_t)qpar_stride(K) * 4u;  off = (off + 15u) & ~15u;
   L.thr = off;     off += (uint32_t)qt * 4u;
-  L.cnt = off;     off += (uint32_t)qt * 4u;                          off = (off + 15u) & ~15u;
+  L.cnt = off;     off += (uint32_t)qt * 4u;
+  L.need = off;    off += 16u;                                        off = (off + 15u) & ~15u;
   L.bars = off;    off += (2u * SU_NSTAGE + 5u) * 8u;
   L.tmem_slot = off; off += 16u;
   L.total = off;
@@ -181,6 +182,7 @@ score_umma_kernel(ScoreArgs A) {
   float* qpar = (float*)(smem + L.qpar);
   float* thr = (float*)(smem + L.thr);
   int* cnt = (int*)(smem + L.cnt);
+  int* need = (int*)(smem + L.need);
   uint64_t* full = (uint64_t*)(smem + L.bars);
   uint64_t* empty = full + SU_NSTAGE;
   uint64_t* tfull = empty + SU_NSTAGE;
@@ -194,7 +196,9 @@ score_umma_kernel(ScoreArgs A) {
   const int nq = (int)((A.Q - q0 < QT) ? (A.Q - q0) : QT);
   const int64_t t0 = A.plan.tiles * part / A.plan.parts;
   const int64_t t1 = A.plan.tiles * (part + 1) / A.plan.parts;
-  const int ntiles = (int)(t1 - t0);
+  const int ts = A.tile_stride;                              // phase 1 visits every ts-th tile
+  const int ntiles = (int)((t1 - t0 + ts - 1) / ts);
+  const bool filter = A.phase == 2;
   const int qps = qpar_stride(K);
 
   // ---- one-time setup ----
@@ -213,10 +217,18 @@ score_umma_kernel(ScoreArgs A) {
   }
   for (int i = tid; i < QT * qps; i += SU_THREADS) qpar[i] = (i < nq * qps) ? A.qpar[q0 * qps + i] : 0.0f;
   // padding queries of the last tile get thr = -inf: they can never be pushed
+  // phase 2: fixed thresholds from the sample pass, bumped one ulp so that the strict compare
+  // below implements dist <= tau (every candidate tied with the bound must be kept)
   for (int i = tid; i < QT; i += SU_THREADS) {
-    thr[i] = __int_as_float(i < nq ? 0x7f800000 : 0xff800000);
+    float th = __int_as_float(i < nq ? 0x7f800000 : 0xff800000);
+    if (filter && i < nq) {
+      const float tau = A.thr_init[q0 + i];
+      th = (tau < 3.0e38f) ? nextafterf(tau, 3.4e38f) : tau;
+    }
+    thr[i] = th;
     cnt[i] = 0;
   }
+  if (tid < 4) need[tid] = 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -255,14 +267,15 @@ score_umma_kernel(ScoreArgs A) {
         uint32_t n = bbytes - o < 32768u ? bbytes - o : 32768u;
         bulk_g2s(b_img + o, qsrc + o, n, bfull);
       }
-      const unsigned char* src = (const unsigned char*)A.cimg + (size_t)t0 * nks * SU_ASTAGE;
-      const int total = ntiles * nks;
       int stage = 0; uint32_t phase = 0;
-      for (int i = 0; i < total; ++i) {
-        mbar_wait(&empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&full[stage], SU_ASTAGE);
-        bulk_g2s(a_ring + stage * SU_ASTAGE, src + (size_t)i * SU_ASTAGE, SU_ASTAGE, &full[stage]);
-        if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
+      for (int t = 0; t < ntiles; ++t) {
+        const unsigned char* src = (const unsigned char*)A.cimg + (size_t)(t0 + (int64_t)t * ts) * nks * SU_ASTAGE;
+        for (int ks = 0; ks < nks; ++ks) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], SU_ASTAGE);
+          bulk_g2s(a_ring + stage * SU_ASTAGE, src + (size_t)ks * SU_ASTAGE, SU_ASTAGE, &full[stage]);
+          if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else {
@@ -274,7 +287,7 @@ score_umma_kernel(ScoreArgs A) {
     const int lrow = lq * 32 + lane;
     const uint32_t lane_lt = (1u << lane) - 1u;
     const bool dense = A.dist_out != nullptr;
-    tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_CAP;
+    tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
     // The lower bound dist >= min_k d_k - cq lets a whole query group skip the soft-min when no
     // lane can beat its threshold.  It only pays when the prototypes of a query are close
     // together relative to the spread of distances, so each warp measures its hit rate over the
@@ -283,12 +296,14 @@ score_umma_kernel(ScoreArgs A) {
     int grp_seen = 0, grp_skipped = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
-      const int64_t row = (t0 + t) * 128 + lrow;
+      const int64_t row = (t0 + (int64_t)t * ts) * 128 + lrow;
       const bool valid = row < A.N;
       const float e2 = __ldg(A.e2 + row);                    // padded to whole tiles
       mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
+      const int nslot = filter ? 2 + ((t >> 2) & 1) : (t & 1);
+      const int trig = filter ? TOPK_STRIDE / 2 : TOPK_TRIGGER;
       for (int g = sub; g * GQ < nq; g += WPQ) {
         float gk[K][GQ];
 #pragma unroll
@@ -335,7 +350,7 @@ score_umma_kernel(ScoreArgs A) {
 #pragma unroll
         for (int i = 0; i < GQ; ++i) bits |= (dist[i] < tg[i]) ? (1u << i) : 0u;
         if (!valid) bits = 0;
-        if (dense && valid) {
+        if (dense && valid && A.phase != 1) {
 #pragma unroll
           for (int i = 0; i < GQ; ++i)
             if (g * GQ + i < nq) A.dist_out[(q0 + g * GQ + i) * A.N + row] = dist[i];
@@ -351,9 +366,12 @@ score_umma_kernel(ScoreArgs A) {
               const int ql = g * GQ + i;
               const int leader = __ffs(m) - 1;
               int basei = 0;
-              if (lane == leader) basei = atomicAdd(&cnt[ql], __popc(m));
+              if (lane == leader) {
+                basei = atomicAdd(&cnt[ql], __popc(m));
+                if (basei + __popc(m) > trig) need[nslot] = 1;
+              }
               basei = __shfl_sync(0xffffffffu, basei, leader);
-              if (pass) kbase[(int64_t)ql * TOPK_CAP + basei + __popc(m & lane_lt)] = pack_key(dist[i], (uint32_t)row);
+              if (pass) kbase[(int64_t)ql * TOPK_STRIDE + basei + __popc(m & lane_lt)] = pack_key(dist[i], (uint32_t)row);
             }
           }
         }
@@ -362,20 +380,39 @@ score_umma_kernel(ScoreArgs A) {
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
       // ---- compaction point: all epilogue warps sort one over-full buffer together ----
-      epi_bar_sync();
-      for (int qb = 0; qb < nq; qb += 32) {
-        const int ql0 = qb + lane;
-        const uint32_t over = __ballot_sync(0xffffffffu, ql0 < nq && cnt[ql0] > TOPK_TRIGGER);
-        for (uint32_t m = over; m; m &= m - 1) {              // identical in every warp
-          const int ql = qb + __ffs(m) - 1;
-          coop_compact<SU_EPI_THREADS>(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch, tid, &cnt[ql], &thr[ql]);
+      // adaptive phases: checked every tile (a tile adds <= 128 keys per query, buffers hold 512);
+      // filter phase: every 4th tile (<= 512 new keys, buffers hold 1024) and it almost never fires.
+      // The decision must be identical in every warp although faster warps may already be pushing
+      // for the next tile: pushes raise need[slot] (slot = parity of the tile / 4-tile epoch), which
+      // is stable once every warp has passed the barrier below.
+      if (!filter || (t & 3) == 3) {
+        epi_bar_sync();
+        if (need[nslot]) {
+          for (int qb = 0; qb < nq; qb += 32) {
+            const int ql0 = qb + lane;
+            const uint32_t over = __ballot_sync(0xffffffffu, ql0 < nq && cnt[ql0] > trig);
+            for (uint32_t m = over; m; m &= m - 1) {          // identical in every warp
+              const int ql = qb + __ffs(m) - 1;
+              if (filter) {
+                coop_compact_big<SU_EPI_THREADS>(kbase + (int64_t)ql * TOPK_STRIDE, cnt[ql], A.plan.kk, scratch, tid, &cnt[ql], &thr[ql]);
+              } else {
+                coop_compact<SU_EPI_THREADS>(kbase + (int64_t)ql * TOPK_STRIDE, cnt[ql], A.plan.kk, scratch, tid, &cnt[ql], &thr[ql]);
+              }
+            }
+          }
+          if (tid == 0) need[nslot] = 0;
+          epi_bar_sync();
         }
       }
-      epi_bar_sync();
     }
-    for (int ql = 0; ql < nq; ++ql) {
-      coop_compact<SU_EPI_THREADS>(kbase + (int64_t)ql * TOPK_CAP, cnt[ql], A.plan.kk, scratch, tid, &cnt[ql], nullptr);
-      if (tid == 0) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
+    if (!filter) {
+      for (int ql = 0; ql < nq; ++ql) {
+        coop_compact<SU_EPI_THREADS>(kbase + (int64_t)ql * TOPK_STRIDE, cnt[ql], A.plan.kk, scratch, tid, &cnt[ql], nullptr);
+        if (tid == 0) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
+      }
+    } else {
+      epi_bar_sync();                                         // all pushes done; lists stay unsorted
+      for (int ql = tid; ql < nq; ql += SU_EPI_THREADS) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
     }
   }
   // ---- teardown ----

@@ -15,7 +15,9 @@
 
 namespace cfl {
 
-constexpr int TOPK_CAP = 512;     // keys per (part, query) buffer
+constexpr int TOPK_CAP = 512;     // keys per (part, query) buffer that the adaptive mode may hold
+constexpr int TOPK_STRIDE = 1024; // keys reserved per (part, query) buffer (filter mode uses all)
+constexpr int TOPK_FILTER_TRIGGER = TOPK_STRIDE - 256;   // filter mode: slow path above this
 constexpr int TOPK_TILE = 128;    // max appends per query between two compaction points
 constexpr int TOPK_TRIGGER = TOPK_CAP - TOPK_TILE;   // compact when cnt > 384 at a tile end
 
@@ -91,6 +93,38 @@ __device__ __forceinline__ void coop_compact(tkey_t* __restrict__ buf, int n, in
   if (t == 0) {
     *cnt_out = nk;
     if (thr_out) *thr_out = (n >= kk) ? ord2f((uint32_t)(scratch[kk - 1] >> 32)) : __int_as_float(0x7f800000);
+  }
+  coop_bar<NT>();
+}
+
+// Generic cooperative sort of NKEYS (power of two) keys by NT threads, one block barrier per
+// stage (used only on the rare overflow path of the filter mode).
+template <int NT, int NKEYS>
+__device__ __forceinline__ void coop_sort_generic(tkey_t* s, int t) {
+  for (int size = 2; size <= NKEYS; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int c = t; c < NKEYS / 2; c += NT) {
+        const int i = ((c & ~(stride - 1)) << 1) | (c & (stride - 1));
+        const int j = i | stride;
+        const bool asc = (i & size) == 0;
+        const tkey_t a = s[i], b = s[j];
+        if ((a > b) == asc) { s[i] = b; s[j] = a; }
+      }
+      coop_bar<NT>();
+    }
+  }
+}
+template <int NT>
+__device__ __forceinline__ void coop_compact_big(tkey_t* __restrict__ buf, int n, int kk, tkey_t* scratch,
+                                                 int t, int* cnt_out, float* thr_out) {
+  for (int i = t; i < TOPK_STRIDE; i += NT) scratch[i] = (i < n) ? buf[i] : CFL_KEY_INF;
+  coop_bar<NT>();
+  coop_sort_generic<NT, TOPK_STRIDE>(scratch, t);
+  const int nk = n < kk ? n : kk;
+  if (t < nk) buf[t] = scratch[t];
+  if (t == 0) {
+    *cnt_out = nk;
+    if (thr_out && n >= kk) *thr_out = ord2f((uint32_t)(scratch[kk - 1] >> 32));
   }
   coop_bar<NT>();
 }

@@ -322,3 +322,45 @@ def test_adam_matches_tf_formula(nat):
         nat.adam_step(tp, dev(g), tm, tv, step, 1e-3)
         po, mo, vo = O.adam_tf(po, g.astype(np.float64), mo, vo, step, 1e-3)
     assert_close(host(tp), po, rtol=1e-6, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------- two-pass / packed
+def test_score_topk_packed_image_equals_raw(nat):
+    rng = np.random.default_rng(21)
+    E = dev(rng.normal(size=(9000, 64)).astype(np.float32))
+    Pq = dev(rng.normal(size=(70, 3, 64)).astype(np.float32))
+    mu = nat.col_mean(E)
+    img = nat.catalog_pack(E, 3, mu)
+    assert img is not None
+    a = nat.score_topk(Pq, E, 100, mu=mu)
+    b = nat.score_topk(Pq, E, 100, mu=mu, image=img)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("K,d,dup", [(3, 64, False), (4, 20, True), (1, 32, False)])
+def test_score_topk_two_pass_equals_single_pass(nat, monkeypatch, K, d, dup):
+    """Sample pass + filter pass (the large-catalog path) must give exactly the single adaptive
+    pass's answer; `dup` plants many exact duplicates so ties sit on the sampled bound."""
+    rng = np.random.default_rng(22 + K)
+    N, Q = 150000, 150
+    E = rng.normal(size=(N, d)).astype(np.float32)
+    if dup:
+        E[1::3] = E[0:-1:3][: len(E[1::3])]
+    Pq = (E[rng.integers(0, N, Q)][:, None, :] + 0.5 * rng.normal(size=(Q, K, d))).astype(np.float32)
+    E, Pq = dev(E), dev(Pq)
+    mu = nat.col_mean(E)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "100000000")
+    a = nat.score_topk(Pq, E, 100, mu=mu)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "2")
+    monkeypatch.setenv("CFL_SCORE_SAMPLE_STRIDE", "4")
+    b = nat.score_topk(Pq, E, 100, mu=mu)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    # and both agree with the oracle on a few queries
+    qs = [0, 7, Q - 1]
+    D = O.all_pairs_dist(host(Pq[qs]).astype(np.float64), host(E).astype(np.float64), block=1)
+    wv, wi = O.rank_topk(D, 100)
+    got = b[1][qs].cpu().numpy()
+    for r in range(len(qs)):
+        sym = set(got[r].tolist()) ^ set(wi[r].tolist())
+        for c_ in sym:
+            assert abs(D[r, c_] - wv[r, -1]) <= 2e-6 * max(wv[r, -1], 1.0) + 1e-7
