@@ -264,17 +264,21 @@ sample_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__
   const int64_t q = blockIdx.x;
   int fill = 0;
   for (int p = 0; p < parts; ++p) {
-    const int c = counts[(int64_t)p * Q + q];
-    if (fill + c > TOPK_CAP) {
-      for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
-      __syncwarp();
-      warp_sort512(s, lane);
-      fill = fill < kk ? fill : kk;
-    }
+    int c = counts[(int64_t)p * Q + q];               // sorted (<= kk) or unsorted (<= TOPK_STRIDE)
     const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
-    for (int i = lane; i < c; i += 32) s[fill + i] = src[i];
-    fill += c;
-    __syncwarp();
+    while (c > 0) {
+      if (fill == TOPK_CAP || (fill > kk && fill + c > TOPK_CAP)) {
+        for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
+        __syncwarp();
+        warp_sort512(s, lane);
+        fill = fill < kk ? fill : kk;
+      }
+      int take = TOPK_CAP - fill;
+      if (take > c) take = c;
+      for (int i = lane; i < take; i += 32) s[fill + i] = src[i];
+      fill += take; src += take; c -= take;
+      __syncwarp();
+    }
   }
   for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
   __syncwarp();
@@ -406,8 +410,30 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       float* tau = (float*)(base + align_up(o_cimg + ((image == (const void*)(base + o_cimg)) ? catalog_image_bytes(N, d) : 0), 1024));
       timer_record(0, cs);
       if (two_pass) {
-        a.phase = 1; a.tile_stride = sstride; a.thr_init = nullptr;
-        st = score_umma_launch(a, cs);
+        // Sample = every sstride-th tile of each part.  When a few collect-everything tiles per
+        // part already give a bound tau_a under which the sample yields <= ~384 keys per buffer,
+        // the sample itself is scored in filter mode (no barriers); otherwise it runs adaptively.
+        const int64_t tpp = plan.tiles / plan.parts;
+        const int64_t tiles_b = (tpp + sstride - 1) / sstride;
+        int64_t tiles_a = ((int64_t)plan.kk * tiles_b + 384 * (int64_t)plan.parts - 1) / (384 * (int64_t)plan.parts);
+        if (tiles_a < 1) tiles_a = 1;
+        const bool cascade = tiles_a <= 7 && tiles_a * 128 * plan.parts >= 2 * plan.kk && !getenv("CFL_SCORE_NO_CASCADE");
+        if (cascade) {
+          a.phase = 2; a.thr_init = nullptr;                 // +inf thresholds: keep every sampled row
+          a.tile_stride = (int)((tpp + tiles_a - 1) / tiles_a);
+          if (a.tile_stride < 1) a.tile_stride = 1;
+          // guard: ceil(range / stride) <= 7 tiles even for the longest part range
+          while ((tpp + 1 + a.tile_stride - 1) / a.tile_stride > 7) ++a.tile_stride;
+          st = score_umma_launch(a, cs);
+          if (st != CFL_OK) return st;
+          sample_threshold_kernel<<<(unsigned)Q, 32, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau);
+          CFL_LAUNCH_CHECK();
+          a.phase = 2; a.tile_stride = sstride; a.thr_init = tau;
+          st = score_umma_launch(a, cs);
+        } else {
+          a.phase = 1; a.tile_stride = sstride; a.thr_init = nullptr;
+          st = score_umma_launch(a, cs);
+        }
         if (st != CFL_OK) return st;
         sample_threshold_kernel<<<(unsigned)Q, 32, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau);
         CFL_LAUNCH_CHECK();

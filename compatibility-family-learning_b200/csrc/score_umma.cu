@@ -221,7 +221,7 @@ score_umma_kernel(ScoreArgs A) {
   // below implements dist <= tau (every candidate tied with the bound must be kept)
   for (int i = tid; i < QT; i += SU_THREADS) {
     float th = __int_as_float(i < nq ? 0x7f800000 : 0xff800000);
-    if (filter && i < nq) {
+    if (filter && i < nq && A.thr_init != nullptr) {
       const float tau = A.thr_init[q0 + i];
       th = (tau < 3.0e38f) ? nextafterf(tau, 3.4e38f) : tau;
     }

@@ -337,8 +337,9 @@ def test_score_topk_packed_image_equals_raw(nat):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
-@pytest.mark.parametrize("K,d,dup", [(3, 64, False), (4, 20, True), (1, 32, False)])
-def test_score_topk_two_pass_equals_single_pass(nat, monkeypatch, K, d, dup):
+@pytest.mark.parametrize("K,d,dup,cascade", [(3, 64, False, True), (4, 20, True, True), (1, 32, False, True),
+                                              (3, 64, True, False), (2, 16, False, False)])
+def test_score_topk_two_pass_equals_single_pass(nat, monkeypatch, K, d, dup, cascade):
     """Sample pass + filter pass (the large-catalog path) must give exactly the single adaptive
     pass's answer; `dup` plants many exact duplicates so ties sit on the sampled bound."""
     rng = np.random.default_rng(22 + K)
@@ -353,6 +354,8 @@ def test_score_topk_two_pass_equals_single_pass(nat, monkeypatch, K, d, dup):
     a = nat.score_topk(Pq, E, 100, mu=mu)
     monkeypatch.setenv("CFL_SCORE_MIN_TILES", "2")
     monkeypatch.setenv("CFL_SCORE_SAMPLE_STRIDE", "4")
+    if not cascade:
+        monkeypatch.setenv("CFL_SCORE_NO_CASCADE", "1")   # adaptive sample pass instead of the filter cascade
     b = nat.score_topk(Pq, E, 100, mu=mu)
     assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
     # and both agree with the oracle on a few queries
