@@ -1,0 +1,1 @@
+from . import base, blocks, cfl, dist  # noqa: F401

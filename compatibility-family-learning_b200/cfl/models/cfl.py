@@ -1,0 +1,184 @@
+"""cfl.models.cfl -- the distance half of the ``CFL`` model (cfl/models/cfl.py: dist_fn 576-612,
+_build_model 683-728, _build_dist_losses 868-949, _build_main_optimizer 1065-1085).  The GAN half
+(MrCGAN generation) is out of scope."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from .. import variables as vs
+from ..utils import reduce_product
+from ._pair_model import PairModel
+from .base import ModelBase
+from .blocks import ConvPCD, FCPCD, Thresholder
+
+
+class CFL(PairModel):
+    def __init__(self, input_shape=(28, 28, 1), latent_shape=None, batch_size=100, latent_size=20,
+                 num_components=2, model_type="linear", dist_type="pcd", act_type=None, data_type="sigmoid",
+                 use_threshold=True, pos_weight=None, caffe_margin=None, lambda_m=None, reg_const=0.0,
+                 directed=False, lr=1e-3, beta1=0.9, beta2=0.999, data_normalizer=None, latent_normalizer=None,
+                 data_norm=None, latent_norm=None, is_double=False, gan=False, run_tag=None, name="CFL",
+                 reuse=False, **unused):
+        if gan:
+            raise NotImplementedError("the generation (GAN) half of CFL is out of scope for the B200 hot path")
+        if dist_type != "siamese" and not use_threshold:
+            raise AssertionError("non-siamese models need --use-threshold (cfl/utils.py:45-81)")
+        if caffe_margin and dist_type != "siamese":
+            raise AssertionError("caffe_margin > 0 needs dist_type siamese (cfl/utils.py:45-81)")
+        self.input_shape = tuple(input_shape)
+        self.latent_shape = tuple(latent_shape) if latent_shape else None
+        self.is_double = is_double
+        self.batch_size = batch_size
+        self.model_type = model_type
+        self.data_type = data_type
+        self.run_tag = run_tag
+        self.data_norm, self.latent_norm = data_norm, latent_norm
+        self.act_type = act_type
+        self.gan = False
+        norm = latent_normalizer if is_double else data_normalizer
+        in_scale = getattr(norm, "in_scale", None) if norm is not None else 1.0
+        self._normalizer = norm
+        shape = self.latent_shape if is_double else self.input_shape
+        with vs.variable_scope(name, reuse=reuse) as scope:
+            ModelBase.__init__(self, scope)
+            if model_type == "linear":
+                if in_scale is None:
+                    raise ValueError("CFL(linear): only pure-scaling normalisers fold into the projection kernel")
+                enc = ("DistEncoderSrc", "DistEncoderDst") if directed else ("DistEncoder", "DistEncoder")
+                self._init_pair_model(
+                    input_size=reduce_product(shape), latent_size=latent_size, num_components=num_components,
+                    dist_type=dist_type, act_type=act_type, weight_norm=True, pos_weight=pos_weight,
+                    use_threshold=use_threshold, caffe_margin=caffe_margin, lambda_m=lambda_m, reg_const=reg_const,
+                    directed=directed, lr=lr, beta1=beta1, beta2=beta2, in_scale=in_scale,
+                    head_names=("outputs", "prototype_outputs"), encoder_names=enc)
+            else:
+                self._init_conv(latent_size, num_components, dist_type, act_type, pos_weight, use_threshold,
+                                caffe_margin, lambda_m, reg_const, directed, lr, beta1, beta2)
+
+    # ---- names (cfl.py:368-412) ---------------------------------------------------------------
+    def get_name(self, no_gan=False):
+        name = "cfl"
+        name += "_" + self.dist_type
+        name += "_" + self.model_type
+        if self.directed:
+            name += "_di"
+        if self.pos_weight:
+            name += "_pw_{}".format(self.pos_weight)
+        if self.caffe_margin:
+            name += "_margin_{}".format(self.caffe_margin)
+        name += "_" + self.data_type
+        name += "_ls_{}".format(self.latent_size)
+        if self.dist_type != "siamese":
+            name += "_nc_{}".format(self.num_components)
+        if self.act_type:
+            name += "_act_{}".format(self.act_type)
+        if self.use_threshold:
+            name += "_ut"
+        if self.reg_const:
+            name += "_reg_{}".format(self.reg_const)
+        if self.data_norm:
+            dn = self.data_norm if isinstance(self.data_norm, (list, tuple)) else (self.data_norm,)
+            name += "_norm_{}".format("_".join(str(n) for n in dn))
+        if self.lambda_m:
+            name += "_lm_{}".format(self.lambda_m)
+        if self.run_tag:
+            name += "_run_" + self.run_tag
+        return name
+
+    # ---- conv model: trunk in torch (plumbing), heads + distance on the kernels via autograd ------
+    def _init_conv(self, latent_size, K, dist_type, act_type, pos_weight, use_threshold, caffe_margin, lambda_m,
+                   reg_const, directed, lr, beta1, beta2):
+        self.latent_size, self.num_components, self.dist_type = latent_size, K, dist_type
+        self.pos_weight, self.use_threshold = pos_weight, use_threshold
+        self.caffe_margin, self.lambda_m, self.reg_const = caffe_margin, lambda_m, reg_const
+        self.directed, self.lr, self.beta1, self.beta2 = directed, lr, beta1, beta2
+        self._conv_built = False
+        self._step = 0
+        self._ema = {}
+        self.ema_decay = 0.99
+
+    def dist_fn(self, inputs, name, reuse=False):
+        """cfl.py:576-612."""
+        act = {None: None, "linear": None, "tanh": "tanh", "sigmoid": "sigmoid", "relu": "relu"}[self.act_type]
+        with vs.variable_scope(self.scope):
+            if self.model_type == "linear":
+                return FCPCD(inputs, input_shape=self.input_shape, num_components=self.num_components,
+                             num_outputs=self.latent_size, batch_size=self.batch_size, dist_type=self.dist_type,
+                             regularizer=self.reg_const, activation_fn=act, name=name, reuse=reuse,
+                             in_scale=getattr(self, "in_scale", 1.0))
+            return ConvPCD(inputs, input_shape=self.input_shape, num_components=self.num_components,
+                           num_outputs=self.latent_size, batch_size=self.batch_size, dist_type=self.dist_type,
+                           regularizer=self.reg_const, activation_fn=act, name=name, reuse=reuse)
+
+    def thres_fn(self, inputs, reuse=False):
+        with vs.variable_scope(self.scope):
+            return Thresholder(inputs, reuse=reuse)
+
+    def _conv_forward(self, xs, xt):
+        names = ("DistEncoderSrc", "DistEncoderDst") if self.directed else ("DistEncoder", "DistEncoder")
+        norm = self._normalizer or (lambda t: t)
+        src = self.dist_fn(norm(xs), names[0], reuse=self._conv_built)
+        self._conv_built = True
+        dst = self.dist_fn(norm(xt), names[1], reuse=True if not self.directed else self._conv_dst_built())
+        dists = src.build_dist(dst)
+        pred = self.thres_fn(dists, reuse=self._thres_built())
+        return src, dst, dists, pred
+
+    def _conv_dst_built(self):
+        return any(k.startswith(self.name + "/DistEncoderDst/") for k in vs.all_variables())
+
+    def _thres_built(self):
+        return (self.name + "/Thresholder/threshold/threshold") in vs.all_variables()
+
+    def predict(self, source, target):
+        if self.model_type == "linear":
+            return super().predict(source, target)
+        with torch.no_grad():
+            return self._conv_forward(self._dev(source), self._dev(target))[3].outputs
+
+    def _dev(self, x):
+        x = torch.as_tensor(x).float()
+        return x if x.is_cuda else x.to(vs.default_device())
+
+    def train_step(self, src_pos, dst_pos, src_neg, dst_neg, val_batches=None):
+        if self.model_type == "linear":
+            return super().train_step(src_pos, dst_pos, src_neg, dst_neg, val_batches)
+        # conv: autograd over torch trunk + kernel heads; loss in torch ops (BASELINE config 1: plumbing)
+        import torch.nn.functional as TF
+        s_pos_src, _, dp, pp = self._conv_forward(self._dev(src_pos), self._dev(dst_pos))
+        _, _, dn, pn = self._conv_forward(self._dev(src_neg), self._dev(dst_neg))
+        lp = TF.softplus(-pp.outputs).mean()
+        ln = TF.softplus(pn.outputs).mean()
+        thres = lp * self.pos_weight + ln if self.pos_weight else lp + ln
+        params = vs.get_collection(self.name)
+        reg = sum(0.5 * self.reg_const * (v ** 2).sum() for k, v in params.items()
+                  if k.rsplit("/", 1)[-1] == "V" or (k.endswith("biases") and "/conv" not in k)) if self.reg_const else 0.0
+        total = reg + (thres if self.use_threshold else 0.0)
+        if self.lambda_m:
+            total = total + dp.mean() * self.lambda_m * (self.pos_weight or 1.0)
+        plist = list(params.values())
+        grads = torch.autograd.grad(total, plist, allow_unused=True)
+        if not hasattr(self, "_adam"):
+            self._adam = {}
+        self._step += 1
+        from .. import _native as nat
+        for p, g in zip(plist, grads):
+            if g is None:
+                continue
+            m, v = self._adam.setdefault(id(p), (torch.zeros_like(p), torch.zeros_like(p)))
+            nat.adam_step(p.data.view(-1), g.contiguous().view(-1), m.view(-1), v.view(-1), self._step, self.lr,
+                          self.beta1, self.beta2)
+        acc = 0.5 * (float((pp.outputs > 0).float().mean()) + float((pn.outputs <= 0).float().mean()))
+        out = dict(s_p_loss_pos=float(lp), s_p_loss_neg=float(ln), s_thres_loss=float(thres),
+                   s_total_loss=float(total), s_accuracy=acc, s_loss_reg=float(reg))
+        self.s_pos_dists, self.s_neg_dists = dp.detach(), dn.detach()
+        for k, v_ in out.items():
+            setattr(self, k, v_)
+        return out
+
+
+def construct_model(**kwargs):
+    """cfl.py:1514-1756 minus the TF queues: returns (model, aux)."""
+    return CFL(**kwargs), SimpleNamespace(queue=None, enqueue_op=None)

@@ -119,11 +119,11 @@ class CatalogIndex:
         if world == 1:
             return tv, ti
         Q = tv.shape[0]
-        gv = torch.empty(world, Q, k, dtype=tv.dtype, device=tv.device)
-        gi = torch.empty(world, Q, k, dtype=ti.dtype, device=ti.device)
-        torch.distributed.all_gather_into_tensor(gv, tv, group=self.group)
-        torch.distributed.all_gather_into_tensor(gi, ti, group=self.group)
-        return nat.topk_merge(gv, gi)
+        gv = torch.empty(world * Q, k, dtype=tv.dtype, device=tv.device)     # concatenated along dim 0
+        gi = torch.empty(world * Q, k, dtype=ti.dtype, device=ti.device)
+        torch.distributed.all_gather_into_tensor(gv, tv.contiguous(), group=self.group)
+        torch.distributed.all_gather_into_tensor(gi, ti.contiguous(), group=self.group)
+        return nat.topk_merge(gv.view(world, Q, k), gi.view(world, Q, k))
 
     def scores(self, dist: torch.Tensor) -> torch.Tensor:
         """Thresholder (blocks.py:21-22): max(theta, 1e-6) - dist."""

@@ -1,0 +1,176 @@
+"""cfl.utils -- evaluation / prediction loops and the flag parsers of the reference
+(cfl/utils.py), with the device-side AUC kernel instead of sklearn on the host.  ``sess`` arguments
+are kept for signature compatibility and ignored (there is no TF session)."""
+from __future__ import annotations
+
+import argparse
+import os
+from argparse import Namespace
+
+import torch
+
+
+def reduce_product(xs):
+    """cfl/utils.py:25-29."""
+    s = 1
+    for x in xs:
+        s *= x
+    return s
+
+
+def load_best_stats(path):
+    """cfl/utils.py:32-42: ``"{epoch}\\t{accuracy}\\t{auc}"``."""
+    stats = Namespace(best_epoch=None, best_accuracy=0.0, best_auc=0.0)
+    if os.path.exists(path):
+        with open(path) as infile:
+            tokens = infile.read().split("\t")
+            best_epoch, best_accuracy = tokens[:2]
+            stats.best_epoch = int(best_epoch)
+            stats.best_accuracy = float(best_accuracy)
+            if len(tokens) >= 3:
+                stats.best_auc = float(tokens[2])
+    return stats
+
+
+class IncrementalAverage(object):
+    """cfl/utils.py:500-507."""
+
+    def __init__(self):
+        self.average = 0.0
+        self.count = 0
+
+    def add(self, value):
+        self.count += 1
+        self.average = (value - self.average) / self.count + self.average
+
+
+def _pair_batches(batches, model):
+    """Feeds of dist_eval (cfl/utils.py:234-243): (source, target) of a batch tuple; for 'double'
+    datasets the latent halves (positions 1 and 3)."""
+    if getattr(model, "is_double", False):
+        return batches[1], batches[3]
+    return batches[0], batches[1]
+
+
+def dist_eval(sess, model, batch_size, data, with_roc=False):
+    """cfl/utils.py:227-274.  Positive pairs then negative pairs go through the model's single
+    scoring node; accuracy at threshold 0; AUC.  The scores stay on the GPU: AUC and the
+    accuracy counts come from the exact integer rank/count kernel (cfl_auc), AUC =
+    twoU / (2 n+ n-), within 2 ulp of sklearn's roc_auc_score."""
+    from . import _native as nat
+    pos, neg = [], []
+    for batches in data.whole_pos_batches(batch_size):
+        pos.append(model.predict(*_pair_batches(batches, model)).reshape(-1))
+    for batches in data.whole_neg_batches(batch_size):
+        neg.append(model.predict(*_pair_batches(batches, model)).reshape(-1))
+    dev = pos[0].device if pos else neg[0].device
+    pos = torch.cat(pos) if pos else torch.empty(0, device=dev)
+    neg = torch.cat(neg) if neg else torch.empty(0, device=dev)
+    two_u, n_pos, n_neg, correct = nat.auc_counts(pos, neg).cpu().tolist()
+    total = n_pos + n_neg
+    auc = two_u / (2.0 * n_pos * n_neg) if n_pos and n_neg else float("nan")
+    roc = None
+    if with_roc:                      # optional host-side curve, not on the hot path
+        from sklearn.metrics import roc_curve
+        y = [1] * n_pos + [0] * n_neg
+        roc = roc_curve(y, torch.cat([pos, neg]).cpu().numpy())
+    return Namespace(error=(total - correct) / total, accuracy=correct / total, auc=auc, roc=roc,
+                     two_u=two_u, n_pos=n_pos, n_neg=n_neg)
+
+
+def dist_predict(sess, model, data, batch_size, predict_dir, output_name):
+    """cfl/utils.py:277-321: writes ``"{id1} match {id2} {score}\\n"``, positives first."""
+    pos, neg = [], []
+    for batches in data.whole_pos_batches(batch_size):
+        pos.append(model.predict(*_pair_batches(batches, model)).reshape(-1))
+    for batches in data.whole_neg_batches(batch_size):
+        neg.append(model.predict(*_pair_batches(batches, model)).reshape(-1))
+    rules = [(torch.cat(pos).cpu().numpy() if pos else [], data.pairs_pos),
+             (torch.cat(neg).cpu().numpy() if neg else [], data.pairs_neg)]
+    os.makedirs(predict_dir, exist_ok=True)
+    with open(os.path.join(predict_dir, output_name), "w") as outfile:
+        for dists, pairs in rules:
+            for pred, (idx1, idx2) in zip(dists, pairs):
+                outfile.write("{} match {} {}\n".format(data.index_to_asins[idx1], data.index_to_asins[idx2], pred))
+
+
+def dist_check_args(args):
+    """cfl/utils.py:45-81 (the checks that concern the distance model)."""
+    for name in ("input_shape", "latent_shape", "data_mean", "data_norm"):
+        v = getattr(args, name, None)
+        if v:
+            setattr(args, name, tuple(v))
+    if args.caffe_margin and args.caffe_margin > 0:
+        assert args.dist_type == "siamese", "only use cd loss in siamese"
+    if args.caffe_margin and args.caffe_margin < 0:
+        assert args.lambda_m > 0
+    if args.lambda_m > 0:
+        assert not args.caffe_margin
+    if args.dist_type != "siamese":
+        assert args.use_threshold, "must use entropy loss"
+
+
+def dist_parser(data_name="mnist", data_root="parsed_data", checkpoint_root="checkpoints", log_root="logs",
+                run_tag=None, seed=633, input_shape=(28, 28, 1), batch_size=100, data_scale=None,
+                data_mean=None, data_norm=None, latent_norm=None, data_type="sigmoid", model_type="conv",
+                dist_type="pcd", act_type=None, use_threshold=False, lr=0.001, beta1=0.9, beta2=0.999,
+                num_components=2, latent_size=20, caffe_margin=None, pos_weight=None, lambda_m=0.0,
+                reg_const=0.0, latent_shape=None):
+    """The distance-model flags of cfl/utils.py:84-224, same names and defaults (GAN flags omitted)."""
+    p = argparse.ArgumentParser()
+    p.add_argument("--data-name", default=data_name)
+    p.add_argument("--data-root", default=data_root)
+    p.add_argument("--checkpoint-root", default=checkpoint_root)
+    p.add_argument("--log-root", default=log_root)
+    p.add_argument("--run-tag", default=run_tag)
+    p.add_argument("--seed", type=int, default=seed)
+    p.add_argument("--input-shape", nargs="+", type=int, default=input_shape)
+    p.add_argument("--latent-shape", nargs="+", type=int, default=latent_shape)
+    p.add_argument("--batch-size", type=int, default=batch_size)
+    p.add_argument("--data-scale", type=float, default=data_scale)
+    p.add_argument("--data-mean", nargs="+", type=float, default=data_mean)
+    p.add_argument("--data-norm", nargs="+", type=float, default=data_norm)
+    p.add_argument("--latent-norm", type=float, default=latent_norm)
+    p.add_argument("--data-type", default=data_type, choices=["sigmoid", "tanh", "relu", "linear"])
+    p.add_argument("--data-is-image", action="store_true")
+    p.add_argument("--data-is-double", action="store_true")
+    p.add_argument("--data-switch", action="store_true")
+    p.add_argument("--directed", action="store_true")
+    p.add_argument("--model-type", default=model_type, choices=["conv", "linear"])
+    p.add_argument("--dist-type", default=dist_type, choices=["pcd", "monomer", "siamese"])
+    p.add_argument("--act-type", default=act_type, choices=[None, "linear", "tanh", "sigmoid", "relu"])
+    p.add_argument("--use-threshold", action="store_true", default=use_threshold)
+    p.add_argument("--lr", type=float, default=lr)
+    p.add_argument("--beta1", type=float, default=beta1)
+    p.add_argument("--beta2", type=float, default=beta2)
+    p.add_argument("--num-components", type=int, default=num_components)
+    p.add_argument("--latent-size", type=int, default=latent_size)
+    p.add_argument("--caffe-margin", type=float, default=caffe_margin)
+    p.add_argument("--pos-weight", type=float, default=pos_weight)
+    p.add_argument("--lambda-m", type=float, default=lambda_m)
+    p.add_argument("--reg-const", type=float, default=reg_const)
+    return p
+
+
+def monomer_parser(data_name="monomer/Baby-also_viewed", data_root="parsed_data", checkpoint_root="checkpoints",
+                   log_root="logs", run_tag=None, seed=633, input_shape=(4096,), batch_size=100,
+                   normalize_value=1.0, num_components=2, latent_size=20, lr=0.001, beta1=0.9, beta2=0.999,
+                   reg_const=0.0):
+    """cfl/utils.py:510-553."""
+    p = argparse.ArgumentParser()
+    p.add_argument("--data-name", default=data_name)
+    p.add_argument("--data-root", default=data_root)
+    p.add_argument("--checkpoint-root", default=checkpoint_root)
+    p.add_argument("--log-root", default=log_root)
+    p.add_argument("--run-tag", default=run_tag)
+    p.add_argument("--seed", type=int, default=seed)
+    p.add_argument("--normalize-value", type=float, default=normalize_value)
+    p.add_argument("--input-shape", nargs="+", type=int, help="shape of input", default=input_shape)
+    p.add_argument("--batch-size", type=int, default=batch_size)
+    p.add_argument("--num-components", type=int, default=num_components)
+    p.add_argument("--latent-size", type=int, default=latent_size)
+    p.add_argument("--lr", type=float, default=lr)
+    p.add_argument("--beta1", type=float, default=beta1)
+    p.add_argument("--beta2", type=float, default=beta2)
+    p.add_argument("--reg-const", type=float, default=reg_const)
+    return p

@@ -1,0 +1,240 @@
+"""Model-level parity on the GPU: the reference-shaped constructors and the fused train step
+(projection -> paired distance + loss -> backward -> TF-style Adam) against an fp64 torch-autograd
+restatement of the reference graph (tests/ref_model.py), same seeded weights and batches."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(__file__))
+import ref_model as R  # noqa: E402
+from oracle import cfl_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def _weights_of(model):
+    def h(head):
+        d = {"V": _np(head.V)}
+        if head.g is not None:
+            d["g"] = _np(head.g)
+        if head.b is not None:
+            d["b"] = _np(head.b)
+        return d
+    out = {}
+    for name, enc in (("src", model.enc_src), ("dst", model.enc_dst)):
+        out[name] = {hn: h(getattr(enc, hn)) for hn in ("e0", "proto", "gate") if getattr(enc, hn) is not None}
+    return out
+
+
+def _batch(rng, B, F):
+    return [np.maximum(rng.normal(size=(B, F)), 0).astype(np.float32) * 3 for _ in range(4)]
+
+
+CASES = [
+    dict(model="dist", F=64, K=4, d=10, norm=58.388599, reg_const=0.0),
+    dict(model="dist", F=96, K=3, d=20, norm=2.0, reg_const=1e-3),
+    dict(model="cfl", F=128, K=3, d=64, dist_type="pcd", pos_weight=0.0625, data_norm=31.9098),
+    dict(model="cfl", F=80, K=4, d=20, dist_type="pcd", pos_weight=0.25, act_type="tanh", reg_const=5e-4, lambda_m=0.5),
+    dict(model="cfl", F=80, K=2, d=12, dist_type="pcd", directed=True, act_type="sigmoid"),
+    dict(model="cfl", F=72, K=3, d=16, dist_type="monomer", act_type="relu", reg_const=1e-3),
+    dict(model="cfl", F=72, K=1, d=16, dist_type="siamese", use_threshold=False, caffe_margin=2.0, pos_weight=0.5),
+    dict(model="cfl", F=72, K=1, d=24, dist_type="siamese", use_threshold=True),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items() if k in ("model", "dist_type", "K", "d", "act_type")))
+def test_train_steps_match_reference_graph(case):
+    from cfl import ops, variables as vs
+    from cfl.models.cfl import CFL
+    from cfl.models.dist import Dist
+    vs.reset_default_graph()
+    vs.set_seed(633)
+    F, K, d = case["F"], case["K"], case["d"]
+    lr = 1e-2
+    if case["model"] == "dist":
+        model = Dist(input_shape=(F,), latent_size=d, num_components=K, batch_size=50, lr=lr, beta1=0.9,
+                     beta2=0.999, normalize_value=case["norm"], data_normalizer=ops.normalizer(case["norm"], 0.0),
+                     reg_const=case["reg_const"])
+        cfg = dict(K=K, d=d, dist_type="pcd", weight_norm=False, in_scale=1.0 / case["norm"], lr=lr,
+                   reg_const=case["reg_const"], shared=True)
+    else:
+        dn = case.get("data_norm")
+        norm = ops.normalizer_v2((F,), norm=dn) if dn else None
+        model = CFL(input_shape=(F,), batch_size=50, latent_size=d, num_components=K, model_type="linear",
+                    dist_type=case["dist_type"], act_type=case.get("act_type"), data_type="linear",
+                    use_threshold=case.get("use_threshold", True), pos_weight=case.get("pos_weight"),
+                    caffe_margin=case.get("caffe_margin"), lambda_m=case.get("lambda_m"),
+                    reg_const=case.get("reg_const", 0.0), directed=case.get("directed", False), lr=lr,
+                    data_normalizer=norm, data_norm=dn)
+        cfg = dict(K=K if case["dist_type"] != "siamese" else 1, d=d, dist_type=case["dist_type"], weight_norm=True,
+                   in_scale=(1.0 / dn) if dn else 1.0, lr=lr, act=case.get("act_type"),
+                   pos_weight=case.get("pos_weight"), use_threshold=case.get("use_threshold", True),
+                   caffe_margin=case.get("caffe_margin"), lambda_m=case.get("lambda_m"),
+                   reg_const=case.get("reg_const", 0.0), shared=not case.get("directed", False))
+    # move theta off the clamp so both branches of the loss are exercised, and perturb g / biases
+    rng = np.random.default_rng(7)
+    with torch.no_grad():
+        model.raw_threshold.fill_(0.8)
+        for p in model._params:
+            if p.dim() == 1:
+                p.add_(torch.as_tensor(0.1 * rng.normal(size=p.shape), dtype=torch.float32, device=p.device))
+    weights = _weights_of(model)
+    if cfg["shared"]:
+        weights = {"src": weights["src"]}
+    theta, state = 0.8, {}
+    B = 50
+    for step in range(1, 4):
+        batch = _batch(rng, B, F)
+        out = model.train_step(*[torch.as_tensor(b).cuda() for b in batch])
+        ref, weights, theta, state = R.train_step(cfg, weights, theta, batch, state, step)
+        np.testing.assert_allclose(out["s_p_loss_pos"], ref["lp"], rtol=1e-4)
+        np.testing.assert_allclose(out["s_p_loss_neg"], ref["ln"], rtol=1e-4)
+        np.testing.assert_allclose(out["s_total_loss"], ref["total"], rtol=1e-4)
+        np.testing.assert_allclose(out["s_accuracy"], ref["acc"], rtol=1e-12)
+        np.testing.assert_allclose(_np(model.s_pos_dists)[:, 0], ref["dp"], rtol=1e-4)
+        got = _weights_of(model)
+        for enc, hs in weights.items():
+            for hn, ps in hs.items():
+                for pn, arr in ps.items():
+                    # Adam's first steps move every weight by ~lr regardless of the gradient's size,
+                    # so compare the UPDATE: tolerance relative to lr
+                    np.testing.assert_allclose(got[enc][hn][pn], arr, atol=2e-3 * lr * step + 1e-7, rtol=0,
+                                               err_msg=f"step {step} {enc}/{hn}/{pn}")
+        np.testing.assert_allclose(float(model.raw_threshold), theta, atol=2e-3 * lr * step + 1e-7)
+
+
+def test_variable_names_follow_the_reference_scopes():
+    from cfl import variables as vs
+    from cfl.models.cfl import CFL
+    from cfl.models.dist import Dist
+    vs.reset_default_graph()
+    CFL(input_shape=(32,), latent_size=8, num_components=2, model_type="linear", dist_type="monomer",
+        use_threshold=True, directed=True)
+    names = set(vs.all_variables())
+    for n in ("CFL/DistEncoderSrc/outputs/fully_connected/V", "CFL/DistEncoderSrc/outputs/fully_connected/g",
+              "CFL/DistEncoderDst/prototype_outputs/fully_connected/V",
+              "CFL/DistEncoderSrc/monomer_outputs/fully_connected/g", "CFL/Thresholder/threshold/threshold"):
+        assert n in names, n
+    assert not any(n.endswith("biases") for n in names), "monomer encoders have no biases (base.py:45-46)"
+    vs.reset_default_graph()
+    Dist(input_shape=(32,), latent_size=8, num_components=2, batch_size=10, lr=1e-3, beta1=0.9, beta2=0.999)
+    names = set(vs.all_variables())
+    for n in ("Dist/Encoder/latent_outputs/fully_connected/weights", "Dist/Encoder/pcd_outputs/fully_connected/biases",
+              "Dist/Thresholder/threshold/threshold"):
+        assert n in names, n
+
+
+def test_eager_constructors_and_autograd_match_oracle():
+    """FCPCD / Thresholder used the reference way (build_dist on two encoder applications), with
+    gradients flowing through the kernels via autograd."""
+    from cfl import variables as vs
+    from cfl.models.blocks import FCPCD, Thresholder
+    vs.reset_default_graph()
+    vs.set_seed(1)
+    rng = np.random.default_rng(3)
+    B, F, K, d = 40, 48, 3, 12
+    xs = torch.as_tensor(rng.normal(size=(B, F)).astype(np.float32)).cuda()
+    xt = torch.as_tensor(rng.normal(size=(B, F)).astype(np.float32)).cuda()
+    src = FCPCD(xs, num_outputs=d, num_components=K, input_shape=(F,), batch_size=B, activation_fn="tanh", name="enc")
+    tgt = FCPCD(xt, num_outputs=d, num_components=K, input_shape=(F,), batch_size=B, activation_fn="tanh", name="enc", reuse=True)
+    dist = src.build_dist(tgt)
+    pred = Thresholder(dist)
+    assert dist.shape == (B, 1) and pred.outputs.shape == (B, 1)
+    V0 = vs.all_variables()["enc/outputs/fully_connected/V"]
+    Vp = vs.all_variables()["enc/prototype_outputs/fully_connected/V"]
+    loss = torch.nn.functional.softplus(-pred.outputs).mean()
+    gV0, gVp, gth = torch.autograd.grad(loss, [V0, Vp, pred.raw_threshold])
+    # oracle
+    p = {k: _np(v) for k, v in vs.all_variables().items()}
+    params = {"outputs": (p["enc/outputs/fully_connected/V"], p["enc/outputs/fully_connected/g"], p["enc/outputs/fully_connected/biases"]),
+              "prototype_outputs": (p["enc/prototype_outputs/fully_connected/V"], p["enc/prototype_outputs/fully_connected/g"],
+                                    p["enc/prototype_outputs/fully_connected/biases"])}
+    so = O.build_prototypes(_np(xs), params, "pcd", K, d, act="tanh")
+    to = O.build_prototypes(_np(xt), params, "pcd", K, d, act="tanh")
+    do = O.pcd_dist(to["activations"], so["prototype_activations"])
+    np.testing.assert_allclose(_np(dist)[:, 0], do, rtol=1e-4)
+    tV0 = torch.tensor(params["outputs"][0], requires_grad=True)
+    tVp = torch.tensor(params["prototype_outputs"][0], requires_grad=True)
+    from oracle import torch_port as T
+    P = torch.tanh(T.fc_weight_norm(torch.tensor(_np(xs)), tVp, torch.tensor(params["prototype_outputs"][1]),
+                                    torch.tensor(params["prototype_outputs"][2]))).reshape(-1, K, d)
+    v = torch.tanh(T.fc_weight_norm(torch.tensor(_np(xt)), tV0, torch.tensor(params["outputs"][1]),
+                                    torch.tensor(params["outputs"][2])))
+    th = torch.tensor(1e-6, dtype=torch.float64, requires_grad=True)
+    lo = torch.nn.functional.softplus(-T.thresholder(T.pcd_dist(v, P), th)).mean()
+    rV0, rVp, rth = torch.autograd.grad(lo, [tV0, tVp, th])
+    np.testing.assert_allclose(_np(gV0), rV0.numpy(), atol=3e-5 * np.abs(rV0.numpy()).max())
+    np.testing.assert_allclose(_np(gVp), rVp.numpy(), atol=3e-5 * np.abs(rVp.numpy()).max())
+    np.testing.assert_allclose(float(gth), float(rth), rtol=1e-4)
+
+
+class _FakeData:
+    """The slice of SemiDataSet dist_eval / dist_predict use (cfl/input_data.py:503-540)."""
+
+    def __init__(self, feats, pairs_pos, pairs_neg):
+        self.feats, self.pairs_pos, self.pairs_neg = feats, pairs_pos, pairs_neg
+        self.index_to_asins = ["A%09d" % i for i in range(len(feats))]
+
+    def whole_pos_batches(self, bs):
+        for i in range(0, len(self.pairs_pos), bs):
+            p = self.pairs_pos[i:i + bs]
+            yield self.feats[p[:, 0]], self.feats[p[:, 1]]
+
+    def whole_neg_batches(self, bs):
+        for i in range(0, len(self.pairs_neg), bs):
+            p = self.pairs_neg[i:i + bs]
+            yield self.feats[p[:, 0]], self.feats[p[:, 1]]
+
+
+def test_dist_eval_and_predict_match_sklearn(tmp_path):
+    from sklearn.metrics import roc_auc_score
+    from cfl import ops, utils, variables as vs
+    from cfl.models.dist import Dist
+    vs.reset_default_graph()
+    vs.set_seed(5)
+    rng = np.random.default_rng(5)
+    F = 64
+    feats = np.maximum(rng.normal(size=(300, F)), 0).astype(np.float32) * 20
+    model = Dist(input_shape=(F,), latent_size=10, num_components=4, batch_size=100, lr=1e-3, beta1=0.9, beta2=0.999,
+                 normalize_value=58.388599, data_normalizer=ops.normalizer(58.388599, 0.0))
+    with torch.no_grad():
+        model.raw_threshold.fill_(0.05)
+    data = _FakeData(feats, rng.integers(0, 300, size=(777, 2)), rng.integers(0, 300, size=(1501, 2)))
+    rep = utils.dist_eval(None, model, 500, data)
+    sp = np.concatenate([_np(model.predict(*b))[:, 0] for b in data.whole_pos_batches(500)])
+    sn = np.concatenate([_np(model.predict(*b))[:, 0] for b in data.whole_neg_batches(500)])
+    y = np.r_[np.ones(len(sp)), np.zeros(len(sn))]
+    s32 = np.r_[sp, sn].astype(np.float32)
+    assert abs(rep.auc - roc_auc_score(y, s32)) < 1e-12
+    assert rep.two_u == O.auc_exact(s32, y)[0]
+    correct = int((sp > 0).sum()) + int((sn <= 0).sum())
+    assert rep.accuracy == correct / len(y) and rep.error == 1 - rep.accuracy or abs(rep.error - (1 - rep.accuracy)) < 1e-15
+    utils.dist_predict(None, model, data, 500, str(tmp_path), "predict.txt")
+    lines = open(tmp_path / "predict.txt").read().splitlines()
+    assert len(lines) == 777 + 1501
+    a, m, b, sc = lines[0].split()
+    assert m == "match" and a == data.index_to_asins[data.pairs_pos[0, 0]] and abs(float(sc) - sp[0]) < 1e-6
+
+
+def test_conv_model_trains_on_synthetic_mnist_pairs():
+    """BASELINE config 1 plumbing: ConvPCD trunk (torch) + kernel heads, a few Adam steps reduce the loss."""
+    from cfl import variables as vs
+    from cfl.models.cfl import CFL
+    vs.reset_default_graph()
+    vs.set_seed(633)
+    rng = np.random.default_rng(633)
+    model = CFL(input_shape=(28, 28, 1), batch_size=100, latent_size=20, num_components=2, model_type="conv",
+                dist_type="pcd", use_threshold=True, reg_const=5e-4, lr=1e-3)
+    x = rng.uniform(size=(4, 100, 784)).astype(np.float32)
+    x[1] = x[0] * 0.9 + 0.05          # positives: near copies; negatives: unrelated
+    losses = [model.train_step(*[torch.as_tensor(b).cuda() for b in x])["s_total_loss"] for _ in range(8)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    assert "CFL/DistEncoder/conv1/Conv/V" in vs.all_variables()
+    assert model.predict(torch.as_tensor(x[0]).cuda(), torch.as_tensor(x[1]).cuda()).shape == (100, 1)
