@@ -221,7 +221,8 @@ def run_ours(args):
 
     line = None
     if rank == 0:
-        cpu = cpu_baseline_sample(target_s=12.0)
+        # the CPU arm is timed on rank 0 at N=1 only (torchrun pins OMP threads and the other ranks spin)
+        cpu = cpu_baseline_sample(target_s=12.0) if world == 1 else None
         line = {
             "metric": "query x candidate scores/sec (fused soft-min scoring + top-100)",
             "value": value, "unit": "scores/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -95,12 +95,319 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
   if (warp == 4) tmem_dealloc(tmem_base, ncols);
 }
 
-// placeholders until the projection kernel lands
-int project_fwd_umma(const float*, int64_t, int, int64_t, const float*, int, int64_t, const float*,
-                     const float*, float, int, float*, int64_t, float*, float*, void*, size_t,
-                     cudaStream_t) { return CFL_ERR_UNSUPPORTED; }
-size_t project_fwd_umma_workspace(int64_t, int, int) { return 0; }
-bool project_fwd_umma_supported(const float*, int64_t, int, int64_t, int) { return false; }
+// ---- projection kernel ------------------------------------------------------------------------
+// C[B, N] = x[B, F] * V[F, N]:  M = 128 items per tile (TMEM lanes), N = N_out padded to 16,
+// MMA-K = the feature dimension F (8 per K-step).  Persistent CTAs (grid = min(tiles, SMs)).
+//   warps 0-3   epilogue: tcgen05.ld 16 columns at a time for the thread's item -> in_scale,
+//               weight-norm scaler, bias, activation -> y (+ pre, z)
+//   warps 4-11  A producers: thread (row r, half h) streams its row of x with 4 batches (64 B each)
+//               of register prefetch, splits hi/lo and writes the canonical layout
+//   warp 12     one lane issues tcgen05.mma (3 per K-step) / tcgen05.commit
+//   warp 13     one lane drives the TMA engine for the pre-split weight image (B operand)
+// Bytes per item: 4F (read once) + 4N (written once); flops 2*F*N (x3 MMAs).
+constexpr int PU_THREADS = 14 * 32;
+constexpr uint32_t PU_ASTAGE = 4u * 128u * 16u;
+constexpr int PU_PF = 4;
+
+struct PuArgs {
+  const float* x; int64_t B; int F; int64_t ldx;
+  const unsigned char* vimg; int N, Npad, nks, nst, kps, nh, nbuf;
+  const float* scaler; const float* bias; float in_scale; int act;
+  float* y; int64_t ldy; float* pre; float* z;
+  int64_t tiles;
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ V, int F, int N, int64_t ldV, int Npad,
+                                    float* __restrict__ img) {
+  const int nks = F / 8;
+  const int64_t total = (int64_t)nks * 2 * Npad;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(e % Npad);
+    const int c = (int)((e / Npad) % 2);
+    const int ks = (int)(e / (2 * Npad));
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* xp = &x.x;
+    if (n < N) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xp[i] = V[(int64_t)(ks * 8 + c * 4 + i) * ldV + n];
+    }
+    float4 hi, lo;
+    split_tf32x4(x, hi, lo);
+    const size_t step = (size_t)ks * 4 * Npad;
+    ((float4*)img)[step + (size_t)(0 * 2 + c) * Npad + n] = hi;
+    ((float4*)img)[step + (size_t)(1 * 2 + c) * Npad + n] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(PU_THREADS, 1)
+project_umma_kernel(PuArgs A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Npad = A.Npad, nks = A.nks, NST = A.nst, KPS = A.kps;   // KPS K-steps per ring stage (2 or 4)
+  const uint32_t bbytes = 4u * (uint32_t)Npad * 16u;
+  const uint32_t stage_bytes = (uint32_t)KPS * (PU_ASTAGE + bbytes);
+  const uint32_t b_off = (uint32_t)KPS * PU_ASTAGE;               // B blocks follow the A blocks of a stage
+  const int spt = (nks + KPS - 1) / KPS;                         // stages per tile
+  unsigned char* ring = smem;
+  float* scs = (float*)(smem + (size_t)NST * stage_bytes);
+  float* bis = scs + Npad;
+  uint64_t* full = (uint64_t*)(bis + Npad);
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  // The tensor core's fp32 accumulate loses about half an ulp per MMA (measured as a systematic
+  // low bias that grows with F), so one output is NOT accumulated in a single TMEM column: the
+  // hi*hi products of alternating K-steps go to NH accumulators and the two small cross terms
+  // (lo*hi, hi*lo) to their own one; the epilogue adds the NACC partials in registers (RN).
+  const int NH = A.nh, NACC = NH + 1, NBUF = A.nbuf;
+  const int acc_cols = NACC * Npad;                              // TMEM columns per tile buffer
+  uint32_t ncols = 32;
+  while ((int)ncols < NBUF * acc_cols) ncols <<= 1;
+  if (warp == 12) {
+    if (lane == 0) {
+      // producers: with 4 K-steps per stage both halves (256 threads) fill a stage, with 2 only one half
+      const uint32_t arrivals = (KPS == 4 ? 256u : 128u) + 1u;
+      for (int s = 0; s < NST; ++s) { mbar_init(&full[s], arrivals); mbar_init(&empty[s], 1); }
+      mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+      mbar_init(&tempty[0], 128); mbar_init(&tempty[1], 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, ncols);
+  }
+  for (int i = tid; i < Npad; i += PU_THREADS) {
+    scs[i] = (A.scaler && i < A.N) ? A.scaler[i] : 1.0f;
+    bis[i] = (A.bias && i < A.N) ? A.bias[i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int my_tiles = (int)((A.tiles - first + stride - 1) / stride);
+
+  if (warp == 12) {
+    if (lane == 0) {
+      const Step3Desc sd = make_step3((uint32_t)Npad, make_idesc_tf32(128, (uint32_t)Npad));
+      const uint32_t ring_u = smem_u32(ring);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int buf = t % NBUF;
+        mbar_wait(&tempty[buf], ((uint32_t)(t / NBUF) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
+        const uint32_t d_lo = d_base + (uint32_t)(NH * Npad);
+        int kidx = 0;
+        for (int s = 0; s < spt; ++s) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = ring_u + stage * stage_bytes;
+          const int nv = (nks - s * KPS) < KPS ? (nks - s * KPS) : KPS;
+          for (int j = 0; j < nv; ++j, ++kidx) {
+            const uint64_t ao = (uint64_t)((sa + j * PU_ASTAGE) >> 4), bo = (uint64_t)((sa + b_off + j * bbytes) >> 4);
+            mma_tf32(d_lo, sd.a_lo + ao, sd.b_hi + bo, sd.idesc, kidx == 0 ? 0u : 1u);
+            mma_tf32(d_lo, sd.a_hi + ao, sd.b_lo + bo, sd.idesc, 1u);
+            mma_tf32(d_base + (uint32_t)((kidx % NH) * Npad), sd.a_hi + ao, sd.b_hi + bo, sd.idesc, kidx < NH ? 0u : 1u);
+          }
+          mma_commit(&empty[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp == 13) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int s = 0; s < spt; ++s) {
+          const int nv = (nks - s * KPS) < KPS ? (nks - s * KPS) : KPS;
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)nv * bbytes);
+          bulk_g2s(ring + stage * stage_bytes + b_off, A.vimg + (size_t)s * KPS * bbytes, (uint32_t)nv * bbytes, &full[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------- A producers ----------------------------------
+    // thread (row r, half h) owns K-steps 4b+2h, 4b+2h+1 of every batch b of 4 K-steps
+    const int pt = tid - 128;
+    const int r = pt & 127, h = pt >> 7;
+    const int nb = (nks + 3) / 4;
+    const int total = my_tiles * nb;
+    float4 q[PU_PF][4];
+    int lt = 0, lb = 0;
+    auto load_item = [&](float4 (&dst)[4]) {
+      const int64_t row = (first + (int64_t)lt * stride) * 128 + r;
+      const int ks0 = lb * 4 + 2 * h;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < A.B) {
+        const float* p = A.x + row * A.ldx + (int64_t)ks0 * 8;
+        if (ks0 < nks) { dst[0] = __ldg((const float4*)p); dst[1] = __ldg((const float4*)(p + 4)); }
+        if (ks0 + 1 < nks) { dst[2] = __ldg((const float4*)(p + 8)); dst[3] = __ldg((const float4*)(p + 12)); }
+      }
+      if (++lb == nb) { lb = 0; ++lt; }
+    };
+#pragma unroll
+    for (int u = 0; u < PU_PF; ++u) { if (u < total) load_item(q[u]); }
+    int ptile = 0, pb = 0;
+    for (int base = 0; base < total; base += PU_PF) {
+#pragma unroll
+      for (int u = 0; u < PU_PF; ++u) {
+        const int i = base + u;
+        if (i < total) {
+          float4 v[4] = {q[u][0], q[u][1], q[u][2], q[u][3]};
+          if (i + PU_PF < total) load_item(q[u]);
+          // stage of this thread's two K-steps and their slot inside it
+          const int sl = (KPS == 4) ? pb : (2 * pb + h);               // stage index within the tile
+          if (sl < spt) {
+            const int sidx = ptile * spt + sl;
+            const int stage = sidx % NST;
+            const uint32_t phase = (uint32_t)((sidx / NST) & 1);
+            const int slot0 = (KPS == 4) ? 2 * h : 0;
+            float4 hh[4], ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_tf32x4(v[e], hh[e], ll[e]);
+            mbar_wait(&empty[stage], phase ^ 1u);
+            unsigned char* st = ring + stage * stage_bytes + slot0 * PU_ASTAGE;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {                               // K-step slot0+e (zeros past nks: harmless)
+              unsigned char* sk = st + e * PU_ASTAGE;
+              *(float4*)(sk + ((0 * 2 + 0) * 128 + r) * 16) = hh[2 * e];
+              *(float4*)(sk + ((0 * 2 + 1) * 128 + r) * 16) = hh[2 * e + 1];
+              *(float4*)(sk + ((1 * 2 + 0) * 128 + r) * 16) = ll[2 * e];
+              *(float4*)(sk + ((1 * 2 + 1) * 128 + r) * 16) = ll[2 * e + 1];
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[stage]);
+          }
+          if (++pb == nb) { pb = 0; ++ptile; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------ epilogue ------------------------------------
+    const int lrow = warp * 32 + lane;
+    const bool vec = ((A.ldy & 3) == 0) && (((uintptr_t)A.y & 15u) == 0) &&
+                     (!A.pre || ((uintptr_t)A.pre & 15u) == 0) && (!A.z || ((uintptr_t)A.z & 15u) == 0);
+    for (int t = 0; t < my_tiles; ++t) {
+      const int buf = t % NBUF;
+      const int64_t row = (first + (int64_t)t * stride) * 128 + lrow;
+      mbar_wait(&tfull[buf], (uint32_t)(t / NBUF) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * acc_cols);
+      const bool two_hi = NH == 2 && nks >= 2;                  // second hi accumulator was written
+      for (int c0 = 0; c0 < Npad; c0 += 16) {
+        float acc[16], part[16];
+        tmem_ld16(taddr + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        if (two_hi) {
+          tmem_ld16(taddr + (uint32_t)(Npad + c0), part);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += part[j];
+        }
+        tmem_ld16(taddr + (uint32_t)(NH * Npad + c0), part);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += part[j];
+        if (row < A.B) {
+          float yv[16], pv[16], zv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            zv[j] = acc[j] * A.in_scale;
+            pv[j] = fmaf(zv[j], scs[c0 + j], bis[c0 + j]);
+            yv[j] = apply_act(pv[j], A.act);
+          }
+          float* yr = A.y + row * A.ldy + c0;
+          if (vec && c0 + 16 <= A.N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *(float4*)(yr + j) = make_float4(yv[j], yv[j + 1], yv[j + 2], yv[j + 3]);
+            if (A.pre) {
+              float* pr = A.pre + row * A.ldy + c0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *(float4*)(pr + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
+            }
+            if (A.z) {
+              float* zr = A.z + row * A.ldy + c0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *(float4*)(zr + j) = make_float4(zv[j], zv[j + 1], zv[j + 2], zv[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (c0 + j < A.N) {
+                yr[j] = yv[j];
+                if (A.pre) A.pre[row * A.ldy + c0 + j] = pv[j];
+                if (A.z) A.z[row * A.ldy + c0 + j] = zv[j];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem_base, ncols);
+}
+
+static int pu_npad(int N) { return (N + 15) / 16 * 16; }
+static int pu_kps(int Npad) { return Npad <= 64 ? 4 : 2; }
+static int pu_stages(int Npad) {
+  const size_t stage = (size_t)pu_kps(Npad) * (PU_ASTAGE + 64u * (size_t)Npad);
+  size_t budget = 200 * 1024;
+  int n = (int)(budget / stage);
+  if (n > 8) n = 8;
+  return n;
+}
+
+bool project_fwd_umma_supported(const float* x, int64_t B, int F, int64_t ldx, int N) {
+  if (getenv("CFL_FORCE_SIMT")) return false;
+  if (B < 1 || N < 1 || N > 256) return false;
+  if (F % 8 != 0 || F < 8) return false;
+  if ((ldx & 3) != 0 || ((uintptr_t)x & 15u) != 0) return false;
+  return pu_stages(pu_npad(N)) >= 3;
+}
+
+size_t project_fwd_umma_workspace(int64_t B, int F, int N) {
+  (void)B;
+  if (N > 256 || F % 8 != 0) return 0;
+  return align_up((size_t)F * pu_npad(N) * 8, 1024) + 1024;
+}
+
+int project_fwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float* V, int N, int64_t ldV,
+                     const float* scaler, const float* bias, float in_scale, int act, float* y, int64_t ldy,
+                     float* pre, float* z, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int Npad = pu_npad(N);
+  CFL_REQUIRE(ws_bytes >= project_fwd_umma_workspace(B, F, N), CFL_ERR_WORKSPACE, "project_umma: workspace too small");
+  unsigned char* vimg = (unsigned char*)align_up((size_t)(uintptr_t)ws, 1024);
+  const int64_t total = (int64_t)(F / 8) * 2 * Npad;
+  int pblocks = (int)((total + 255) / 256);
+  if (pblocks > 1184) pblocks = 1184;
+  pack_weights_kernel<<<pblocks, 256, 0, st>>>(V, F, N, ldV, Npad, (float*)vimg);
+  CFL_LAUNCH_CHECK();
+  PuArgs a;
+  a.x = x; a.B = B; a.F = F; a.ldx = ldx; a.vimg = vimg; a.N = N; a.Npad = Npad; a.nks = F / 8;
+  a.nst = pu_stages(Npad);
+  a.kps = pu_kps(Npad);
+  a.nh = Npad <= 80 ? 2 : 1;
+  a.nbuf = (2 * (a.nh + 1) * Npad <= 512) ? 2 : 1;
+  a.scaler = scaler; a.bias = bias; a.in_scale = in_scale; a.act = act;
+  a.y = y; a.ldy = ldy; a.pre = pre; a.z = z;
+  a.tiles = (B + 127) / 128;
+  const size_t smem = (size_t)a.nst * a.kps * (PU_ASTAGE + 64u * (size_t)Npad) + (size_t)Npad * 8 + (2u * a.nst + 4u) * 8 + 64 + 1024;
+  CFL_CUDA(cudaFuncSetAttribute(project_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)(a.tiles < sm_count() ? a.tiles : sm_count());
+  project_umma_kernel<<<grid, PU_THREADS, smem, st>>>(a);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
 
 }  // namespace cfl
 

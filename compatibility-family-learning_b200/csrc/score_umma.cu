@@ -31,7 +31,7 @@ using namespace umma;
 constexpr int SU_NEPI = 12;                         // epilogue warps (3 per TMEM lane quarter)
 constexpr int SU_THREADS = (SU_NEPI + 2) * 32;
 constexpr int SU_EPI_THREADS = SU_NEPI * 32;
-constexpr int SU_NSTAGE = 12;
+constexpr int SU_NSTAGE = 6;                        // ring stages of up to 2 K-steps (16 KB) each
 constexpr uint32_t SU_ASTAGE = 4u * 128u * 16u;     // [hl][chunk][128 rows][16 B] = 8 KB
 constexpr size_t SU_B_BUDGET = 96 * 1024;
 
@@ -112,7 +112,7 @@ __host__ __device__ inline SuLayout su_layout(int K, int qt, int dpad) {
   SuLayout L;
   uint32_t off = 0;
   L.b_img = off;   off += (uint32_t)dpad * 8u * (uint32_t)(K * qt);   off = (off + 1023u) & ~1023u;
-  L.a_ring = off;  off += SU_NSTAGE * SU_ASTAGE;
+  L.a_ring = off;  off += SU_NSTAGE * 2u * SU_ASTAGE;
   L.scratch = off; off += TOPK_STRIDE * 8u;
   L.qpar = off;    off += (uint32_t)qt * (uint32_t)qpar_stride(K) * 4u;  off = (off + 15u) & ~15u;
   L.thr = off;     off += (uint32_t)qt * 4u;
@@ -200,6 +200,7 @@ score_umma_kernel(ScoreArgs A) {
   const int ntiles = (int)((t1 - t0 + ts - 1) / ts);
   const bool filter = A.phase == 2;
   const int qps = qpar_stride(K);
+  const int kss = (nks % 2 == 0) ? 2 : 1;                    // K-steps per ring stage
 
   // ---- one-time setup ----
   uint32_t ncols = 32;
@@ -238,7 +239,7 @@ score_umma_kernel(ScoreArgs A) {
     // ================================ MMA issuer (one lane) =================================
     if (lane == 0) {
       mbar_wait(bfull, 0);
-      const uint32_t idesc = make_idesc_tf32(128, (uint32_t)NC);
+      const Step3Desc sd = make_step3((uint32_t)NC, make_idesc_tf32(128, (uint32_t)NC));
       const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_img);
       const uint32_t b_step = 4u * (uint32_t)NC * 16u;
       int stage = 0; uint32_t phase = 0;
@@ -247,10 +248,11 @@ score_umma_kernel(ScoreArgs A) {
         mbar_wait(&tempty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
-        for (int ks = 0; ks < nks; ++ks) {
+        for (int ks = 0; ks < nks; ks += kss) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          mma_step_3xtf32(d_tmem, a_base + stage * SU_ASTAGE, b_base + ks * b_step, (uint32_t)NC, idesc, ks == 0);
+          for (int j = 0; j < kss; ++j)
+            mma_step3(sd, d_tmem, a_base + (stage * 2 + j) * SU_ASTAGE, b_base + (ks + j) * b_step, ks + j == 0);
           mma_commit(&empty[stage]);
           if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
         }
@@ -270,10 +272,10 @@ score_umma_kernel(ScoreArgs A) {
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         const unsigned char* src = (const unsigned char*)A.cimg + (size_t)(t0 + (int64_t)t * ts) * nks * SU_ASTAGE;
-        for (int ks = 0; ks < nks; ++ks) {
+        for (int ks = 0; ks < nks; ks += kss) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full[stage], SU_ASTAGE);
-          bulk_g2s(a_ring + stage * SU_ASTAGE, src + (size_t)ks * SU_ASTAGE, SU_ASTAGE, &full[stage]);
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)kss * SU_ASTAGE);
+          bulk_g2s(a_ring + stage * 2 * SU_ASTAGE, src + (size_t)ks * SU_ASTAGE, (uint32_t)kss * SU_ASTAGE, &full[stage]);
           if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
         }
       }

@@ -164,6 +164,30 @@ __device__ __forceinline__ void split_tf32x4(const float4& x, float4& hi, float4
   split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
 }
 
+// Precomputed descriptor parts for a run of K-steps: only the 14-bit start-address field of an
+// smem descriptor changes from K-step to K-step (addresses < 256 KB, so no carry leaves the field).
+struct Step3Desc {
+  uint64_t a_hi, a_lo, b_hi, b_lo;
+  uint32_t idesc;
+};
+__device__ __forceinline__ Step3Desc make_step3(uint32_t N, uint32_t idesc) {
+  Step3Desc d;
+  d.a_hi = make_smem_desc(0, 128u * 16u, 128u);
+  d.a_lo = make_smem_desc(2u * 128u * 16u, 128u * 16u, 128u);
+  d.b_hi = make_smem_desc(0, N * 16u, 128u);
+  d.b_lo = make_smem_desc(2u * N * 16u, N * 16u, 128u);
+  d.idesc = idesc;
+  return d;
+}
+// a_addr / b_addr: shared addresses of the K-step's A block and B block
+__device__ __forceinline__ void mma_step3(const Step3Desc& d, uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr,
+                                          bool first) {
+  const uint64_t ao = (uint64_t)(a_addr >> 4), bo = (uint64_t)(b_addr >> 4);
+  mma_tf32(d_tmem, d.a_lo + ao, d.b_hi + bo, d.idesc, first ? 0u : 1u);
+  mma_tf32(d_tmem, d.a_hi + ao, d.b_lo + bo, d.idesc, 1u);
+  mma_tf32(d_tmem, d.a_hi + ao, d.b_hi + bo, d.idesc, 1u);
+}
+
 // Issues the three MMAs of one K-step (8 tf32): small terms first.
 //   a_stage: [hl][chunk][128 rows][16 B]   (hl stride 2*128*16 = 4096 B)
 //   b_step : [hl][chunk][N rows][16 B]     (hl stride 2*N*16 B)

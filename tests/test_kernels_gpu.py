@@ -169,9 +169,17 @@ def test_project_fwd_shapes(nat, B, F, N):
     gg = rng.uniform(0.5, 1.5, N).astype(np.float32)
     b = (0.1 * rng.normal(size=N)).astype(np.float32)
     y, _, _ = nat.project_fwd(dev(x), dev(V), dev(gg), dev(b), True, 0.5, "tanh")
-    want = O.fc_weight_norm(0.5 * x.astype(np.float64), V.astype(np.float64), gg.astype(np.float64),
-                            b.astype(np.float64), "tanh")
-    assert_close(host(y), want, atol=2e-6, msg="project fwd")
+    x6, V6 = 0.5 * x.astype(np.float64), V.astype(np.float64)
+    want = O.fc_weight_norm(x6, V6, gg.astype(np.float64), b.astype(np.float64), "tanh")
+    # tolerance written out: 1e-4 relative, plus the 3xTF32 error relative to S = sum|x||V| (times the
+    # weight-norm scaler; tanh' <= 1): 3*2^-22 ~ 7e-7 from the split (measured 4e-7..1e-6 for F up to
+    # 4096 with the split TMEM accumulators, tools/project_perf.py); the bar is 2x that.  What it means
+    # for distances is pinned at model level: test_models_gpu.py::test_c2_shape_train_step_parity.
+    bound = (np.abs(x6) @ np.abs(V6)) * (gg / np.sqrt((V6 ** 2).sum(0)))[None, :]
+    err = np.abs(host(y) - want)
+    coef = 1.5e-6
+    assert (err <= 1e-4 * np.abs(want) + coef * bound + 1e-7).all(), \
+        f"project fwd: worst {np.max(err / (coef * bound + 1e-7)):.2f}x bound"
 
 
 @pytest.mark.parametrize("B,F,N,wn,act", [(100, 512, 80, True, "linear"), (3000, 256, 33, True, "tanh"),

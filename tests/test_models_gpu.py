@@ -110,6 +110,34 @@ def test_train_steps_match_reference_graph(case):
         np.testing.assert_allclose(float(model.raw_threshold), theta, atol=2e-3 * lr * step + 1e-7)
 
 
+def test_c2_shape_train_step_parity():
+    """BASELINE config 2 at its real shape (monomer run.sh: F=4096 fc7-like features, K=4, d=20, B=100,
+    normalize 58.388599): distances and losses of the fused step within 1e-4 of the fp64 graph even
+    though the projection runs as 3xTF32 on tensor cores."""
+    from cfl import ops, variables as vs
+    from cfl.models.dist import Dist
+    vs.reset_default_graph()
+    vs.set_seed(633)
+    F, K, d, B, lr = 4096, 4, 20, 100, 1e-3
+    model = Dist(input_shape=(F,), latent_size=d, num_components=K, batch_size=B, lr=lr, beta1=0.9, beta2=0.999,
+                 normalize_value=58.388599, data_normalizer=ops.normalizer(58.388599, 0.0))
+    cfg = dict(K=K, d=d, dist_type="pcd", weight_norm=False, in_scale=1.0 / 58.388599, lr=lr, reg_const=0.0, shared=True)
+    rng = np.random.default_rng(2)
+    with torch.no_grad():
+        model.raw_threshold.fill_(0.3)
+    weights = {"src": _weights_of(model)["src"]}
+    theta, state = 0.3, {}
+    for step in range(1, 3):
+        batch = [np.minimum(np.maximum(rng.normal(size=(B, F)), 0) * 20, 58.388599).astype(np.float32) for _ in range(4)]
+        batch[1] = (batch[0] * 0.97 + 0.03 * batch[1]).astype(np.float32)      # positives: close pairs
+        out = model.train_step(*[torch.as_tensor(b).cuda() for b in batch])
+        ref, weights, theta, state = R.train_step(cfg, weights, theta, batch, state, step)
+        np.testing.assert_allclose(_np(model.s_pos_dists)[:, 0], ref["dp"], rtol=1e-4)
+        np.testing.assert_allclose(_np(model.s_neg_dists)[:, 0], ref["dn"], rtol=1e-4)
+        np.testing.assert_allclose(out["s_total_loss"], ref["total"], rtol=1e-4)
+        np.testing.assert_allclose(out["s_accuracy"], ref["acc"], rtol=1e-12)
+
+
 def test_variable_names_follow_the_reference_scopes():
     from cfl import variables as vs
     from cfl.models.cfl import CFL
