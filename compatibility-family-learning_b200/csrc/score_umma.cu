@@ -28,7 +28,10 @@ namespace cfl {
 
 using namespace umma;
 
-constexpr int SU_NEPI = 12;                         // epilogue warps (3 per TMEM lane quarter)
+#ifndef CFL_SU_NEPI
+#define CFL_SU_NEPI 16
+#endif
+constexpr int SU_NEPI = CFL_SU_NEPI;                // epilogue warps (a multiple of 4: TMEM lane quarters)
 constexpr int SU_THREADS = (SU_NEPI + 2) * 32;
 constexpr int SU_EPI_THREADS = SU_NEPI * 32;
 constexpr int SU_NSTAGE = 6;                        // ring stages of up to 2 K-steps (16 KB) each
