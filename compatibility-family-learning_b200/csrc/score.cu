@@ -174,43 +174,69 @@ static int launch_simt(const ScoreArgs& a, cudaStream_t st) {
   return CFL_OK;
 }
 
+// ---- block-wide selection of the kk smallest keys over all catalog parts -----------------------
+// 256 threads per query.  Keys stream through a 512-slot shared buffer; once kk keys are known,
+// later keys must beat the current kk-th best to be admitted, so most of them never reach a sort.
+constexpr int MRG_THREADS = 256;
+
+__device__ __forceinline__ void mrg_compact(tkey_t* s, int* s_fill, tkey_t* s_thr, int kk, int t) {
+  const int fill = *s_fill;
+  for (int i = fill + t; i < TOPK_CAP; i += MRG_THREADS) s[i] = CFL_KEY_INF;
+  __syncthreads();
+  coop_sort512<MRG_THREADS>(s, t);                 // ends with a block barrier (256 == whole block)
+  if (t == 0) {
+    const int nf = fill < kk ? fill : kk;
+    *s_fill = nf;
+    *s_thr = (nf >= kk) ? s[kk - 1] : CFL_KEY_INF;
+  }
+  __syncthreads();
+}
+
+// returns the number of keys kept (<= kk), sorted ascending in s[0..)
+__device__ __forceinline__ int block_merge_topkk(const tkey_t* __restrict__ keys, const int* __restrict__ counts,
+                                                 int parts, int64_t Q, int64_t q, int kk, tkey_t* s, int* s_fill,
+                                                 tkey_t* s_thr) {
+  const int t = threadIdx.x;
+  if (t == 0) { *s_fill = 0; *s_thr = CFL_KEY_INF; }
+  __syncthreads();
+  for (int p = 0; p < parts; ++p) {
+    const int c = counts[(int64_t)p * Q + q];
+    const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
+    for (int base = 0; base < c; base += MRG_THREADS) {
+      // every thread must take the same branch: read the fill level between two barriers, before
+      // any thread of this round can append
+      const int f0 = *s_fill;
+      __syncthreads();
+      if (f0 + MRG_THREADS > TOPK_CAP) mrg_compact(s, s_fill, s_thr, kk, t);
+      const int i = base + t;
+      if (i < c) {
+        const tkey_t key = src[i];
+        if (key < *s_thr) s[atomicAdd(s_fill, 1)] = key;
+      }
+      __syncthreads();
+    }
+  }
+  mrg_compact(s, s_fill, s_thr, kk, t);
+  return *s_fill;
+}
+
 // ---- merge of the catalog parts + direct-form rescoring + final sort ---------------------
-// One warp per query.  Exact distance of the kk survivors in direct-difference form
-// (cfl/models/base.py:129-138 arithmetic), then (value, index) order, best k written out.
-__global__ void __launch_bounds__(32)
+// Exact distance of the kk survivors in direct-difference form (cfl/models/base.py:129-138
+// arithmetic) on the raw rows, then (value, index) order, best k written out.
+__global__ void __launch_bounds__(MRG_THREADS)
 merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __restrict__ counts,
                      int parts, int64_t Q, int kk, int k, const float* __restrict__ Pq,
                      int64_t ldq, int K, int d, const float* __restrict__ E, int64_t lde,
                      int64_t idx_base, float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
   __shared__ tkey_t s[TOPK_CAP];
-  const int lane = threadIdx.x;
+  __shared__ int s_fill;
+  __shared__ tkey_t s_thr;
+  const int t = threadIdx.x;
   const int64_t q = blockIdx.x;
-  int fill = 0;
-  for (int p = 0; p < parts; ++p) {
-    int c = counts[(int64_t)p * Q + q];               // sorted (<= kk) or unsorted (<= TOPK_STRIDE)
-    const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
-    while (c > 0) {
-      if (fill == TOPK_CAP || (fill > kk && fill + c > TOPK_CAP)) {
-        for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
-        __syncwarp();
-        warp_sort512(s, lane);
-        fill = fill < kk ? fill : kk;
-      }
-      int take = TOPK_CAP - fill;
-      if (take > c) take = c;
-      for (int i = lane; i < take; i += 32) s[fill + i] = src[i];
-      fill += take; src += take; c -= take;
-      __syncwarp();
-    }
-  }
-  for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
-  __syncwarp();
-  warp_sort512(s, lane);
-  fill = fill < kk ? fill : kk;
-  // rescoring in direct form on the raw (uncentred) rows
+  const int fill = block_merge_topkk(keys, counts, parts, Q, q, kk, s, &s_fill, &s_thr);
   const float* pq = Pq + q * ldq;
-  for (int i = lane; i < fill; i += 32) {
-    uint32_t idx = (uint32_t)(s[i] & 0xffffffffu);
+  if (t < fill) {
+    const uint32_t idx = (uint32_t)(s[t] & 0xffffffffu);
     const float* e = E + (int64_t)idx * lde;
     float dk[CFL_MAX_K];
     float mn = 3.0e38f;
@@ -235,13 +261,13 @@ merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __res
         dist = fmaf(r, r, dist);
       }
     }
-    s[i] = pack_key(dist, idx);
+    s[t] = pack_key(dist, idx);
   }
-  __syncwarp();
-  for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
-  __syncwarp();
-  warp_sort512(s, lane);
-  for (int i = lane; i < k; i += 32) {
+  __syncthreads();
+  if (t == 0) s_fill = fill;
+  __syncthreads();
+  mrg_compact(s, &s_fill, &s_thr, kk, t);           // re-sort by the exact values
+  for (int i = t; i < k; i += MRG_THREADS) {
     if (i < fill) {
       top_val[q * k + i] = ord2f((uint32_t)(s[i] >> 32));
       top_idx[q * k + i] = idx_base + (int64_t)(uint32_t)(s[i] & 0xffffffffu);
@@ -253,37 +279,19 @@ merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __res
 }
 
 // ---- thresholds from the sample pass ------------------------------------------------------
-// tau[q] = kk-th smallest distance among the sampled candidates of ALL parts (sorted lists of
-// <= kk keys per part).  Any subset's kk-th best is an upper bound of the catalog's kk-th best,
-// so every member of the final top-kk satisfies dist <= tau[q].
-__global__ void __launch_bounds__(32)
+// tau[q] = kk-th smallest distance among the sampled candidates of ALL parts.  Any subset's kk-th
+// best is an upper bound of the catalog's kk-th best, so every member of the final top-kk
+// satisfies dist <= tau[q].
+__global__ void __launch_bounds__(MRG_THREADS)
 sample_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ counts, int parts,
                         int64_t Q, int kk, float* __restrict__ tau) {
   __shared__ tkey_t s[TOPK_CAP];
-  const int lane = threadIdx.x;
+  __shared__ int s_fill;
+  __shared__ tkey_t s_thr;
   const int64_t q = blockIdx.x;
-  int fill = 0;
-  for (int p = 0; p < parts; ++p) {
-    int c = counts[(int64_t)p * Q + q];               // sorted (<= kk) or unsorted (<= TOPK_STRIDE)
-    const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
-    while (c > 0) {
-      if (fill == TOPK_CAP || (fill > kk && fill + c > TOPK_CAP)) {
-        for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
-        __syncwarp();
-        warp_sort512(s, lane);
-        fill = fill < kk ? fill : kk;
-      }
-      int take = TOPK_CAP - fill;
-      if (take > c) take = c;
-      for (int i = lane; i < take; i += 32) s[fill + i] = src[i];
-      fill += take; src += take; c -= take;
-      __syncwarp();
-    }
-  }
-  for (int i = fill + lane; i < TOPK_CAP; i += 32) s[i] = CFL_KEY_INF;
-  __syncwarp();
-  warp_sort512(s, lane);
-  if (lane == 0) tau[q] = (fill >= kk) ? ord2f((uint32_t)(s[kk - 1] >> 32)) : __int_as_float(0x7f800000);
+  const int fill = block_merge_topkk(keys, counts, parts, Q, q, kk, s, &s_fill, &s_thr);
+  if (threadIdx.x == 0)
+    tau[q] = (fill >= kk) ? ord2f((uint32_t)(s[kk - 1] >> 32)) : __int_as_float(0x7f800000);
 }
 
 // ---- cross-rank merge: rank-based merge of R sorted lists --------------------------------
@@ -426,7 +434,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
           while ((tpp + 1 + a.tile_stride - 1) / a.tile_stride > 7) ++a.tile_stride;
           st = score_umma_launch(a, cs);
           if (st != CFL_OK) return st;
-          sample_threshold_kernel<<<(unsigned)Q, 32, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau);
+          sample_threshold_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau);
           CFL_LAUNCH_CHECK();
           a.phase = 2; a.tile_stride = sstride; a.thr_init = tau;
           st = score_umma_launch(a, cs);
@@ -435,7 +443,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
           st = score_umma_launch(a, cs);
         }
         if (st != CFL_OK) return st;
-        sample_threshold_kernel<<<(unsigned)Q, 32, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau);
+        sample_threshold_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau);
         CFL_LAUNCH_CHECK();
         a.phase = 2; a.tile_stride = 1; a.thr_init = tau;
         st = score_umma_launch(a, cs);
@@ -461,7 +469,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       if (st != CFL_OK) return st;
     }
   }
-  merge_rescore_kernel<<<(unsigned)Q, 32, 0, cs>>>(mode, a.keys, a.counts, plan.parts, Q, plan.kk, k,
+  merge_rescore_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(mode, a.keys, a.counts, plan.parts, Q, plan.kk, k,
                                                   Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
