@@ -211,13 +211,19 @@ def run_ours(args):
     flops = 2.0 * K * D * Q * N_PER_GPU                           # 2*K*d per score
     achieved = flops / (k_ms / 1e3) / 1e12
     tf32_peak = pk["bf16_sus"] / 2.0                              # TF32 dense = bf16/2 (not in MEASURED_PEAKS)
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu
+    # capture of the same command (profiles/r1_03_score_umma_final.md); algorithmic bytes = the
+    # catalog image, N * (8*d + 4).
+    traffic = 537.2e6 if (N_PER_GPU, D, K, Q) == (1_000_000, 64, 3, 1024) else None
     roofline = dict(bound="tensor", achieved=round(achieved, 2), peak=round(tf32_peak, 1), unit="TFLOP/s",
-                    frac=round(achieved / tf32_peak, 4), traffic=None,
-                    kernel="score_topk main kernel", kernel_ms=round(k_ms, 4),
-                    peak_source=f"{pk['src']} bf16_tflops_sustained/2 (1xTF32); the kernel issues 3 TF32 MMAs per "
-                                f"product (3xTF32 compensation), so frac of the 3x-effective peak is "
-                                f"{round(3 * achieved / tf32_peak, 4)}",
-                    hbm_gbs_catalog=round(N_PER_GPU * (4 * D) / (k_ms / 1e3) / 1e9, 1))
+                    frac=round(achieved / tf32_peak, 4), traffic=traffic,
+                    kernel="score_umma_kernel<3>, full filter pass (the dominant launch of cfl_score_topk_packed)",
+                    kernel_ms=round(k_ms, 4), algorithmic_flops_per_launch=flops,
+                    algorithmic_bytes_per_launch=N_PER_GPU * (8 * D + 4),
+                    peak_source=f"{pk['src']} bf16_tflops_sustained/2 (1xTF32; TF32 is not in MEASURED_PEAKS.json). The "
+                                f"kernel issues 3 TF32 MMAs per product (3xTF32 error compensation, needed for the 1e-4 "
+                                f"parity bar), so the fraction of the 3x-effective peak is {round(3 * achieved / tf32_peak, 4)}",
+                    hbm_gbs=round((traffic or N_PER_GPU * (8 * D + 4)) / (k_ms / 1e3) / 1e9, 1))
 
     line = None
     if rank == 0:

@@ -375,3 +375,69 @@ def test_score_topk_two_pass_equals_single_pass(nat, monkeypatch, K, d, dup, cas
         sym = set(got[r].tolist()) ^ set(wi[r].tolist())
         for c_ in sym:
             assert abs(D[r, c_] - wv[r, -1]) <= 2e-6 * max(wv[r, -1], 1.0) + 1e-7
+
+
+# ---------------------------------------------------------------------------- full-size properties
+def test_full_size_catalog_properties(nat):
+    """BASELINE config 3 size (1M-item catalog, K=3, d=64): size-independent properties instead of a
+    brute-force oracle -- (a) sharded + merged == unsharded, bit for bit; (b) every reported distance
+    equals the PAIRED kernel's distance of that (query, candidate) pair (all-pairs and paired paths
+    agree); (c) ascending order, valid unique indices; (d) planted exact duplicates of a query's best
+    candidate show up, ties ordered by index; (e) no candidate outside the list beats the k-th."""
+    g = torch.Generator(device="cuda").manual_seed(633)
+    N, d, K, Q, k = 1_000_000, 64, 3, 96, 100
+    E = torch.randn(N, d, generator=g, device="cuda")
+    anchors = torch.randint(0, N, (Q,), generator=g, device="cuda")
+    Pq = E[anchors][:, None, :] + 0.5 * torch.randn(Q, K, d, generator=g, device="cuda")
+    E[123456] = E[anchors[0]]; E[900001] = E[anchors[0]]            # exact duplicates (planted ties)
+    mu = nat.col_mean(E)
+    img = nat.catalog_pack(E, K, mu)
+    tv, ti = nat.score_topk(Pq, E, k, mu=mu, image=img)
+    # (a) 4 shards
+    vs_, is_ = [], []
+    for r in range(4):
+        lo, hi = r * N // 4, (r + 1) * N // 4
+        v, i = nat.score_topk(Pq, E[lo:hi], k, mu=mu, idx_base=lo)
+        vs_.append(v); is_.append(i)
+    mv, mi = nat.topk_merge(torch.stack(vs_), torch.stack(is_))
+    assert torch.equal(mi, ti) and torch.equal(mv, tv)
+    # (b) paired kernel on the winners
+    qq = torch.arange(Q, device="cuda").repeat_interleave(k)
+    dist, *_ = nat.pair_loss_fwd("pcd", E[ti.reshape(-1)], Pq[qq])
+    np.testing.assert_allclose(host(tv).reshape(-1), host(dist), rtol=1e-5)   # two fp32 summation orders
+    # (c)
+    assert bool((tv[:, 1:] >= tv[:, :-1]).all()) and int(ti.min()) >= 0 and int(ti.max()) < N
+    assert all(len(set(r)) == k for r in ti.cpu().tolist())
+    # (d) the anchor of query 0 and its two planted copies tie exactly: ordered by index
+    row = ti[0].cpu().tolist()
+    trio = sorted([int(anchors[0]), 123456, 900001])
+    pos = [row.index(c) for c in trio]
+    assert pos == sorted(pos) and float(tv[0, pos[0]]) == float(tv[0, pos[2]])
+    # (e) a random 200k-candidate slice contains nothing better than the k-th that is not listed
+    sl = torch.randint(0, N, (200_000,), generator=g, device="cuda")
+    for q in (0, 17, Q - 1):
+        dq, *_ = nat.pair_loss_fwd("pcd", E[sl], Pq[q:q + 1].expand(sl.numel(), K, d).contiguous())
+        better = sl[dq < tv[q, -1]]
+        assert set(better.cpu().tolist()) <= set(ti[q].cpu().tolist())
+
+
+def test_full_size_paired_and_auc_properties(nat):
+    """2M labelled pairs (config 3 eval size): AUC integers are invariant under shuffling and under
+    splitting the negatives in two (counts add up); paired distances are batch-size independent."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    n_pos, n_neg = 120_000, 1_920_000
+    pos = torch.randn(n_pos, generator=g, device="cuda") + 0.4
+    neg = torch.randn(n_neg, generator=g, device="cuda")
+    a = nat.auc_counts(pos, neg).cpu().tolist()
+    b = nat.auc_counts(pos[torch.randperm(n_pos, device="cuda")], neg[torch.randperm(n_neg, device="cuda")]).cpu().tolist()
+    assert a == b
+    h = n_neg // 2
+    c1 = nat.auc_counts(pos, neg[:h]).cpu().tolist()
+    c2 = nat.auc_counts(pos, neg[h:]).cpu().tolist()
+    assert c1[0] + c2[0] == a[0] and c1[2] + c2[2] == a[2]
+    assert 0.55 < a[0] / (2.0 * n_pos * n_neg) < 0.7
+    v = torch.randn(300_000, 64, generator=g, device="cuda")
+    P = torch.randn(300_000, 3, 64, generator=g, device="cuda")
+    full, *_ = nat.pair_loss_fwd("pcd", v, P)
+    part, *_ = nat.pair_loss_fwd("pcd", v[1000:1500], P[1000:1500])
+    assert torch.equal(full[1000:1500], part)
