@@ -106,7 +106,12 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
 //   warp 13     one lane drives the TMA engine for the pre-split weight image (B operand)
 // Bytes per item: 4F (read once) + 4N (written once); flops 2*F*N (x3 MMAs).
 constexpr int PU_THREADS = 14 * 32;
-constexpr uint32_t PU_ASTAGE = 4u * 128u * 16u;
+// A-operand block of one K-step: 4 planes [hi c0][hi c1][lo c0][lo c1] of 128 rows x 16 B.  The plane
+// stride (= the descriptor's LBO) and the block stride are padded so that the producers' coalesced
+// mapping (4 lanes per row) stores without shared-memory bank conflicts: 8 lanes of a store phase
+// write 2 rows x 4 planes, and 2080 B / 8384 B shift the planes by 8 / 16 banks.
+constexpr uint32_t PU_APLANE = 128u * 16u + 32u;              // 2080
+constexpr uint32_t PU_ASTAGE = 4u * PU_APLANE + 64u;          // 8384
 constexpr int PU_PF = 4;
 
 struct PuArgs {
@@ -190,7 +195,9 @@ project_umma_kernel(PuArgs A) {
 
   if (warp == 12) {
     if (lane == 0) {
-      const Step3Desc sd = make_step3((uint32_t)Npad, make_idesc_tf32(128, (uint32_t)Npad));
+      Step3Desc sd = make_step3((uint32_t)Npad, make_idesc_tf32(128, (uint32_t)Npad));
+      sd.a_hi = make_smem_desc(0, PU_APLANE, 128u);
+      sd.a_lo = make_smem_desc(2u * PU_APLANE, PU_APLANE, 128u);
       const uint32_t ring_u = smem_u32(ring);
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < my_tiles; ++t) {
@@ -232,22 +239,26 @@ project_umma_kernel(PuArgs A) {
     }
   } else if (warp >= 4) {
     // ---------------------------------- A producers ----------------------------------
-    // thread (row r, half h) owns K-steps 4b+2h, 4b+2h+1 of every batch b of 4 K-steps
+    // Batch = 4 K-steps = 128 B of every row.  Half h (warps 4-7 / 8-11) owns K-steps 2h, 2h+1 of
+    // each batch; inside a half, warp w covers rows 32w..32w+31 with 4 coalesced LDG.128: lane l of
+    // load i reads 16 B chunk (l & 3) of row 32w + 8i + (l >> 2)  (4 lanes = 64 contiguous bytes).
     const int pt = tid - 128;
-    const int r = pt & 127, h = pt >> 7;
+    const int h = pt >> 7, w = (pt >> 5) & 3, l = pt & 31;
+    const int cc = l & 3;                                        // 16-byte chunk inside the half's 64 B
+    const int kj = cc >> 1, kc = cc & 1;                         // K-step within the half, chunk within K-step
+    const int rbase = 32 * w + (l >> 2);
     const int nb = (nks + 3) / 4;
     const int total = my_tiles * nb;
     float4 q[PU_PF][4];
     int lt = 0, lb = 0;
     auto load_item = [&](float4 (&dst)[4]) {
-      const int64_t row = (first + (int64_t)lt * stride) * 128 + r;
-      const int ks0 = lb * 4 + 2 * h;
+      const int ks = lb * 4 + 2 * h + kj;
+      const int64_t row0 = (first + (int64_t)lt * stride) * 128 + rbase;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < A.B) {
-        const float* p = A.x + row * A.ldx + (int64_t)ks0 * 8;
-        if (ks0 < nks) { dst[0] = __ldg((const float4*)p); dst[1] = __ldg((const float4*)(p + 4)); }
-        if (ks0 + 1 < nks) { dst[2] = __ldg((const float4*)(p + 8)); dst[3] = __ldg((const float4*)(p + 12)); }
+      for (int i = 0; i < 4; ++i) {
+        const int64_t row = row0 + 8 * i;
+        dst[i] = (row < A.B && ks < nks) ? __ldg((const float4*)(A.x + row * A.ldx + (int64_t)ks * 8 + kc * 4))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (++lb == nb) { lb = 0; ++lt; }
     };
@@ -261,25 +272,21 @@ project_umma_kernel(PuArgs A) {
         if (i < total) {
           float4 v[4] = {q[u][0], q[u][1], q[u][2], q[u][3]};
           if (i + PU_PF < total) load_item(q[u]);
-          // stage of this thread's two K-steps and their slot inside it
           const int sl = (KPS == 4) ? pb : (2 * pb + h);               // stage index within the tile
           if (sl < spt) {
             const int sidx = ptile * spt + sl;
             const int stage = sidx % NST;
             const uint32_t phase = (uint32_t)((sidx / NST) & 1);
-            const int slot0 = (KPS == 4) ? 2 * h : 0;
+            const int slot = ((KPS == 4) ? 2 * h : 0) + kj;            // K-step slot inside the stage
             float4 hh[4], ll[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) split_tf32x4(v[e], hh[e], ll[e]);
             mbar_wait(&empty[stage], phase ^ 1u);
-            unsigned char* st = ring + stage * stage_bytes + slot0 * PU_ASTAGE;
+            unsigned char* st = ring + stage * stage_bytes + slot * PU_ASTAGE + kc * PU_APLANE;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {                               // K-step slot0+e (zeros past nks: harmless)
-              unsigned char* sk = st + e * PU_ASTAGE;
-              *(float4*)(sk + ((0 * 2 + 0) * 128 + r) * 16) = hh[2 * e];
-              *(float4*)(sk + ((0 * 2 + 1) * 128 + r) * 16) = hh[2 * e + 1];
-              *(float4*)(sk + ((1 * 2 + 0) * 128 + r) * 16) = ll[2 * e];
-              *(float4*)(sk + ((1 * 2 + 1) * 128 + r) * 16) = ll[2 * e + 1];
+            for (int e = 0; e < 4; ++e) {
+              *(float4*)(st + (rbase + 8 * e) * 16) = hh[e];
+              *(float4*)(st + 2 * PU_APLANE + (rbase + 8 * e) * 16) = ll[e];
             }
             fence_proxy_async();
             mbar_arrive(&full[stage]);
