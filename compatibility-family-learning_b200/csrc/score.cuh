@@ -113,6 +113,80 @@ __device__ __forceinline__ float softmin_from_gram(const float (&g)[K], float e2
   // dist = e2 + inv * (-2 t1 + inv * 2 t2)
   return fmaf(inv + inv, fmaf(inv, t2, -t1), e2);
 }
+
+// ---- packed (two queries per instruction) variant for the tensor-core kernel's epilogue ---------
+// sm_100 has FP32x2 FMA/ADD/MUL (FFMA2...): the soft-min of two queries of the same catalog row is
+// evaluated with one instruction per pair wherever the math is FMA-shaped; max / ex2 / rcp stay
+// scalar.  qp2[j] = (block_A[j], block_B[j]) with entries [0,K) NEGATED (-log2e*|p_k|^2).
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+template <int K>
+__device__ __forceinline__ void softmin_pair(const float (&gA)[K], const float (&gB)[K], float e2,
+                                             const f2_t* __restrict__ qp2, float& dA, float& dB) {
+  const f2_t C2 = pk2(2.0f * CFL_LOG2E, 2.0f * CFL_LOG2E);
+  const f2_t e2p = pk2(e2, e2);
+  f2_t g[K], a[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { g[k] = pk2(gA[k], gB[k]); a[k] = fma2(C2, g[k], qp2[k]); }
+  if (K == 1) {
+    upk2(fma2(pk2(-CFL_LN2, -CFL_LN2), a[0], e2p), dA, dB);
+    return;
+  }
+  float mA, mB;
+  upk2(a[0], mA, mB);
+#pragma unroll
+  for (int k = 1; k < K; ++k) { float x, y; upk2(a[k], x, y); mA = fmaxf(mA, x); mB = fmaxf(mB, y); }
+  const f2_t nm = pk2(-mA, -mB);
+  f2_t w[K];
+  f2_t sum;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float x, y;
+    upk2(add2(a[k], nm), x, y);
+    w[k] = pk2(fast_ex2(x), fast_ex2(y));
+    sum = (k == 0) ? w[0] : add2(sum, w[k]);
+  }
+  float sA, sB;
+  upk2(sum, sA, sB);
+  const f2_t ninv = pk2(fast_rcp(-sA), fast_rcp(-sB));     // -1/sum
+  f2_t t1, t2;
+  int o = K;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    t1 = (k == 0) ? mul2(w[0], g[0]) : fma2(w[k], g[k], t1);
+    f2_t row = mul2(qp2[o], w[k]);                          // diagonal is stored pre-halved
+#pragma unroll
+    for (int l = k + 1; l < K; ++l) row = fma2(qp2[o + l - k], w[l], row);
+    o += K - k;
+    t2 = (k == 0) ? mul2(w[0], row) : fma2(w[k], row, t2);  // half of sum_kl w_k w_l pp_kl
+  }
+  // dist = e2 - 2 inv (t1 - inv t2)
+  const f2_t v = fma2(ninv, t2, t1);
+  upk2(fma2(add2(ninv, ninv), v, e2p), dA, dB);
+}
 #endif
 
 }  // namespace cfl

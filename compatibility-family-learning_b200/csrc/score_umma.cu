@@ -219,7 +219,14 @@ score_umma_kernel(ScoreArgs A) {
     __syncwarp();
     tmem_alloc(tmem_slot, ncols);
   }
-  for (int i = tid; i < QT * qps; i += SU_THREADS) qpar[i] = (i < nq * qps) ? A.qpar[q0 * qps + i] : 0.0f;
+  // per-query blocks are stored interleaved by query PAIR: qpar[(pair*qps + j)*2 + (q&1)], with the
+  // first K entries negated, ready for the packed (FP32x2) epilogue
+  for (int i = tid; i < QT * qps; i += SU_THREADS) {
+    const int ql = i / qps, j = i % qps;
+    float v = (ql < nq) ? A.qpar[(q0 + ql) * qps + j] : 0.0f;
+    if (j < K) v = -v;
+    qpar[((ql >> 1) * qps + j) * 2 + (ql & 1)] = v;
+  }
   // padding queries of the last tile get thr = -inf: they can never be pushed
   // phase 2: fixed thresholds from the sample pass, bumped one ulp so that the strict compare
   // below implements dist <= tau (every candidate tied with the bound must be kept)
@@ -317,7 +324,7 @@ score_umma_kernel(ScoreArgs A) {
           else                    tmem_ld8(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
         }
         tmem_ld_wait();
-        const float* qg = qpar + g * GQ * QPS;
+        const float* qg = qpar + g * GQ * QPS;                 // GQ/2 pair blocks of 2*QPS floats
         float tg[GQ];
 #pragma unroll
         for (int i = 0; i < GQ; i += 4) {
@@ -328,10 +335,11 @@ score_umma_kernel(ScoreArgs A) {
           bool need = false;
 #pragma unroll
           for (int i = 0; i < GQ; ++i) {
-            float gv[K];
+            const float* qb = qg + (i >> 1) * QPS * 2 + (i & 1);
+            float mx = fmaf(2.0f * CFL_LOG2E, gk[0][i], qb[0]);
 #pragma unroll
-            for (int k = 0; k < K; ++k) gv[k] = gk[k][i];
-            const float lower = fmaf(-CFL_LN2, softmin_max2<K>(gv, qg + i * QPS), e2) - qg[i * QPS + CQ];
+            for (int k = 1; k < K; ++k) mx = fmaxf(mx, fmaf(2.0f * CFL_LOG2E, gk[k][i], qb[2 * k]));
+            const float lower = fmaf(-CFL_LN2, mx, e2) - qb[2 * CQ];
             need |= lower < tg[i];
           }
           ++grp_seen;
@@ -339,17 +347,15 @@ score_umma_kernel(ScoreArgs A) {
         }
         float dist[GQ];
 #pragma unroll
-        for (int i = 0; i < GQ; ++i) {
-          float qv[QPS];
+        for (int pi = 0; pi < GQ / 2; ++pi) {
+          f2_t qv[QPS];
+          const ulonglong2* src = (const ulonglong2*)(qg + pi * QPS * 2);
 #pragma unroll
-          for (int j = 0; j < QPS; j += 4) {
-            const float4 q4 = *(const float4*)(qg + i * QPS + j);
-            qv[j] = q4.x; qv[j + 1] = q4.y; qv[j + 2] = q4.z; qv[j + 3] = q4.w;
-          }
-          float gv[K];
+          for (int j = 0; j < QPS; j += 2) { const ulonglong2 u = src[j >> 1]; qv[j] = u.x; qv[j + 1] = u.y; }
+          float gA[K], gB[K];
 #pragma unroll
-          for (int k = 0; k < K; ++k) gv[k] = gk[k][i];
-          dist[i] = softmin_from_gram<K>(gv, e2, qv);
+          for (int k = 0; k < K; ++k) { gA[k] = gk[k][2 * pi]; gB[k] = gk[k][2 * pi + 1]; }
+          softmin_pair<K>(gA, gB, e2, qv, dist[2 * pi], dist[2 * pi + 1]);
         }
         uint32_t bits = 0;
 #pragma unroll
