@@ -41,7 +41,7 @@ constexpr size_t SU_B_BUDGET = 96 * 1024;
 int score_umma_qt(int K, int d) {
   if (K < 1 || K > CFL_MAX_K || d < 1 || d > 128) return 0;
   const int dpad = (d + 7) / 8 * 8;
-  const int gq = K <= 2 ? 16 : 8;
+  const int gq = K <= 2 ? 16 : (K <= 4 ? 8 : 4);
   const int cand[] = {128, 64, 48, 32, 16, 8};
   for (int qt : cand) {
     int nc = K * qt;
@@ -173,7 +173,7 @@ template <int K>
 __global__ void __launch_bounds__(SU_THREADS, 1)
 score_umma_kernel(ScoreArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int GQ = K <= 2 ? 16 : 8;
+  constexpr int GQ = K <= 2 ? 16 : (K <= 4 ? 8 : 4);     // queries per epilogue group (register budget)
   const int QT = A.plan.qt;
   const int NC = K * QT;
   const int dpad = A.plan.dpad;
@@ -320,8 +320,9 @@ score_umma_kernel(ScoreArgs A) {
         float gk[K][GQ];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          if constexpr (GQ == 16) tmem_ld16(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
-          else                    tmem_ld8(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
+          if constexpr (GQ == 16)     tmem_ld16(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
+          else if constexpr (GQ == 8) tmem_ld8(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
+          else                        tmem_ld4(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
         }
         tmem_ld_wait();
         const float* qg = qpar + g * GQ * QPS;                 // GQ/2 pair blocks of 2*QPS floats
