@@ -37,17 +37,20 @@ radix_hist(const uint32_t* __restrict__ keys, int64_t n, int shift, int nblocks,
   hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of the digit-major histogram (single block, chunked)
-__global__ void __launch_bounds__(1024)
-radix_scan(uint32_t* __restrict__ hist, int64_t total) {
-  __shared__ uint32_t wsum[32];
+// exclusive scan of the digit-major histogram, two levels: block d scans row d (the per-block
+// counts of digit d) in place and publishes the digit total; one small block then scans the 256
+// totals.  The scatter kernel adds the two.
+__global__ void __launch_bounds__(256)
+radix_scan_rows(uint32_t* __restrict__ hist, int nblocks, uint32_t* __restrict__ digit_total) {
+  __shared__ uint32_t wsum[8];
   __shared__ uint32_t carry;
+  uint32_t* row = hist + (int64_t)blockIdx.x * nblocks;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int64_t c0 = 0; c0 < total; c0 += 1024) {
-    int64_t i = c0 + threadIdx.x;
-    uint32_t v = (i < total) ? hist[i] : 0u;
+  for (int c0 = 0; c0 < nblocks; c0 += 256) {
+    const int i = c0 + threadIdx.x;
+    const uint32_t v = (i < nblocks) ? row[i] : 0u;
     uint32_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -56,35 +59,40 @@ radix_scan(uint32_t* __restrict__ hist, int64_t total) {
     }
     if (lane == 31) wsum[wid] = x;
     __syncthreads();
-    if (wid == 0) {
-      uint32_t w = wsum[lane];
-      uint32_t xs = w;
+    uint32_t woff = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
-        if (lane >= o) xs += y;
-      }
-      wsum[lane] = xs - w;                      // exclusive warp offsets
-    }
+    for (int w = 0; w < 8; ++w) woff += (w < wid) ? wsum[w] : 0u;
+    const uint32_t excl = carry + woff + (x - v);
+    if (i < nblocks) row[i] = excl;
     __syncthreads();
-    uint32_t excl = carry + wsum[wid] + (x - v);
-    if (i < total) hist[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
+    if (threadIdx.x == 255) carry = excl + v;
     __syncthreads();
   }
+  if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
+}
+__global__ void __launch_bounds__(256)
+radix_scan_digits(uint32_t* __restrict__ digit_total) {
+  __shared__ uint32_t s[256];
+  s[threadIdx.x] = digit_total[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int d = 0; d < 256; ++d) { uint32_t c = s[d]; s[d] = run; run += c; }
+  }
+  __syncthreads();
+  digit_total[threadIdx.x] = s[threadIdx.x];
 }
 
 // stable scatter: warp w owns the contiguous slice [w*256, (w+1)*256) of the tile and walks
 // it 32 keys at a time, so (warp, step, lane) order == tile order.
 __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n, int shift,
-              int nblocks, const uint32_t* __restrict__ offs) {
+              int nblocks, const uint32_t* __restrict__ offs, const uint32_t* __restrict__ digit_base) {
   __shared__ uint32_t wcnt[RS_WARPS][256];     // per-warp running digit counts
   __shared__ uint32_t dbase[256];              // global offset of (digit, this block)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
-  dbase[threadIdx.x] = offs[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+  dbase[threadIdx.x] = digit_base[threadIdx.x] + offs[(int64_t)threadIdx.x * nblocks + blockIdx.x];
   __syncthreads();
   const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)wid * (RS_TILE / RS_WARPS);
   uint32_t key[RS_ITEMS];
@@ -177,7 +185,7 @@ size_t cfl_auc_workspace_bytes(int64_t n_pos, int64_t n_neg) {
   (void)n_pos;
   int64_t nb = (n_neg + RS_TILE - 1) / RS_TILE;
   if (nb < 1) nb = 1;
-  return align_up((size_t)(n_neg > 0 ? n_neg : 1) * 4, 256) * 2 + align_up((size_t)nb * 256 * 4, 256) + 1024;
+  return align_up((size_t)(n_neg > 0 ? n_neg : 1) * 4, 256) * 2 + align_up((size_t)nb * 256 * 4, 256) + 4096;
 }
 
 int cfl_auc(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg, int64_t* out4,
@@ -196,6 +204,7 @@ int cfl_auc(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg, in
   uint32_t* kb = W.take<uint32_t>(nalloc);
   int nb = (int)((n_neg + RS_TILE - 1) / RS_TILE);
   uint32_t* hist = W.take<uint32_t>((size_t)(nb > 0 ? nb : 1) * 256);
+  uint32_t* dtot = W.take<uint32_t>(256);
   if (n_neg > 0) {
     keys_from_scores<<<(unsigned)((n_neg + 255) / 256), 256, 0, cs>>>(neg, n_neg, ka);
     CFL_LAUNCH_CHECK();
@@ -203,9 +212,11 @@ int cfl_auc(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg, in
       int shift = pass * 8;
       radix_hist<<<nb, RS_THREADS, 0, cs>>>(ka, n_neg, shift, nb, hist);
       CFL_LAUNCH_CHECK();
-      radix_scan<<<1, 1024, 0, cs>>>(hist, (int64_t)nb * 256);
+      radix_scan_rows<<<256, 256, 0, cs>>>(hist, nb, dtot);
       CFL_LAUNCH_CHECK();
-      radix_scatter<<<nb, RS_THREADS, 0, cs>>>(ka, kb, n_neg, shift, nb, hist);
+      radix_scan_digits<<<1, 256, 0, cs>>>(dtot);
+      CFL_LAUNCH_CHECK();
+      radix_scatter<<<nb, RS_THREADS, 0, cs>>>(ka, kb, n_neg, shift, nb, hist, dtot);
       CFL_LAUNCH_CHECK();
       uint32_t* t = ka; ka = kb; kb = t;
     }
