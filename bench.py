@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q_}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q_}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -233,7 +233,8 @@ def run_ours(args):
             "metric": "query x candidate scores/sec (fused soft-min scoring + top-100)",
             "value": value, "unit": "scores/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core MMA, fp32 accumulate)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32", "dtype_note": "fp32 in/out; GEMMs as error-compensated 3xTF32 tcgen05 MMA with fp32 accumulation",
+            "data": "synthetic",
             "config": {"workload": WORKLOAD, "F": F, "K": K, "d": D, "catalog_per_gpu": N_PER_GPU,
                        "catalog_total": n_total, "queries_per_step": Q, "topk": TOPK,
                        "l2": "catalog 256 MB/GPU > 126 MB L2: streamed every step, no flush needed",
@@ -255,8 +256,9 @@ def run_ours(args):
 
 
 def launches_per_step(world):
-    # project (colnorm + GEMM) + prep_queries + [pack] + score + merge_rescore (+ merge for N>1)
-    return 5 + (1 if world > 1 else 0)
+    # colnorm, pack_weights, project_umma, prep_queries, pack_queries, score_umma x3 (passes A/B/C),
+    # sample_threshold x2, merge_rescore (+ topk_merge after the all-gather for N>1)
+    return 11 + (1 if world > 1 else 0)
 
 
 # ------------------------------------------------------------------------------------------
@@ -355,7 +357,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
