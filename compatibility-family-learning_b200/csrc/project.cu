@@ -115,6 +115,62 @@ project_fwd_simt(const float* __restrict__ x, int64_t B, int F, int64_t ldx,
   }
 }
 
+// Small batches (the reference trains at B = 100): one 128-row tile cannot fill the GPU, and its
+// F/8 K-steps would run serially on one SM.  Split the feature dimension over CTAs instead
+// (fp32 FFMA partial sums per slice), then reduce the slices in a fixed order with the epilogue.
+__global__ void __launch_bounds__(256)
+project_fwd_splitk(const float* __restrict__ x, int64_t B, int F, int64_t ldx,
+                   const float* __restrict__ V, int N, int64_t ldV, int fslice,
+                   float* __restrict__ part) {
+  float acc[4][4] = {};
+  int64_t m0 = (int64_t)blockIdx.y * TM;
+  int n0 = blockIdx.x * TN;
+  int64_t k0 = (int64_t)blockIdx.z * fslice;
+  int64_t k1 = k0 + fslice; if (k1 > F) k1 = F;
+  tile_mainloop<false>(x, ldx, V, ldV, B, N, k0, k1, m0, n0, acc);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float* P = part + (int64_t)blockIdx.z * B * N;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t b = m0 + ty * 4 + i;
+    if (b >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < N) P[b * N + n] = acc[i][j];
+    }
+  }
+}
+__global__ void project_fwd_splitk_final(const float* __restrict__ part, int slices, int64_t B, int N,
+                                         const float* __restrict__ scaler, const float* __restrict__ bias,
+                                         float in_scale, int act, float* __restrict__ y, int64_t ldy,
+                                         float* __restrict__ pre, float* __restrict__ z) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  int64_t b = i / N; int n = (int)(i % N);
+  float a = 0.0f;
+  for (int s = 0; s < slices; ++s) a += part[(int64_t)s * B * N + i];
+  float zz = a * in_scale;
+  float p = zz * (scaler ? scaler[n] : 1.0f) + (bias ? bias[n] : 0.0f);
+  if (z) z[b * ldy + n] = zz;
+  if (pre) pre[b * ldy + n] = p;
+  y[b * ldy + n] = apply_act(p, act);
+}
+
+static int splitk_slices(int64_t B, int F, int N, int* fslice) {
+  int64_t tiles = ((B + TM - 1) / TM) * ((N + TN - 1) / TN);
+  int sms = sm_count(); if (sms <= 0) sms = 148;
+  int64_t want = (2 * (int64_t)sms + tiles - 1) / tiles;     // ~2 CTAs per SM
+  int64_t maxs = (F + 63) / 64;                              // at least 64 features per slice
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  int fs = (int)((F + want - 1) / want);
+  fs = (fs + TK - 1) / TK * TK;
+  *fslice = fs;
+  return (int)((F + fs - 1) / fs);
+}
+static bool use_splitk(int64_t B) { return B <= 512; }
+
 // ---- backward ----------------------------------------------------------------------------
 __device__ __forceinline__ float dpre_of(const float* __restrict__ dy, int64_t lddy,
                                          const float* __restrict__ y, int64_t ldy, int act,
@@ -250,7 +306,10 @@ using namespace cfl;
 extern "C" {
 
 size_t cfl_project_fwd_workspace_bytes(int64_t B, int F, int N) {
-  return align_up((size_t)N * 2 * sizeof(float), 256) + project_fwd_umma_workspace(B, F, N) + 512;
+  size_t sk = 0;
+  if (use_splitk(B)) { int fs; sk = (size_t)splitk_slices(B, F, N, &fs) * (size_t)B * N * sizeof(float) + 256; }
+  size_t um = project_fwd_umma_workspace(B, F, N);
+  return align_up((size_t)N * 2 * sizeof(float), 256) + (sk > um ? sk : um) + 512;
 }
 
 int cfl_project_fwd(const float* x, int64_t B, int F, int64_t ldx, const float* V, int N,
@@ -272,6 +331,20 @@ int cfl_project_fwd(const float* x, int64_t B, int F, int64_t ldx, const float* 
     scaler = W.take<float>(N);
     colnorm_kernel<<<(N + 31) / 32, dim3(32, 8), 0, cs>>>(V, F, N, ldV, g, scaler, nullptr);
     CFL_LAUNCH_CHECK();
+  }
+  if (use_splitk(B)) {
+    int fs;
+    const int slices = splitk_slices(B, F, N, &fs);
+    W.off = align_up(W.off, 256);
+    float* part = (float*)(W.base + W.off);
+    dim3 grid((N + TN - 1) / TN, (unsigned)((B + TM - 1) / TM), slices);
+    project_fwd_splitk<<<grid, 256, 0, cs>>>(x, B, F, ldx, V, N, ldV, fs, part);
+    CFL_LAUNCH_CHECK();
+    const int64_t total = B * N;
+    project_fwd_splitk_final<<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(part, slices, B, N, scaler, bias,
+                                                                         in_scale, act, y, ldy, pre, z);
+    CFL_LAUNCH_CHECK();
+    return CFL_OK;
   }
   if (project_fwd_umma_supported(x, B, F, ldx, N)) {
     W.off = align_up(W.off, 256);
