@@ -260,6 +260,7 @@ class PairModel(ModelBase):
         if val_batches is not None:
             out["val_s_accuracy"] = self.val_accuracy(*val_batches)
             self.val_s_accuracy = out["val_s_accuracy"]
+            self._ema_one("val_s_accuracy", out["val_s_accuracy"])
         return out
 
     def val_accuracy(self, src_pos, dst_pos, src_neg, dst_neg):
@@ -299,13 +300,84 @@ class PairModel(ModelBase):
                     tot = tot + 0.5 * self.reg_const * (h.b.detach() ** 2).sum()
         return tot
 
+    def _ema_one(self, k, value):
+        b = self._ema.get(k, 0.0) * self.ema_decay + (1 - self.ema_decay) * value
+        self._ema[k] = b
+        setattr(self, k + "_avg", b / (1 - self.ema_decay ** self._step))
+
     def _update_ema(self, out):
         """tf.train.ExponentialMovingAverage(0.99) over tensors (zero-debiased), cfl.py:528,903-949."""
-        t = self._step
         for k in ("s_accuracy", "s_margin_adapt", "s_pos_dists_adapt", "s_neg_dists_adapt"):
-            b = self._ema.get(k, 0.0) * self.ema_decay + (1 - self.ema_decay) * out[k]
-            self._ema[k] = b
-            setattr(self, k + "_avg", b / (1 - self.ema_decay ** t))
+            self._ema_one(k, out[k])
+
+    # ------------------------------------------------------------------------------------------
+    def train(self, sess, data, start_iter, epochs, post_epochs, best_dir, best_acc_dir, checkpoint_dir,
+              epoch_callback=None, post_epoch_callback=None, save_epochs=1, eval_epochs=1, save_iters=None,
+              disable_eval=False, saver=None, best_saver=None, best_acc_saver=None, writer=None, check=None):
+        """The epoch loop of cfl/models/cfl.py:1349-1511 for the distance model (post epochs belong to
+        the GAN half and are always 0 here, as in the reference when ``gan`` is off): per step one
+        labelled train batch + one val batch; per ``eval_epochs`` a full ``dist_eval`` on val, and on a
+        new best val AUC / best val accuracy a ``best_model`` / ``best_acc_model`` checkpoint plus the
+        ``best_accuracy`` / ``best_accuracy_by_th`` stats files (written exactly as the reference
+        writes them, including that both files carry the best-AUC triple)."""
+        import logging
+        import os
+        from ..utils import dist_eval, load_best_stats
+        log = logging.getLogger(__name__)
+        nb_train = max(data.train.num_examples_labeled_pos, data.train.num_examples_labeled_neg)
+        log.warning("%d pairs / %d images", nb_train, data.train.num_examples)
+        nb_batch = nb_train // self.batch_size
+        log.warning("%d batches per epoch", nb_batch)
+        if nb_batch == 0:
+            raise ValueError("batch_size %d exceeds the %d labelled training pairs" % (self.batch_size, nb_train))
+        best_auc_path = os.path.join(best_dir, "best_accuracy")
+        best_acc_path = os.path.join(best_acc_dir, "best_accuracy_by_th")
+        stats, stats_acc = load_best_stats(best_auc_path), load_best_stats(best_acc_path)
+        if sess is not None and getattr(sess, "model", None) is None:
+            sess.model = self
+        start_epoch = start_iter // nb_batch
+        log.warning("start epoch %d of %d", start_epoch, epochs)
+        train_avg = val_avg = 0.0
+        for e in range(start_epoch, epochs):
+            first = start_iter % nb_batch if e == start_epoch else 0
+            for i in range(first, nb_batch):
+                out = self.train_step(*data.train.next_batch(self.batch_size),
+                                      val_batches=data.val.next_batch(self.batch_size))
+                train_avg, val_avg = self.s_accuracy_avg, self.val_s_accuracy_avg
+                if writer is not None:
+                    writer.add_summary(out, nb_batch * e + i)
+                if save_iters and i > 0 and i % save_iters == 0 and saver is not None:
+                    saver.save(sess, os.path.join(checkpoint_dir, "model"), global_step=nb_batch * e + i)
+            if e % eval_epochs == 0 and not disable_eval:
+                val_stats = dist_eval(sess, self, self.batch_size, data.val)
+                if val_stats.auc > stats.best_auc or val_stats.accuracy > stats_acc.best_accuracy:
+                    test_stats = dist_eval(sess, self, self.batch_size, data.test)
+                    log.warning("epoch %d: current error = train: %f val: %f test: %f / auc = val: %f test: %f", e,
+                                1. - train_avg, 1. - val_stats.accuracy, 1. - test_stats.accuracy, val_stats.auc,
+                                test_stats.auc)
+                    if val_stats.auc > stats.best_auc:
+                        stats.best_accuracy, stats.best_auc, stats.best_epoch = val_stats.accuracy, val_stats.auc, e
+                        if best_saver is not None:
+                            best_saver.save(sess, os.path.join(best_dir, "model"), global_step=stats.best_epoch)
+                        with open(best_auc_path, "w") as outfile:
+                            outfile.write("{}\t{}\t{}".format(stats.best_epoch, stats.best_accuracy, stats.best_auc))
+                    if val_stats.accuracy > stats_acc.best_accuracy:
+                        stats_acc.best_accuracy, stats_acc.best_auc, stats_acc.best_epoch = \
+                            val_stats.accuracy, val_stats.auc, e
+                        if best_acc_saver is not None:
+                            best_acc_saver.save(sess, os.path.join(best_acc_dir, "model"),
+                                                global_step=stats.best_epoch if stats.best_epoch is not None else e)
+                        with open(best_acc_path, "w") as outfile:
+                            outfile.write("{}\t{}\t{}".format(stats.best_epoch, stats.best_accuracy, stats.best_auc))
+                else:
+                    log.warning("epoch %d: current error = train: %f val: %f / auc = val: %f", e, 1. - train_avg,
+                                1. - val_stats.accuracy, val_stats.auc)
+            else:
+                log.warning("epoch %d: avg error = train: %f val: %f", e, 1. - train_avg, 1. - val_avg)
+            if epoch_callback is not None:
+                epoch_callback(e)
+            if e % save_epochs == 0 and saver is not None:
+                saver.save(sess, os.path.join(checkpoint_dir, "model"), global_step=(e + 1) * nb_batch)
 
     # ------------------------------------------------------------------------------------------
     def state_dict(self):

@@ -176,6 +176,11 @@ class CFL(PairModel):
         self.s_pos_dists, self.s_neg_dists = dp.detach(), dn.detach()
         for k, v_ in out.items():
             setattr(self, k, v_)
+        self._ema_one("s_accuracy", acc)
+        if val_batches is not None:
+            out["val_s_accuracy"] = self.val_accuracy(*val_batches)
+            self.val_s_accuracy = out["val_s_accuracy"]
+            self._ema_one("val_s_accuracy", out["val_s_accuracy"])
         return out
 
 

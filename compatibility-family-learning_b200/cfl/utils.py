@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import argparse
 import os
+import re
 from argparse import Namespace
 
 import torch
@@ -25,11 +26,105 @@ def load_best_stats(path):
         with open(path) as infile:
             tokens = infile.read().split("\t")
             best_epoch, best_accuracy = tokens[:2]
-            stats.best_epoch = int(best_epoch)
+            stats.best_epoch = int(best_epoch) if best_epoch.strip() != "None" else None
             stats.best_accuracy = float(best_accuracy)
             if len(tokens) >= 3:
                 stats.best_auc = float(tokens[2])
     return stats
+
+
+class Session(object):
+    """Stand-in for ``tf.Session``: there is no graph, so the only thing a "session" carries is the
+    model whose variables a Saver reads and writes."""
+
+    def __init__(self, model=None):
+        self.model = model
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def get_checkpoint_state(checkpoint_dir):
+    """``tf.train.get_checkpoint_state``: parses the text-proto ``checkpoint`` file the Saver keeps."""
+    path = os.path.join(checkpoint_dir, "checkpoint")
+    if not os.path.exists(path):
+        return None
+    latest, every = None, []
+    with open(path) as infile:
+        for line in infile:
+            m = re.match(r'\s*(model_checkpoint_path|all_model_checkpoint_paths):\s*"(.*)"', line)
+            if not m:
+                continue
+            full = m.group(2) if os.path.isabs(m.group(2)) else os.path.join(checkpoint_dir, m.group(2))
+            if m.group(1) == "model_checkpoint_path":
+                latest = full
+            else:
+                every.append(full)
+    return Namespace(model_checkpoint_path=latest, all_model_checkpoint_paths=every) if latest else None
+
+
+class Saver(object):
+    """``tf.train.Saver`` for this package: ``save(sess, prefix, global_step)`` writes
+    ``{prefix}-{step}.pt`` (variables under their reference names + Adam slots, see
+    ``PairModel.state_dict``) and maintains the ``checkpoint`` index file with the same keys TF uses,
+    keeping the newest ``max_to_keep`` files."""
+
+    SUFFIX = ".pt"
+
+    def __init__(self, max_to_keep=5):
+        self.max_to_keep = max_to_keep
+        self._kept = []
+
+    def save(self, sess, save_path, global_step=None):
+        prefix = save_path if global_step is None else "{}-{}".format(save_path, global_step)
+        d = os.path.dirname(prefix)
+        os.makedirs(d, exist_ok=True)
+        torch.save({k: v.cpu() for k, v in sess.model.state_dict().items()}, prefix + self.SUFFIX)
+        if prefix in self._kept:
+            self._kept.remove(prefix)
+        self._kept.append(prefix)
+        while self.max_to_keep and len(self._kept) > self.max_to_keep:
+            old = self._kept.pop(0)
+            if os.path.exists(old + self.SUFFIX):
+                os.remove(old + self.SUFFIX)
+        with open(os.path.join(d, "checkpoint"), "w") as out:
+            out.write('model_checkpoint_path: "{}"\n'.format(os.path.basename(prefix)))
+            for k in self._kept:
+                out.write('all_model_checkpoint_paths: "{}"\n'.format(os.path.basename(k)))
+        return prefix
+
+    def restore(self, sess, save_path, trainable_only=False):
+        sd = torch.load(save_path + self.SUFFIX, map_location="cpu")
+        if trainable_only:          # assign_from_checkpoint_fn(trainable_variables(), ignore_missing_vars=True)
+            sd = {k: v for k, v in sd.items() if not (k.endswith("/Adam") or k.endswith("/Adam_1") or k == "__step__")}
+        sess.model.load_state_dict(sd)
+
+
+def _step_of(checkpoint_path):
+    return int(re.search(r"(\d+)", os.path.basename(checkpoint_path).split("-")[-1]).group(1))
+
+
+def load_model(sess, checkpoint_dir, load_pre_weights=None):
+    """cfl/utils.py:465-497: restore the newest checkpoint of ``checkpoint_dir`` and return
+    ``(saver, start_step)`` with start_step = its global step + 1; with ``load_pre_weights`` and no
+    own checkpoint, take the trainable variables of ``<load_pre_weights>/best_model``."""
+    saver = Saver()
+    ckpt = get_checkpoint_state(checkpoint_dir)
+    if ckpt and ckpt.model_checkpoint_path:
+        saver.restore(sess, ckpt.model_checkpoint_path)
+        return saver, _step_of(ckpt.model_checkpoint_path) + 1
+    start_step = 0
+    if load_pre_weights:
+        best_model = os.path.join(load_pre_weights, "best_model")
+        ckpt, ckpt_all = get_checkpoint_state(best_model), get_checkpoint_state(load_pre_weights)
+        if not (ckpt and ckpt_all):
+            raise Exception("must have best model! %s" % best_model)
+        saver.restore(sess, ckpt.model_checkpoint_path, trainable_only=True)
+        start_step = _step_of(ckpt_all.model_checkpoint_path) + 1
+    return saver, start_step
 
 
 class IncrementalAverage(object):
@@ -134,8 +229,8 @@ def dist_parser(data_name="mnist", data_root="parsed_data", checkpoint_root="che
     p.add_argument("--data-type", default=data_type, choices=["sigmoid", "tanh", "relu", "linear"])
     p.add_argument("--data-is-image", action="store_true")
     p.add_argument("--data-is-double", action="store_true")
-    p.add_argument("--data-switch", action="store_true")
     p.add_argument("--directed", action="store_true")
+    p.add_argument("--data-directed", action="store_true")
     p.add_argument("--model-type", default=model_type, choices=["conv", "linear"])
     p.add_argument("--dist-type", default=dist_type, choices=["pcd", "monomer", "siamese"])
     p.add_argument("--act-type", default=act_type, choices=[None, "linear", "tanh", "sigmoid", "relu"])
