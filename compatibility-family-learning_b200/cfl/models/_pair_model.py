@@ -22,6 +22,11 @@ from .base import ModelBase
 _ACT = {None: None, "linear": None, "tanh": "tanh", "sigmoid": "sigmoid", "relu": "relu"}
 
 
+# tf.maximum(raw_threshold, 1e-6) compares in float32: theta is INITIALISED at float32(1e-6), which is
+# below the double 1e-6, so the floor must be the float32 constant for the tie to pass the gradient
+_THETA_FLOOR32 = float(torch.tensor(1e-6, dtype=torch.float32))
+
+
 class Head:
     """One FC head: weight-normalised (g, V, biases) or plain (weights, biases)."""
 
@@ -227,7 +232,8 @@ class PairModel(ModelBase):
         stp, stn, dthp, dthn = host[0:8], host[8:16], host[16], host[17]
         out = self._losses_from_stats(stp, stn, Bp, Bn)
         # theta gradient: -(sum CE part) with the tf.maximum tie rule (blocks.py:20-21)
-        th_grad = (dthp + dthn) if float(self.raw_threshold.detach()) >= 1e-6 else 0.0
+        th_live = float(self.raw_threshold.detach()) >= _THETA_FLOOR32
+        th_grad = (dthp + dthn) if th_live else 0.0
         if not self.use_threshold:
             # theta is trained by its own Adam on s_thres_loss (cfl.py:1076-1079): recompute the CE sums
             pw = self.pos_weight if self.pos_weight else 1.0
@@ -235,8 +241,21 @@ class PairModel(ModelBase):
                                             c_ce=pw / Bp, want_dtheta=True)
             _, _, _, b_ = nat.pair_loss_bwd(sn.mode, sn.a, sn.P3, w=sn.w, theta=self.raw_threshold, label=0,
                                             c_ce=1.0 / Bn, want_dtheta=True)
-            th_grad = float(a_ + b_) if float(self.raw_threshold.detach()) >= 1e-6 else 0.0
+            th_grad = float(a_ + b_) if th_live else 0.0
         self._grads[id(self.raw_threshold)].fill_(th_grad)
+        # heads the loss never reads (directed models: e.g. DistEncoderSrc/outputs under pcd): TF gives
+        # their g no gradient (Adam skips it) and their V / biases only the regulariser's c*w
+        idle = set()
+        for enc in ([self.enc_src] if not self.directed else [self.enc_src, self.enc_dst]):
+            for h in enc.heads():
+                if not first[id(h.V)]:
+                    continue
+                for p_ in h.params():
+                    if self.reg_const and p_ is not h.g:
+                        self._grads[id(p_)].copy_(p_.detach()).mul_(self.reg_const)
+                    else:
+                        self._grads[id(p_)].zero_()
+                        idle.add(id(p_))
         if world > 1:
             flat = torch.cat([self._grads[id(p)].reshape(-1) for p in self._params + self.th_vars])
             torch.distributed.all_reduce(flat)
@@ -247,6 +266,8 @@ class PairModel(ModelBase):
                 o += n
         self._step += 1
         for p in self._params + self.th_vars:
+            if id(p) in idle:
+                continue
             m, v = self._adam[id(p)]
             nat.adam_step(p.data.view(-1), self._grads[id(p)].view(-1), m.view(-1), v.view(-1), self._step,
                           self.lr, self.beta1, self.beta2, 1e-8, 1.0 / world)

@@ -266,3 +266,84 @@ def test_conv_model_trains_on_synthetic_mnist_pairs():
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
     assert "CFL/DistEncoder/conv1/Conv/V" in vs.all_variables()
     assert model.predict(torch.as_tensor(x[0]).cuda(), torch.as_tensor(x[1]).cuda()).shape == (100, 1)
+
+
+# ---- fixtures produced by executing the reference's own graph code (tests/golden/ref_*.npz) ---------
+import ast as _ast
+import glob as _glob
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_REF_CFL = sorted(_glob.glob(os.path.join(_GOLDEN, "ref_cfl_*.npz")))
+_REF_DIST = sorted(_glob.glob(os.path.join(_GOLDEN, "ref_dist_*.npz")))
+
+
+def _check_against_reference_fixture(model, z, prefix, loss_keys):
+    from cfl import variables as vs
+    named = vs.get_collection(model.name)
+    sd = {k: torch.tensor(z["var:" + k], dtype=torch.float32) for k in named}
+    model.load_state_dict(sd)
+    before = {k: v.detach().clone() for k, v in named.items()}
+    c = lambda a: torch.tensor(a, dtype=torch.float32).cuda()
+    batch = [c(z["in_" + n]) for n in ("pos_source", "pos_target", "neg_source", "neg_target")]
+    val = [c(z["in_val_" + n]) for n in ("pos_source", "pos_target", "neg_source", "neg_target")]
+    # scores of the evaluation node, before the step moves the weights
+    for lab, b in (("pos", batch[:2]), ("neg", batch[2:])):
+        np.testing.assert_allclose(model.predict(*b).reshape(-1).cpu().numpy(), z["out_s_%s_predicts" % lab][:, 0],
+                                   rtol=2e-4, atol=2e-5)
+    out = model.train_step(*batch, val_batches=None)
+    np.testing.assert_allclose(model.s_pos_dists.reshape(-1).cpu().numpy(), z["out_s_pos_dists"][:, 0], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(model.s_neg_dists.reshape(-1).cpu().numpy(), z["out_s_neg_dists"][:, 0], rtol=2e-4, atol=1e-6)
+    for mine, ref in loss_keys:
+        np.testing.assert_allclose(out[mine], float(z["out_" + ref]), rtol=2e-4, atol=1e-6, err_msg=ref)
+    ref_grads = {k.split(":", 1)[1]: z[k] for k in z.files if k.startswith("grad_")}
+    assert set(ref_grads) == set(named)
+    for k, g in ref_grads.items():
+        mine = model._grads[id(named[k])].cpu().numpy()
+        scale = max(np.abs(g).max(), 1e-12)
+        np.testing.assert_allclose(mine, g, rtol=0, atol=3e-4 * scale + 1e-9, err_msg=k)
+        if not np.any(g):      # heads the loss never reads must not move (TF skips None gradients)
+            assert torch.equal(named[k].detach(), before[k]), k
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", _REF_CFL, ids=[os.path.basename(p)[8:-4] for p in _REF_CFL])
+def test_cfl_model_matches_reference_graph_fixture(path):
+    from cfl import variables as vs
+    from cfl.models.cfl import CFL
+    from cfl.ops import dist_normalizer
+    z = np.load(path)
+    cfg = _ast.literal_eval(str(z["cfg"]))
+    vs.reset_default_graph()
+    norms = dist_normalizer(input_shape=(cfg["F"],), ae_shape=None, data_scale=None, data_mean=None,
+                            data_norm=cfg["data_norm"], latent_norm=None, data_type="linear")
+    m = CFL(input_shape=(cfg["F"],), batch_size=cfg["B"], latent_size=cfg["d"], num_components=cfg["K"],
+            model_type="linear", dist_type=cfg["dist_type"], act_type=cfg["act_type"], data_type="linear",
+            use_threshold=cfg["use_threshold"], pos_weight=cfg["pos_weight"], caffe_margin=cfg["caffe_margin"],
+            lambda_m=cfg["lambda_m"], reg_const=cfg["reg_const"], directed=cfg["directed"], data_normalizer=norms[0],
+            data_norm=cfg["data_norm"])
+    keys = [("s_p_loss_pos", "s_p_loss_pos"), ("s_p_loss_neg", "s_p_loss_neg"), ("s_thres_loss", "s_thres_loss"),
+            ("s_total_loss", "s_total_loss"), ("s_loss_reg", "s_loss_reg"), ("s_accuracy", "s_accuracy"),
+            ("s_margins", "s_margins"), ("s_pos_dists_adapt", "s_pos_dists_adapt"),
+            ("s_neg_dists_adapt", "s_neg_dists_adapt"), ("s_margin_adapt", "s_margin_adapt")]
+    if cfg["caffe_margin"] or cfg["lambda_m"]:
+        keys.append(("s_cd_loss", "s_cd_loss"))
+    _check_against_reference_fixture(m, z, "CFL", keys)
+    c = lambda a: torch.tensor(a, dtype=torch.float32).cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", _REF_DIST, ids=[os.path.basename(p)[9:-4] for p in _REF_DIST])
+def test_dist_model_matches_reference_graph_fixture(path):
+    from cfl import variables as vs
+    from cfl.models.dist import Dist
+    from cfl.ops import normalizer
+    z = np.load(path)
+    cfg = _ast.literal_eval(str(z["cfg"]))
+    vs.reset_default_graph()
+    m = Dist(input_shape=(cfg["F"],), latent_size=cfg["d"], num_components=cfg["K"], batch_size=cfg["B"], lr=1e-3,
+             beta1=0.9, beta2=0.999, normalize_value=cfg["normalize_value"],
+             data_normalizer=normalizer(cfg["normalize_value"], 0.0), reg_const=cfg["reg_const"])
+    _check_against_reference_fixture(m, z, "Dist", [("s_p_loss_pos", "s_p_loss_pos"), ("s_p_loss_neg", "s_p_loss_neg"),
+                                                    ("s_thres_loss", "thres_loss"), ("s_total_loss", "s_total_loss"),
+                                                    ("s_accuracy", "s_accuracy"), ("s_margins", "s_margins")])
