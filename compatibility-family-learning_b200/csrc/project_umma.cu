@@ -194,7 +194,7 @@ project_umma_kernel(PuArgs A) {
   const int my_tiles = (int)((A.tiles - first + stride - 1) / stride);
 
   if (warp == 12) {
-    if (lane == 0) {
+    if (elect_one()) {
       Step3Desc sd = make_step3((uint32_t)Npad, make_idesc_tf32(128, (uint32_t)Npad));
       sd.a_hi = make_smem_desc(0, PU_APLANE, 128u);
       sd.a_lo = make_smem_desc(2u * PU_APLANE, PU_APLANE, 128u);
@@ -225,7 +225,7 @@ project_umma_kernel(PuArgs A) {
       }
     }
   } else if (warp == 13) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < my_tiles; ++t) {
         for (int s = 0; s < spt; ++s) {

@@ -41,8 +41,12 @@ ScorePlan make_score_plan(int64_t Q, int K, int d, int64_t N, int k, bool umma_o
 // ---- query prep: centre, |p_k|^2, p_k.p_l --------------------------------------------------
 __global__ void prep_queries_kernel(const float* __restrict__ Pq, int64_t Q, int K, int d,
                                     int64_t ldq, const float* __restrict__ mu,
-                                    float* __restrict__ Pc, float* __restrict__ qpar) {
-  int64_t q = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+                                    float* __restrict__ Pc, float* __restrict__ qpar,
+                                    float* __restrict__ qplane) {
+  __shared__ float sD[4][8][8];
+  __shared__ float sN[4][8];
+  const int w = threadIdx.x / 32;
+  int64_t q = (int64_t)blockIdx.x * (blockDim.x / 32) + w;
   int lane = threadIdx.x & 31;
   if (q >= Q) return;
   const float* src = Pq + q * ldq;
@@ -68,8 +72,9 @@ __global__ void prep_queries_kernel(const float* __restrict__ Pq, int64_t Q, int
       dmax = fmaxf(dmax, dkl);
       if (k == l) pmax = fmaxf(pmax, acc);
       if (lane == 0) {
-        if (k == l) { qp[k] = CFL_LOG2E * acc; qp[o] = 0.5f * acc; }
+        if (k == l) { qp[k] = CFL_LOG2E * acc; qp[o] = 0.5f * acc; sN[w][k] = acc; }
         else qp[o + l - k] = acc;
+        sD[w][k][l] = dkl; sD[w][l][k] = dkl;
       }
     }
     o += K - k;
@@ -79,6 +84,59 @@ __global__ void prep_queries_kernel(const float* __restrict__ Pq, int64_t Q, int
     qp[K + qpar_tri(K)] = 0.5f * (1.0f - 1.0f / K) * dmax * 1.0001f + 1e-5f * pmax;
     for (int i = K + qpar_tri(K) + 1; i < qpar_stride(K); ++i) qp[i] = 0.0f;
   }
+  if (lane != 0 || qplane == nullptr) return;
+  // ---- plane bound: invert the (scaled) KKT matrix [D/dmax 1; 1^T 0] in fp64 ----
+  float* pl = qplane + q * (int64_t)qplane_stride(K);
+  for (int i = 0; i < qplane_stride(K); ++i) pl[i] = 0.0f;
+  if (K < 2) return;
+  const int ci = 2 * (K - 1) + qplane_tri(K);
+  const float NEG_INF = __int_as_float(0xff800000);
+  pl[ci] = NEG_INF;
+  if (!(dmax > 0.0f)) return;
+  const int n = K + 1;
+  double M[9][18];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double v = (i < K && j < K) ? (double)sD[w][i][j] / (double)dmax : ((i < K) != (j < K) ? 1.0 : 0.0);
+      M[i][j] = v;
+      M[i][n + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r) if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
+    if (fabs(M[piv][c]) < 1e-6) return;                       // prototypes affinely dependent
+    if (piv != c) for (int j = 0; j < 2 * n; ++j) { double t = M[c][j]; M[c][j] = M[piv][j]; M[piv][j] = t; }
+    const double inv = 1.0 / M[c][c];
+    for (int j = 0; j < 2 * n; ++j) M[c][j] *= inv;
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = M[r][c];
+      if (f != 0.0) for (int j = 0; j < 2 * n; ++j) M[r][j] -= f * M[c][j];
+    }
+  }
+  // inverse = M[:, n:]: A' (K x K), a' (last column), alpha' (corner); A = A'/dmax, alpha = alpha'*dmax
+  double amax = 0.0;
+  for (int i = 0; i < K; ++i) {
+    for (int j = 0; j < K; ++j) amax = fmax(amax, fabs(M[i][n + j]));
+    amax = fmax(amax, fabs(M[i][n + K]));
+  }
+  if (!(amax < 1.0e3)) return;                                // ill-conditioned: leave the bound off
+  const double n0 = (double)sN[w][0];
+  double nmax = 0.0;
+  for (int k = 0; k < K; ++k) nmax = fmax(nmax, (double)sN[w][k]);
+  for (int j = 1; j < K; ++j) {
+    pl[j - 1] = (float)(-0.5 * ((double)sN[w][j] - n0));
+    pl[K - 1 + j - 1] = (float)(-2.0 * M[j][n + K]);
+  }
+  int oo = 2 * (K - 1);
+  for (int i = 1; i < K; ++i) {
+    for (int j = i; j < K; ++j)
+      pl[oo + j - i] = (float)((i == j ? 2.0 : 4.0) * M[i][n + j] / (double)dmax);
+    oo += K - i;
+  }
+  const double alpha = M[K][n + K] * (double)dmax;
+  const double margin = (double)CFL_PLANE_REL * (nmax + fabs(0.5 * alpha) + (double)dmax);
+  pl[ci] = (float)(0.5 * alpha + n0 - margin);
 }
 
 // ---- CUDA-core scoring kernel ---------------------------------------------------------------
@@ -284,14 +342,35 @@ merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __res
 // satisfies dist <= tau[q].
 __global__ void __launch_bounds__(MRG_THREADS)
 sample_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ counts, int parts,
-                        int64_t Q, int kk, float* __restrict__ tau) {
+                        int64_t Q, int kk, float* __restrict__ tau, float* __restrict__ tau_opt = nullptr,
+                        int r_opt = 0) {
   __shared__ tkey_t s[TOPK_CAP];
   __shared__ int s_fill;
   __shared__ tkey_t s_thr;
   const int64_t q = blockIdx.x;
   const int fill = block_merge_topkk(keys, counts, parts, Q, q, kk, s, &s_fill, &s_thr);
-  if (threadIdx.x == 0)
-    tau[q] = (fill >= kk) ? ord2f((uint32_t)(s[kk - 1] >> 32)) : __int_as_float(0x7f800000);
+  if (threadIdx.x == 0) {
+    const float safe = (fill >= kk) ? ord2f((uint32_t)(s[kk - 1] >> 32)) : __int_as_float(0x7f800000);
+    tau[q] = safe;
+    // optimistic bound: the r_opt-th best of the 1/S sample.  About r_opt*S candidates of the whole
+    // range lie under it -- several times kk, but not guaranteed: verify_counts_kernel checks.
+    if (tau_opt) tau_opt[q] = (r_opt >= 1 && r_opt < kk && fill >= kk) ? ord2f((uint32_t)(s[r_opt - 1] >> 32)) : safe;
+  }
+}
+
+// After the filter pass under the optimistic thresholds: a query whose parts hold fewer than kk keys
+// in total may have lost members of its top-kk; it is redone under the safe threshold.  (A part's
+// count is either the number of rows it pushed or, after a compaction, still >= kk.)
+__global__ void verify_counts_kernel(const int* __restrict__ counts, int parts, int64_t Q, int kk, int qt,
+                                     const float* __restrict__ tau, const float* __restrict__ tau_opt,
+                                     float* __restrict__ thr_redo, int* __restrict__ redo_tile) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  long long tot = 0;
+  for (int p = 0; p < parts; ++p) tot += counts[(int64_t)p * Q + q];
+  const bool redo = tot < kk && tau_opt[q] < tau[q];
+  thr_redo[q] = redo ? tau[q] : __int_as_float(0xff800000);
+  if (redo) redo_tile[q / qt] = 1;
 }
 
 // ---- cross-rank merge: rank-based merge of R sorted lists --------------------------------
@@ -334,12 +413,13 @@ static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePla
                               size_t* o_cimg) {
   size_t off = 0;
   *o_pc = off;   off = align_up(off + (size_t)Q * K * d * 4, 256);
-  *o_qpar = off; off = align_up(off + (size_t)Q * qpar_stride(K) * 4, 256);
+  *o_qpar = off; off = align_up(off + (size_t)Q * (qpar_stride(K) + qplane_stride(K)) * 4, 256);
   *o_qimg = off; off = align_up(off + (p.impl ? score_umma_qimg_bytes(p, K) : 0), 1024);
   *o_keys = off; off = align_up(off + (size_t)p.parts * Q * TOPK_STRIDE * sizeof(tkey_t), 256);
   *o_cnt = off;  off = align_up(off + (size_t)p.parts * Q * sizeof(int), 1024);
   *o_cimg = off; off = align_up(off + ((p.impl && own_image) ? catalog_image_bytes(N, d) : 0), 1024);
-  off = align_up(off + (size_t)Q * sizeof(float), 256);      // tau[Q] lives right after (see o_tau)
+  // tau[Q], tau_opt[Q], thr_redo[Q], redo flags per query tile: live right after (see `tau` below)
+  off = align_up(off + (size_t)(3 * Q + p.nqt + 4) * sizeof(float), 256);
   return off + 1024;
 }
 
@@ -387,15 +467,20 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   ScoreArgs a;
   a.mode = mode; a.K = K; a.d = d; a.Q = Q; a.N = N; a.lde = lde; a.E = E; a.mu = mu;
   a.Pc = (float*)(base + o_pc); a.qpar = (float*)(base + o_qpar); a.qimg = base + o_qimg;
+  a.qplane = a.qpar + (size_t)Q * qpar_stride(K);
   a.keys = (tkey_t*)(base + o_keys); a.counts = (int*)(base + o_cnt); a.dist_out = dist_out;
   a.cimg = nullptr; a.e2 = nullptr;
   a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
+  a.dbg = nullptr; a.redo_tile = nullptr;
+  static unsigned long long* dbg_dev = nullptr;
+  const bool dbg_on = getenv("CFL_SCORE_DEBUG") != nullptr;
+  if (dbg_on && !dbg_dev) CFL_CUDA(cudaMalloc(&dbg_dev, 4 * sizeof(unsigned long long)));
   a.plan = plan;
   if (N == 0) {
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
   } else {
     prep_queries_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, cs>>>(Pq, Q, K, d, ldq, mu,
-                                                                (float*)a.Pc, (float*)a.qpar);
+                                                                (float*)a.Pc, (float*)a.qpar, (float*)a.qplane);
     CFL_LAUNCH_CHECK();
     if (plan.impl == 1) {
       if (!image) {
@@ -443,17 +528,46 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
           st = score_umma_launch(a, cs);
         }
         if (st != CFL_OK) return st;
-        sample_threshold_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau);
+        // Final pass: filter under an OPTIMISTIC threshold (r_opt-th best of the sample: about 4*kk
+        // rows of the whole range pass instead of sstride*kk), which lets the affine-hull bound
+        // reject almost every (row, query) before the soft-min.  The key counts then prove, per
+        // query, that at least kk rows passed; the rare query that fails is redone under the safe
+        // bound by a second launch whose CTAs exit at once when their query tile has nothing to redo.
+        float* tau_opt = tau + Q;
+        float* thr_redo = tau + 2 * Q;
+        int* redo_tile = (int*)(tau + 3 * Q);
+        int r_opt = (int)((4 * (int64_t)plan.kk + sstride - 1) / sstride);
+        if (getenv("CFL_SCORE_NO_OPTIMISTIC")) r_opt = 0;
+        sample_threshold_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau,
+                                                                     tau_opt, r_opt);
         CFL_LAUNCH_CHECK();
-        a.phase = 2; a.tile_stride = 1; a.thr_init = tau;
+        CFL_CUDA(cudaMemsetAsync(redo_tile, 0, (size_t)plan.nqt * sizeof(int), cs));
+        a.phase = 2; a.tile_stride = 1; a.thr_init = tau_opt;
         timer_record(0, cs);                 // bench.py times the dominant launch: the full filter pass
+        if (dbg_on) { CFL_CUDA(cudaMemsetAsync(dbg_dev, 0, 32, cs)); a.dbg = dbg_dev; }
         st = score_umma_launch(a, cs);
+        timer_record(1, cs);
+        if (st != CFL_OK) return st;
+        a.dbg = nullptr;
+        verify_counts_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, cs>>>(a.counts, plan.parts, Q, plan.kk, plan.qt,
+                                                                         tau, tau_opt, thr_redo, redo_tile);
+        CFL_LAUNCH_CHECK();
+        a.thr_init = thr_redo; a.redo_tile = redo_tile;
+        st = score_umma_launch(a, cs);
+        a.redo_tile = nullptr;
       } else {
         a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
         st = score_umma_launch(a, cs);
       }
-      timer_record(1, cs);
+      if (!two_pass) timer_record(1, cs);
       if (st != CFL_OK) return st;
+      if (dbg_on) {
+        unsigned long long h[4];
+        CFL_CUDA(cudaMemcpyAsync(h, dbg_dev, 32, cudaMemcpyDeviceToHost, cs));
+        CFL_CUDA(cudaStreamSynchronize(cs));
+        fprintf(stderr, "[cfl score] filter pass groups: bound tested %llu, skipped %llu, selective %llu, full soft-min %llu\n",
+                h[0], h[1], h[2], h[3]);
+      }
     } else {
       timer_record(0, cs);
       switch (K) {

@@ -25,6 +25,7 @@ struct ScoreArgs {
   const float* mu;       // centring vector or NULL
   const float* Pc;       // centred query prototypes [Q,K,d] (dense)
   const float* qpar;     // per query: p2[K] then pp[K*K]
+  const float* qplane;   // per query: plane-bound block (qplane_stride floats)
   const void* qimg;      // tcgen05 B-operand image per query tile (score_umma.cu)
   const void* cimg;      // tcgen05 A-operand image of the catalog (cfl_catalog_pack)
   const float* e2;       // |e - mu|^2 per catalog row, padded to whole tiles (part of the image)
@@ -36,6 +37,8 @@ struct ScoreArgs {
   // phase 2 = full pass filtering against the fixed per-query thresholds thr_init (dist <= thr).
   int phase, tile_stride;
   const float* thr_init; // [Q], phase 2
+  const int* redo_tile;  // phase 2 redo launch: per query tile, 1 = some query must be redone (else the CTA exits)
+  unsigned long long* dbg; // optional counters {groups seen, skipped, selective, full} (CFL_SCORE_DEBUG)
   ScorePlan plan;
 };
 
@@ -46,6 +49,22 @@ struct ScoreArgs {
 //                cq = (1-1/K)/2 * max_kl |p_k-p_l|^2, padded for fp32 rounding
 __host__ __device__ constexpr int qpar_tri(int K) { return K * (K + 1) / 2; }
 __host__ __device__ constexpr int qpar_stride(int K) { return (K + qpar_tri(K) + 1 + 3) / 4 * 4; }
+
+// Plane-bound block per query (K >= 2), used by the tensor-core kernel to skip the soft-min:
+// dist = |e - sum_k s_k p_k|^2 with s on the plane sum(s) = 1, so dist >= the squared distance from
+// e to the AFFINE HULL of the prototypes, which is a quadratic in the Gram values.  With
+// n_k = |p_k|^2, D_kl = |p_k - p_l|^2, [A a; a^T alpha] = inverse of the KKT matrix [D 1; 1^T 0],
+// w_j = (g_j - g_0) - (n_j - n_0)/2 for j = 1..K-1:
+//   LB = |e|^2 - 2 g_0 + c0 + sum_i w_i (bm2_i + sum_{j>=i} M4_ij w_j)
+//   [0,K-1)          dnh_j = -(n_j - n_0)/2
+//   [K-1,2K-2)       bm2_j = -2 a_j
+//   [2K-2,2K-2+T')   M4 upper triangle (i <= j), row-major: 2 A_ii on the diagonal, 4 A_ij off it
+//   [2K-2+T']        c0 = alpha/2 + n_0 - margin   (-inf: bound unavailable, prototypes degenerate)
+__host__ __device__ constexpr int qplane_tri(int K) { return (K - 1) * K / 2; }
+__host__ __device__ constexpr int qplane_stride(int K) {
+  return K < 2 ? 4 : (2 * (K - 1) + qplane_tri(K) + 1 + 3) / 4 * 4;
+}
+constexpr float CFL_PLANE_REL = 2.0e-4f;     // relative safety margin of the bound (fp32 / 3xTF32 rounding)
 
 ScorePlan make_score_plan(int64_t Q, int K, int d, int64_t N, int k, bool umma_ok);
 bool score_umma_supported(int K, int d);
@@ -186,6 +205,40 @@ __device__ __forceinline__ void softmin_pair(const float (&gA)[K], const float (
   // dist = e2 - 2 inv (t1 - inv t2)
   const f2_t v = fma2(ninv, t2, t1);
   upk2(fma2(add2(ninv, ninv), v, e2p), dA, dB);
+}
+
+// Same as softmin_from_gram, reading the pair-interleaved shared-memory block of the tensor-core
+// kernel (element j of this query at qb[2*j], first K entries negated).
+template <int K>
+__device__ __forceinline__ float softmin_from_gram_il(const float (&g)[K], float e2,
+                                                      const float* __restrict__ qb) {
+  constexpr int NP = K + K * (K + 1) / 2;
+  float qp[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) qp[j] = (j < K) ? -qb[2 * j] : qb[2 * j];
+  return softmin_from_gram<K>(g, e2, qp);
+}
+
+// Affine-hull lower bound of two queries (packed), pl2 = pair-interleaved plane block.
+template <int K>
+__device__ __forceinline__ void plane_bound_pair(const float (&gA)[K], const float (&gB)[K], f2_t e2sp,
+                                                 const f2_t* __restrict__ pl2, float& lA, float& lB) {
+  const f2_t M1 = pk2(-1.0f, -1.0f), M2 = pk2(-2.0f, -2.0f);
+  const f2_t g0 = pk2(gA[0], gB[0]);
+  f2_t w[K - 1];
+#pragma unroll
+  for (int j = 1; j < K; ++j) w[j - 1] = fma2(g0, M1, add2(pk2(gA[j], gB[j]), pl2[j - 1]));
+  f2_t acc = fma2(g0, M2, add2(pl2[2 * (K - 1) + qplane_tri(K)], e2sp));
+  int o = 2 * (K - 1);
+#pragma unroll
+  for (int i = 0; i < K - 1; ++i) {
+    f2_t t = fma2(pl2[o], w[i], pl2[K - 1 + i]);
+#pragma unroll
+    for (int j = i + 1; j < K - 1; ++j) t = fma2(pl2[o + j - i], w[j], t);
+    o += K - 1 - i;
+    acc = fma2(w[i], t, acc);
+  }
+  upk2(acc, lA, lB);
 }
 #endif
 

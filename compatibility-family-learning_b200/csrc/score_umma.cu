@@ -109,7 +109,7 @@ int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const flo
 }
 
 struct SuLayout {
-  uint32_t b_img, a_ring, scratch, qpar, thr, cnt, need, bars, tmem_slot, total;
+  uint32_t b_img, a_ring, scratch, qpar, qpl, thr, cnt, need, bars, tmem_slot, total;
 };
 __host__ __device__ inline SuLayout su_layout(int K, int qt, int dpad) {
   SuLayout L;
@@ -118,6 +118,7 @@ __host__ __device__ inline SuLayout su_layout(int K, int qt, int dpad) {
   L.a_ring = off;  off += SU_NSTAGE * 2u * SU_ASTAGE;
   L.scratch = off; off += TOPK_STRIDE * 8u;
   L.qpar = off;    off += (uint32_t)qt * (uint32_t)qpar_stride(K) * 4u;  off = (off + 15u) & ~15u;
+  L.qpl = off;     off += (uint32_t)qt * (uint32_t)qplane_stride(K) * 4u; off = (off + 15u) & ~15u;
   L.thr = off;     off += (uint32_t)qt * 4u;
   L.cnt = off;     off += (uint32_t)qt * 4u;
   L.need = off;    off += 16u;                                        off = (off + 15u) & ~15u;
@@ -183,6 +184,7 @@ score_umma_kernel(ScoreArgs A) {
   unsigned char* a_ring = smem + L.a_ring;
   tkey_t* scratch = (tkey_t*)(smem + L.scratch);
   float* qpar = (float*)(smem + L.qpar);
+  float* qpl = (float*)(smem + L.qpl);
   float* thr = (float*)(smem + L.thr);
   int* cnt = (int*)(smem + L.cnt);
   int* need = (int*)(smem + L.need);
@@ -195,6 +197,8 @@ score_umma_kernel(ScoreArgs A) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int part = blockIdx.x, qtile = blockIdx.y;
+  const bool redo = A.redo_tile != nullptr;
+  if (redo && A.redo_tile[qtile] == 0) return;               // nothing to redo for this query tile
   const int64_t q0 = (int64_t)qtile * QT;
   const int nq = (int)((A.Q - q0 < QT) ? (A.Q - q0) : QT);
   const int64_t t0 = A.plan.tiles * part / A.plan.parts;
@@ -227,6 +231,13 @@ score_umma_kernel(ScoreArgs A) {
     if (j < K) v = -v;
     qpar[((ql >> 1) * qps + j) * 2 + (ql & 1)] = v;
   }
+  {
+    const int pbs = qplane_stride(K);                        // same pair interleave for the plane blocks
+    for (int i = tid; i < QT * pbs; i += SU_THREADS) {
+      const int ql = i / pbs, j = i % pbs;
+      qpl[((ql >> 1) * pbs + j) * 2 + (ql & 1)] = (ql < nq) ? A.qplane[(q0 + ql) * pbs + j] : 0.0f;
+    }
+  }
   // padding queries of the last tile get thr = -inf: they can never be pushed
   // phase 2: fixed thresholds from the sample pass, bumped one ulp so that the strict compare
   // below implements dist <= tau (every candidate tied with the bound must be kept)
@@ -247,7 +258,7 @@ score_umma_kernel(ScoreArgs A) {
 
   if (warp == SU_NEPI) {
     // ================================ MMA issuer (one lane) =================================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(bfull, 0);
       const Step3Desc sd = make_step3((uint32_t)NC, make_idesc_tf32(128, (uint32_t)NC));
       const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_img);
@@ -271,7 +282,7 @@ score_umma_kernel(ScoreArgs A) {
     }
   } else if (warp == SU_NEPI + 1) {
     // ================================ TMA producer (one lane) ===============================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t bbytes = (uint32_t)dpad * 8u * (uint32_t)NC;
       const unsigned char* qsrc = (const unsigned char*)A.qimg + (size_t)qtile * bbytes;
       mbar_arrive_expect_tx(bfull, bbytes);
@@ -300,12 +311,16 @@ score_umma_kernel(ScoreArgs A) {
     const uint32_t lane_lt = (1u << lane) - 1u;
     const bool dense = A.dist_out != nullptr;
     tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
-    // The lower bound dist >= min_k d_k - cq lets a whole query group skip the soft-min when no
-    // lane can beat its threshold.  It only pays when the prototypes of a query are close
-    // together relative to the spread of distances, so each warp measures its hit rate over the
-    // first tiles and switches the test off when it rarely fires.
+    // dist >= squared distance from e to the affine hull of the query's prototypes (a quadratic in
+    // the Gram values, score.cuh): in the usual regime it is within a few percent of dist, so almost
+    // every (row, query) is rejected by ~11 packed FMAs per query pair and the soft-min runs only for
+    // the queries of a group where some lane survives.  When the bound is loose for the data at hand
+    // (prototypes far apart relative to the spread of the distances) each warp measures its hit rate
+    // and switches the test off.
+    constexpr int PBS = qplane_stride(K);
     bool bound_on = (K > 1) && !dense;
     int grp_seen = 0, grp_skipped = 0;
+    unsigned dbg_seen = 0, dbg_skip = 0, dbg_sel = 0, dbg_full = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const int64_t row = (t0 + (int64_t)t * ts) * 128 + lrow;
@@ -316,6 +331,19 @@ score_umma_kernel(ScoreArgs A) {
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
       const int nslot = filter ? 2 + ((t >> 2) & 1) : (t & 1);
       const int trig = filter ? TOPK_STRIDE / 2 : TOPK_TRIGGER;
+      // push the passing lanes of query ql (warp-uniform call) into its key buffer
+      auto push = [&](int ql, bool pass, float dv) {
+        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+        if (m == 0) return;
+        const int leader = __ffs(m) - 1;
+        int basei = 0;
+        if (lane == leader) {
+          basei = atomicAdd(&cnt[ql], __popc(m));
+          if (basei + __popc(m) > trig) need[nslot] = 1;
+        }
+        basei = __shfl_sync(0xffffffffu, basei, leader);
+        if (pass) kbase[(int64_t)ql * TOPK_STRIDE + basei + __popc(m & lane_lt)] = pack_key(dv, (uint32_t)row);
+      };
       for (int g = sub; g * GQ < nq; g += WPQ) {
         float gk[K][GQ];
 #pragma unroll
@@ -332,20 +360,48 @@ score_umma_kernel(ScoreArgs A) {
           const float4 t4 = *(const float4*)(thr + g * GQ + i);
           tg[i] = t4.x; tg[i + 1] = t4.y; tg[i + 2] = t4.z; tg[i + 3] = t4.w;
         }
-        if (bound_on) {
-          bool need = false;
+        if constexpr (K > 1) {
+          if (bound_on) {
+            const float e2s = e2 * (1.0f - CFL_PLANE_REL);
+            const f2_t e2sp = pk2(e2s, e2s);
+            float lb[GQ];
+            bool nd = false;
 #pragma unroll
-          for (int i = 0; i < GQ; ++i) {
-            const float* qb = qg + (i >> 1) * QPS * 2 + (i & 1);
-            float mx = fmaf(2.0f * CFL_LOG2E, gk[0][i], qb[0]);
+            for (int pi = 0; pi < GQ / 2; ++pi) {
+              f2_t pv[PBS];
+              const ulonglong2* src = (const ulonglong2*)(qpl + (g * (GQ / 2) + pi) * PBS * 2);
 #pragma unroll
-            for (int k = 1; k < K; ++k) mx = fmaxf(mx, fmaf(2.0f * CFL_LOG2E, gk[k][i], qb[2 * k]));
-            const float lower = fmaf(-CFL_LN2, mx, e2) - qb[2 * CQ];
-            need |= lower < tg[i];
+              for (int j = 0; j < PBS; j += 2) { const ulonglong2 u = src[j >> 1]; pv[j] = u.x; pv[j + 1] = u.y; }
+              float gA[K], gB[K];
+#pragma unroll
+              for (int k = 0; k < K; ++k) { gA[k] = gk[k][2 * pi]; gB[k] = gk[k][2 * pi + 1]; }
+              plane_bound_pair<K>(gA, gB, e2sp, pv, lb[2 * pi], lb[2 * pi + 1]);
+              nd |= (lb[2 * pi] < tg[2 * pi]) | (lb[2 * pi + 1] < tg[2 * pi + 1]);
+            }
+            ++grp_seen; ++dbg_seen;
+            if (!__any_sync(0xffffffffu, nd && valid)) { ++grp_skipped; ++dbg_skip; continue; }
+            uint32_t nb = 0;
+#pragma unroll
+            for (int i = 0; i < GQ; ++i) nb |= (lb[i] < tg[i]) ? (1u << i) : 0u;
+            if (!valid) nb = 0;
+            const uint32_t anyn = __reduce_or_sync(0xffffffffu, nb);
+            if (__popc(anyn) <= GQ / 4) {                      // a few queries: soft-min only for those
+              ++dbg_sel;
+#pragma unroll
+              for (int i = 0; i < GQ; ++i) {
+                if (anyn & (1u << i)) {                        // warp-uniform
+                  float gi[K];
+#pragma unroll
+                  for (int k = 0; k < K; ++k) gi[k] = gk[k][i];
+                  const float dv = softmin_from_gram_il<K>(gi, e2, qg + (i >> 1) * QPS * 2 + (i & 1));
+                  push(g * GQ + i, valid && dv < tg[i], dv);
+                }
+              }
+              continue;
+            }
           }
-          ++grp_seen;
-          if (!__any_sync(0xffffffffu, need && valid)) { ++grp_skipped; continue; }
         }
+        ++dbg_full;
         float dist[GQ];
 #pragma unroll
         for (int pi = 0; pi < GQ / 2; ++pi) {
@@ -371,24 +427,16 @@ score_umma_kernel(ScoreArgs A) {
         const uint32_t anyq = __reduce_or_sync(0xffffffffu, bits);
         if (anyq) {
 #pragma unroll
-          for (int i = 0; i < GQ; ++i) {
-            if (anyq & (1u << i)) {                            // warp-uniform
-              const bool pass = (bits >> i) & 1u;
-              const uint32_t m = __ballot_sync(0xffffffffu, pass);
-              const int ql = g * GQ + i;
-              const int leader = __ffs(m) - 1;
-              int basei = 0;
-              if (lane == leader) {
-                basei = atomicAdd(&cnt[ql], __popc(m));
-                if (basei + __popc(m) > trig) need[nslot] = 1;
-              }
-              basei = __shfl_sync(0xffffffffu, basei, leader);
-              if (pass) kbase[(int64_t)ql * TOPK_STRIDE + basei + __popc(m & lane_lt)] = pack_key(dist[i], (uint32_t)row);
-            }
-          }
+          for (int i = 0; i < GQ; ++i)
+            if (anyq & (1u << i)) push(g * GQ + i, (bits >> i) & 1u, dist[i]);     // warp-uniform
         }
       }
-      if (t == 15 && bound_on && grp_skipped * 2 < grp_seen) bound_on = false;
+      // hit-rate check of the plane bound: in the filter pass over tiles [0,16); in the adaptive
+      // passes over tiles [16,32), once the running thresholds have tightened
+      if (bound_on) {
+        if (!filter && t == 15) { grp_seen = 0; grp_skipped = 0; }
+        if (t == (filter ? 15 : 31) && grp_skipped * 2 < grp_seen) bound_on = false;
+      }
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
       // ---- compaction point: all epilogue warps sort one over-full buffer together ----
@@ -417,6 +465,10 @@ score_umma_kernel(ScoreArgs A) {
         }
       }
     }
+    if (A.dbg != nullptr && lane == 0) {
+      atomicAdd(&A.dbg[0], (unsigned long long)dbg_seen); atomicAdd(&A.dbg[1], (unsigned long long)dbg_skip);
+      atomicAdd(&A.dbg[2], (unsigned long long)dbg_sel);  atomicAdd(&A.dbg[3], (unsigned long long)dbg_full);
+    }
     if (!filter) {
       for (int ql = 0; ql < nq; ++ql) {
         coop_compact<SU_EPI_THREADS>(kbase + (int64_t)ql * TOPK_STRIDE, cnt[ql], A.plan.kk, scratch, tid, &cnt[ql], nullptr);
@@ -424,7 +476,11 @@ score_umma_kernel(ScoreArgs A) {
       }
     } else {
       epi_bar_sync();                                         // all pushes done; lists stay unsorted
-      for (int ql = tid; ql < nq; ql += SU_EPI_THREADS) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
+      for (int ql = tid; ql < nq; ql += SU_EPI_THREADS) {
+        // a redo launch restarts only the queries it was asked to redo (thr_init > -inf)
+        if (redo && !(A.thr_init[q0 + ql] > __int_as_float(0xff800000))) continue;
+        A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
+      }
     }
   }
   // ---- teardown ----

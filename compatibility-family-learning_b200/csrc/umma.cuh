@@ -23,6 +23,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---- mbarrier -----------------------------------------------------------------------------
+// One lane of a converged warp (elect.sync).  Code under `if (elect_one())` is known to the compiler
+// to run in a single thread, so the uniform-datapath instructions in it (UTCHMMA, UTCBAR, UBLKCP) are
+// issued directly; under `if (lane == 0)` each of them is wrapped in an ELECT / BRA.U.ANY waterfall
+// loop that costs more than the MMA it issues.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
