@@ -88,7 +88,10 @@ __global__ void prep_queries_kernel(const float* __restrict__ Pq, int64_t Q, int
   // ---- plane bound: invert the (scaled) KKT matrix [D/dmax 1; 1^T 0] in fp64 ----
   float* pl = qplane + q * (int64_t)qplane_stride(K);
   for (int i = 0; i < qplane_stride(K); ++i) pl[i] = 0.0f;
-  if (K < 2) return;
+  if (K < 2) {                                               // K = 1: dist = |e|^2 + |p|^2 - 2 g exactly
+    pl[0] = sN[w][0] * (1.0f - CFL_PLANE_REL);
+    return;
+  }
   const int ci = 2 * (K - 1) + qplane_tri(K);
   const float NEG_INF = __int_as_float(0xff800000);
   pl[ci] = NEG_INF;
@@ -336,6 +339,204 @@ merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __res
   }
 }
 
+// ---- merge after the lower-bound filter pass: EVERY surviving row is scored exactly -------------
+// The keys of score_lb_kernel carry a lower bound, not the distance, so nothing may be discarded
+// before its exact value is known: each thread evaluates the direct-difference form (the arithmetic
+// of cfl/models/base.py:129-138) of one (query, row), then the keys stream through the same
+// 512-slot selection as block_merge_topkk.  Output as merge_rescore_kernel.
+__device__ __forceinline__ float exact_softmin_dist(const float* __restrict__ e, const float* __restrict__ pq,
+                                                    int K, int d, int ldp) {
+  float dk[CFL_MAX_K];
+  float mn = 3.0e38f;
+  for (int kq = 0; kq < K; ++kq) {
+    float acc = 0.0f;
+    for (int j = 0; j < d; ++j) { float df = e[j] - pq[kq * ldp + j]; acc = fmaf(df, df, acc); }
+    dk[kq] = acc;
+    mn = fminf(mn, acc);
+  }
+  if (K == 1) return dk[0];
+  float sum = 0.0f;
+  for (int kq = 0; kq < K; ++kq) { dk[kq] = expf(mn - dk[kq]); sum += dk[kq]; }
+  const float inv = 1.0f / sum;
+  float dist = 0.0f;
+  for (int j = 0; j < d; ++j) {
+    float m = 0.0f;
+    for (int kq = 0; kq < K; ++kq) m = fmaf(dk[kq] * inv, pq[kq * ldp + j], m);
+    const float r = e[j] - m;
+    dist = fmaf(r, r, dist);
+  }
+  return dist;
+}
+
+// Stage 1 (all survivors): each warp stages 32 candidate rows through shared memory with coalesced
+// reads, 32 dimensions at a time; every thread then owns one row and accumulates d_k = |e - p_k|^2,
+// from which dist = sum_k s_k d_k - sum_{k<l} s_k s_l |p_k - p_l|^2 (the same quantity as the direct
+// form, SURVEY App. A.3, good to a few ulp) picks the kk best.  Stage 2 rescores those kk in the
+// direct-difference form and sorts by (value, index), exactly as merge_rescore_kernel does.
+constexpr int RSC_CH = 32;                 // dimensions per staging chunk
+constexpr int RSC_LD = RSC_CH + 4;         // row stride in floats: 16 B aligned, conflict-free LDS.128
+
+template <int K>
+__global__ void __launch_bounds__(MRG_THREADS)
+rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ counts, int parts, int64_t Q,
+                     int kk, int k, const float* __restrict__ Pq, int64_t ldq, int d,
+                     const float* __restrict__ E, int64_t lde, int64_t idx_base,
+                     float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
+  extern __shared__ __align__(16) float s_dyn[];
+  const int dp = (d + RSC_CH - 1) / RSC_CH * RSC_CH;        // d padded to whole chunks
+  float* s_pq = s_dyn;                                       // [K][dp], zero padded
+  float* s_rows = s_pq + K * dp;                             // [warps][32][RSC_LD]
+  int* s_pref = (int*)(s_rows + (MRG_THREADS / 32) * 32 * RSC_LD);   // [parts + 1]
+  __shared__ tkey_t s[TOPK_CAP];
+  __shared__ int s_fill;
+  __shared__ tkey_t s_thr;
+  __shared__ float s_D[K * K];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int64_t q = blockIdx.x;
+  for (int i = t; i < K * dp; i += MRG_THREADS) {
+    const int kq = i / dp, j = i % dp;
+    s_pq[i] = (j < d) ? Pq[q * ldq + kq * d + j] : 0.0f;
+  }
+  if (t == 0) {
+    s_fill = 0; s_thr = CFL_KEY_INF;
+    int acc = 0;
+    for (int p = 0; p < parts; ++p) {
+      s_pref[p] = acc;
+      int c = counts[(int64_t)p * Q + q];
+      acc += c > TOPK_STRIDE ? TOPK_STRIDE : c;
+    }
+    s_pref[parts] = acc;
+  }
+  __syncthreads();
+  for (int i = t; i < K * K; i += MRG_THREADS) {
+    const int a = i / K, b = i % K;
+    float acc = 0.0f;
+    for (int j = 0; j < d; ++j) { const float df = s_pq[a * dp + j] - s_pq[b * dp + j]; acc = fmaf(df, df, acc); }
+    s_D[i] = acc;
+  }
+  __syncthreads();
+  const int total = s_pref[parts];
+  float* my_rows = s_rows + wid * 32 * RSC_LD;
+  for (int base = 0; base < total; base += MRG_THREADS) {
+    const int f = base + t;
+    uint32_t idx = 0;
+    const bool have = f < total;
+    if (have) {
+      int p = 0;
+      while (s_pref[p + 1] <= f) ++p;
+      idx = (uint32_t)(keys[((int64_t)p * Q + q) * TOPK_STRIDE + (f - s_pref[p])] & 0xffffffffu);
+    }
+    float dk[K];
+#pragma unroll
+    for (int kq = 0; kq < K; ++kq) dk[kq] = 0.0f;
+    for (int c0 = 0; c0 < dp; c0 += RSC_CH) {
+      __syncwarp();
+      const int j = c0 + lane;
+      for (int r0 = 0; r0 < 32; r0 += 16) {                  // coalesced: one 128 B row segment per load,
+        float v[16];                                         // 16 independent loads in flight per thread
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const uint32_t ridx = __shfl_sync(0xffffffffu, idx, r0 + r);
+          v[r] = (j < d) ? __ldg(E + (int64_t)ridx * lde + j) : 0.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) my_rows[(r0 + r) * RSC_LD + lane] = v[r];
+      }
+      __syncwarp();
+      const float4* er = (const float4*)(my_rows + lane * RSC_LD);
+#pragma unroll
+      for (int j4 = 0; j4 < RSC_CH / 4; ++j4) {
+        const float4 e4 = er[j4];
+#pragma unroll
+        for (int kq = 0; kq < K; ++kq) {
+          const float4 p4 = *(const float4*)(s_pq + kq * dp + c0 + j4 * 4);
+          const float a0 = e4.x - p4.x, a1 = e4.y - p4.y, a2 = e4.z - p4.z, a3 = e4.w - p4.w;
+          dk[kq] = fmaf(a3, a3, fmaf(a2, a2, fmaf(a1, a1, fmaf(a0, a0, dk[kq]))));
+        }
+      }
+    }
+    float dist = dk[0];
+    if (K > 1) {
+      float mn = dk[0];
+#pragma unroll
+      for (int kq = 1; kq < K; ++kq) mn = fminf(mn, dk[kq]);
+      float w[K], sum = 0.0f;
+#pragma unroll
+      for (int kq = 0; kq < K; ++kq) { w[kq] = __expf(mn - dk[kq]); sum += w[kq]; }
+      const float inv = 1.0f / sum;
+      float lin = 0.0f, quad = 0.0f;
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        lin = fmaf(w[a], dk[a], lin);
+#pragma unroll
+        for (int b = a + 1; b < K; ++b) quad = fmaf(w[a] * w[b], s_D[a * K + b], quad);
+      }
+      dist = inv * (lin - inv * quad);
+    }
+    // selection protocol of block_merge_topkk: uniform branch on the fill level read between barriers
+    const int f0 = s_fill;
+    __syncthreads();
+    if (f0 + MRG_THREADS > TOPK_CAP) mrg_compact(s, &s_fill, &s_thr, kk, t);
+    if (have) {
+      const tkey_t key = pack_key(dist, idx);
+      if (key < s_thr) s[atomicAdd(&s_fill, 1)] = key;
+    }
+    __syncthreads();
+  }
+  mrg_compact(s, &s_fill, &s_thr, kk, t);
+  const int fill = s_fill;
+  __syncthreads();
+  {                                                          // stage 2: direct form for the kk survivors,
+    const int ld2 = dp + 1;                                  // rows staged in full (stride dp+1: conflict-free)
+    int wcap = ((MRG_THREADS / 32) * 32 * RSC_LD) / (32 * ld2);
+    if (wcap > MRG_THREADS / 32) wcap = MRG_THREADS / 32;
+    for (int w0 = 0; w0 * 32 < fill; w0 += (wcap > 0 ? wcap : 1)) {
+      const int kidx = (w0 + wid) * 32 + lane;
+      const bool mine = wid < wcap && kidx < fill;
+      float dist = 0.0f;
+      uint32_t idx = mine ? (uint32_t)(s[kidx] & 0xffffffffu) : 0u;
+      if (wcap > 0) {
+        if (wid < wcap && (w0 + wid) * 32 < fill) {
+          float* rows = s_rows + wid * 32 * ld2;
+          for (int c0 = 0; c0 < dp; c0 += 32) {
+            const int j = c0 + lane;
+            for (int r0 = 0; r0 < 32; r0 += 16) {
+              float v[16];
+#pragma unroll
+              for (int r = 0; r < 16; ++r) {
+                const uint32_t ridx = __shfl_sync(0xffffffffu, idx, r0 + r);
+                v[r] = (j < d) ? __ldg(E + (int64_t)ridx * lde + j) : 0.0f;
+              }
+#pragma unroll
+              for (int r = 0; r < 16; ++r) rows[(r0 + r) * ld2 + j] = v[r];
+            }
+          }
+          __syncwarp();
+          if (mine) dist = exact_softmin_dist(rows + lane * ld2, s_pq, K, d, dp);
+        }
+      } else if (mine) {                                     // very wide rows: straight from global memory
+        dist = exact_softmin_dist(E + (int64_t)idx * lde, s_pq, K, d, dp);
+      }
+      __syncthreads();
+      if (mine) s[kidx] = pack_key(dist, idx);
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (t == 0) s_fill = fill;
+  __syncthreads();
+  mrg_compact(s, &s_fill, &s_thr, kk, t);
+  for (int i = t; i < k; i += MRG_THREADS) {
+    if (i < fill) {
+      top_val[q * k + i] = ord2f((uint32_t)(s[i] >> 32));
+      top_idx[q * k + i] = idx_base + (int64_t)(uint32_t)(s[i] & 0xffffffffu);
+    } else {
+      top_val[q * k + i] = __int_as_float(0x7f800000);
+      top_idx[q * k + i] = -1;
+    }
+  }
+}
+
 // ---- thresholds from the sample pass ------------------------------------------------------
 // tau[q] = kk-th smallest distance among the sampled candidates of ALL parts.  Any subset's kk-th
 // best is an upper bound of the catalog's kk-th best, so every member of the final top-kk
@@ -367,8 +568,13 @@ __global__ void verify_counts_kernel(const int* __restrict__ counts, int parts, 
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
   long long tot = 0;
-  for (int p = 0; p < parts; ++p) tot += counts[(int64_t)p * Q + q];
-  const bool redo = tot < kk && tau_opt[q] < tau[q];
+  bool over = false;                                         // a lower-bound pass buffer overflowed
+  for (int p = 0; p < parts; ++p) {
+    const int c = counts[(int64_t)p * Q + q];
+    tot += c;
+    over |= c > TOPK_STRIDE;
+  }
+  const bool redo = over || (tot < kk && tau_opt[q] < tau[q]);
   thr_redo[q] = redo ? tau[q] : __int_as_float(0xff800000);
   if (redo) redo_tile[q / qt] = 1;
 }
@@ -472,6 +678,8 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   a.cimg = nullptr; a.e2 = nullptr;
   a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
   a.dbg = nullptr; a.redo_tile = nullptr;
+  bool lb_pass = false;
+  a.dbg_mode = getenv("CFL_SCORE_DBG_MODE") ? atoi(getenv("CFL_SCORE_DBG_MODE")) : 0;
   static unsigned long long* dbg_dev = nullptr;
   const bool dbg_on = getenv("CFL_SCORE_DEBUG") != nullptr;
   if (dbg_on && !dbg_dev) CFL_CUDA(cudaMalloc(&dbg_dev, 4 * sizeof(unsigned long long)));
@@ -545,7 +753,11 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         a.phase = 2; a.tile_stride = 1; a.thr_init = tau_opt;
         timer_record(0, cs);                 // bench.py times the dominant launch: the full filter pass
         if (dbg_on) { CFL_CUDA(cudaMemsetAsync(dbg_dev, 0, 32, cs)); a.dbg = dbg_dev; }
-        st = score_umma_launch(a, cs);
+        // single-product lower-bound filter (survivors rescored exactly by rescore_merge_kernel), or
+        // the exact 3xTF32 filter when disabled
+        lb_pass = !getenv("CFL_SCORE_NO_LB");
+        if (lb_pass) { a.phase = 3; st = score_lb_launch(a, cs); a.phase = 2; }
+        else st = score_umma_launch(a, cs);
         timer_record(1, cs);
         if (st != CFL_OK) return st;
         a.dbg = nullptr;
@@ -584,8 +796,25 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       if (st != CFL_OK) return st;
     }
   }
-  merge_rescore_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(mode, a.keys, a.counts, plan.parts, Q, plan.kk, k,
-                                                  Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx);
+  if (lb_pass) {
+    const int dp = (d + RSC_CH - 1) / RSC_CH * RSC_CH;
+    const size_t rs_smem = ((size_t)K * dp + (size_t)(MRG_THREADS / 32) * 32 * RSC_LD + plan.parts + 1 + 4) * sizeof(float);
+#define CFL_RSC_CASE(KK)                                                                                        \
+  case KK:                                                                                                      \
+    CFL_CUDA(cudaFuncSetAttribute(rescore_merge_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                  (int)rs_smem));                                                               \
+    rescore_merge_kernel<KK><<<(unsigned)Q, MRG_THREADS, rs_smem, cs>>>(                                        \
+        a.keys, a.counts, plan.parts, Q, plan.kk, k, Pq, ldq, d, E, lde, idx_base, top_val, top_idx);           \
+    break;
+    switch (K) {
+      CFL_RSC_CASE(1) CFL_RSC_CASE(2) CFL_RSC_CASE(3) CFL_RSC_CASE(4)
+      CFL_RSC_CASE(5) CFL_RSC_CASE(6) CFL_RSC_CASE(7) CFL_RSC_CASE(8)
+    }
+#undef CFL_RSC_CASE
+  } else {
+    merge_rescore_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(mode, a.keys, a.counts, plan.parts, Q, plan.kk, k,
+                                                    Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx);
+  }
   CFL_LAUNCH_CHECK();
   return CFL_OK;
 }

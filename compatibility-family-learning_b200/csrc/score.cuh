@@ -38,6 +38,7 @@ struct ScoreArgs {
   int phase, tile_stride;
   const float* thr_init; // [Q], phase 2
   const int* redo_tile;  // phase 2 redo launch: per query tile, 1 = some query must be redone (else the CTA exits)
+  int dbg_mode;          // experiments (CFL_SCORE_DBG_MODE): 1 = epilogue does nothing, 2 = no TMA / no full-barrier waits
   unsigned long long* dbg; // optional counters {groups seen, skipped, selective, full} (CFL_SCORE_DEBUG)
   ScorePlan plan;
 };
@@ -74,6 +75,7 @@ int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const flo
 size_t score_umma_qimg_bytes(const ScorePlan& p, int K);
 int score_umma_pack_queries(const ScoreArgs& a, void* qimg, cudaStream_t st);
 int score_umma_launch(const ScoreArgs& a, cudaStream_t st);
+int score_lb_launch(const ScoreArgs& a, cudaStream_t st);
 int score_umma_qt(int K, int d);
 
 #ifdef __CUDACC__
@@ -225,7 +227,11 @@ __device__ __forceinline__ void plane_bound_pair(const float (&gA)[K], const flo
                                                  const f2_t* __restrict__ pl2, float& lA, float& lB) {
   const f2_t M1 = pk2(-1.0f, -1.0f), M2 = pk2(-2.0f, -2.0f);
   const f2_t g0 = pk2(gA[0], gB[0]);
-  f2_t w[K - 1];
+  if constexpr (K == 1) {                                   // dist = |e|^2 + |p|^2 - 2 g exactly: c0 at [0]
+    upk2(fma2(g0, M2, add2(pl2[0], e2sp)), lA, lB);
+    return;
+  }
+  f2_t w[K > 1 ? K - 1 : 1];
 #pragma unroll
   for (int j = 1; j < K; ++j) w[j - 1] = fma2(g0, M1, add2(pk2(gA[j], gB[j]), pl2[j - 1]));
   f2_t acc = fma2(g0, M2, add2(pl2[2 * (K - 1) + qplane_tri(K)], e2sp));

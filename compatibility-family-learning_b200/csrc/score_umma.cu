@@ -270,7 +270,7 @@ score_umma_kernel(ScoreArgs A) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
         for (int ks = 0; ks < nks; ks += kss) {
-          mbar_wait(&full[stage], phase);
+          if (!(A.dbg_mode & 2)) mbar_wait(&full[stage], phase);
           tc_fence_after();
           for (int j = 0; j < kss; ++j)
             mma_step3(sd, d_tmem, a_base + (stage * 2 + j) * SU_ASTAGE, b_base + (ks + j) * b_step, ks + j == 0);
@@ -291,7 +291,7 @@ score_umma_kernel(ScoreArgs A) {
         bulk_g2s(b_img + o, qsrc + o, n, bfull);
       }
       int stage = 0; uint32_t phase = 0;
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < ((A.dbg_mode & 2) ? 0 : ntiles); ++t) {
         const unsigned char* src = (const unsigned char*)A.cimg + (size_t)(t0 + (int64_t)t * ts) * nks * SU_ASTAGE;
         for (int ks = 0; ks < nks; ks += kss) {
           mbar_wait(&empty[stage], phase ^ 1u);
@@ -331,6 +331,7 @@ score_umma_kernel(ScoreArgs A) {
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
       const int nslot = filter ? 2 + ((t >> 2) & 1) : (t & 1);
       const int trig = filter ? TOPK_STRIDE / 2 : TOPK_TRIGGER;
+      if (A.dbg_mode & 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); continue; }
       // push the passing lanes of query ql (warp-uniform call) into its key buffer
       auto push = [&](int ql, bool pass, float dv) {
         const uint32_t m = __ballot_sync(0xffffffffu, pass);
@@ -487,6 +488,258 @@ score_umma_kernel(ScoreArgs A) {
   tc_fence_before();
   __syncthreads();
   if (warp == SU_NEPI) tmem_dealloc(tmem_base, ncols);
+}
+
+// =====================================================================================================
+// Lower-bound filter pass (phase 3).  Same images, ring and TMEM double buffer as score_umma_kernel, but
+//  * ONE TF32 MMA per K-step (hi x hi planes only; only the hi half of every catalog K-step block is
+//    copied), so the accumulators are swept 8x per tile instead of 24x -- the tensor memory port that
+//    MMA accumulation and the epilogue's tcgen05.ld share is what bounds the 3xTF32 kernel;
+//  * the epilogue never evaluates the soft-min: it pushes every (row, query) whose affine-hull lower
+//    bound, lowered by a rigorous bound on the single-product rounding error, is under the threshold.
+//    dist = |e - sum s_k p_k|^2 with s in the simplex, so an error delta_k on the Gram values moves it
+//    by at most 2 max_k |delta_k| <= 2 u |p|max |e|, u = 2^-10 (two RN tf32 roundings per product);
+//  * no compaction, no barriers: an over-full key buffer is only counted (counts > TOPK_STRIDE) and
+//    the query is redone by the exact kernel.
+// The survivors are rescored exactly by rescore_merge_kernel (score.cu).
+constexpr float CFL_TF32_PRODUCT_U = 1.1f / 1024.0f;
+
+template <int K>
+__global__ void __launch_bounds__(SU_THREADS, 1)
+score_lb_kernel(ScoreArgs A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int GQ = K <= 2 ? 16 : (K <= 4 ? 8 : 4);
+  constexpr int PBS = qplane_stride(K);
+  const int QT = A.plan.qt;
+  const int NC = K * QT;
+  const int dpad = A.plan.dpad;
+  const int nks = dpad / 8;
+  const SuLayout L = su_layout(K, QT, dpad);
+  unsigned char* b_img = smem + L.b_img;
+  unsigned char* a_ring = smem + L.a_ring;
+  float* red = (float*)(smem + L.scratch);
+  float* qpl = (float*)(smem + L.qpl);
+  float* thr = (float*)(smem + L.thr);
+  int* cnt = (int*)(smem + L.cnt);
+  uint64_t* full = (uint64_t*)(smem + L.bars);
+  uint64_t* empty = full + SU_NSTAGE;
+  uint64_t* tfull = empty + SU_NSTAGE;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(smem + L.tmem_slot);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int part = blockIdx.x, qtile = blockIdx.y;
+  const int64_t q0 = (int64_t)qtile * QT;
+  const int nq = (int)((A.Q - q0 < QT) ? (A.Q - q0) : QT);
+  const int64_t t0 = A.plan.tiles * part / A.plan.parts;
+  const int64_t t1 = A.plan.tiles * (part + 1) / A.plan.parts;
+  const int ts = A.tile_stride;
+  const int ntiles = (int)((t1 - t0 + ts - 1) / ts);
+  const int kss = (nks % 4 == 0) ? 4 : ((nks % 2 == 0) ? 2 : 1);   // K-steps (4 KB hi blocks) per ring stage
+  constexpr uint32_t HI_BYTES = SU_ASTAGE / 2;                     // [chunk][128 rows][16 B]
+  constexpr uint32_t STAGE_BYTES = 2 * SU_ASTAGE;
+
+  uint32_t ncols = 32;
+  while ((int)ncols < 2 * NC) ncols <<= 1;
+  if (warp == SU_NEPI) {
+    if (lane == 0) {
+      for (int s = 0; s < SU_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+      mbar_init(&tempty[0], SU_EPI_THREADS); mbar_init(&tempty[1], SU_EPI_THREADS);
+      mbar_init(bfull, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, ncols);
+  }
+  for (int i = tid; i < QT * PBS; i += SU_THREADS) {
+    const int ql = i / PBS, j = i % PBS;
+    qpl[((ql >> 1) * PBS + j) * 2 + (ql & 1)] = (ql < nq) ? A.qplane[(q0 + ql) * PBS + j] : 0.0f;
+  }
+  // largest prototype norm of the tile (qpar[k] = log2e |p_k|^2): one margin factor for the whole CTA
+  float pm = 0.0f;
+  for (int i = tid; i < nq * K; i += SU_THREADS) pm = fmaxf(pm, A.qpar[(q0 + i / K) * qpar_stride(K) + i % K]);
+  pm = warp_max(pm);
+  if (lane == 0) red[warp] = pm;
+  for (int i = tid; i < QT; i += SU_THREADS) {
+    float th = __int_as_float(0xff800000);
+    if (i < nq) {
+      const float tau = A.thr_init ? A.thr_init[q0 + i] : __int_as_float(0x7f800000);
+      th = (tau < 3.0e38f) ? nextafterf(tau, 3.4e38f) : tau;
+    }
+    thr[i] = th;
+    cnt[i] = 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == SU_NEPI) {
+    if (elect_one()) {
+      mbar_wait(bfull, 0);
+      const uint64_t a_desc = make_smem_desc(0, 128u * 16u, 128u);
+      const uint64_t b_desc = make_smem_desc(0, (uint32_t)NC * 16u, 128u);
+      const uint32_t idesc = make_idesc_tf32(128, (uint32_t)NC);
+      const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_img);
+      const uint32_t b_step = 4u * (uint32_t)NC * 16u;
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&tempty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
+        for (int ks = 0; ks < nks; ks += kss) {
+          if (!(A.dbg_mode & 2)) mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          for (int j = 0; j < kss; ++j)
+            mma_tf32(d_tmem, a_desc + (uint64_t)((a_base + stage * STAGE_BYTES + j * HI_BYTES) >> 4),
+                     b_desc + (uint64_t)((b_base + (ks + j) * b_step) >> 4), idesc, (ks + j) ? 1u : 0u);
+          mma_commit(&empty[stage]);
+          if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp == SU_NEPI + 1) {
+    if (elect_one()) {
+      const uint32_t bbytes = (uint32_t)dpad * 8u * (uint32_t)NC;
+      const unsigned char* qsrc = (const unsigned char*)A.qimg + (size_t)qtile * bbytes;
+      mbar_arrive_expect_tx(bfull, bbytes);
+      for (uint32_t o = 0; o < bbytes; o += 32768u) {
+        uint32_t n = bbytes - o < 32768u ? bbytes - o : 32768u;
+        bulk_g2s(b_img + o, qsrc + o, n, bfull);
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ((A.dbg_mode & 2) ? 0 : ntiles); ++t) {
+        const unsigned char* src = (const unsigned char*)A.cimg + (size_t)(t0 + (int64_t)t * ts) * nks * SU_ASTAGE;
+        for (int ks = 0; ks < nks; ks += kss) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)kss * HI_BYTES);
+          for (int j = 0; j < kss; ++j)
+            bulk_g2s(a_ring + stage * STAGE_BYTES + j * HI_BYTES, src + (size_t)(ks + j) * SU_ASTAGE, HI_BYTES, &full[stage]);
+          if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    constexpr int WPQ = SU_NEPI / 4;
+    const int lq = warp & 3, sub = warp >> 2;
+    const int lrow = lq * 32 + lane;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
+    float pmax = 0.0f;
+    for (int i = 0; i < SU_THREADS / 32; ++i) pmax = fmaxf(pmax, red[i]);
+    // 2 u |p|max, |p|max^2 = pmax / log2e
+    const float mfac = 2.0f * CFL_TF32_PRODUCT_U * sqrtf(pmax * CFL_LN2) * 1.0001f;
+    unsigned dbg_seen = 0, dbg_skip = 0, dbg_push = 0;
+    float e2_next = (ntiles > 0) ? __ldg(A.e2 + t0 * 128 + lrow) : 0.0f;      // prefetched one tile ahead
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const int64_t row = (t0 + (int64_t)t * ts) * 128 + lrow;
+      const bool valid = row < A.N;
+      const float e2 = e2_next;
+      if (t + 1 < ntiles) e2_next = __ldg(A.e2 + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
+      // |e|^2 lowered by the fp32 evaluation margin and by the single-product error bound
+      const float e2s = fmaf(-mfac, sqrtf(e2), e2 * (1.0f - CFL_PLANE_REL));
+      const f2_t e2sp = pk2(e2s, e2s);
+      mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
+      if (A.dbg_mode & 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); continue; }
+      for (int g = sub; g * GQ < nq; g += WPQ) {
+        float gk[K][GQ];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if constexpr (GQ == 16)     tmem_ld16(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
+          else if constexpr (GQ == 8) tmem_ld8(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
+          else                        tmem_ld4(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
+        }
+        float tg[GQ];
+#pragma unroll
+        for (int i = 0; i < GQ; i += 4) {
+          const float4 t4 = *(const float4*)(thr + g * GQ + i);
+          tg[i] = t4.x; tg[i + 1] = t4.y; tg[i + 2] = t4.z; tg[i + 3] = t4.w;
+        }
+        tmem_ld_wait();
+        float lb[GQ];
+        bool nd = false;
+#pragma unroll
+        for (int pi = 0; pi < GQ / 2; ++pi) {
+          f2_t pv[PBS];
+          const ulonglong2* src = (const ulonglong2*)(qpl + (g * (GQ / 2) + pi) * PBS * 2);
+#pragma unroll
+          for (int j = 0; j < PBS; j += 2) { const ulonglong2 u = src[j >> 1]; pv[j] = u.x; pv[j + 1] = u.y; }
+          float gA[K], gB[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) { gA[k] = gk[k][2 * pi]; gB[k] = gk[k][2 * pi + 1]; }
+          plane_bound_pair<K>(gA, gB, e2sp, pv, lb[2 * pi], lb[2 * pi + 1]);
+          nd |= (lb[2 * pi] < tg[2 * pi]) | (lb[2 * pi + 1] < tg[2 * pi + 1]);
+        }
+        ++dbg_seen;
+        if (!__any_sync(0xffffffffu, nd && valid)) { ++dbg_skip; continue; }
+        uint32_t nb = 0;
+#pragma unroll
+        for (int i = 0; i < GQ; ++i) nb |= (lb[i] < tg[i]) ? (1u << i) : 0u;
+        if (!valid) nb = 0;
+        const uint32_t anyn = __reduce_or_sync(0xffffffffu, nb);
+#pragma unroll
+        for (int i = 0; i < GQ; ++i) {
+          if (anyn & (1u << i)) {                              // warp-uniform
+            const bool pass = (nb >> i) & 1u;
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            const int ql = g * GQ + i;
+            const int leader = __ffs(m) - 1;
+            int basei = 0;
+            if (lane == leader) basei = atomicAdd(&cnt[ql], __popc(m));
+            basei = __shfl_sync(0xffffffffu, basei, leader);
+            const int slot = basei + __popc(m & lane_lt);
+            if (pass && slot < TOPK_STRIDE) kbase[(int64_t)ql * TOPK_STRIDE + slot] = pack_key(lb[i], (uint32_t)row);
+            dbg_push += __popc(m);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+    if (A.dbg != nullptr && lane == 0) {
+      atomicAdd(&A.dbg[0], (unsigned long long)dbg_seen); atomicAdd(&A.dbg[1], (unsigned long long)dbg_skip);
+      atomicAdd(&A.dbg[2], (unsigned long long)dbg_push);
+    }
+    epi_bar_sync();
+    // counts may exceed TOPK_STRIDE: that marks an over-full buffer (verify_counts_kernel redoes the query)
+    for (int ql = tid; ql < nq; ql += SU_EPI_THREADS) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == SU_NEPI) tmem_dealloc(tmem_base, ncols);
+}
+
+template <int K>
+static int launch_lb(const ScoreArgs& a, cudaStream_t st) {
+  SuLayout L = su_layout(K, a.plan.qt, a.plan.dpad);
+  size_t smem = L.total + 1024;
+  CFL_CUDA(cudaFuncSetAttribute(score_lb_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(a.plan.parts, a.plan.nqt);
+  score_lb_kernel<K><<<grid, SU_THREADS, smem, st>>>(a);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+int score_lb_launch(const ScoreArgs& a, cudaStream_t st) {
+  switch (a.K) {
+    case 1: return launch_lb<1>(a, st);
+    case 2: return launch_lb<2>(a, st);
+    case 3: return launch_lb<3>(a, st);
+    case 4: return launch_lb<4>(a, st);
+    case 5: return launch_lb<5>(a, st);
+    case 6: return launch_lb<6>(a, st);
+    case 7: return launch_lb<7>(a, st);
+    case 8: return launch_lb<8>(a, st);
+  }
+  set_error("score_lb: K=%d unsupported", a.K);
+  return CFL_ERR_UNSUPPORTED;
 }
 
 template <int K>
