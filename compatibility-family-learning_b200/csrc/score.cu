@@ -288,12 +288,15 @@ __global__ void __launch_bounds__(MRG_THREADS)
 merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __restrict__ counts,
                      int parts, int64_t Q, int kk, int k, const float* __restrict__ Pq,
                      int64_t ldq, int K, int d, const float* __restrict__ E, int64_t lde,
-                     int64_t idx_base, float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
+                     int64_t idx_base, float* __restrict__ top_val, int64_t* __restrict__ top_idx,
+                     const float* __restrict__ only_redo = nullptr) {
   __shared__ tkey_t s[TOPK_CAP];
   __shared__ int s_fill;
   __shared__ tkey_t s_thr;
   const int t = threadIdx.x;
   const int64_t q = blockIdx.x;
+  // second merge after a lower-bound pass: only the queries that were redone by the exact kernel
+  if (only_redo != nullptr && !(only_redo[q] > __int_as_float(0xff800000))) return;
   const int fill = block_merge_topkk(keys, counts, parts, Q, q, kk, s, &s_fill, &s_thr);
   const float* pq = Pq + q * ldq;
   if (t < fill) {
@@ -381,7 +384,9 @@ __global__ void __launch_bounds__(MRG_THREADS)
 rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ counts, int parts, int64_t Q,
                      int kk, int k, const float* __restrict__ Pq, int64_t ldq, int d,
                      const float* __restrict__ E, int64_t lde, int64_t idx_base,
-                     float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
+                     float* __restrict__ top_val, int64_t* __restrict__ top_idx,
+                     const float* __restrict__ tau, const float* __restrict__ tau_opt, int qt,
+                     float* __restrict__ thr_redo, int* __restrict__ redo_tile, unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(16) float s_dyn[];
   const int dp = (d + RSC_CH - 1) / RSC_CH * RSC_CH;        // d padded to whole chunks
   float* s_pq = s_dyn;                                       // [K][dp], zero padded
@@ -397,15 +402,18 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
     const int kq = i / dp, j = i % dp;
     s_pq[i] = (j < d) ? Pq[q * ldq + kq * d + j] : 0.0f;
   }
+  __shared__ int s_over, s_redo;
   if (t == 0) {
     s_fill = 0; s_thr = CFL_KEY_INF;
-    int acc = 0;
+    int acc = 0, over = 0;
     for (int p = 0; p < parts; ++p) {
       s_pref[p] = acc;
       int c = counts[(int64_t)p * Q + q];
+      over |= c > TOPK_STRIDE;                               // the filter pass dropped keys of this query
       acc += c > TOPK_STRIDE ? TOPK_STRIDE : c;
     }
     s_pref[parts] = acc;
+    s_over = over;
   }
   __syncthreads();
   for (int i = t; i < K * K; i += MRG_THREADS) {
@@ -485,7 +493,21 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
   }
   mrg_compact(s, &s_fill, &s_thr, kk, t);
   const int fill = s_fill;
+  // Verification.  The filter kept every row whose LOWER BOUND is under the threshold, so a key count
+  // proves nothing; the exact values do: if kk survivors have dist <= tau_opt, no row outside the
+  // survivor set (all of which have dist >= bound > tau_opt) can belong to the top-kk.  Under the safe
+  // threshold (tau_opt == tau) the survivor set always contains the top-kk.  Otherwise -- or when a
+  // key buffer overflowed -- the query is handed to the exact kernel (thr_redo / redo_tile).
+  if (t == 0) {
+    const bool optimistic = tau_opt[q] < tau[q];
+    const bool proven = !optimistic || (fill >= kk && ord2f((uint32_t)(s[kk - 1] >> 32)) <= tau_opt[q] * (1.0f - 4e-6f));
+    const int redo = (s_over || !proven) ? 1 : 0;
+    s_redo = redo;
+    thr_redo[q] = redo ? tau[q] : __int_as_float(0xff800000);
+    if (redo) { redo_tile[q / qt] = 1; if (dbg) atomicAdd(&dbg[3], 1ull); }
+  }
   __syncthreads();
+  if (s_redo) return;
   {                                                          // stage 2: direct form for the kk survivors,
     const int ld2 = dp + 1;                                  // rows staged in full (stride dp+1: conflict-free)
     int wcap = ((MRG_THREADS / 32) * 32 * RSC_LD) / (32 * ld2);
@@ -564,7 +586,8 @@ sample_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__
 // count is either the number of rows it pushed or, after a compaction, still >= kk.)
 __global__ void verify_counts_kernel(const int* __restrict__ counts, int parts, int64_t Q, int kk, int qt,
                                      const float* __restrict__ tau, const float* __restrict__ tau_opt,
-                                     float* __restrict__ thr_redo, int* __restrict__ redo_tile) {
+                                     float* __restrict__ thr_redo, int* __restrict__ redo_tile,
+                                     unsigned long long* __restrict__ dbg) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
   long long tot = 0;
@@ -577,6 +600,7 @@ __global__ void verify_counts_kernel(const int* __restrict__ counts, int parts, 
   const bool redo = over || (tot < kk && tau_opt[q] < tau[q]);
   thr_redo[q] = redo ? tau[q] : __int_as_float(0xff800000);
   if (redo) redo_tile[q / qt] = 1;
+  if (redo && dbg) atomicAdd(&dbg[3], 1ull);
 }
 
 // ---- cross-rank merge: rank-based merge of R sorted lists --------------------------------
@@ -679,6 +703,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
   a.dbg = nullptr; a.redo_tile = nullptr;
   bool lb_pass = false;
+  const float* redo_only = nullptr;
   a.dbg_mode = getenv("CFL_SCORE_DBG_MODE") ? atoi(getenv("CFL_SCORE_DBG_MODE")) : 0;
   static unsigned long long* dbg_dev = nullptr;
   const bool dbg_on = getenv("CFL_SCORE_DEBUG") != nullptr;
@@ -744,7 +769,9 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         float* tau_opt = tau + Q;
         float* thr_redo = tau + 2 * Q;
         int* redo_tile = (int*)(tau + 3 * Q);
-        int r_opt = (int)((4 * (int64_t)plan.kk + sstride - 1) / sstride);
+        const char* eo = getenv("CFL_SCORE_OPT_MULT");
+        const int opt_mult = eo ? atoi(eo) : 4;
+        int r_opt = (int)((opt_mult * (int64_t)plan.kk + sstride - 1) / sstride);
         if (getenv("CFL_SCORE_NO_OPTIMISTIC")) r_opt = 0;
         sample_threshold_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau,
                                                                      tau_opt, r_opt);
@@ -760,13 +787,33 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         else st = score_umma_launch(a, cs);
         timer_record(1, cs);
         if (st != CFL_OK) return st;
+        if (lb_pass) {
+          // exact rescoring of every survivor + verification; flagged queries are redone below
+          const int dp = (d + RSC_CH - 1) / RSC_CH * RSC_CH;
+          const size_t rs_smem = ((size_t)K * dp + (size_t)(MRG_THREADS / 32) * 32 * RSC_LD + plan.parts + 1 + 4) * sizeof(float);
+#define CFL_RSC_CASE(KK)                                                                                        \
+  case KK:                                                                                                      \
+    CFL_CUDA(cudaFuncSetAttribute(rescore_merge_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                  (int)rs_smem));                                                               \
+    rescore_merge_kernel<KK><<<(unsigned)Q, MRG_THREADS, rs_smem, cs>>>(                                        \
+        a.keys, a.counts, plan.parts, Q, plan.kk, k, Pq, ldq, d, E, lde, idx_base, top_val, top_idx, tau,       \
+        tau_opt, plan.qt, thr_redo, redo_tile, a.dbg);                                                          \
+    break;
+          switch (K) {
+            CFL_RSC_CASE(1) CFL_RSC_CASE(2) CFL_RSC_CASE(3) CFL_RSC_CASE(4)
+            CFL_RSC_CASE(5) CFL_RSC_CASE(6) CFL_RSC_CASE(7) CFL_RSC_CASE(8)
+          }
+#undef CFL_RSC_CASE
+        } else {
+          verify_counts_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, cs>>>(a.counts, plan.parts, Q, plan.kk, plan.qt,
+                                                                           tau, tau_opt, thr_redo, redo_tile, a.dbg);
+        }
         a.dbg = nullptr;
-        verify_counts_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, cs>>>(a.counts, plan.parts, Q, plan.kk, plan.qt,
-                                                                         tau, tau_opt, thr_redo, redo_tile);
         CFL_LAUNCH_CHECK();
         a.thr_init = thr_redo; a.redo_tile = redo_tile;
         st = score_umma_launch(a, cs);
         a.redo_tile = nullptr;
+        redo_only = lb_pass ? thr_redo : nullptr;
       } else {
         a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
         st = score_umma_launch(a, cs);
@@ -777,7 +824,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         unsigned long long h[4];
         CFL_CUDA(cudaMemcpyAsync(h, dbg_dev, 32, cudaMemcpyDeviceToHost, cs));
         CFL_CUDA(cudaStreamSynchronize(cs));
-        fprintf(stderr, "[cfl score] filter pass groups: bound tested %llu, skipped %llu, selective %llu, full soft-min %llu\n",
+        fprintf(stderr, "[cfl score] filter pass groups: bound tested %llu, skipped %llu, pushed keys %llu, queries redone %llu\n",
                 h[0], h[1], h[2], h[3]);
       }
     } else {
@@ -796,25 +843,9 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       if (st != CFL_OK) return st;
     }
   }
-  if (lb_pass) {
-    const int dp = (d + RSC_CH - 1) / RSC_CH * RSC_CH;
-    const size_t rs_smem = ((size_t)K * dp + (size_t)(MRG_THREADS / 32) * 32 * RSC_LD + plan.parts + 1 + 4) * sizeof(float);
-#define CFL_RSC_CASE(KK)                                                                                        \
-  case KK:                                                                                                      \
-    CFL_CUDA(cudaFuncSetAttribute(rescore_merge_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                  (int)rs_smem));                                                               \
-    rescore_merge_kernel<KK><<<(unsigned)Q, MRG_THREADS, rs_smem, cs>>>(                                        \
-        a.keys, a.counts, plan.parts, Q, plan.kk, k, Pq, ldq, d, E, lde, idx_base, top_val, top_idx);           \
-    break;
-    switch (K) {
-      CFL_RSC_CASE(1) CFL_RSC_CASE(2) CFL_RSC_CASE(3) CFL_RSC_CASE(4)
-      CFL_RSC_CASE(5) CFL_RSC_CASE(6) CFL_RSC_CASE(7) CFL_RSC_CASE(8)
-    }
-#undef CFL_RSC_CASE
-  } else {
-    merge_rescore_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(mode, a.keys, a.counts, plan.parts, Q, plan.kk, k,
-                                                    Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx);
-  }
+  // after a lower-bound pass the verified queries are already written; only the redone ones remain
+  merge_rescore_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(mode, a.keys, a.counts, plan.parts, Q, plan.kk, k,
+                                                  Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx, redo_only);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
 }

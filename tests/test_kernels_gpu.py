@@ -377,6 +377,55 @@ def test_score_topk_two_pass_equals_single_pass(nat, monkeypatch, K, d, dup, cas
             assert abs(D[r, c_] - wv[r, -1]) <= 2e-6 * max(wv[r, -1], 1.0) + 1e-7
 
 
+@pytest.mark.parametrize("case", ["protos_far_apart", "protos_duplicated", "protos_collinear", "optimism_fails",
+                                  "no_lower_bound_pass", "offset_uncentred"])
+def test_score_topk_lower_bound_pass_regimes(nat, monkeypatch, case):
+    """The large-catalog path = single-product lower-bound filter + exact rescoring, with an optimistic
+    threshold that is verified by key counts.  Every regime must reproduce the single adaptive pass bit for
+    bit: prototypes far apart (affine-hull bound loose: one-hot soft-min), duplicated / collinear
+    prototypes (KKT system singular -> bound switched off -> buffers overflow -> exact redo), an
+    optimistic threshold that is too tight for about half the queries (-> redo under the safe bound),
+    the lower-bound pass disabled, and an uncentred catalog far from the origin (large error margins)."""
+    rng = np.random.default_rng(77)
+    N, Q, K, d = 150000, 130, 3, 64
+    E = rng.normal(size=(N, d)).astype(np.float32)
+    base = E[rng.integers(0, N, Q)][:, None, :]
+    Pq = (base + 0.5 * rng.normal(size=(Q, K, d))).astype(np.float32)
+    mu_on = True
+    if case == "protos_far_apart":
+        Pq = (base + 6.0 * rng.normal(size=(Q, K, d))).astype(np.float32)
+    elif case == "protos_duplicated":
+        Pq[::2, 1] = Pq[::2, 0]
+    elif case == "protos_collinear":
+        Pq[::3, 2] = 0.5 * (Pq[::3, 0] + Pq[::3, 1])
+    elif case == "offset_uncentred":
+        E = E + 10.0
+        Pq = Pq + 10.0
+        mu_on = False
+    E, Pq = dev(E), dev(Pq)
+    mu = nat.col_mean(E) if mu_on else None
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "100000000")
+    a = nat.score_topk(Pq, E, 100, mu=mu)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "2")
+    monkeypatch.setenv("CFL_SCORE_SAMPLE_STRIDE", "8")
+    if case == "optimism_fails":
+        monkeypatch.setenv("CFL_SCORE_OPT_MULT", "1")
+    if case == "no_lower_bound_pass":
+        monkeypatch.setenv("CFL_SCORE_NO_LB", "1")
+    b = nat.score_topk(Pq, E, 100, mu=mu)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    qs = [0, 1, 2, 3, Q - 1]
+    D = O.all_pairs_dist(host(Pq[qs]).astype(np.float64), host(E).astype(np.float64), block=1)
+    wv, wi = O.rank_topk(D, 100)
+    got = b[1][qs].cpu().numpy()
+    # far-apart prototypes: distances of ~1e3 make the fp32 soft-min weights themselves uncertain to ~1e-3
+    rtol = 2e-3 if case == "protos_far_apart" else (2e-4 if not mu_on else 2e-5)
+    np.testing.assert_allclose(b[0][qs].cpu().numpy(), wv, rtol=rtol)
+    for r in range(len(qs)):
+        for c_ in set(got[r].tolist()) ^ set(wi[r].tolist()):
+            assert abs(D[r, c_] - wv[r, -1]) <= rtol * 0.5 * max(wv[r, -1], 1.0) + 1e-7
+
+
 # ---------------------------------------------------------------------------- full-size properties
 def test_full_size_catalog_properties(nat):
     """BASELINE config 3 size (1M-item catalog, K=3, d=64): size-independent properties instead of a
