@@ -212,18 +212,20 @@ def run_ours(args):
     achieved = flops / (k_ms / 1e3) / 1e12
     tf32_peak = pk["bf16_sus"] / 2.0                              # TF32 dense = bf16/2 (not in MEASURED_PEAKS)
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu
-    # capture of the same command (profiles/r1_03_score_umma_final.md); algorithmic bytes = the
-    # catalog image, N * (8*d + 4).
-    traffic = 537.2e6 if (N_PER_GPU, D, K, Q) == (1_000_000, 64, 3, 1024) else None
+    # capture of the same command (profiles/r1_09_lower_bound_pass.md); algorithmic bytes = the hi
+    # (tf32) plane of the catalog image + |e|^2, N * (4*d + 4).
+    traffic = 273.9e6 if (N_PER_GPU, D, K, Q) == (1_000_000, 64, 3, 1024) else None
     roofline = dict(bound="tensor", achieved=round(achieved, 2), peak=round(tf32_peak, 1), unit="TFLOP/s",
                     frac=round(achieved / tf32_peak, 4), traffic=traffic,
-                    kernel="score_umma_kernel<3>, full filter pass (the dominant launch of cfl_score_topk_packed)",
+                    kernel="score_lb_kernel<3>: single-product TF32 tcgen05 pass + affine-hull lower-bound filter "
+                           "(the dominant launch of cfl_score_topk_packed; survivors are rescored exactly)",
                     kernel_ms=round(k_ms, 4), algorithmic_flops_per_launch=flops,
-                    algorithmic_bytes_per_launch=N_PER_GPU * (8 * D + 4),
-                    peak_source=f"{pk['src']} bf16_tflops_sustained/2 (1xTF32; TF32 is not in MEASURED_PEAKS.json). The "
-                                f"kernel issues 3 TF32 MMAs per product (3xTF32 error compensation, needed for the 1e-4 "
-                                f"parity bar), so the fraction of the 3x-effective peak is {round(3 * achieved / tf32_peak, 4)}",
-                    hbm_gbs=round((traffic or N_PER_GPU * (8 * D + 4)) / (k_ms / 1e3) / 1e9, 1))
+                    algorithmic_bytes_per_launch=N_PER_GPU * (4 * D + 4),
+                    peak_source=f"{pk['src']} bf16_tflops_sustained/2 (dense TF32 = bf16/2; TF32 is not in "
+                                f"MEASURED_PEAKS.json). One TF32 MMA per product; the kernel is bound by the tensor-memory "
+                                f"port shared by MMA accumulation and the epilogue's tcgen05.ld (see DESIGN.md), not by "
+                                f"the MMA rate",
+                    hbm_gbs=round((traffic or N_PER_GPU * (4 * D + 4)) / (k_ms / 1e3) / 1e9, 1))
 
     line = None
     if rank == 0:
@@ -233,7 +235,7 @@ def run_ours(args):
             "metric": "query x candidate scores/sec (fused soft-min scoring + top-100)",
             "value": value, "unit": "scores/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "dtype_note": "fp32 in/out; GEMMs as error-compensated 3xTF32 tcgen05 MMA with fp32 accumulation",
+            "vs_baseline": None, "dtype": "f32", "dtype_note": "fp32 in/out. Sample passes and projections: error-compensated 3xTF32 tcgen05 MMA; full pass: single TF32 MMA used only as a rigorous lower-bound filter, every survivor rescored in fp32 direct form (results identical to the 3xTF32 path)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "F": F, "K": K, "d": D, "catalog_per_gpu": N_PER_GPU,
                        "catalog_total": n_total, "queries_per_step": Q, "topk": TOPK,
@@ -256,9 +258,10 @@ def run_ours(args):
 
 
 def launches_per_step(world):
-    # colnorm, pack_weights, project_umma, prep_queries, pack_queries, score_umma x3 (passes A/B/C),
-    # sample_threshold x2, merge_rescore (+ topk_merge after the all-gather for N>1)
-    return 11 + (1 if world > 1 else 0)
+    # colnorm, pack_weights, project_umma, prep_queries, pack_queries, score_umma x2 (passes A/B),
+    # sample_threshold x2, score_lb (pass C), rescore_merge, score_umma (redo, exits when nothing failed
+    # verification), merge_rescore (redone queries only) (+ topk_merge after the all-gather for N>1)
+    return 13 + (1 if world > 1 else 0)
 
 
 # ------------------------------------------------------------------------------------------

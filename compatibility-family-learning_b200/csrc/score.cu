@@ -248,7 +248,7 @@ __device__ __forceinline__ void mrg_compact(tkey_t* s, int* s_fill, tkey_t* s_th
   if (t == 0) {
     const int nf = fill < kk ? fill : kk;
     *s_fill = nf;
-    *s_thr = (nf >= kk) ? s[kk - 1] : CFL_KEY_INF;
+    if (nf >= kk) *s_thr = s[kk - 1];                // otherwise the admission bound stays as it was
   }
   __syncthreads();
 }
@@ -376,7 +376,7 @@ __device__ __forceinline__ float exact_softmin_dist(const float* __restrict__ e,
 // from which dist = sum_k s_k d_k - sum_{k<l} s_k s_l |p_k - p_l|^2 (the same quantity as the direct
 // form, SURVEY App. A.3, good to a few ulp) picks the kk best.  Stage 2 rescores those kk in the
 // direct-difference form and sorts by (value, index), exactly as merge_rescore_kernel does.
-constexpr int RSC_CH = 32;                 // dimensions per staging chunk
+constexpr int RSC_CH = 16;                 // dimensions per staging chunk (small: 8 CTAs per SM = one wave)
 constexpr int RSC_LD = RSC_CH + 4;         // row stride in floats: 16 B aligned, conflict-free LDS.128
 
 template <int K>
@@ -404,7 +404,9 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
   }
   __shared__ int s_over, s_redo;
   if (t == 0) {
-    s_fill = 0; s_thr = CFL_KEY_INF;
+    // under an optimistic threshold only rows with dist <= tau_opt can be in a VERIFIED top-kk
+    s_fill = 0;
+    s_thr = (tau_opt[q] < tau[q]) ? pack_key(tau_opt[q] * (1.0f + 1e-5f) + 1e-30f, 0u) : CFL_KEY_INF;
     int acc = 0, over = 0;
     for (int p = 0; p < parts; ++p) {
       s_pref[p] = acc;
@@ -439,17 +441,16 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
     for (int kq = 0; kq < K; ++kq) dk[kq] = 0.0f;
     for (int c0 = 0; c0 < dp; c0 += RSC_CH) {
       __syncwarp();
-      const int j = c0 + lane;
-      for (int r0 = 0; r0 < 32; r0 += 16) {                  // coalesced: one 128 B row segment per load,
-        float v[16];                                         // 16 independent loads in flight per thread
+      // coalesced: a load covers 16 dimensions (64 B) of TWO rows; 16 independent loads per thread
+      const int j = c0 + (lane & 15), half = lane >> 4;
+      float v[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const uint32_t ridx = __shfl_sync(0xffffffffu, idx, r0 + r);
-          v[r] = (j < d) ? __ldg(E + (int64_t)ridx * lde + j) : 0.0f;
-        }
-#pragma unroll
-        for (int r = 0; r < 16; ++r) my_rows[(r0 + r) * RSC_LD + lane] = v[r];
+      for (int r = 0; r < 16; ++r) {
+        const uint32_t ridx = __shfl_sync(0xffffffffu, idx, 2 * r + half);
+        v[r] = (j < d) ? __ldg(E + (int64_t)ridx * lde + j) : 0.0f;
       }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) my_rows[(2 * r + half) * RSC_LD + (lane & 15)] = v[r];
       __syncwarp();
       const float4* er = (const float4*)(my_rows + lane * RSC_LD);
 #pragma unroll
@@ -530,7 +531,7 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
                 v[r] = (j < d) ? __ldg(E + (int64_t)ridx * lde + j) : 0.0f;
               }
 #pragma unroll
-              for (int r = 0; r < 16; ++r) rows[(r0 + r) * ld2 + j] = v[r];
+              for (int r = 0; r < 16; ++r) if (j < dp) rows[(r0 + r) * ld2 + j] = v[r];
             }
           }
           __syncwarp();
