@@ -582,6 +582,107 @@ sample_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__
   }
 }
 
+// Same thresholds by radix selection instead of sorting: only the VALUES of the kk-th and r_opt-th
+// smallest distances are needed, so four 8-bit passes over the 32-bit ordered distances (staged in
+// shared memory when they fit) replace the ~20 cooperative sorts of block_merge_topkk.
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_SMEM_KEYS = 12288;
+
+__device__ __forceinline__ uint32_t radix_select(const uint32_t* __restrict__ sv, const tkey_t* __restrict__ keys,
+                                                 const int* __restrict__ s_pref, int parts, int64_t Q, int64_t q,
+                                                 int total, bool in_smem, int rank, int* hist, int* s_sel) {
+  // rank is 1-based; returns the ordered-uint value of the rank-th smallest
+  const int t = threadIdx.x;
+  uint32_t prefix = 0, mask = 0;
+  int want = rank;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = t; i < 256; i += SEL_THREADS) hist[i] = 0;
+    __syncthreads();
+    if (in_smem) {
+      for (int i = t; i < total; i += SEL_THREADS) {
+        const uint32_t v = sv[i];
+        if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1);
+      }
+    } else {
+      for (int p = 0; p < parts; ++p) {
+        const int c = s_pref[p + 1] - s_pref[p];
+        const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
+        for (int i = t; i < c; i += SEL_THREADS) {
+          const uint32_t v = (uint32_t)(src[i] >> 32);
+          if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1);
+        }
+      }
+    }
+    __syncthreads();
+    if (t < 32) {                                            // warp 0: find the bin holding the want-th key
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { loc[j] = hist[t * 8 + j]; sum += loc[j]; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (t >= o) incl += n; }
+      const int excl = incl - sum;
+      if (want > excl && want <= incl) {
+        int acc = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (want > acc && want <= acc + loc[j]) { s_sel[0] = t * 8 + j; s_sel[1] = want - acc; }
+          acc += loc[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (uint32_t)s_sel[0] << shift;
+    mask |= 255u << shift;
+    want = s_sel[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+select_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ counts, int parts,
+                        int64_t Q, int kk, float* __restrict__ tau, float* __restrict__ tau_opt, int r_opt) {
+  extern __shared__ uint32_t s_sel_dyn[];
+  int* s_pref = (int*)s_sel_dyn;                             // [parts + 1]
+  uint32_t* sv = s_sel_dyn + parts + 1;                      // [SEL_SMEM_KEYS]
+  __shared__ int hist[256];
+  __shared__ int s_sel[2];
+  const int t = threadIdx.x;
+  const int64_t q = blockIdx.x;
+  if (t == 0) {
+    int acc = 0;
+    for (int p = 0; p < parts; ++p) {
+      s_pref[p] = acc;
+      const int c = counts[(int64_t)p * Q + q];
+      acc += c > TOPK_STRIDE ? TOPK_STRIDE : (c < 0 ? 0 : c);
+    }
+    s_pref[parts] = acc;
+  }
+  __syncthreads();
+  const int total = s_pref[parts];
+  const float INF = __int_as_float(0x7f800000);
+  if (total < kk) {
+    if (t == 0) { tau[q] = INF; if (tau_opt) tau_opt[q] = INF; }
+    return;
+  }
+  const bool in_smem = total <= SEL_SMEM_KEYS;
+  if (in_smem) {
+    for (int p = 0; p < parts; ++p) {
+      const int c = s_pref[p + 1] - s_pref[p];
+      const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
+      for (int i = t; i < c; i += SEL_THREADS) sv[s_pref[p] + i] = (uint32_t)(src[i] >> 32);
+    }
+    __syncthreads();
+  }
+  const uint32_t vk = radix_select(sv, keys, s_pref, parts, Q, q, total, in_smem, kk, hist, s_sel);
+  const float safe = ord2f(vk);
+  float opt = safe;
+  if (tau_opt && r_opt >= 1 && r_opt < kk)
+    opt = ord2f(radix_select(sv, keys, s_pref, parts, Q, q, total, in_smem, r_opt, hist, s_sel));
+  if (t == 0) { tau[q] = safe; if (tau_opt) tau_opt[q] = opt; }
+}
+
 // After the filter pass under the optimistic thresholds: a query whose parts hold fewer than kk keys
 // in total may have lost members of its top-kk; it is redone under the safe threshold.  (A part's
 // count is either the number of rows it pushed or, after a compaction, still >= kk.)
@@ -736,7 +837,9 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       const bool two_pass = sstride > 1 && !dist_out && plan.tiles / plan.parts >= min_tiles;
       float* tau = (float*)(base + align_up(o_cimg + ((image == (const void*)(base + o_cimg)) ? catalog_image_bytes(N, d) : 0), 1024));
       if (!two_pass) timer_record(0, cs);
+      const size_t sel_smem = ((size_t)plan.parts + 1 + SEL_SMEM_KEYS) * sizeof(uint32_t);
       if (two_pass) {
+        CFL_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
         // Sample = every sstride-th tile of each part.  When a few collect-everything tiles per
         // part already give a bound tau_a under which the sample yields <= ~384 keys per buffer,
         // the sample itself is scored in filter mode (no barriers); otherwise it runs adaptively.
@@ -753,7 +856,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
           while ((tpp + 1 + a.tile_stride - 1) / a.tile_stride > 7) ++a.tile_stride;
           st = score_umma_launch(a, cs);
           if (st != CFL_OK) return st;
-          sample_threshold_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau);
+          select_threshold_kernel<<<(unsigned)Q, SEL_THREADS, sel_smem, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau, nullptr, 0);
           CFL_LAUNCH_CHECK();
           a.phase = 2; a.tile_stride = sstride; a.thr_init = tau;
           st = score_umma_launch(a, cs);
@@ -774,8 +877,8 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         const int opt_mult = eo ? atoi(eo) : 4;
         int r_opt = (int)((opt_mult * (int64_t)plan.kk + sstride - 1) / sstride);
         if (getenv("CFL_SCORE_NO_OPTIMISTIC")) r_opt = 0;
-        sample_threshold_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau,
-                                                                     tau_opt, r_opt);
+        select_threshold_kernel<<<(unsigned)Q, SEL_THREADS, sel_smem, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau,
+                                                                            tau_opt, r_opt);
         CFL_LAUNCH_CHECK();
         CFL_CUDA(cudaMemsetAsync(redo_tile, 0, (size_t)plan.nqt * sizeof(int), cs));
         a.phase = 2; a.tile_stride = 1; a.thr_init = tau_opt;
