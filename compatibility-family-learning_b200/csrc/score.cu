@@ -683,6 +683,23 @@ select_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__
   if (t == 0) { tau[q] = safe; if (tau_opt) tau_opt[q] = opt; }
 }
 
+// Probe of the lower-bound filter: score_lb_kernel over a few tiles per part under tau_opt.  A query
+// whose projected number of survivors over the whole range would swamp its key buffers (prototypes
+// nearly affinely dependent, or so far apart that the soft-min is one-hot: the affine-hull bound is
+// off or loose) is taken out of the lower-bound pass (tau_opt = -inf: nothing is pushed, verification
+// fails, the exact kernel redoes it) -- and a query tile with no live query costs nothing there.
+__global__ void probe_classify_kernel(const int* __restrict__ counts, int parts, int64_t Q, float scale,
+                                      float limit, float* __restrict__ tau_opt, unsigned long long* __restrict__ dbg) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  long long tot = 0;
+  for (int p = 0; p < parts; ++p) tot += counts[(int64_t)p * Q + q];
+  if ((float)tot * scale > limit) {
+    tau_opt[q] = __int_as_float(0xff800000);
+    (void)dbg;
+  }
+}
+
 // After the filter pass under the optimistic thresholds: a query whose parts hold fewer than kk keys
 // in total may have lost members of its top-kk; it is redone under the safe threshold.  (A part's
 // count is either the number of rows it pushed or, after a compaction, still >= kk.)
@@ -887,6 +904,22 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         // single-product lower-bound filter (survivors rescored exactly by rescore_merge_kernel), or
         // the exact 3xTF32 filter when disabled
         lb_pass = !getenv("CFL_SCORE_NO_LB");
+        if (lb_pass && !getenv("CFL_SCORE_NO_PROBE")) {
+          int probe_stride = (int)((tpp + 3) / 4);           // about 4 tiles per part
+          if (probe_stride < 1) probe_stride = 1;
+          const int64_t probe_tiles = (tpp + probe_stride - 1) / probe_stride;
+          a.phase = 3; a.tile_stride = probe_stride; a.dbg = nullptr;
+          st = score_lb_launch(a, cs);
+          if (st != CFL_OK) return st;
+          // only the pathological regimes (most rows survive) are taken out: 4x the total key capacity
+          const float limit = 4.0f * (float)plan.parts * (float)TOPK_STRIDE;
+          probe_classify_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, cs>>>(
+              a.counts, plan.parts, Q, (float)tpp / (float)probe_tiles, limit, tau_opt, dbg_on ? dbg_dev : nullptr);
+          CFL_LAUNCH_CHECK();
+          a.phase = 2; a.tile_stride = 1;
+          if (dbg_on) a.dbg = dbg_dev;
+          timer_record(0, cs);
+        }
         if (lb_pass) { a.phase = 3; st = score_lb_launch(a, cs); a.phase = 2; }
         else st = score_umma_launch(a, cs);
         timer_record(1, cs);

@@ -537,6 +537,14 @@ score_lb_kernel(ScoreArgs A) {
   const int ts = A.tile_stride;
   const int ntiles = (int)((t1 - t0 + ts - 1) / ts);
   const int kss = (nks % 4 == 0) ? 4 : ((nks % 2 == 0) ? 2 : 1);   // K-steps (4 KB hi blocks) per ring stage
+  if (A.thr_init != nullptr) {                               // no live query in this tile: nothing to do
+    bool live = false;
+    for (int i = tid; i < nq; i += SU_THREADS) live |= A.thr_init[q0 + i] > __int_as_float(0xff800000);
+    if (!__syncthreads_or(live)) {
+      for (int ql = tid; ql < nq; ql += SU_THREADS) A.counts[(int64_t)part * A.Q + q0 + ql] = 0;
+      return;
+    }
+  }
   constexpr uint32_t HI_BYTES = SU_ASTAGE / 2;                     // [chunk][128 rows][16 B]
   constexpr uint32_t STAGE_BYTES = 2 * SU_ASTAGE;
 
