@@ -261,7 +261,8 @@ __device__ __forceinline__ int block_merge_topkk(const tkey_t* __restrict__ keys
   if (t == 0) { *s_fill = 0; *s_thr = CFL_KEY_INF; }
   __syncthreads();
   for (int p = 0; p < parts; ++p) {
-    const int c = counts[(int64_t)p * Q + q];
+    int c = counts[(int64_t)p * Q + q];
+    if (c > TOPK_STRIDE) c = TOPK_STRIDE;                    // an over-full lower-bound buffer (flagged for redo)
     const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
     for (int base = 0; base < c; base += MRG_THREADS) {
       // every thread must take the same branch: read the fill level between two barriers, before
