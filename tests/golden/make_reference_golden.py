@@ -242,6 +242,75 @@ def evaluate_total_case():
         print("ref_evaluate_total[%s]: %s" % (k, v.strip()))
 
 
+# ---- dist_eval / dist_predict over a dataset directory -----------------------------------------------
+class _EagerSession(object):
+    """``sess.run(model.val_s_pos_predicts.outputs, feed_dict)`` for an eager stand-in: the fed
+    batches go through the reference's own val branch (cfl/models/cfl.py:710-722: dist_fn with
+    reuse=True on source and target, build_dist, thres_fn with reuse=True)."""
+
+    def __init__(self, model):
+        self.model = model
+
+    def run(self, fetch, feed_dict=None):
+        m = self.model
+        assert fetch is m.val_s_pos_predicts.outputs
+        src = tf_shim.T(np.asarray(feed_dict[m.val_input_data_pos_source], dtype=np.float64))
+        dst = tf_shim.T(np.asarray(feed_dict[m.val_input_data_pos_target], dtype=np.float64))
+        with tf.variable_scope(m.scope, reuse=True):
+            s_ = m.dist_fn(m.data_normalizer(src), name=m.dist_name_src, reuse=True)
+            t_ = m.dist_fn(m.data_normalizer(dst), name=m.dist_name_dst, reuse=True)
+            return _np(m.thres_fn(s_.build_dist(t_), reuse=True).outputs)
+
+
+def eval_predict_case():
+    from cfl import input_data as ref_input
+    from cfl import utils as ref_utils
+    rng = np.random.default_rng(21)
+    n, F, d, K, B = 60, 12, 6, 3, 16
+    ids = ["B%09d" % i for i in range(n)]
+    feats = (np.maximum(rng.normal(size=(n, F)), 0) * 4).astype(np.float32)
+    pos, neg = rng.integers(0, n, (37, 2)), rng.integers(0, n, (53, 2))
+    tf_shim.reset_default_graph()
+    presets = {"CFL/Thresholder/threshold/threshold": np.float64(1.3)}
+    presets.update(_wn_head(rng, "CFL/DistEncoder/outputs", F, d, True))
+    presets.update(_wn_head(rng, "CFL/DistEncoder/prototype_outputs", F, d * K, True))
+    tf_shim.preset_variables(presets)
+    data_norm = (4.0,)
+    norms = ref_ops.dist_normalizer(input_shape=(F,), ae_shape=None, data_scale=None, data_mean=None,
+                                    data_norm=data_norm, latent_norm=None, data_type="linear")
+    dummy = [tf_shim.T(np.zeros((B, F))) for _ in range(4)]
+    model = ref_cfl.CFL(
+        is_double=False, disable_double=False, latent_shape=None, source_shape=None, input_shape=(F,), ae_shape=None,
+        batch_size=B, data_norm=data_norm, data_type="linear", num_components=K, pos_weight=None, latent_size=d,
+        caffe_margin=None, gan=False, cgan=False, t_dim=None, dist_type="pcd", act_type=None, use_threshold=True,
+        lr=1e-3, beta1=0.9, beta2=0.999, z_dim=20, z_stddev=1.0, g_dim=64, g_lr=2e-4, g_beta1=0.5, g_beta2=0.999,
+        m_prj=None, m_enc=None, d_dim=64, d_lr=2e-4, d_beta1=0.5, d_beta2=0.999, lambda_gp=None, lambda_m=0.0,
+        lambda_dra=0.5, directed=False, data_directed=False, model_type="linear", gan_type="conv", reg_const=0.0,
+        batches=dummy, val_batches=list(dummy), unlabeled_batches=list(dummy), data_normalizer=norms[0],
+        data_unnormalizer=norms[1], ae_normalizer=norms[2], ae_unnormalizer=norms[3], latent_normalizer=norms[4])
+    out = {"ids": np.array(ids), "feats": feats, "pos": pos, "neg": neg, "F": F, "d": d, "K": K, "B": B,
+           "data_norm": np.array(data_norm)}
+    for k, v in presets.items():
+        out["var:" + k] = v
+    with tempfile.TemporaryDirectory() as dd:
+        with open(os.path.join(dd, "features.b"), "wb") as f:
+            for i, x in zip(ids, feats):
+                f.write(i.encode("ascii"))
+                f.write(x.astype("<f4").tobytes())
+        for name, pairs in (("pairs_pos.txt", pos), ("pairs_neg.txt", neg)):
+            with open(os.path.join(dd, name), "w") as f:
+                for a, b in pairs:
+                    f.write("%s match %s\n" % (ids[a], ids[b]))
+        ds = ref_input.SemiDataSet(dd, input_size=F, seed=633)
+        sess = _EagerSession(model)
+        rep = ref_utils.dist_eval(sess, model, B, ds)
+        out["eval_accuracy"], out["eval_error"], out["eval_auc"] = rep.accuracy, rep.error, rep.auc
+        ref_utils.dist_predict(sess, model, ds, B, os.path.join(dd, "pred"), "predict.txt")
+        out["predict_txt"] = np.array(open(os.path.join(dd, "pred", "predict.txt")).read())
+    np.savez_compressed(os.path.join(HERE, "ref_eval_predict.npz"), **out)
+    print("ref_eval_predict: accuracy=%.4f auc=%.6f, %d lines" % (rep.accuracy, rep.auc, len(str(out["predict_txt"]).splitlines())))
+
+
 if __name__ == "__main__":
     cfl_case("pcd_k3_dyadic", F=48, d=16, K=3, B=12, dist_type="pcd", pos_weight=0.0625, data_norm=(31.9098,), seed=1)
     cfl_case("pcd_k1", F=20, d=8, K=1, B=9, dist_type="pcd", seed=2)
@@ -260,3 +329,4 @@ if __name__ == "__main__":
     dist_case("k1_reg", F=20, d=6, K=1, B=8, normalize_value=2.0, reg_const=0.05, seed=12)
     dataset_case()
     evaluate_total_case()
+    eval_predict_case()

@@ -347,3 +347,45 @@ def test_dist_model_matches_reference_graph_fixture(path):
     _check_against_reference_fixture(m, z, "Dist", [("s_p_loss_pos", "s_p_loss_pos"), ("s_p_loss_neg", "s_p_loss_neg"),
                                                     ("s_thres_loss", "thres_loss"), ("s_total_loss", "s_total_loss"),
                                                     ("s_accuracy", "s_accuracy"), ("s_margins", "s_margins")])
+
+
+@pytest.mark.gpu
+def test_dist_eval_and_predict_file_match_reference_utils(tmp_path):
+    """tests/golden/ref_eval_predict.npz: the reference's cfl.utils.dist_eval / dist_predict run over its
+    own SemiDataSet and CFL graph (eager stand-in).  Ours: same weights, same directory, CUDA scoring
+    node + cfl_auc."""
+    from cfl import input_data as I
+    from cfl import variables as vs
+    from cfl.models.cfl import CFL
+    from cfl.ops import dist_normalizer
+    from cfl.utils import dist_eval, dist_predict
+    z = np.load(os.path.join(_GOLDEN, "ref_eval_predict.npz"))
+    F, d, K, B = (int(z[k]) for k in ("F", "d", "K", "B"))
+    ids = [str(s) for s in z["ids"]]
+    dd = str(tmp_path)
+    I.write_features(os.path.join(dd, "features.b"), ids, z["feats"])
+    for name, pairs in (("pairs_pos.txt", z["pos"]), ("pairs_neg.txt", z["neg"])):
+        with open(os.path.join(dd, name), "w") as f:
+            for a, b in pairs:
+                f.write("%s match %s\n" % (ids[a], ids[b]))
+    vs.reset_default_graph()
+    data_norm = tuple(float(x) for x in z["data_norm"])
+    norms = dist_normalizer(input_shape=(F,), ae_shape=None, data_scale=None, data_mean=None, data_norm=data_norm,
+                            latent_norm=None, data_type="linear")
+    m = CFL(input_shape=(F,), batch_size=B, latent_size=d, num_components=K, model_type="linear", dist_type="pcd",
+            data_type="linear", use_threshold=True, data_normalizer=norms[0], data_norm=data_norm)
+    m.load_state_dict({k: torch.tensor(z["var:" + k], dtype=torch.float32) for k in vs.get_collection(m.name)})
+    ds = I.SemiDataSet(dd, input_size=F, seed=633)
+    rep = dist_eval(None, m, B, ds)
+    assert rep.accuracy == pytest.approx(float(z["eval_accuracy"]), abs=1e-12)
+    assert rep.error == pytest.approx(float(z["eval_error"]), abs=1e-12)
+    assert rep.auc == pytest.approx(float(z["eval_auc"]), abs=1e-12)
+    dist_predict(None, m, ds, B, os.path.join(dd, "pred"), "predict.txt")
+    got = open(os.path.join(dd, "pred", "predict.txt")).read().splitlines()
+    want = str(z["predict_txt"]).splitlines()
+    assert len(got) == len(want) == len(z["pos"]) + len(z["neg"])
+    for g, w in zip(got, want):
+        ga, gm, gb, gs = g.split()
+        wa, wm, wb, ws = w.split()
+        assert (ga, gm, gb) == (wa, wm, wb)
+        assert float(gs) == pytest.approx(float(ws), rel=2e-4, abs=2e-5)
