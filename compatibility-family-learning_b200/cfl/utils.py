@@ -97,10 +97,26 @@ class Saver(object):
         return prefix
 
     def restore(self, sess, save_path, trainable_only=False):
-        sd = torch.load(save_path + self.SUFFIX, map_location="cpu")
+        if not os.path.exists(save_path + self.SUFFIX) and os.path.exists(save_path + ".index"):
+            # a checkpoint written by the reference's tf.train.Saver (V2 tensor bundle)
+            from .tf_checkpoint import load_tf_checkpoint, tf_to_state_dict
+            sd = tf_to_state_dict(load_tf_checkpoint(save_path), beta1=getattr(sess.model, "beta1", 0.9))
+        else:
+            sd = torch.load(save_path + self.SUFFIX, map_location="cpu")
         if trainable_only:          # assign_from_checkpoint_fn(trainable_variables(), ignore_missing_vars=True)
             sd = {k: v for k, v in sd.items() if not (k.endswith("/Adam") or k.endswith("/Adam_1") or k == "__step__")}
         sess.model.load_state_dict(sd)
+
+
+def export_tf_checkpoint(model, prefix):
+    """Write the model's variables (and Adam slots) as a TensorFlow V2 checkpoint that the reference's
+    ``saver.restore`` can read (cfl/utils.py:465-497)."""
+    from .tf_checkpoint import state_dict_to_tf, write_tf_checkpoint
+    write_tf_checkpoint(prefix, state_dict_to_tf(model.state_dict(), getattr(model, "beta1", 0.9),
+                                                 getattr(model, "beta2", 0.999)))
+    d = os.path.dirname(os.path.abspath(prefix))
+    with open(os.path.join(d, "checkpoint"), "w") as out:
+        out.write('model_checkpoint_path: "{0}"\nall_model_checkpoint_paths: "{0}"\n'.format(os.path.basename(prefix)))
 
 
 def _step_of(checkpoint_path):

@@ -115,3 +115,38 @@ def test_dataset_gathers_on_device_match_file_reads(tmp_path):
     sp, dp, sn, dn = ds.next_batch(64)
     np.testing.assert_array_equal(sp.cpu().numpy(), I.load_features_by_positions(path, ds.pairs_pos[:64, 0], 32))
     np.testing.assert_array_equal(dn.cpu().numpy(), I.load_features_by_positions(path, ds.pairs_neg[:64, 1], 32))
+
+
+def test_tf_checkpoint_round_trip_through_a_model(tmp_path):
+    """Variables + Adam slots + step leave as a TF V2 checkpoint under the reference's names and come
+    back into a fresh model: same scores, and the next train step continues identically."""
+    from cfl import tf_checkpoint as T
+    from cfl import variables as vs
+    from cfl.models.cfl import CFL
+    from cfl.utils import Session, export_tf_checkpoint, load_model
+    g = torch.Generator().manual_seed(3)
+    F, d, K, B = 40, 8, 3, 64
+    mk = lambda: CFL(input_shape=(F,), batch_size=B, latent_size=d, num_components=K, model_type="linear",
+                     dist_type="pcd", data_type="linear", use_threshold=True, reg_const=0.001, lr=0.01)
+    batch = [torch.randn(B, F, generator=g).clamp_(min=0).cuda() for _ in range(4)]
+    vs.reset_default_graph()
+    m = mk()
+    for _ in range(3):
+        m.train_step(*batch)
+    ck = str(tmp_path / "ck")
+    export_tf_checkpoint(m, os.path.join(ck, "model-2"))
+    names = set(T.load_tf_checkpoint(os.path.join(ck, "model-2")))
+    assert {"CFL/DistEncoder/outputs/fully_connected/V", "CFL/DistEncoder/prototype_outputs/fully_connected/g",
+            "CFL/Thresholder/threshold/threshold", "CFL/DistEncoder/outputs/fully_connected/V/Adam",
+            "CFL/DistEncoder/outputs/fully_connected/V/Adam_1", "beta1_power", "beta2_power"} <= names
+    want = m.predict(batch[0], batch[1]).clone()
+    out_a = m.train_step(*batch)
+    after_a = m.predict(batch[0], batch[1]).clone()
+    vs.reset_default_graph()
+    m2 = mk()
+    _, start = load_model(Session(m2), ck)
+    assert start == 3 and m2._step == 3
+    assert torch.equal(m2.predict(batch[0], batch[1]), want)
+    out_b = m2.train_step(*batch)
+    assert out_b["s_total_loss"] == out_a["s_total_loss"]
+    assert torch.equal(m2.predict(batch[0], batch[1]), after_a)
