@@ -58,6 +58,7 @@ SIGNATURES = {
     "cfl_auc_workspace_bytes": (_sz, [_i64, _i64]),
     "cfl_auc": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "cfl_adam_step": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "cfl_adam_step_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),
     "cfl_set_kernel_timer": (_int, [_vp, _vp]),
     "cfl_selftest_umma": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
 }
@@ -342,6 +343,19 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale
     _check(lib().cfl_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), int(step), float(lr),
                                float(beta1), float(beta2), float(eps), float(grad_scale), _stream()),
            "cfl_adam_step")
+
+
+def adam_step_dev(p, g, m, v, step_dev, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """adam_step with the step count read from a device int32 tensor when the kernel runs (CUDA graphs)."""
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _f32c(t, n)
+        if not t.is_contiguous():
+            raise CflNativeError(f"adam_step_dev: {n} must be contiguous")
+    if step_dev.dtype != torch.int32 or not step_dev.is_cuda:
+        raise CflNativeError("adam_step_dev: step_dev must be a CUDA int32 tensor")
+    _check(lib().cfl_adam_step_dev(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(step_dev), float(lr),
+                                   float(beta1), float(beta2), float(eps), float(grad_scale), _stream()),
+           "cfl_adam_step_dev")
 
 
 def set_kernel_timer(start_event=None, stop_event=None):

@@ -28,7 +28,7 @@ def train_dist(args):
         model.train(sess=sess, data=data, start_iter=start_iter, epochs=args.epochs, post_epochs=args.post_epochs,
                     best_dir=best_dir, best_acc_dir=best_acc_dir, checkpoint_dir=checkpoint_dir,
                     eval_epochs=args.eval_epochs, disable_eval=args.disable_eval, saver=saver, best_saver=Saver(),
-                    best_acc_saver=Saver(), save_iters=args.save_iters)
+                    best_acc_saver=Saver(), save_iters=args.save_iters, cuda_graph=args.cuda_graph)
     return model
 
 
@@ -42,6 +42,8 @@ def parse_args(argv=None):
     parser.add_argument("--eval-epochs", type=int, default=1)
     parser.add_argument("--disable-eval", action="store_true")
     parser.add_argument("--reset", action="store_true")
+    parser.add_argument("--cuda-graph", action="store_true",
+                        help="replay each train step as one CUDA graph (linear models, single process)")
     args = parser.parse_args(argv)
     dist_check_args(args)
     return args

@@ -284,6 +284,132 @@ class PairModel(ModelBase):
             self._ema_one("val_s_accuracy", out["val_s_accuracy"])
         return out
 
+    # ---- the same step with no host round trip, replayed as ONE CUDA graph --------------------------
+    _SCALARS = ("s_p_loss_pos", "s_p_loss_neg", "s_thres_loss", "s_cd_loss", "s_loss_reg", "s_total_loss",
+                "s_accuracy", "s_margins", "s_pos_dists_adapt", "s_neg_dists_adapt", "s_margin_adapt",
+                "val_s_accuracy")
+    _EMA_KEYS = ("s_accuracy", "s_margin_adapt", "s_pos_dists_adapt", "s_neg_dists_adapt", "val_s_accuracy")
+
+    def _device_step(self, xsp, xtp, xsn, xtn, val=None):
+        """train_step with every decision taken on the device: theta's tf.maximum gate, Adam's step count
+        (cfl_adam_step_dev), the fetched scalars and their moving averages stay in device tensors
+        (``fetch_scalars`` reads them).  ~60 small launches: captured once, replayed per batch."""
+        Bp, Bn = xsp.shape[0], xsn.shape[0]
+        sp = self._pair_fwd(self._encode(xsp, xtp, True), 1)
+        sn = self._pair_fwd(self._encode(xsn, xtn, True), 0)
+        first = {id(p): True for p in self._params}
+        dth_p = self._pair_bwd(sp, 1, Bp, first, want_ce=True)
+        dth_n = self._pair_bwd(sn, 0, Bn, first, want_ce=True)
+        th_sum = dth_p + dth_n
+        if not self.use_threshold:
+            pw = self.pos_weight if self.pos_weight else 1.0
+            _, _, _, a_ = nat.pair_loss_bwd(sp.mode, sp.a, sp.P3, w=sp.w, theta=self.raw_threshold, label=1,
+                                            c_ce=pw / Bp, want_dtheta=True)
+            _, _, _, b_ = nat.pair_loss_bwd(sn.mode, sn.a, sn.P3, w=sn.w, theta=self.raw_threshold, label=0,
+                                            c_ce=1.0 / Bn, want_dtheta=True)
+            th_sum = a_ + b_
+        live = self.raw_threshold.detach() >= _THETA_FLOOR32
+        self._grads[id(self.raw_threshold)].copy_(
+            torch.where(live, th_sum.reshape(()).to(torch.float32), torch.zeros((), device=th_sum.device)))
+        idle = set()
+        for enc in ([self.enc_src] if not self.directed else [self.enc_src, self.enc_dst]):
+            for h in enc.heads():
+                if not first[id(h.V)]:
+                    continue
+                for p_ in h.params():
+                    if self.reg_const and p_ is not h.g:
+                        self._grads[id(p_)].copy_(p_.detach()).mul_(self.reg_const)
+                    else:
+                        self._grads[id(p_)].zero_()
+                        idle.add(id(p_))
+        reg = self.reg_loss_value()                          # of the weights the losses were computed with
+        self._step_dev.add_(1)
+        for p in self._params + self.th_vars:
+            if id(p) in idle:
+                continue
+            m, v = self._adam[id(p)]
+            nat.adam_step_dev(p.data.view(-1), self._grads[id(p)].view(-1), m.view(-1), v.view(-1), self._step_dev,
+                              self.lr, self.beta1, self.beta2, 1e-8, 1.0)
+        # the scalars of _losses_from_stats, on the device (float64)
+        stp, stn = sp.stats, sn.stats
+        pw = self.pos_weight
+        lp, ln = stp[0] / Bp, stn[0] / Bn
+        thres = lp * pw + ln if pw else lp + ln
+        reg = reg.double() if torch.is_tensor(reg) else torch.zeros((), dtype=torch.float64, device=stp.device)
+        total = reg + (thres if self.use_threshold else 0.0)
+        mean_dp, mean_dn = stp[2] / Bp, stn[2] / Bn
+        cd = torch.zeros((), dtype=torch.float64, device=stp.device)
+        if self.caffe_margin:
+            cd = 0.5 * ((mean_dp * pw if pw else mean_dp) + stn[4] / Bn)
+            total = total + cd
+        elif self.lambda_m:
+            cd = mean_dp * self.lambda_m * (pw if pw else 1.0)
+            total = total + cd
+        acc = 0.5 * (stp[1] / Bp + stn[1] / Bn)
+        pda, nda = stp[3] / Bp, stn[3] / Bn
+        if val is not None:
+            vp, vn = self.predict(val[0], val[1]), self.predict(val[2], val[3])
+            vacc = 0.5 * ((vp > 0).double().mean() + (vn <= 0).double().mean())
+        else:
+            vacc = torch.zeros((), dtype=torch.float64, device=stp.device)
+        vals = torch.stack([lp, ln, thres, cd, reg, total, acc, mean_dp - mean_dn, pda, nda, 0.5 * (pda + nda), vacc])
+        self._dev_scalars.copy_(vals)
+        sel = torch.stack([acc, 0.5 * (pda + nda), pda, nda, vacc])
+        self._dev_ema.mul_(self.ema_decay).add_(sel, alpha=1.0 - self.ema_decay)
+        self.s_pos_dists, self.s_neg_dists = sp.dist.view(-1, 1), sn.dist.view(-1, 1)
+        self.s_pos_predicts = SimpleNamespace(outputs=sp.score.view(-1, 1), threshold=self.threshold)
+        self.s_neg_predicts = SimpleNamespace(outputs=sn.score.view(-1, 1), threshold=self.threshold)
+
+    def train_step_graph(self, src_pos, dst_pos, src_neg, dst_neg, val_batches=None):
+        """One optimiser step replayed from a CUDA graph (single process only).  The first two calls of a
+        given batch shape run the same device-only step eagerly (they warm every workspace), the third
+        captures, later ones copy the batch into the graph's static inputs and replay.  Returns nothing:
+        ``fetch_scalars()`` reads the last step's scalars and moving averages when they are wanted."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+                torch.distributed.get_world_size() > 1:
+            raise RuntimeError("train_step_graph is single-process; use train_step for data-parallel training")
+        xs = [self._prep(t) for t in (src_pos, dst_pos, src_neg, dst_neg)]
+        vx = [self._prep(t) for t in val_batches] if val_batches is not None else None
+        dev = xs[0].device
+        if not hasattr(self, "_step_dev"):
+            self._step_dev = torch.tensor(self._step, dtype=torch.int32, device=dev)
+            self._dev_scalars = torch.zeros(len(self._SCALARS), dtype=torch.float64, device=dev)
+            self._dev_ema = torch.zeros(len(self._EMA_KEYS), dtype=torch.float64, device=dev)
+            self._graph, self._graph_key, self._graph_warm = None, None, 0
+        key = (tuple(tuple(x.shape) for x in xs), None if vx is None else tuple(tuple(x.shape) for x in vx))
+        if key != self._graph_key:
+            self._graph, self._graph_key, self._graph_warm = None, key, 0
+        if self._graph is None and self._graph_warm < 2:
+            self._step_dev.fill_(self._step)
+            self._device_step(*xs, val=vx)
+            self._graph_warm += 1
+        else:
+            if self._graph is None:
+                self._static_in = [torch.empty_like(x) for x in xs]
+                self._static_val = [torch.empty_like(x) for x in vx] if vx is not None else None
+                torch.cuda.synchronize()
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._device_step(*self._static_in, val=self._static_val)
+            for s_, x in zip(self._static_in, xs):
+                s_.copy_(x)
+            if vx is not None:
+                for s_, x in zip(self._static_val, vx):
+                    s_.copy_(x)
+            self._graph.replay()
+        self._step += 1
+
+    def fetch_scalars(self):
+        """Scalars of the last graph step (one device->host read), attributes and averages as train_step sets."""
+        vals = self._dev_scalars.cpu().tolist()
+        ema = self._dev_ema.cpu().tolist()
+        out = dict(zip(self._SCALARS, vals))
+        for k, v_ in out.items():
+            setattr(self, k, v_)
+        for k, b in zip(self._EMA_KEYS, ema):
+            setattr(self, k + "_avg", b / (1 - self.ema_decay ** max(self._step, 1)))
+        return out
+
     def val_accuracy(self, src_pos, dst_pos, src_neg, dst_neg):
         """cfl.py:941-949: accuracy of the val batch evaluated alongside each train step."""
         sp, sn = self.predict(src_pos, dst_pos), self.predict(src_neg, dst_neg)
@@ -334,7 +460,8 @@ class PairModel(ModelBase):
     # ------------------------------------------------------------------------------------------
     def train(self, sess, data, start_iter, epochs, post_epochs, best_dir, best_acc_dir, checkpoint_dir,
               epoch_callback=None, post_epoch_callback=None, save_epochs=1, eval_epochs=1, save_iters=None,
-              disable_eval=False, saver=None, best_saver=None, best_acc_saver=None, writer=None, check=None):
+              disable_eval=False, saver=None, best_saver=None, best_acc_saver=None, writer=None, check=None,
+              cuda_graph=False):
         """The epoch loop of cfl/models/cfl.py:1349-1511 for the distance model (post epochs belong to
         the GAN half and are always 0 here, as in the reference when ``gan`` is off): per step one
         labelled train batch + one val batch; per ``eval_epochs`` a full ``dist_eval`` on val, and on a
@@ -362,8 +489,15 @@ class PairModel(ModelBase):
         for e in range(start_epoch, epochs):
             first = start_iter % nb_batch if e == start_epoch else 0
             for i in range(first, nb_batch):
-                out = self.train_step(*data.train.next_batch(self.batch_size),
-                                      val_batches=data.val.next_batch(self.batch_size))
+                if cuda_graph:                               # no host round trip per step; scalars read per epoch
+                    self.train_step_graph(*data.train.next_batch(self.batch_size),
+                                          val_batches=data.val.next_batch(self.batch_size))
+                    if i + 1 < nb_batch and not (save_iters and i > 0 and i % save_iters == 0):
+                        continue
+                    out = self.fetch_scalars()
+                else:
+                    out = self.train_step(*data.train.next_batch(self.batch_size),
+                                          val_batches=data.val.next_batch(self.batch_size))
                 train_avg, val_avg = self.s_accuracy_avg, self.val_s_accuracy_avg
                 if writer is not None:
                     writer.add_summary(out, nb_batch * e + i)

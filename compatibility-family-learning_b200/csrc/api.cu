@@ -77,6 +77,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                const int* __restrict__ step_dev, float lr, float b1, float b2, float eps,
+                                float gscale) {
+  const int t = *step_dev;
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float gi = g[i] * gscale;
+    float mi = b1 * m[i] + (1.0f - b1) * gi;
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
 // ---- column mean (centring vector) ------------------------------------------------------
 // stage 1: each block sums a contiguous slab of rows in double, fixed order per block.
 __global__ void col_sum_partial(const float* __restrict__ E, int64_t N, int d, int64_t lde,
@@ -135,6 +152,21 @@ int cfl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int s
   if (blocks > cap) blocks = cap;
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)lr_t, beta1, beta2,
                                                        eps, grad_scale);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+int cfl_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const int* step_dev, float lr,
+                      float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(p && g && m && v && step_dev && n >= 0, CFL_ERR_INVALID, "adam_dev: bad arguments");
+  if (n == 0) return CFL_OK;
+  int blocks = (int)((n + 255) / 256);
+  int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  adam_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step_dev, lr, beta1, beta2, eps,
+                                                           grad_scale);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
 }

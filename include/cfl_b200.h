@@ -176,6 +176,10 @@ int cfl_auc(const float* pos_scores, int64_t n_pos, const float* neg_scores, int
  * p -= lr_t*m/(sqrt(v)+eps).  grad_scale multiplies g first (1/world for DP averaging). */
 int cfl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step,
                   float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* Same update with the step count t read from DEVICE memory (*step_dev >= 1) when the kernel runs, so
+ * a CUDA graph of the whole train step can be replayed while the count advances on the device. */
+int cfl_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const int* step_dev,
+                      float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* Measurement hook: when both events are non-NULL, cfl_score_topk records them (cudaEventRecord
  * on the call's stream) immediately before and after its dominant scoring kernel, so bench.py can

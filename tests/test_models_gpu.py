@@ -389,3 +389,46 @@ def test_dist_eval_and_predict_file_match_reference_utils(tmp_path):
         wa, wm, wb, ws = w.split()
         assert (ga, gm, gb) == (wa, wm, wb)
         assert float(gs) == pytest.approx(float(ws), rel=2e-4, abs=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["cfl_pcd", "cfl_monomer_reg", "dist", "siamese_margin"])
+def test_graph_train_step_equals_eager(kind):
+    """train_step_graph (device-only step replayed as a CUDA graph) follows train_step exactly."""
+    from cfl import variables as vs
+    from cfl.models.cfl import CFL
+    from cfl.models.dist import Dist
+    from cfl.ops import normalizer
+    F, d, K, B = 48, 8, 3, 32
+
+    def make():
+        vs.reset_default_graph()
+        vs.set_seed(5)
+        if kind == "dist":
+            return Dist(input_shape=(F,), latent_size=d, num_components=K, batch_size=B, lr=1e-2, beta1=0.9,
+                        beta2=0.999, normalize_value=2.0, data_normalizer=normalizer(2.0, 0.0), reg_const=0.01)
+        kw = dict(input_shape=(F,), batch_size=B, latent_size=d, num_components=K, model_type="linear",
+                  data_type="linear", lr=1e-2)
+        if kind == "cfl_pcd":
+            return CFL(dist_type="pcd", use_threshold=True, pos_weight=0.25, **kw)
+        if kind == "cfl_monomer_reg":
+            return CFL(dist_type="monomer", act_type="tanh", use_threshold=True, reg_const=0.01, **kw)
+        return CFL(dist_type="siamese", use_threshold=False, caffe_margin=2.0, pos_weight=0.5, **{**kw, "num_components": 1})
+
+    g = torch.Generator().manual_seed(9)
+    batches = [[torch.randn(B, F, generator=g).clamp_(min=0).cuda() for _ in range(4)] for _ in range(7)]
+    vals = [[torch.randn(B, F, generator=g).clamp_(min=0).cuda() for _ in range(4)] for _ in range(7)]
+    a = make()
+    outs = [a.train_step(*b, val_batches=v) for b, v in zip(batches, vals)]
+    pa = {k: v.detach().clone() for k, v in vs.get_collection(a.name).items()}
+    avg_a = (a.s_accuracy_avg, a.val_s_accuracy_avg, a.s_margin_adapt_avg)
+    b_ = make()
+    for bt, v in zip(batches, vals):
+        b_.train_step_graph(*bt, val_batches=v)
+    got = b_.fetch_scalars()
+    assert b_._graph is not None and b_._step == 7
+    for k, v in vs.get_collection(b_.name).items():
+        torch.testing.assert_close(v.detach(), pa[k], rtol=2e-6, atol=1e-7, msg=k)
+    for k in ("s_total_loss", "s_thres_loss", "s_accuracy", "s_margins", "s_loss_reg", "val_s_accuracy"):
+        assert got[k] == pytest.approx(outs[-1][k], rel=1e-6, abs=1e-9), k
+    assert (b_.s_accuracy_avg, b_.val_s_accuracy_avg, b_.s_margin_adapt_avg) == pytest.approx(avg_a, rel=1e-9)

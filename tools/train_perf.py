@@ -37,3 +37,27 @@ for B in (100, 4096, 65536):
     print(json.dumps(dict(B=B, step_ms=round(ms, 3), pairs_per_s=round(2 * B / ms * 1e3), proj_fwd_ms=round(fwd, 4),
                           proj_bwd_ms=round(bwd, 4), proj_fwd_tflops=round(2.0 * B * F * K * d / fwd / 1e9, 1),
                           proj_bwd_tflops=round(2.0 * B * F * K * d / bwd / 1e9, 1))), flush=True)
+
+
+def bench_graph(B, F, K, d, reps=200):
+    """Same model, step replayed as one CUDA graph (no host round trip)."""
+    import time
+    from cfl import variables as vs
+    from cfl.models.dist import Dist
+    from cfl.ops import normalizer
+    vs.reset_default_graph()
+    model = Dist(input_shape=(F,), latent_size=d, num_components=K, batch_size=B, lr=1e-3, beta1=0.9, beta2=0.999,
+                 normalize_value=58.388599, data_normalizer=normalizer(58.388599, 0.0))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    batch = [torch.randn(B, F, generator=g, device="cuda").clamp_(min=0) * 20 for _ in range(4)]
+    for _ in range(5): model.train_step_graph(*batch)
+    torch.cuda.synchronize(); t0 = time.time()
+    for _ in range(reps): model.train_step_graph(*batch)
+    torch.cuda.synchronize()
+    ms = (time.time() - t0) / reps * 1e3
+    print(json.dumps(dict(mode="cuda_graph", B=B, F=F, K=K, d=d, ms_per_step=round(ms, 4), pairs_per_s=round(2 * B / ms * 1e3))))
+
+
+if __name__ == "__main__":
+    for B in (100, 1000, 8192):
+        bench_graph(B, 4096, 4, 20)
