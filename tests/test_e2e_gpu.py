@@ -150,3 +150,31 @@ def test_tf_checkpoint_round_trip_through_a_model(tmp_path):
     out_b = m2.train_step(*batch)
     assert out_b["s_total_loss"] == out_a["s_total_loss"]
     assert torch.equal(m2.predict(batch[0], batch[1]), after_a)
+
+
+def test_cfl_train_with_cuda_graph_matches_eager_run(tmp_path):
+    """`python -m cfl.bin.train --cuda-graph` writes the same checkpoints and best-model statistics as the
+    eager loop on the same data and seed."""
+    from cfl import variables as vs
+    from cfl.bin import train
+    from cfl.utils import load_best_stats
+    root = str(tmp_path)
+    _make_dataset(os.path.join(root, "parsed_data", "toy"))
+    stats = []
+    for tag, extra in (("eager", []), ("graph", ["--cuda-graph"])):
+        vs.reset_default_graph()
+        common = ["--data-name", "toy", "--data-root", os.path.join(root, "parsed_data"), "--checkpoint-root",
+                  os.path.join(root, "ck_" + tag), "--log-root", os.path.join(root, "logs_" + tag), "--model-type",
+                  "linear", "--data-type", "linear", "--data-norm", "8.0", "--input-shape", "32", "--dist-type", "pcd",
+                  "--use-threshold", "--num-components", "2", "--latent-size", "16", "--lr", "0.03",
+                  "--batch-size", "100", "--epochs", "4", "--data-switch"]
+        m = train.main(common + extra)
+        ck = os.path.join(root, "ck_" + tag, "toy", m.get_name())
+        stats.append((load_best_stats(os.path.join(ck, "best_model", "best_accuracy")), m._step,
+                      {k: v.detach().clone() for k, v in vs.get_collection(m.name).items()}))
+    (sa, na, pa), (sb, nb, pb) = stats
+    assert na == nb == 60
+    assert sa.best_epoch == sb.best_epoch
+    assert sb.best_auc == pytest.approx(sa.best_auc, abs=2e-4) and sb.best_accuracy == pytest.approx(sa.best_accuracy, abs=5e-3)
+    for k in pa:
+        torch.testing.assert_close(pb[k], pa[k], rtol=1e-3, atol=1e-4, msg=k)
