@@ -387,12 +387,13 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
                      const float* __restrict__ E, int64_t lde, int64_t idx_base,
                      float* __restrict__ top_val, int64_t* __restrict__ top_idx,
                      const float* __restrict__ tau, const float* __restrict__ tau_opt, int qt,
-                     float* __restrict__ thr_redo, int* __restrict__ redo_tile, unsigned long long* __restrict__ dbg) {
+                     float* __restrict__ thr_redo, int* __restrict__ redo_tile, unsigned long long* __restrict__ dbg,
+                     const tkey_t* __restrict__ spill, const int* __restrict__ spill_cnt) {
   extern __shared__ __align__(16) float s_dyn[];
   const int dp = (d + RSC_CH - 1) / RSC_CH * RSC_CH;        // d padded to whole chunks
   float* s_pq = s_dyn;                                       // [K][dp], zero padded
   float* s_rows = s_pq + K * dp;                             // [warps][32][RSC_LD]
-  int* s_pref = (int*)(s_rows + (MRG_THREADS / 32) * 32 * RSC_LD);   // [parts + 1]
+  int* s_pref = (int*)(s_rows + (MRG_THREADS / 32) * 32 * RSC_LD);   // [parts + 2]
   __shared__ tkey_t s[TOPK_CAP];
   __shared__ int s_fill;
   __shared__ tkey_t s_thr;
@@ -412,10 +413,14 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
     for (int p = 0; p < parts; ++p) {
       s_pref[p] = acc;
       int c = counts[(int64_t)p * Q + q];
-      over |= c > TOPK_STRIDE;                               // the filter pass dropped keys of this query
+      // (keys beyond a full part buffer went to the query's spill list; only ITS overflow loses keys)
       acc += c > TOPK_STRIDE ? TOPK_STRIDE : c;
     }
-    s_pref[parts] = acc;
+    s_pref[parts] = acc;                                     // list `parts` = this query's spill list
+    int sc = spill_cnt[q];
+    over |= sc > LB_SPILL;
+    acc += sc > LB_SPILL ? LB_SPILL : sc;
+    s_pref[parts + 1] = acc;
     s_over = over;
   }
   __syncthreads();
@@ -426,7 +431,7 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
     s_D[i] = acc;
   }
   __syncthreads();
-  const int total = s_pref[parts];
+  const int total = s_pref[parts + 1];
   float* my_rows = s_rows + wid * 32 * RSC_LD;
   for (int base = 0; base < total; base += MRG_THREADS) {
     const int f = base + t;
@@ -435,7 +440,8 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
     if (have) {
       int p = 0;
       while (s_pref[p + 1] <= f) ++p;
-      idx = (uint32_t)(keys[((int64_t)p * Q + q) * TOPK_STRIDE + (f - s_pref[p])] & 0xffffffffu);
+      const tkey_t* src = (p < parts) ? keys + ((int64_t)p * Q + q) * TOPK_STRIDE : spill + q * (int64_t)LB_SPILL;
+      idx = (uint32_t)(src[f - s_pref[p]] & 0xffffffffu);
     }
     float dk[K];
 #pragma unroll
@@ -690,10 +696,11 @@ select_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__
 // off or loose) is taken out of the lower-bound pass (tau_opt = -inf: nothing is pushed, verification
 // fails, the exact kernel redoes it) -- and a query tile with no live query costs nothing there.
 __global__ void probe_classify_kernel(const int* __restrict__ counts, int parts, int64_t Q, float scale,
-                                      float limit, float* __restrict__ tau_opt, unsigned long long* __restrict__ dbg) {
+                                      float limit, float* __restrict__ tau_opt, unsigned long long* __restrict__ dbg,
+                                      const int* __restrict__ spill_cnt) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
-  long long tot = 0;
+  long long tot = spill_cnt ? spill_cnt[q] : 0;
   for (int p = 0; p < parts; ++p) tot += counts[(int64_t)p * Q + q];
   if ((float)tot * scale > limit) {
     tau_opt[q] = __int_as_float(0xff800000);
@@ -770,6 +777,8 @@ static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePla
   *o_cimg = off; off = align_up(off + ((p.impl && own_image) ? catalog_image_bytes(N, d) : 0), 1024);
   // tau[Q], tau_opt[Q], thr_redo[Q], redo flags per query tile: live right after (see `tau` below)
   off = align_up(off + (size_t)(3 * Q + p.nqt + 4) * sizeof(float), 256);
+  // lower-bound pass: per-query spill list for keys that do not fit their (part, query) buffer + counters
+  if (p.impl) off = align_up(off + (size_t)Q * LB_SPILL * sizeof(tkey_t) + (size_t)Q * sizeof(int), 256);
   return off + 1024;
 }
 
@@ -821,7 +830,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   a.keys = (tkey_t*)(base + o_keys); a.counts = (int*)(base + o_cnt); a.dist_out = dist_out;
   a.cimg = nullptr; a.e2 = nullptr;
   a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
-  a.dbg = nullptr; a.redo_tile = nullptr;
+  a.dbg = nullptr; a.redo_tile = nullptr; a.spill = nullptr; a.spill_cnt = nullptr;
   bool lb_pass = false;
   const float* redo_only = nullptr;
   a.dbg_mode = getenv("CFL_SCORE_DBG_MODE") ? atoi(getenv("CFL_SCORE_DBG_MODE")) : 0;
@@ -891,6 +900,8 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         float* tau_opt = tau + Q;
         float* thr_redo = tau + 2 * Q;
         int* redo_tile = (int*)(tau + 3 * Q);
+        a.spill = (tkey_t*)((char*)tau + align_up((size_t)(3 * Q + plan.nqt + 4) * sizeof(float), 256));
+        a.spill_cnt = (int*)(a.spill + (size_t)Q * LB_SPILL);
         const char* eo = getenv("CFL_SCORE_OPT_MULT");
         const int opt_mult = eo ? atoi(eo) : 4;
         int r_opt = (int)((opt_mult * (int64_t)plan.kk + sstride - 1) / sstride);
@@ -904,38 +915,46 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         if (dbg_on) { CFL_CUDA(cudaMemsetAsync(dbg_dev, 0, 32, cs)); a.dbg = dbg_dev; }
         // single-product lower-bound filter (survivors rescored exactly by rescore_merge_kernel), or
         // the exact 3xTF32 filter when disabled
-        lb_pass = !getenv("CFL_SCORE_NO_LB");
+        // the affine hull of K prototypes has K-1 dimensions: for K > 4 it swallows so much of a
+        // low-dimensional embedding that the bound stops rejecting (measured: K=8 survivors overflow
+        // at d=20..64), so those shapes keep the exact filter (optimistic threshold + exact counts)
+        lb_pass = !getenv("CFL_SCORE_NO_LB") && (K <= 4 || getenv("CFL_SCORE_FORCE_LB"));
         if (lb_pass && !getenv("CFL_SCORE_NO_PROBE")) {
           int probe_stride = (int)((tpp + 3) / 4);           // about 4 tiles per part
           if (probe_stride < 1) probe_stride = 1;
           const int64_t probe_tiles = (tpp + probe_stride - 1) / probe_stride;
           a.phase = 3; a.tile_stride = probe_stride; a.dbg = nullptr;
+          CFL_CUDA(cudaMemsetAsync(a.spill_cnt, 0, (size_t)Q * sizeof(int), cs));
           st = score_lb_launch(a, cs);
           if (st != CFL_OK) return st;
           // only the pathological regimes (most rows survive) are taken out: 4x the total key capacity
-          const float limit = 4.0f * (float)plan.parts * (float)TOPK_STRIDE;
+          const float limit = 4.0f * ((float)plan.parts * (float)TOPK_STRIDE + (float)LB_SPILL);
           probe_classify_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, cs>>>(
-              a.counts, plan.parts, Q, (float)tpp / (float)probe_tiles, limit, tau_opt, dbg_on ? dbg_dev : nullptr);
+              a.counts, plan.parts, Q, (float)tpp / (float)probe_tiles, limit, tau_opt, dbg_on ? dbg_dev : nullptr,
+              a.spill_cnt);
           CFL_LAUNCH_CHECK();
           a.phase = 2; a.tile_stride = 1;
           if (dbg_on) a.dbg = dbg_dev;
           timer_record(0, cs);
         }
-        if (lb_pass) { a.phase = 3; st = score_lb_launch(a, cs); a.phase = 2; }
+        if (lb_pass) {
+          CFL_CUDA(cudaMemsetAsync(a.spill_cnt, 0, (size_t)Q * sizeof(int), cs));
+          a.phase = 3; st = score_lb_launch(a, cs); a.phase = 2;
+        }
         else st = score_umma_launch(a, cs);
         timer_record(1, cs);
         if (st != CFL_OK) return st;
         if (lb_pass) {
           // exact rescoring of every survivor + verification; flagged queries are redone below
           const int dp = (d + RSC_CH - 1) / RSC_CH * RSC_CH;
-          const size_t rs_smem = ((size_t)K * dp + (size_t)(MRG_THREADS / 32) * 32 * RSC_LD + plan.parts + 1 + 4) * sizeof(float);
+          const size_t rs_smem = ((size_t)K * dp + (size_t)(MRG_THREADS / 32) * 32 * RSC_LD + plan.parts + 2 + 4) * sizeof(float);
 #define CFL_RSC_CASE(KK)                                                                                        \
   case KK:                                                                                                      \
     CFL_CUDA(cudaFuncSetAttribute(rescore_merge_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                   (int)rs_smem));                                                               \
     rescore_merge_kernel<KK><<<(unsigned)Q, MRG_THREADS, rs_smem, cs>>>(                                        \
         a.keys, a.counts, plan.parts, Q, plan.kk, k, Pq, ldq, d, E, lde, idx_base, top_val, top_idx, tau,       \
-        tau_opt, plan.qt, thr_redo, redo_tile, a.dbg);                                                          \
+        tau_opt, plan.qt, thr_redo, redo_tile, a.dbg, a.spill, a.spill_cnt);                                    \
     break;
           switch (K) {
             CFL_RSC_CASE(1) CFL_RSC_CASE(2) CFL_RSC_CASE(3) CFL_RSC_CASE(4)

@@ -37,6 +37,8 @@ struct ScoreArgs {
   // phase 2 = full pass filtering against the fixed per-query thresholds thr_init (dist <= thr).
   int phase, tile_stride;
   const float* thr_init; // [Q], phase 2
+  tkey_t* spill;         // lower-bound pass: [Q, LB_SPILL] keys that did not fit their (part, query) buffer
+  int* spill_cnt;        // [Q]
   const int* redo_tile;  // phase 2 redo launch: per query tile, 1 = some query must be redone (else the CTA exits)
   int dbg_mode;          // experiments (CFL_SCORE_DBG_MODE): 1 = epilogue does nothing, 2 = no TMA / no full-barrier waits
   unsigned long long* dbg; // optional counters {groups seen, skipped, selective, full} (CFL_SCORE_DEBUG)

@@ -703,7 +703,21 @@ score_lb_kernel(ScoreArgs A) {
             if (lane == leader) basei = atomicAdd(&cnt[ql], __popc(m));
             basei = __shfl_sync(0xffffffffu, basei, leader);
             const int slot = basei + __popc(m & lane_lt);
-            if (pass && slot < TOPK_STRIDE) kbase[(int64_t)ql * TOPK_STRIDE + slot] = pack_key(lb[i], (uint32_t)row);
+            if (basei + __popc(m) <= TOPK_STRIDE) {                // warp-uniform
+              if (pass) kbase[(int64_t)ql * TOPK_STRIDE + slot] = pack_key(lb[i], (uint32_t)row);
+            } else {                                           // this part's buffer is full: spill list of the query
+              const uint32_t sm = __ballot_sync(0xffffffffu, pass && slot >= TOPK_STRIDE);
+              int sb = 0;
+              if (lane == leader && sm) sb = atomicAdd(&A.spill_cnt[q0 + ql], __popc(sm));
+              sb = __shfl_sync(0xffffffffu, sb, leader);
+              if (pass) {
+                if (slot < TOPK_STRIDE) kbase[(int64_t)ql * TOPK_STRIDE + slot] = pack_key(lb[i], (uint32_t)row);
+                else {
+                  const int sp = sb + __popc(sm & lane_lt);
+                  if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = pack_key(lb[i], (uint32_t)row);
+                }
+              }
+            }
             dbg_push += __popc(m);
           }
         }

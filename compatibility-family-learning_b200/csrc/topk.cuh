@@ -18,6 +18,7 @@ namespace cfl {
 constexpr int TOPK_CAP = 512;     // keys per (part, query) buffer that the adaptive mode may hold
 constexpr int TOPK_STRIDE = 2048; // keys reserved per (part, query) buffer (filter / lower-bound passes use all)
 constexpr int TOPK_FILTER_TRIGGER = TOPK_STRIDE - 256;   // filter mode: slow path above this
+constexpr int LB_SPILL = 16384;   // per-QUERY spill list of the lower-bound pass (keys beyond a full part buffer)
 constexpr int TOPK_TILE = 128;    // max appends per query between two compaction points
 constexpr int TOPK_TRIGGER = TOPK_CAP - TOPK_TILE;   // compact when cnt > 384 at a tile end
 
