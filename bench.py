@@ -162,13 +162,17 @@ def run_ours(args):
     def step_device(i):
         return index.rank(xq_dev[i % nb], TOPK)
 
+    out_ring = [(out_v, out_i), (torch.empty_like(out_v).pin_memory(), torch.empty_like(out_i).pin_memory())]
+    pending = []
+
     def step_e2e(i):
-        xq = xq_host[i % nb].to(device, non_blocking=True)        # H2D inside the timed region
-        tv, ti = index.rank(xq, TOPK)
-        out_v.copy_(tv, non_blocking=True)                        # D2H of the step's result
-        out_i.copy_(ti, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return tv, ti
+        # the call a user with HOST buffers makes: pinned features in, pinned top-k out.  H2D of this
+        # batch, scoring and D2H of its result are all inside the timed region; consecutive batches
+        # overlap (copy / compute / copy-back streams), the loop's closing synchronize waits for all.
+        ov, oi = out_ring[i & 1]
+        if len(pending) >= 2:
+            pending.pop(0).synchronize()                          # the ring slot's previous result was delivered
+        pending.append(index.rank_host(xq_host[i % nb], TOPK, ov, oi))
 
     def timed(step_fn, steps, warmup, kernel_events=False):
         for i in range(warmup):
@@ -186,6 +190,9 @@ def run_ours(args):
                 nat.set_kernel_timer(a, b)
                 ks.append(a); ke.append(b)
             step_fn(i)
+        for ev_ in pending:
+            ev_.synchronize()
+        pending.clear()
         e1.record()
         barrier()
         nat.set_kernel_timer(None, None)

@@ -125,6 +125,52 @@ class CatalogIndex:
         torch.distributed.all_gather_into_tensor(gi, ti.contiguous(), group=self.group)
         return nat.topk_merge(gv.view(world, Q, k), gi.view(world, Q, k))
 
+    def rank_host(self, xq_host: torch.Tensor, k: int, out_val: torch.Tensor, out_idx: torch.Tensor):
+        """Host-buffer entry point: pinned query features in, pinned results out, nothing blocks.
+
+        The batch is copied on a copy stream into one of two device staging slots while the previous
+        batch is still being scored; scoring waits for its copy, the results go back on a third stream.
+        Returns a ``torch.cuda.Event`` that fires when ``out_val`` / ``out_idx`` are complete."""
+        dev = self.E.device
+        if not hasattr(self, "_h2d"):
+            self._h2d, self._d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._slots, self._slot_free, self._turn = [None, None], [None, None], 0
+        s = self._turn
+        self._turn ^= 1
+        if self._slots[s] is None or self._slots[s].shape != xq_host.shape:
+            self._slots[s] = torch.empty(xq_host.shape, dtype=torch.float32, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(self._h2d):
+            if self._slot_free[s] is not None:
+                self._h2d.wait_event(self._slot_free[s])           # the batch that used this slot has been projected
+            self._slots[s].copy_(xq_host, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._h2d)
+        cur.wait_event(ready)
+        Pq = self.project_queries(self._slots[s])
+        self._slot_free[s] = torch.cuda.Event()
+        self._slot_free[s].record(cur)
+        tv, ti = self.rank_local(Pq, k)
+        world = self._world()
+        if world > 1:
+            Q = tv.shape[0]
+            gv = torch.empty(world * Q, k, dtype=tv.dtype, device=dev)
+            gi = torch.empty(world * Q, k, dtype=ti.dtype, device=dev)
+            torch.distributed.all_gather_into_tensor(gv, tv.contiguous(), group=self.group)
+            torch.distributed.all_gather_into_tensor(gi, ti.contiguous(), group=self.group)
+            tv, ti = nat.topk_merge(gv.view(world, Q, k), gi.view(world, Q, k))
+        scored = torch.cuda.Event()
+        scored.record(cur)
+        with torch.cuda.stream(self._d2h):
+            self._d2h.wait_event(scored)
+            out_val.copy_(tv, non_blocking=True)
+            out_idx.copy_(ti, non_blocking=True)
+            tv.record_stream(self._d2h)
+            ti.record_stream(self._d2h)
+            done = torch.cuda.Event()
+            done.record(self._d2h)
+        return done
+
     def scores(self, dist: torch.Tensor) -> torch.Tensor:
         """Thresholder (blocks.py:21-22): max(theta, 1e-6) - dist."""
         return max(self.theta, 1e-6) - dist

@@ -178,3 +178,28 @@ def test_cfl_train_with_cuda_graph_matches_eager_run(tmp_path):
     assert sb.best_auc == pytest.approx(sa.best_auc, abs=2e-4) and sb.best_accuracy == pytest.approx(sa.best_accuracy, abs=5e-3)
     for k in pa:
         torch.testing.assert_close(pb[k], pa[k], rtol=1e-3, atol=1e-4, msg=k)
+
+
+def test_rank_host_pipeline_equals_rank():
+    """CatalogIndex.rank_host (pinned in / pinned out, copies overlapped with scoring) returns what rank does,
+    batch after batch, with the staging slots and output buffers reused."""
+    from cfl.ranking import CatalogIndex, EncoderWeights
+    g = torch.Generator().manual_seed(11)
+    F, K, d, N, Q, k = 64, 3, 16, 30000, 48, 20
+    lim = (6.0 / (F + d)) ** 0.5
+    w = EncoderWeights(V0=((torch.rand(F, d, generator=g) * 2 - 1) * lim).cuda(),
+                       Vp=((torch.rand(F, K * d, generator=g) * 2 - 1) * lim).cuda(), g0=torch.ones(d).cuda(),
+                       gp=torch.ones(K * d).cuda(), b0=torch.zeros(d).cuda(), bp=torch.zeros(K * d).cuda(),
+                       weight_norm=True, in_scale=0.5)
+    from cfl import _native as nat
+    X = torch.randn(N, F, generator=g).clamp_(min=0).cuda()
+    E, _, _ = nat.project_fwd(X, w.V0, w.g0, w.b0, True, w.in_scale, None)
+    index = CatalogIndex(w, E)
+    batches = [torch.randn(Q, F, generator=g).clamp_(min=0).pin_memory() for _ in range(5)]
+    outs = [(torch.empty(Q, k).pin_memory(), torch.empty(Q, k, dtype=torch.int64).pin_memory()) for _ in range(5)]
+    events = [index.rank_host(b, k, ov, oi) for b, (ov, oi) in zip(batches, outs)]
+    for ev in events:
+        ev.synchronize()
+    for b, (ov, oi) in zip(batches, outs):
+        tv, ti = index.rank(b.cuda(), k)
+        assert torch.equal(ti.cpu(), oi) and torch.equal(tv.cpu(), ov)
