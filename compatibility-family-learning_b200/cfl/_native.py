@@ -52,6 +52,9 @@ SIGNATURES = {
     "cfl_score_topk_packed_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
     "cfl_score_topk_packed": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _i64,
                                      _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cfl_score_topk_monomer_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
+    "cfl_score_topk_monomer": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _i64, _i64, _int, _i64,
+                                      _vp, _vp, _vp, _vp, _sz, _vp]),
     "cfl_topk_merge": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
     "cfl_col_mean_workspace_bytes": (_sz, [_i64, _int]),
     "cfl_col_mean": (_int, [_vp, _i64, _int, _i64, _vp, _vp, _sz, _vp]),
@@ -307,6 +310,30 @@ def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False, imag
         _check(lib().cfl_score_topk(MODES[mode], _ptr(Pq2), Q, K, d, ldq, _ptr(E), N, lde, _ptr(mu),
                                     int(k), int(idx_base), _ptr(top_val), _ptr(top_idx), _ptr(dense),
                                     _ptr(ws), ws.numel(), _stream()), "cfl_score_topk")
+    return (top_val, top_idx, dense) if want_dense else (top_val, top_idx)
+
+
+def score_topk_monomer(a, w, P, k, idx_base=0, want_dense=False):
+    """Monomer mode on the cross product (base.py:109-117): a [Q,d] and w [Q,K] of the query
+    (source) items, P [N,K,d] prototypes of the catalog (target) items -> top-k per query."""
+    a, lda = _rows(a, "a")
+    w = _f32c(w, "w").contiguous()
+    P = _f32c(P, "P")
+    if P.dim() != 3:
+        raise CflNativeError("score_topk_monomer: P must be [N,K,d]")
+    N, K, d = P.shape
+    Q = a.shape[0]
+    if a.shape[1] != d or tuple(w.shape) != (Q, K):
+        raise CflNativeError(f"score_topk_monomer: a {tuple(a.shape)}, w {tuple(w.shape)} do not match P {tuple(P.shape)}")
+    P2, ldp = _rows(P.reshape(N, K * d), "P")
+    dev = P.device
+    top_val = torch.empty(Q, k, dtype=torch.float32, device=dev)
+    top_idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    dense = torch.empty(Q, N, dtype=torch.float32, device=dev) if want_dense else None
+    ws = _ws.get(lib().cfl_score_topk_monomer_workspace_bytes(Q, K, d, N, k), dev)
+    _check(lib().cfl_score_topk_monomer(_ptr(a), lda, _ptr(w), Q, K, d, _ptr(P2), N, ldp, int(k), int(idx_base),
+                                        _ptr(top_val), _ptr(top_idx), _ptr(dense), _ptr(ws), ws.numel(), _stream()),
+           "cfl_score_topk_monomer")
     return (top_val, top_idx, dense) if want_dense else (top_val, top_idx)
 
 

@@ -32,6 +32,8 @@ class EncoderWeights:
     weight_norm: bool = True
     in_scale: float = 1.0                 # 1/normalize_value (cfl/ops.py:198) or 1/data_norm
     act: Optional[str] = None             # --act-type
+    Vg: Optional[torch.Tensor] = None     # monomer gate head [d, K] (monomer_outputs/fully_connected/V)
+    gg: Optional[torch.Tensor] = None     # its weight-norm scaler g [K] (the gate never has a bias, base.py:96-103)
 
     @property
     def d(self):
@@ -173,4 +175,80 @@ class CatalogIndex:
 
     def scores(self, dist: torch.Tensor) -> torch.Tensor:
         """Thresholder (blocks.py:21-22): max(theta, 1e-6) - dist."""
+        return max(self.theta, 1e-6) - dist
+
+
+def _gather_merge(tv, ti, group, world):
+    """The one exchange step of the sharded ranking: all-gather the per-rank [Q,k] lists, merge."""
+    Q, k = tv.shape
+    gv = torch.empty(world * Q, k, dtype=tv.dtype, device=tv.device)
+    gi = torch.empty(world * Q, k, dtype=ti.dtype, device=ti.device)
+    torch.distributed.all_gather_into_tensor(gv, tv.contiguous(), group=group)
+    torch.distributed.all_gather_into_tensor(gi, ti.contiguous(), group=group)
+    return nat.topk_merge(gv.view(world, Q, k), gi.view(world, Q, k))
+
+
+class MonomerCatalogIndex:
+    """Monomer ranking (``--dist-type monomer``): the pair scorer's monomer branch
+    (DistBase.build_dist, cfl/models/base.py:109-117) on the query x catalog cross product.
+
+    The roles are the reference's: the SOURCE (query) item supplies ``a = act(e0)`` and the gate
+    ``w = softmax(FC_wn(e0 pre-activation -> K, no bias))`` (base.py:94-105); the TARGET (catalog)
+    item supplies its K prototypes, so one shard holds ``[N, K, d]`` resident on the GPU.
+    Sharding, the all-gather + merge and the tie rule are those of ``CatalogIndex``."""
+
+    def __init__(self, weights: EncoderWeights, prototypes: torch.Tensor, idx_base: int = 0,
+                 n_total: Optional[int] = None, theta: float = 1e-6, group=None):
+        if not prototypes.is_cuda:
+            raise nat.CflNativeError("MonomerCatalogIndex needs CUDA prototypes (there is no CPU path)")
+        if weights.Vg is None:
+            raise nat.CflNativeError("MonomerCatalogIndex needs the gate head (EncoderWeights.Vg)")
+        self.w = weights
+        self.P = prototypes.view(prototypes.shape[0], weights.K, weights.d)
+        self.idx_base = int(idx_base)
+        self.n_total = int(n_total if n_total is not None else prototypes.shape[0])
+        self.theta = float(theta)
+        self.group = group
+
+    @classmethod
+    def from_features(cls, weights: EncoderWeights, features: torch.Tensor, idx_base: int = 0,
+                      n_total: Optional[int] = None, chunk: int = 1 << 16, **kw):
+        """Projects this rank's catalog rows through the prototype head (no communication)."""
+        dev = weights.Vp.device
+        n = features.shape[0]
+        P = torch.empty(n, weights.K * weights.d, dtype=torch.float32, device=dev)
+        for lo in range(0, n, chunk):
+            xb = features[lo:lo + chunk]
+            if not xb.is_cuda:
+                xb = xb.to(dev, non_blocking=True)
+            y, _, _ = nat.project_fwd(xb, weights.Vp, weights.gp, weights.bp, weights.weight_norm,
+                                      weights.in_scale, weights.act)
+            P[lo:lo + chunk] = y
+        return cls(weights, P, idx_base=idx_base, n_total=n_total, **kw)
+
+    def _world(self):
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_world_size(self.group)
+        return 1
+
+    def project_queries(self, xq: torch.Tensor):
+        """-> (a [Q,d], w [Q,K]): embedding and gate softmax of the source items (base.py:94-105)."""
+        if not xq.is_cuda:
+            xq = xq.to(self.P.device, non_blocking=True)
+        w = self.w
+        a, pre, _ = nat.project_fwd(xq, w.V0, w.g0, w.b0, w.weight_norm, w.in_scale, w.act, want_pre=True)
+        logits, _, _ = nat.project_fwd(pre, w.Vg, w.gg, None, True, 1.0, None)
+        return a, torch.softmax(logits, dim=-1)
+
+    def rank_local(self, a: torch.Tensor, gate: torch.Tensor, k: int):
+        return nat.score_topk_monomer(a, gate, self.P, k, idx_base=self.idx_base)
+
+    def rank(self, xq: torch.Tensor, k: int = 100):
+        """-> (dist [Q,k] ascending, index [Q,k] int64 global).  score = theta+ - dist."""
+        a, gate = self.project_queries(xq)
+        tv, ti = self.rank_local(a, gate, k)
+        world = self._world()
+        return (tv, ti) if world == 1 else _gather_merge(tv, ti, self.group, world)
+
+    def scores(self, dist: torch.Tensor) -> torch.Tensor:
         return max(self.theta, 1e-6) - dist

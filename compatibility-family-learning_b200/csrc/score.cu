@@ -235,53 +235,6 @@ static int launch_simt(const ScoreArgs& a, cudaStream_t st) {
   return CFL_OK;
 }
 
-// ---- block-wide selection of the kk smallest keys over all catalog parts -----------------------
-// 256 threads per query.  Keys stream through a 512-slot shared buffer; once kk keys are known,
-// later keys must beat the current kk-th best to be admitted, so most of them never reach a sort.
-constexpr int MRG_THREADS = 256;
-
-__device__ __forceinline__ void mrg_compact(tkey_t* s, int* s_fill, tkey_t* s_thr, int kk, int t) {
-  const int fill = *s_fill;
-  for (int i = fill + t; i < TOPK_CAP; i += MRG_THREADS) s[i] = CFL_KEY_INF;
-  __syncthreads();
-  coop_sort512<MRG_THREADS>(s, t);                 // ends with a block barrier (256 == whole block)
-  if (t == 0) {
-    const int nf = fill < kk ? fill : kk;
-    *s_fill = nf;
-    if (nf >= kk) *s_thr = s[kk - 1];                // otherwise the admission bound stays as it was
-  }
-  __syncthreads();
-}
-
-// returns the number of keys kept (<= kk), sorted ascending in s[0..)
-__device__ __forceinline__ int block_merge_topkk(const tkey_t* __restrict__ keys, const int* __restrict__ counts,
-                                                 int parts, int64_t Q, int64_t q, int kk, tkey_t* s, int* s_fill,
-                                                 tkey_t* s_thr) {
-  const int t = threadIdx.x;
-  if (t == 0) { *s_fill = 0; *s_thr = CFL_KEY_INF; }
-  __syncthreads();
-  for (int p = 0; p < parts; ++p) {
-    int c = counts[(int64_t)p * Q + q];
-    if (c > TOPK_STRIDE) c = TOPK_STRIDE;                    // an over-full lower-bound buffer (flagged for redo)
-    const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
-    for (int base = 0; base < c; base += MRG_THREADS) {
-      // every thread must take the same branch: read the fill level between two barriers, before
-      // any thread of this round can append
-      const int f0 = *s_fill;
-      __syncthreads();
-      if (f0 + MRG_THREADS > TOPK_CAP) mrg_compact(s, s_fill, s_thr, kk, t);
-      const int i = base + t;
-      if (i < c) {
-        const tkey_t key = src[i];
-        if (key < *s_thr) s[atomicAdd(s_fill, 1)] = key;
-      }
-      __syncthreads();
-    }
-  }
-  mrg_compact(s, s_fill, s_thr, kk, t);
-  return *s_fill;
-}
-
 // ---- merge of the catalog parts + direct-form rescoring + final sort ---------------------
 // Exact distance of the kk survivors in direct-difference form (cfl/models/base.py:129-138
 // arithmetic) on the raw rows, then (value, index) order, best k written out.

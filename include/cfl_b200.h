@@ -120,7 +120,7 @@ int cfl_pair_loss_bwd(int mode, const float* a, int64_t lda, const float* P, int
 
 /* ---------------------------------------------------------------------------------------
  * Stage 2, all pairs (extension, SURVEY App. A.6: the pair scorer on the QxN cross
- * product; no reference call site).  pcd (K>=1) and siamese (K=1).
+ * product; no reference call site).  pcd (K>=1) and siamese (K=1); monomer: cfl_score_topk_monomer.
  *   Pq[Q,K,d] query prototypes, E[N,d] catalog embeddings, mu[d] optional centring vector
  *   (distance is translation invariant; centring keeps the Gram form accurate).
  * Gram form d_k = |e|^2+|p_k|^2-2 p_k.e on tensor cores (3xTF32), soft-min epilogue and a
@@ -151,6 +151,20 @@ int cfl_score_topk_packed(int mode, const float* Pq, int64_t Q, int K, int d, in
                           int k, int64_t idx_base,
                           float* top_val, int64_t* top_idx, float* dist_out,
                           void* ws, size_t ws_bytes, void* stream);
+
+/* Monomer mode on the cross product (SURVEY App. A.6 applied to DistBase.build_dist, monomer branch,
+ * cfl/models/base.py:109-117; gate cfl/models/base.py:94-105).  The roles follow the reference:
+ *   Aq[Q,d]  = act(e0) of the SOURCE (query) items,  Wq[Q,K] = their gate softmax (dense, row-major),
+ *   Pc[N,K,d] = the K prototypes of the TARGET (catalog) items (prototype k of row c at columns
+ *   [k*d,(k+1)*d) of a row of length ldp), so the catalog side carries K*d floats per row;
+ *   dist(q,c) = sum_k Wq[q,k] * |Aq[q] - Pc[c,k]|^2   (direct-difference form, fp32: values are final).
+ * Outputs as cfl_score_topk: top_val ascending, top_idx = idx_base + row, ties -> lower index;
+ * dist_out[Q,N] optional (parity/debug).  CUDA-core kernel (packed FP32x2), no tensor-core image. */
+size_t cfl_score_topk_monomer_workspace_bytes(int64_t Q, int K, int d, int64_t N, int k);
+int cfl_score_topk_monomer(const float* Aq, int64_t lda, const float* Wq, int64_t Q, int K, int d,
+                           const float* Pc, int64_t N, int64_t ldp, int k, int64_t idx_base,
+                           float* top_val, int64_t* top_idx, float* dist_out,
+                           void* ws, size_t ws_bytes, void* stream);
 
 /* Merge R sorted lists per query (the per-rank results after ncclAllGather) into one:
  * vals[R,Q,k], idx[R,Q,k] -> top_val[Q,k], top_idx[Q,k]; order (value, index). */
