@@ -58,6 +58,8 @@ SIGNATURES = {
     "cfl_topk_merge": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
     "cfl_col_mean_workspace_bytes": (_sz, [_i64, _int]),
     "cfl_col_mean": (_int, [_vp, _i64, _int, _i64, _vp, _vp, _sz, _vp]),
+    "cfl_pair_dist_rows": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _vp, _vp]),
+    "cfl_rank_counts": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _vp, _vp]),
     "cfl_auc_workspace_bytes": (_sz, [_i64, _i64]),
     "cfl_auc": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "cfl_adam_step": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _f32, _f32, _f32, _f32, _f32, _vp]),
@@ -349,6 +351,55 @@ def topk_merge(vals, idx):
     _check(lib().cfl_topk_merge(_ptr(vals), _ptr(idx), R, Q, k, _ptr(tv), _ptr(ti), _stream()),
            "cfl_topk_merge")
     return tv, ti
+
+
+def _rank_operands(mode, query, catalog, w):
+    """(Pq2, Q, K, d, ldq, w, E2, N, lde) for cfl_pair_dist_rows / cfl_rank_counts."""
+    if mode == "monomer":
+        if catalog.dim() != 3 or w is None:
+            raise CflNativeError("rank counts (monomer): catalog must be [N,K,d] prototypes and w the [Q,K] gate")
+        N, K, d = catalog.shape
+        q2, ldq = _rows(query, "query")
+        E2, lde = _rows(_f32c(catalog, "catalog").reshape(N, K * d), "catalog")
+        w = _f32c(w, "w").contiguous()
+        if q2.shape[1] != d or tuple(w.shape) != (q2.shape[0], K):
+            raise CflNativeError("rank counts (monomer): query/gate shapes do not match the catalog")
+        return q2, q2.shape[0], K, d, ldq, w, E2, N, lde
+    query = _f32c(query, "query")
+    if query.dim() == 2:
+        query = query[:, None, :]
+    Q, K, d = query.shape
+    q2, ldq = _rows(query.reshape(Q, K * d), "query")
+    E2, lde = _rows(catalog, "catalog")
+    if E2.shape[1] != d:
+        raise CflNativeError(f"rank counts: query has d={d} but the catalog is {tuple(E2.shape)}")
+    return q2, Q, K, d, ldq, None, E2, E2.shape[0], lde
+
+
+def pair_dist_rows(mode, query, catalog, pos_idx, w=None):
+    """dist(q, catalog[pos_idx[q,j]]) -> [Q,J] float32; NaN where pos_idx is outside this shard."""
+    q2, Q, K, d, ldq, w, E2, N, lde = _rank_operands(mode, query, catalog, w)
+    pos_idx = pos_idx.contiguous()
+    if pos_idx.dtype != torch.int64 or pos_idx.dim() != 2 or pos_idx.shape[0] != Q or not pos_idx.is_cuda:
+        raise CflNativeError("pair_dist_rows: pos_idx must be a CUDA int64 [Q,J] tensor")
+    J = pos_idx.shape[1]
+    out = torch.empty(Q, J, dtype=torch.float32, device=E2.device)
+    _check(lib().cfl_pair_dist_rows(MODES[mode], _ptr(q2), Q, K, d, ldq, _ptr(w), _ptr(E2), N, lde, _ptr(pos_idx), J,
+                                    _ptr(out), _stream()), "cfl_pair_dist_rows")
+    return out
+
+
+def rank_counts(mode, query, catalog, pos_dist, w=None):
+    """-> int64 [Q,J,2]: (#{c: dist(q,c) < pos_dist[q,j]}, #{c: dist(q,c) == pos_dist[q,j]}) over this shard."""
+    q2, Q, K, d, ldq, w, E2, N, lde = _rank_operands(mode, query, catalog, w)
+    pos_dist = _f32c(pos_dist, "pos_dist").contiguous()
+    if pos_dist.dim() != 2 or pos_dist.shape[0] != Q:
+        raise CflNativeError("rank_counts: pos_dist must be [Q,J]")
+    J = pos_dist.shape[1]
+    out = torch.empty(Q, J, 2, dtype=torch.int64, device=E2.device)
+    _check(lib().cfl_rank_counts(MODES[mode], _ptr(q2), Q, K, d, ldq, _ptr(w), _ptr(E2), N, lde, _ptr(pos_dist), J,
+                                 _ptr(out), _stream()), "cfl_rank_counts")
+    return out
 
 
 def auc_counts(pos_scores, neg_scores):

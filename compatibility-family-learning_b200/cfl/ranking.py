@@ -11,6 +11,7 @@ one contiguous shard, ranks locally, all-gathers the [Q,k] lists (NCCL) and merg
 from __future__ import annotations
 
 from dataclasses import dataclass
+from types import SimpleNamespace
 from typing import Optional
 
 import torch
@@ -173,9 +174,60 @@ class CatalogIndex:
             done.record(self._d2h)
         return done
 
+    def auc_per_query(self, xq: torch.Tensor, pos_idx: torch.Tensor):
+        """All-candidate AUC of every query: ``pos_idx`` [Q,J] int64 = GLOBAL catalog rows of the query's
+        labelled positives (unique per query; -1 pads), every other catalog row is a negative.  Exact
+        integer rank counts, independent of the sharding.  -> namespace(auc, two_u, n_pos, n_neg, ...)."""
+        Pq = self.project_queries(xq)
+        return _auc_per_query("pcd", Pq, self.E, None, pos_idx, self.idx_base, self.n_total, self.group, self._world())
+
     def scores(self, dist: torch.Tensor) -> torch.Tensor:
         """Thresholder (blocks.py:21-22): max(theta, 1e-6) - dist."""
         return max(self.theta, 1e-6) - dist
+
+
+def auc_from_rank_counts(counts: torch.Tensor, pos_dist: torch.Tensor, n_total: int):
+    """Per-query AUC from the exact rank counts of ``cfl_rank_counts`` (integer arithmetic; any device).
+
+    counts [Q,J,2] int64 = (#{c: dist(q,c) < t_qj}, #{c: dist(q,c) == t_qj}) over ALL ``n_total`` candidates
+    (positives included), pos_dist [Q,J] = t (NaN = no positive in that slot).  The positives of a query are
+    removed from its counts, the rest are its negatives:  2U_q = sum_j 2 #{neg: dist > t_j} + #{neg: dist == t_j}
+    -- the rank statistic of ``roc_auc_score`` on scores theta+ - dist (cfl/utils.py:267-268).
+    Returns (auc [Q] float64 (NaN when a query has no positive or no negative), two_u [Q], n_pos [Q], n_neg [Q])."""
+    valid = ~torch.isnan(pos_dist)
+    t = pos_dist
+    both = valid[:, :, None] & valid[:, None, :]
+    lt_pos = ((t[:, None, :] < t[:, :, None]) & both).sum(-1)          # [Q,J]: positives j' strictly closer than j
+    eq_pos = ((t[:, None, :] == t[:, :, None]) & both).sum(-1)         # includes j itself
+    n_pos = valid.sum(-1)
+    n_neg = int(n_total) - n_pos
+    neg_lt = counts[..., 0] - lt_pos
+    neg_eq = counts[..., 1] - eq_pos
+    neg_gt = n_neg[:, None] - neg_lt - neg_eq
+    two_u = ((2 * neg_gt + neg_eq) * valid).sum(-1)
+    den = (2 * n_pos * n_neg).double()
+    auc = torch.where(den > 0, two_u.double() / den.clamp(min=1), torch.full_like(den, float("nan")))
+    return auc, two_u, n_pos, n_neg
+
+
+def _auc_per_query(mode, query, catalog, gate, pos_idx, idx_base, n_total, group, world):
+    """Positives' distances where they live, summed over shards; exact counts per shard, summed."""
+    n_local = catalog.shape[0]
+    pos_idx = pos_idx.to(catalog.device)
+    local = pos_idx - idx_base
+    local = torch.where((pos_idx >= 0) & (local >= 0) & (local < n_local), local, torch.full_like(local, -1))
+    pos_dist = nat.pair_dist_rows(mode, query, catalog, local, w=gate)
+    if world > 1:
+        have = (~torch.isnan(pos_dist)).to(torch.int32)
+        val = torch.nan_to_num(pos_dist, nan=0.0)
+        torch.distributed.all_reduce(have, group=group)
+        torch.distributed.all_reduce(val, group=group)               # one owner per positive: the sum is its value
+        pos_dist = torch.where(have > 0, val, torch.full_like(val, float("nan")))
+    counts = nat.rank_counts(mode, query, catalog, pos_dist, w=gate)
+    if world > 1:
+        torch.distributed.all_reduce(counts, group=group)
+    auc, two_u, n_pos, n_neg = auc_from_rank_counts(counts, pos_dist, n_total)
+    return SimpleNamespace(auc=auc, two_u=two_u, n_pos=n_pos, n_neg=n_neg, counts=counts, pos_dist=pos_dist)
 
 
 def _gather_merge(tv, ti, group, world):
@@ -249,6 +301,12 @@ class MonomerCatalogIndex:
         tv, ti = self.rank_local(a, gate, k)
         world = self._world()
         return (tv, ti) if world == 1 else _gather_merge(tv, ti, self.group, world)
+
+    def auc_per_query(self, xq: torch.Tensor, pos_idx: torch.Tensor):
+        """As ``CatalogIndex.auc_per_query`` with the monomer distance."""
+        a, gate = self.project_queries(xq)
+        return _auc_per_query("monomer", a, self.P, gate, pos_idx, self.idx_base, self.n_total, self.group,
+                              self._world())
 
     def scores(self, dist: torch.Tensor) -> torch.Tensor:
         return max(self.theta, 1e-6) - dist

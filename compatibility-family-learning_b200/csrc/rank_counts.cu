@@ -1,0 +1,266 @@
+// Per-query all-candidate AUC (SURVEY 8d C3 "per-query all-candidate AUC with J planted positives",
+// 8e "AUC across ranks"): the rank statistic of roc_auc_score (cfl/utils.py:267-268) for ONE query
+// against EVERY catalog row, without materialising the Q x N scores.
+//
+//   cfl_pair_dist_rows : t[q,j] = dist(query q, catalog row pos_idx[q,j])        (the labelled positives)
+//   cfl_rank_counts    : counts[q,j] = ( #{c : dist(q,c) < t[q,j]},  #{c : dist(q,c) == t[q,j]} )  over a shard
+//
+// Both evaluate the pair scorer (DistBase.build_dist, cfl/models/base.py:107-146) in fp32
+// direct-difference form through the SAME device function, operation for operation, so a positive
+// compares equal to itself and the integer counts are exact for the fp32 distances; they add over
+// catalog shards (int64 all-reduce), which makes the AUC independent of the sharding.  The pcd
+// arithmetic is that of merge_rescore_kernel (score.cu), i.e. of the values cfl_score_topk reports;
+// the monomer arithmetic is that of score_monomer_kernel.
+#include "common.cuh"
+
+namespace cfl {
+
+constexpr int RC_QT = 8;          // queries per CTA
+constexpr int RC_THREADS = 128;   // one thread per catalog row of a 128-row tile
+constexpr int RC_MAX_J = 32;
+
+// pcd / siamese: e = candidate embedding (target e0), p = the query's K prototypes.
+template <int K, class EAcc, class PAcc>
+__device__ __forceinline__ float pcd_direct(EAcc e, PAcc p, int d) {
+  float dk[K];
+  float mn = 3.0e38f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float acc = 0.0f;
+    for (int j = 0; j < d; ++j) { const float df = e(j) - p(k, j); acc = fmaf(df, df, acc); }
+    dk[k] = acc;
+    mn = fminf(mn, acc);
+  }
+  if (K == 1) return dk[0];
+  float sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { dk[k] = expf(mn - dk[k]); sum += dk[k]; }
+  const float inv = 1.0f / sum;
+  float dist = 0.0f;
+  for (int j = 0; j < d; ++j) {
+    float m = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) m = fmaf(dk[k] * inv, p(k, j), m);
+    const float r = e(j) - m;
+    dist = fmaf(r, r, dist);
+  }
+  return dist;
+}
+
+// monomer: a = the query's embedding, w = its gate softmax, e(k, j) = prototype k of the candidate.
+template <int K, class EAcc, class AAcc, class WAcc>
+__device__ __forceinline__ float monomer_direct(EAcc e, AAcc a, WAcc w, int d) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float dk = 0.0f;
+    for (int j = 0; j < d; ++j) { const float df = a(j) + (-e(k, j)); dk = fmaf(df, df, dk); }
+    acc = fmaf(w(k), dk, acc);
+  }
+  return acc;
+}
+
+struct RcArgs {
+  int mode, K, d, J;
+  int64_t Q, N, ldq, lde;
+  const float* Pq;         // pcd: [Q, ldq] K prototypes per query; monomer: [Q, ldq] embedding a_q
+  const float* Wq;         // monomer: [Q, K]
+  const float* E;          // pcd: [N, lde] embeddings; monomer: [N, lde] K prototypes per row
+  const float* thr;        // [Q, J] distances of the positives (NaN = no positive)
+  const int64_t* pos_idx;  // [Q, J] gather kernel
+  float* pos_dist;         // [Q, J] gather kernel output
+  unsigned long long* counts;   // [Q, J, 2]
+  int parts;
+  int64_t tiles;
+};
+
+template <int K, bool MONO>
+__global__ void __launch_bounds__(RC_THREADS)
+rank_count_kernel(RcArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int d = A.d, J = A.J;
+  const int ew = MONO ? K * d : d;            // floats per catalog row
+  const int qw = MONO ? d : K * d;            // floats per query
+  const int ldt = ew + 1;
+  float* et = (float*)smem_raw;                               // [128][ew+1]
+  float* qs = et + 128 * ldt;                                 // [QT][qw]
+  float* ws = qs + RC_QT * qw;                                // [QT][K] (monomer)
+  float* thr = ws + RC_QT * K;                                // [QT][J]
+  int* cnt = (int*)(thr + RC_QT * J);                         // [4 warps][QT][J][2]
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int part = blockIdx.x;
+  const int64_t q0 = (int64_t)blockIdx.y * RC_QT;
+  const int nq = (int)((A.Q - q0 < RC_QT) ? (A.Q - q0) : RC_QT);
+  for (int i = tid; i < nq * qw; i += RC_THREADS) qs[i] = A.Pq[(q0 + i / qw) * A.ldq + i % qw];
+  if (MONO) for (int i = tid; i < nq * K; i += RC_THREADS) ws[i] = A.Wq[q0 * K + i];
+  for (int i = tid; i < nq * J; i += RC_THREADS) thr[i] = A.thr[q0 * J + i];
+  for (int i = tid; i < (RC_THREADS / 32) * RC_QT * J * 2; i += RC_THREADS) cnt[i] = 0;
+  int* mycnt = cnt + wid * RC_QT * J * 2;
+  const int64_t t0 = A.tiles * part / A.parts;
+  const int64_t t1 = A.tiles * (part + 1) / A.parts;
+  const int sr0 = tid / ew, sj0 = tid % ew, sdr = RC_THREADS / ew, sdj = RC_THREADS % ew;
+
+  for (int64_t tile = t0; tile < t1; ++tile) {
+    const int64_t r0 = tile * 128;
+    __syncthreads();
+    for (int i = tid, r = sr0, j = sj0; i < 128 * ew; i += RC_THREADS) {
+      const int64_t row = r0 + r;
+      et[r * ldt + j] = row < A.N ? A.E[row * A.lde + j] : 0.0f;
+      r += sdr; j += sdj;
+      if (j >= ew) { j -= ew; ++r; }
+    }
+    __syncthreads();
+    const bool valid = r0 + tid < A.N;
+    const float* er = et + tid * ldt;
+    for (int ql = 0; ql < nq; ++ql) {
+      const float* qv = qs + ql * qw;
+      float dist;
+      if (MONO) {
+        const float* wv = ws + ql * K;
+        dist = monomer_direct<K>([&](int k, int j) { return er[k * d + j]; }, [&](int j) { return qv[j]; },
+                                 [&](int k) { return wv[k]; }, d);
+      } else {
+        dist = pcd_direct<K>([&](int j) { return er[j]; }, [&](int k, int j) { return qv[k * d + j]; }, d);
+      }
+      for (int j = 0; j < J; ++j) {
+        const float t = thr[ql * J + j];
+        const unsigned lt = __ballot_sync(0xffffffffu, valid && dist < t);
+        const unsigned eq = __ballot_sync(0xffffffffu, valid && dist == t);
+        if (lane == 0) {
+          mycnt[(ql * J + j) * 2] += __popc(lt);
+          mycnt[(ql * J + j) * 2 + 1] += __popc(eq);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nq * J * 2; i += RC_THREADS) {
+    unsigned long long s = 0;
+    for (int w = 0; w < RC_THREADS / 32; ++w) s += (unsigned long long)cnt[w * RC_QT * J * 2 + i];
+    if (s) atomicAdd(&A.counts[q0 * J * 2 + i], s);
+  }
+}
+
+// One thread per (query, positive): the same device functions on rows gathered from global memory.
+template <int K, bool MONO>
+__global__ void pair_dist_rows_kernel(RcArgs A) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.Q * A.J) return;
+  const int64_t q = i / A.J;
+  const int64_t row = A.pos_idx[i];
+  float dist = __int_as_float(0x7fc00000);                   // NaN: no positive here
+  if (row >= 0 && row < A.N) {
+    const float* er = A.E + row * A.lde;
+    const float* qv = A.Pq + q * A.ldq;
+    const int d = A.d;
+    if (MONO) {
+      const float* wv = A.Wq + q * K;
+      dist = monomer_direct<K>([&](int k, int j) { return er[k * d + j]; }, [&](int j) { return qv[j]; },
+                               [&](int k) { return wv[k]; }, d);
+    } else {
+      dist = pcd_direct<K>([&](int j) { return er[j]; }, [&](int k, int j) { return qv[k * d + j]; }, d);
+    }
+  }
+  A.pos_dist[i] = dist;
+}
+
+static size_t rc_smem_bytes(int K, int d, int J, bool mono) {
+  const int ew = mono ? K * d : d, qw = mono ? d : K * d;
+  return (size_t)128 * (ew + 1) * 4 + (size_t)RC_QT * qw * 4 + (size_t)RC_QT * K * 4 + (size_t)RC_QT * J * 4 +
+         (size_t)(RC_THREADS / 32) * RC_QT * J * 2 * 4;
+}
+
+template <int K, bool MONO>
+static int rc_launch(const RcArgs& a, bool gather, cudaStream_t cs) {
+  if (gather) {
+    const int64_t n = a.Q * a.J;
+    pair_dist_rows_kernel<K, MONO><<<(unsigned)((n + 127) / 128), 128, 0, cs>>>(a);
+  } else {
+    const size_t smem = rc_smem_bytes(K, a.d, a.J, MONO);
+    CFL_CUDA(cudaFuncSetAttribute(rank_count_kernel<K, MONO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(a.parts, (unsigned)((a.Q + RC_QT - 1) / RC_QT));
+    rank_count_kernel<K, MONO><<<grid, RC_THREADS, smem, cs>>>(a);
+  }
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+static int rc_dispatch(const RcArgs& a, bool gather, cudaStream_t cs) {
+  const bool mono = a.mode == CFL_MONOMER;
+#define CFL_RC_CASE(KK) case KK: return mono ? rc_launch<KK, true>(a, gather, cs) : rc_launch<KK, false>(a, gather, cs);
+  switch (a.K) {
+    CFL_RC_CASE(1) CFL_RC_CASE(2) CFL_RC_CASE(3) CFL_RC_CASE(4)
+    CFL_RC_CASE(5) CFL_RC_CASE(6) CFL_RC_CASE(7) CFL_RC_CASE(8)
+  }
+#undef CFL_RC_CASE
+  return CFL_ERR_UNSUPPORTED;
+}
+
+static int rc_check(const char* what, int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* Wq,
+                    const float* E, int64_t N, int64_t lde, int J) {
+  CFL_REQUIRE(mode == CFL_PCD || mode == CFL_SIAMESE || mode == CFL_MONOMER, CFL_ERR_INVALID, "%s: bad mode %d", what, mode);
+  CFL_REQUIRE(mode != CFL_SIAMESE || K == 1, CFL_ERR_INVALID, "%s: siamese needs K=1", what);
+  CFL_REQUIRE(K >= 1 && K <= CFL_MAX_K, CFL_ERR_UNSUPPORTED, "%s: K=%d outside [1,%d]", what, K, CFL_MAX_K);
+  CFL_REQUIRE(d >= 1 && d <= 128, CFL_ERR_UNSUPPORTED, "%s: d=%d outside [1,128]", what, d);
+  CFL_REQUIRE(J >= 1 && J <= RC_MAX_J, CFL_ERR_UNSUPPORTED, "%s: J=%d outside [1,%d]", what, J, RC_MAX_J);
+  CFL_REQUIRE(Q >= 0 && N >= 0, CFL_ERR_INVALID, "%s: bad Q/N", what);
+  const bool mono = mode == CFL_MONOMER;
+  CFL_REQUIRE(ldq >= (mono ? d : (int64_t)K * d) && lde >= (mono ? (int64_t)K * d : d), CFL_ERR_INVALID,
+              "%s: leading dimension too small", what);
+  CFL_REQUIRE(Q == 0 || (Pq && (!mono || Wq)), CFL_ERR_INVALID, "%s: NULL query argument", what);
+  CFL_REQUIRE(Q == 0 || N == 0 || E, CFL_ERR_INVALID, "%s: NULL catalog", what);
+  // the tile of a monomer catalog (K*d floats per row) must fit the shared memory of one CTA
+  CFL_REQUIRE(rc_smem_bytes(K, d, J, mono) <= 200 * 1024, CFL_ERR_UNSUPPORTED,
+              "%s: K*d = %d too large for the monomer rank-count tile", what, K * d);
+  return CFL_OK;
+}
+
+}  // namespace cfl
+
+using namespace cfl;
+
+extern "C" {
+
+int cfl_pair_dist_rows(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* Wq,
+                       const float* E, int64_t N, int64_t lde, const int64_t* pos_idx, int J,
+                       float* pos_dist, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  st = rc_check("pair_dist_rows", mode, Pq, Q, K, d, ldq, Wq, E, N, lde, J);
+  if (st != CFL_OK) return st;
+  if (Q == 0) return CFL_OK;
+  CFL_REQUIRE(pos_idx && pos_dist, CFL_ERR_INVALID, "pair_dist_rows: NULL argument");
+  RcArgs a = {};
+  a.mode = mode; a.K = K; a.d = d; a.J = J; a.Q = Q; a.N = N; a.ldq = ldq; a.lde = lde;
+  a.Pq = Pq; a.Wq = Wq; a.E = E; a.pos_idx = pos_idx; a.pos_dist = pos_dist;
+  return rc_dispatch(a, true, (cudaStream_t)stream);
+}
+
+int cfl_rank_counts(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* Wq,
+                    const float* E, int64_t N, int64_t lde, const float* pos_dist, int J,
+                    int64_t* counts, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  st = rc_check("rank_counts", mode, Pq, Q, K, d, ldq, Wq, E, N, lde, J);
+  if (st != CFL_OK) return st;
+  if (Q == 0) return CFL_OK;
+  CFL_REQUIRE(pos_dist && counts, CFL_ERR_INVALID, "rank_counts: NULL argument");
+  cudaStream_t cs = (cudaStream_t)stream;
+  CFL_CUDA(cudaMemsetAsync(counts, 0, (size_t)Q * J * 2 * sizeof(int64_t), cs));
+  if (N == 0) return CFL_OK;
+  RcArgs a = {};
+  a.mode = mode; a.K = K; a.d = d; a.J = J; a.Q = Q; a.N = N; a.ldq = ldq; a.lde = lde;
+  a.Pq = Pq; a.Wq = Wq; a.E = E; a.thr = pos_dist; a.counts = (unsigned long long*)counts;
+  a.tiles = (N + 127) / 128;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  const int64_t nqt = (Q + RC_QT - 1) / RC_QT;
+  int64_t parts = (4 * (int64_t)sms) / nqt;
+  if (parts > a.tiles) parts = a.tiles;
+  if (parts < 1) parts = 1;
+  a.parts = (int)parts;
+  return rc_dispatch(a, false, cs);
+}
+
+}  // extern "C"

@@ -186,6 +186,30 @@ size_t cfl_auc_workspace_bytes(int64_t n_pos, int64_t n_neg);
 int cfl_auc(const float* pos_scores, int64_t n_pos, const float* neg_scores, int64_t n_neg,
             int64_t* out4, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Per-query all-candidate AUC -- the rank statistic of roc_auc_score (cfl/utils.py:267-268) for one
+ * query against EVERY catalog row, without materialising the Q x N scores.
+ * Operands per mode (the pair scorer's roles, cfl/models/base.py:107-146):
+ *   pcd / siamese: Pq[Q,K,d] query prototypes (ldq >= K*d), Wq NULL, E[N,d] candidate embeddings;
+ *   monomer:       Pq[Q,d] query embeddings (ldq >= d), Wq[Q,K] gate softmax, E[N,K,d] candidate
+ *                  prototypes (lde >= K*d).
+ * cfl_pair_dist_rows: pos_dist[q,j] = dist(q, row pos_idx[q,j]) for the J labelled positives of each
+ *   query; pos_idx is LOCAL to this shard, entries outside [0,N) (e.g. -1: positive lives on another
+ *   shard, or padding) give NaN.
+ * cfl_rank_counts: counts[q,j,0] = #{c < N : dist(q,c) <  pos_dist[q,j]},
+ *                  counts[q,j,1] = #{c < N : dist(q,c) == pos_dist[q,j]}   (int64; NaN counts nothing).
+ * Both evaluate the distance in fp32 direct-difference form through one device function, so a positive
+ * compares equal to itself and the counts are exact integers that ADD over catalog shards.  With n
+ * candidates in total and the positives' own contributions removed, AUC_q = 2U_q / (2 J (n - J)).
+ * ------------------------------------------------------------------------------------- */
+#define CFL_MAX_RANK_J 32
+int cfl_pair_dist_rows(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* Wq,
+                       const float* E, int64_t N, int64_t lde, const int64_t* pos_idx, int J,
+                       float* pos_dist, void* stream);
+int cfl_rank_counts(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* Wq,
+                    const float* E, int64_t N, int64_t lde, const float* pos_dist, int J,
+                    int64_t* counts, void* stream);
+
 /* TF-1.x Adam (cfl/models/cfl.py:1083-1085): lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
  * p -= lr_t*m/(sqrt(v)+eps).  grad_scale multiplies g first (1/world for DP averaging). */
 int cfl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step,

@@ -1,0 +1,36 @@
+"""Per-query all-candidate AUC kernels (cfl_pair_dist_rows + cfl_rank_counts) at the C3 / C2 shapes (run under gpurun)."""
+import json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "compatibility-family-learning_b200"))
+from cfl import _native as nat
+
+
+def timeit(fn, reps=5):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+g = torch.Generator(device="cuda").manual_seed(633)
+for (mode, N, K, d, Q, J) in [("pcd", 1_000_000, 3, 64, 1024, 8), ("pcd", 1_000_000, 4, 20, 1024, 8), ("pcd", 1_000_000, 1, 64, 1024, 8),
+                              ("monomer", 1_000_000, 4, 20, 1024, 8)]:
+    pos = torch.randint(0, N, (Q, J), generator=g, device="cuda")
+    if mode == "pcd":
+        cat = torch.randn(N, d, generator=g, device="cuda")
+        qry = cat[torch.randint(0, N, (Q,), generator=g, device="cuda")][:, None, :] + 0.5 * torch.randn(Q, K, d, generator=g, device="cuda")
+        w = None
+    else:
+        cat = torch.randn(N, K, d, generator=g, device="cuda")
+        qry = cat[torch.randint(0, N, (Q,), generator=g, device="cuda"), 0] + 0.5 * torch.randn(Q, d, generator=g, device="cuda")
+        w = torch.softmax(torch.randn(Q, K, generator=g, device="cuda"), -1)
+    t = nat.pair_dist_rows(mode, qry, cat, pos, w=w)
+    ms_t = timeit(lambda: nat.pair_dist_rows(mode, qry, cat, pos, w=w))
+    ms = timeit(lambda: nat.rank_counts(mode, qry, cat, t, w=w))
+    print(json.dumps(dict(kernel="rank_counts", mode=mode, N=N, K=K, d=d, Q=Q, J=J, pos_dist_ms=round(ms_t, 3), ms=round(ms, 3),
+                          gscores_s=round(Q * N / ms / 1e6, 1))), flush=True)
+    del cat, qry
