@@ -189,6 +189,64 @@ def dist_eval(sess, model, batch_size, data, with_roc=False):
                      two_u=two_u, n_pos=n_pos, n_neg=n_neg)
 
 
+def sharded_auc_counts(pos, neg, group=None):
+    """AUC / accuracy integers of labelled pairs whose SCORES are sharded over ranks:
+    the (smaller) positive-score arrays are all-gathered, every rank counts its own negatives against
+    all positives with the exact rank/count kernel (cfl_auc), and the integers are summed
+    (``all_reduce``) -- bit-identical for any number of ranks.  ``pos`` / ``neg`` = this rank's scores
+    (either may be empty).  -> (two_u, n_pos, n_neg, correct) python ints, the same on every rank."""
+    from . import _native as nat
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    pos, neg = pos.reshape(-1).float(), neg.reshape(-1).float()
+    if world > 1:
+        sizes = torch.zeros(world, dtype=torch.int64, device=pos.device)
+        sizes[dist.get_rank(group)] = pos.numel()
+        dist.all_reduce(sizes, group=group)
+        cap = int(sizes.max())
+        padded = torch.zeros(cap, dtype=torch.float32, device=pos.device)
+        padded[:pos.numel()] = pos
+        gathered = torch.empty(world * cap, dtype=torch.float32, device=pos.device)
+        dist.all_gather_into_tensor(gathered, padded, group=group)
+        pos = torch.cat([gathered[r * cap:r * cap + int(sizes[r])] for r in range(world)])
+    pos_correct = int((pos > 0).sum())
+    if neg.numel() and pos.numel():
+        two_u, _, n_neg, correct = nat.auc_counts(pos, neg).cpu().tolist()
+        part = [two_u, n_neg, correct - pos_correct]
+    else:
+        part = [0, neg.numel(), int((neg <= 0).sum())]
+    if world > 1:
+        t = torch.tensor(part, dtype=torch.int64, device=pos.device)
+        dist.all_reduce(t, group=group)
+        part = t.tolist()
+    return part[0], pos.numel(), part[1], part[2] + pos_correct
+
+
+def dist_eval_sharded(sess, model, batch_size, data, rank=None, world=None, group=None):
+    """``dist_eval`` with the labelled pairs dealt to the ranks batch by batch (batch b -> rank b mod world):
+    each rank scores its share, ``sharded_auc_counts`` combines the integers.  Same Namespace as ``dist_eval``,
+    identical on every rank and identical to the single-process result."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    rank = (dist.get_rank(group) if on else 0) if rank is None else rank
+    world = (dist.get_world_size(group) if on else 1) if world is None else world
+    pos, neg = [], []
+    for b, batches in enumerate(data.whole_pos_batches(batch_size)):
+        if b % world == rank:
+            pos.append(model.predict(*_pair_batches(batches, model)).reshape(-1))
+    for b, batches in enumerate(data.whole_neg_batches(batch_size)):
+        if b % world == rank:
+            neg.append(model.predict(*_pair_batches(batches, model)).reshape(-1))
+    dev = getattr(model, "device", None) or (pos[0].device if pos else neg[0].device if neg else "cpu")
+    pos = torch.cat(pos) if pos else torch.empty(0, device=dev)
+    neg = torch.cat(neg) if neg else torch.empty(0, device=dev)
+    two_u, n_pos, n_neg, correct = sharded_auc_counts(pos, neg, group)
+    total = n_pos + n_neg
+    auc = two_u / (2.0 * n_pos * n_neg) if n_pos and n_neg else float("nan")
+    return Namespace(error=(total - correct) / total, accuracy=correct / total, auc=auc, roc=None,
+                     two_u=two_u, n_pos=n_pos, n_neg=n_neg)
+
+
 def dist_predict(sess, model, data, batch_size, predict_dir, output_name):
     """cfl/utils.py:277-321: writes ``"{id1} match {id2} {score}\\n"``, positives first."""
     pos, neg = [], []

@@ -158,3 +158,49 @@ def test_sharded_ranking_world2_gloo_matches_single_process(tmp_path):
     assert (got["ti"] == wi).all()
     np.testing.assert_allclose(got["tv"], wv, rtol=1e-6)
     np.testing.assert_allclose(got["mu"], E.astype(np.float64).mean(0), rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+def _auc_counts_double(pos, neg):
+    """Oracle-backed stand-in for cfl_auc (CPU, test only): [twoU, n_pos, n_neg, correct@0]."""
+    s = np.concatenate([pos.numpy(), neg.numpy()])
+    y = np.concatenate([np.ones(pos.numel(), np.uint8), np.zeros(neg.numel(), np.uint8)])
+    two_u, n_pos, n_neg = O.auc_exact(s, y)
+    correct = int((pos > 0).sum()) + int((neg <= 0).sum())
+    return torch.tensor([two_u, n_pos, n_neg, correct], dtype=torch.int64)
+
+
+def _pair_scores():
+    rng = np.random.default_rng(21)
+    pos = np.round(rng.normal(size=1001) + 0.4, 1).astype(np.float32)     # rounded: many exact ties
+    neg = np.round(rng.normal(size=4003), 1).astype(np.float32)
+    return pos, neg
+
+
+def _sharded_auc_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "compatibility-family-learning_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cfl import _native as nat
+    from cfl import utils
+    nat.auc_counts = _auc_counts_double
+    pos, neg = _pair_scores()
+    # uneven shards; rank 1 holds no positives at all in the second case
+    a = utils.sharded_auc_counts(torch.as_tensor(pos[rank::world]), torch.as_tensor(neg[rank::world]))
+    b = utils.sharded_auc_counts(torch.as_tensor(pos if rank == 0 else pos[:0]), torch.as_tensor(neg[rank * 3000:(rank + 1) * 3000]))
+    if rank == 1:
+        np.savez(os.path.join(out_dir, "a.npz"), a=np.array(a, dtype=np.int64), b=np.array(b, dtype=np.int64))
+    dist.destroy_process_group()
+
+
+def test_sharded_pair_auc_world2_gloo_equals_single_process(tmp_path):
+    """labelled-pair scores sharded over ranks -> the same AUC / accuracy integers as one process."""
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_sharded_auc_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "a.npz")
+    pos, neg = _pair_scores()
+    want = _auc_counts_double(torch.as_tensor(pos), torch.as_tensor(neg)).tolist()
+    assert got["a"].tolist() == want and got["b"].tolist() == want

@@ -255,7 +255,7 @@ def test_catalog_index_auc_per_query_planted_positives(nat):
     index = CatalogIndex.from_features(w, dev(X))
     xq = X[:Q]
     Pq = index.project_queries(dev(xq))
-    pos = _planted(rng, Q, N, J, pad=False)
+    pos = rng.permutation(np.arange(Q, N))[:Q * J].reshape(Q, J).astype(np.int64)   # disjoint sets, not the queries' own rows
     # plant: overwrite the positives' embeddings with noisy copies of the query's prototypes
     E = index.E
     for q in range(Q):

@@ -29,8 +29,11 @@ def timeit(fn, reps=10):
 
 
 g = torch.Generator(device="cuda").manual_seed(633)
-for (N, K, d, Q) in [(1_000_000, 4, 20, 1024), (1_000_000, 4, 10, 1024), (1_000_000, 4, 20, 64), (1_000_000, 3, 64, 1024),
-                     (250_000, 8, 128, 1024)]:
+CASES = [(1_000_000, 4, 20, 1024), (1_000_000, 4, 10, 1024), (1_000_000, 4, 20, 64), (1_000_000, 3, 64, 1024),
+                     (250_000, 8, 128, 1024)]
+if os.environ.get("CFL_PERF_ONLY"):
+    CASES = [CASES[int(os.environ["CFL_PERF_ONLY"])]]
+for (N, K, d, Q) in CASES:
     P = torch.randn(N, K, d, generator=g, device="cuda")
     a = P[torch.randint(0, N, (Q,), generator=g, device="cuda"), 0] + 0.5 * torch.randn(Q, d, generator=g, device="cuda")
     w = torch.softmax(2 * torch.randn(Q, K, generator=g, device="cuda"), -1)

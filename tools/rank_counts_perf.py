@@ -17,8 +17,11 @@ def timeit(fn, reps=5):
 
 
 g = torch.Generator(device="cuda").manual_seed(633)
-for (mode, N, K, d, Q, J) in [("pcd", 1_000_000, 3, 64, 1024, 8), ("pcd", 1_000_000, 4, 20, 1024, 8), ("pcd", 1_000_000, 1, 64, 1024, 8),
-                              ("monomer", 1_000_000, 4, 20, 1024, 8)]:
+CASES = [("pcd", 1_000_000, 3, 64, 1024, 8), ("pcd", 1_000_000, 4, 20, 1024, 8), ("pcd", 1_000_000, 1, 64, 1024, 8),
+                              ("monomer", 1_000_000, 4, 20, 1024, 8)]
+if os.environ.get("CFL_PERF_ONLY"):
+    CASES = [CASES[int(os.environ["CFL_PERF_ONLY"])]]
+for (mode, N, K, d, Q, J) in CASES:
     pos = torch.randint(0, N, (Q, J), generator=g, device="cuda")
     if mode == "pcd":
         cat = torch.randn(N, d, generator=g, device="cuda")
