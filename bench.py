@@ -233,6 +233,11 @@ def run_ours(args):
                                 f"port shared by MMA accumulation and the epilogue's tcgen05.ld (see DESIGN.md), not by "
                                 f"the MMA rate",
                     hbm_gbs=round((traffic or N_PER_GPU * (4 * D + 4)) / (k_ms / 1e3) / 1e9, 1))
+    probe = os.path.join(ROOT, "profiles", "r1_11_tf32_peak.json")     # tools/tf32_peak.py on this pool's B200
+    if os.path.exists(probe):
+        tp = json.load(open(probe))
+        roofline["measured_tf32_tflops_sustained"] = tp["tf32_tflops_sustained"]
+        roofline["frac_of_measured_tf32"] = round(achieved / tp["tf32_tflops_sustained"], 4)
 
     line = None
     if rank == 0:
