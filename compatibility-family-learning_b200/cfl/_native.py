@@ -60,6 +60,7 @@ SIGNATURES = {
     "cfl_col_mean": (_int, [_vp, _i64, _int, _i64, _vp, _vp, _sz, _vp]),
     "cfl_pair_dist_rows": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _vp, _vp]),
     "cfl_rank_counts": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _vp, _vp]),
+    "cfl_dense_rank_counts": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
     "cfl_auc_workspace_bytes": (_sz, [_i64, _i64]),
     "cfl_auc": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "cfl_adam_step": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _f32, _f32, _f32, _f32, _f32, _vp]),
@@ -399,6 +400,20 @@ def rank_counts(mode, query, catalog, pos_dist, w=None):
     out = torch.empty(Q, J, 2, dtype=torch.int64, device=E2.device)
     _check(lib().cfl_rank_counts(MODES[mode], _ptr(q2), Q, K, d, ldq, _ptr(w), _ptr(E2), N, lde, _ptr(pos_dist), J,
                                  _ptr(out), _stream()), "cfl_rank_counts")
+    return out
+
+
+def dense_rank_counts(dense, pos_dist):
+    """Counts of ``rank_counts`` over a dense [Q,N] distance matrix (score_topk's want_dense output)."""
+    dense, ldn = _rows(dense, "dense")
+    pos_dist = _f32c(pos_dist, "pos_dist").contiguous()
+    Q, N = dense.shape
+    if pos_dist.dim() != 2 or pos_dist.shape[0] != Q:
+        raise CflNativeError("dense_rank_counts: pos_dist must be [Q,J]")
+    J = pos_dist.shape[1]
+    out = torch.empty(Q, J, 2, dtype=torch.int64, device=dense.device)
+    _check(lib().cfl_dense_rank_counts(_ptr(dense), Q, N, ldn, _ptr(pos_dist), J, _ptr(out), _stream()),
+           "cfl_dense_rank_counts")
     return out
 
 

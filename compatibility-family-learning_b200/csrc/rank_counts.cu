@@ -27,6 +27,7 @@ __device__ __forceinline__ float pcd_direct(EAcc e, PAcc p, int d) {
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     float acc = 0.0f;
+#pragma unroll 4
     for (int j = 0; j < d; ++j) { const float df = e(j) - p(k, j); acc = fmaf(df, df, acc); }
     dk[k] = acc;
     mn = fminf(mn, acc);
@@ -37,6 +38,7 @@ __device__ __forceinline__ float pcd_direct(EAcc e, PAcc p, int d) {
   for (int k = 0; k < K; ++k) { dk[k] = expf(mn - dk[k]); sum += dk[k]; }
   const float inv = 1.0f / sum;
   float dist = 0.0f;
+#pragma unroll 4
   for (int j = 0; j < d; ++j) {
     float m = 0.0f;
 #pragma unroll
@@ -54,6 +56,7 @@ __device__ __forceinline__ float monomer_direct(EAcc e, AAcc a, WAcc w, int d) {
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     float dk = 0.0f;
+#pragma unroll 4
     for (int j = 0; j < d; ++j) { const float df = a(j) + (-e(k, j)); dk = fmaf(df, df, dk); }
     acc = fmaf(w(k), dk, acc);
   }
@@ -165,6 +168,45 @@ __global__ void pair_dist_rows_kernel(RcArgs A) {
   A.pos_dist[i] = dist;
 }
 
+// Counts over a DENSE distance matrix (the tensor-core route: cfl_score_topk's dist_out holds the Gram-form
+// distance of every (query, row); thresholds taken from the same matrix make the counts self-consistent).
+// grid (chunks, Q): each CTA streams a slice of one query's row with 128-bit loads.
+constexpr int DRC_THREADS = 256;
+template <int JM>
+__global__ void __launch_bounds__(DRC_THREADS)
+dense_rank_count_kernel(const float* __restrict__ dense, int64_t N, int64_t ldn, const float* __restrict__ thr, int J,
+                        unsigned long long* __restrict__ counts) {
+  __shared__ float st[JM];
+  __shared__ unsigned int sc[JM * 2];
+  const int64_t q = blockIdx.y;
+  const int t = threadIdx.x;
+  if (t < JM) st[t] = t < J ? thr[q * J + t] : __int_as_float(0x7fc00000);   // NaN pads: count nothing
+  if (t < 2 * JM) sc[t] = 0u;
+  __syncthreads();
+  const float* row = dense + q * ldn;
+  const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per;
+  const int64_t hi = lo + per < N ? lo + per : N;
+  unsigned int lt[JM], eq[JM];
+  float tj[JM];
+#pragma unroll
+  for (int j = 0; j < JM; ++j) { lt[j] = 0u; eq[j] = 0u; tj[j] = st[j]; }
+  for (int64_t i = lo + t; i < hi; i += DRC_THREADS) {
+    const float v = row[i];
+#pragma unroll
+    for (int j = 0; j < JM; ++j) { lt[j] += v < tj[j]; eq[j] += v == tj[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < JM; ++j) {
+    unsigned int a = lt[j], b = eq[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((t & 31) == 0) { if (a) atomicAdd(&sc[2 * j], a); if (b) atomicAdd(&sc[2 * j + 1], b); }
+  }
+  __syncthreads();
+  if (t < 2 * J && sc[t]) atomicAdd(&counts[q * J * 2 + t], (unsigned long long)sc[t]);
+}
+
 static size_t rc_smem_bytes(int K, int d, int J, bool mono) {
   const int ew = mono ? K * d : d, qw = mono ? d : K * d;
   return (size_t)128 * (ew + 1) * 4 + (size_t)RC_QT * qw * 4 + (size_t)RC_QT * K * 4 + (size_t)RC_QT * J * 4 +
@@ -256,11 +298,37 @@ int cfl_rank_counts(int mode, const float* Pq, int64_t Q, int K, int d, int64_t 
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   const int64_t nqt = (Q + RC_QT - 1) / RC_QT;
-  int64_t parts = (4 * (int64_t)sms) / nqt;
+  int64_t parts = (8 * (int64_t)sms) / nqt;          // only resident warps hide the shared-memory latency (ncu: 4/SM left 78 % of the slots empty)
   if (parts > a.tiles) parts = a.tiles;
   if (parts < 1) parts = 1;
   a.parts = (int)parts;
   return rc_dispatch(a, false, cs);
+}
+
+int cfl_dense_rank_counts(const float* dense, int64_t Q, int64_t N, int64_t ldn, const float* pos_dist, int J,
+                          int64_t* counts, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(J >= 1 && J <= RC_MAX_J, CFL_ERR_UNSUPPORTED, "dense_rank_counts: J=%d outside [1,%d]", J, RC_MAX_J);
+  CFL_REQUIRE(Q >= 0 && N >= 0 && ldn >= N && Q <= 65535, CFL_ERR_INVALID, "dense_rank_counts: bad Q/N/ldn");
+  if (Q == 0) return CFL_OK;
+  CFL_REQUIRE(pos_dist && counts && (N == 0 || dense), CFL_ERR_INVALID, "dense_rank_counts: NULL argument");
+  cudaStream_t cs = (cudaStream_t)stream;
+  CFL_CUDA(cudaMemsetAsync(counts, 0, (size_t)Q * J * 2 * sizeof(int64_t), cs));
+  if (N == 0) return CFL_OK;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int64_t chunks = (8 * (int64_t)sms + Q - 1) / Q;                 // ~8 CTAs per SM in flight
+  const int64_t max_chunks = (N + 4 * DRC_THREADS - 1) / (4 * DRC_THREADS);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  dim3 grid((unsigned)chunks, (unsigned)Q);
+  unsigned long long* c64 = (unsigned long long*)counts;
+  if (J <= 8) dense_rank_count_kernel<8><<<grid, DRC_THREADS, 0, cs>>>(dense, N, ldn, pos_dist, J, c64);
+  else if (J <= 16) dense_rank_count_kernel<16><<<grid, DRC_THREADS, 0, cs>>>(dense, N, ldn, pos_dist, J, c64);
+  else dense_rank_count_kernel<32><<<grid, DRC_THREADS, 0, cs>>>(dense, N, ldn, pos_dist, J, c64);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
 }
 
 }  // extern "C"

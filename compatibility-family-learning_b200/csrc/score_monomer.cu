@@ -11,12 +11,15 @@
 // row segments), the query vectors sit in shared memory as query PAIRS so the inner loop is packed
 // FP32x2 (add.f32x2 + fma.f32x2: two queries per instruction), and the running per-query top-k is the
 // machinery of topk.cuh (append buffers in the workspace, warp compaction, block merge).
+#include <stdlib.h>
 #include "score.cuh"
 
 namespace cfl {
 
 constexpr int MONO_QT = 16;        // queries per CTA (8 packed pairs per thread)
 constexpr int MONO_THREADS = 128;  // one thread per catalog row of a tile
+constexpr int MONO_KSTRIDE = TOPK_CAP;   // keys per (part, query) buffer: the adaptive mode never holds more than 512
+constexpr int MONO_PF = 16;        // float2 staging loads a thread keeps in flight across the compute phase (d <= 32)
 
 struct MonoArgs {
   int K, d;
@@ -24,13 +27,17 @@ struct MonoArgs {
   const float* A;    // [Q, lda]  query embeddings a_q
   const float* W;    // [Q, K]    query gate weights (softmax), dense
   const float* P;    // [N, ldp]  catalog prototypes, prototype k of row c at columns [k*d, (k+1)*d)
-  tkey_t* keys;      // [parts, Q, TOPK_STRIDE]
+  tkey_t* keys;      // [parts, Q, MONO_KSTRIDE]
   int* counts;       // [parts, Q]
   float* dist_out;   // optional dense [Q, N]
   int parts, kk;
   int64_t tiles;
 };
 
+// VEC2: d, ldp even and the catalog 8-byte aligned -> prototype tiles are staged with 64-bit loads, and for
+// d <= 32 the loads of the NEXT prototype (or the next tile's first one) are issued before the compute phase
+// of the current one and parked in registers, so their latency hides behind the FP work.
+template <bool VEC2>
 __global__ void __launch_bounds__(MONO_THREADS)
 score_monomer_kernel(MonoArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -58,9 +65,26 @@ score_monomer_kernel(MonoArgs A) {
   if (tid < MONO_QT) { thr[tid] = __int_as_float(0x7f800000); cnt[tid] = 0; }
   const int64_t t0 = A.tiles * part / A.parts;
   const int64_t t1 = A.tiles * (part + 1) / A.parts;
-  tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
-  // staging walk: element i = r*d + j of a [128][d] prototype tile, advanced by 128 without divisions
-  const int sr0 = tid / d, sj0 = tid % d, sdr = MONO_THREADS / d, sdj = MONO_THREADS % d;
+  tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * MONO_KSTRIDE;
+  // staging walk: element i = r*dv + j of a [128][dv] prototype tile (dv = d floats, or d/2 float2), advanced
+  // by 128 without divisions
+  const int dv = VEC2 ? d / 2 : d;
+  const int sr0 = tid / dv, sj0 = tid % dv, sdr = MONO_THREADS / dv, sdj = MONO_THREADS % dv;
+  const bool prefetch = VEC2 && dv <= MONO_PF;             // 128*dv/128 = dv loads per thread and stage
+  float2 pf[MONO_PF];
+  auto issue_loads = [&](int64_t r0, int k) {
+    int r = sr0, j = sj0;
+#pragma unroll
+    for (int m = 0; m < MONO_PF; ++m) {
+      if (m < dv) {
+        const int64_t row = r0 + r;
+        pf[m] = row < A.N ? *(const float2*)(A.P + row * A.ldp + (int64_t)k * d + 2 * j) : make_float2(0.0f, 0.0f);
+        r += sdr; j += sdj;
+        if (j >= dv) { j -= dv; ++r; }
+      }
+    }
+  };
+  if (prefetch && t0 < t1) issue_loads(t0 * 128, 0);
 
   for (int64_t tile = t0; tile < t1; ++tile) {
     const int64_t r0 = tile * 128;
@@ -69,13 +93,39 @@ score_monomer_kernel(MonoArgs A) {
     for (int p = 0; p < MONO_QT / 2; ++p) acc[p] = pk2(0.0f, 0.0f);
     for (int k = 0; k < K; ++k) {
       __syncthreads();                                   // queries loaded / previous prototype consumed
-      for (int i = tid, r = sr0, j = sj0; i < 128 * d; i += MONO_THREADS) {
-        const int64_t row = r0 + r;
-        et[r * ldt + j] = row < A.N ? A.P[row * A.ldp + (int64_t)k * d + j] : 0.0f;
-        r += sdr; j += sdj;
-        if (j >= d) { j -= d; ++r; }
+      if (prefetch) {
+        int r = sr0, j = sj0;
+#pragma unroll
+        for (int m = 0; m < MONO_PF; ++m) {
+          if (m < dv) {
+            et[r * ldt + 2 * j] = pf[m].x;
+            et[r * ldt + 2 * j + 1] = pf[m].y;
+            r += sdr; j += sdj;
+            if (j >= dv) { j -= dv; ++r; }
+          }
+        }
+      } else if (VEC2) {
+        for (int i = tid, r = sr0, j = sj0; i < 128 * dv; i += MONO_THREADS) {
+          const int64_t row = r0 + r;
+          const float2 v = row < A.N ? *(const float2*)(A.P + row * A.ldp + (int64_t)k * d + 2 * j) : make_float2(0.0f, 0.0f);
+          et[r * ldt + 2 * j] = v.x;
+          et[r * ldt + 2 * j + 1] = v.y;
+          r += sdr; j += sdj;
+          if (j >= dv) { j -= dv; ++r; }
+        }
+      } else {
+        for (int i = tid, r = sr0, j = sj0; i < 128 * d; i += MONO_THREADS) {
+          const int64_t row = r0 + r;
+          et[r * ldt + j] = row < A.N ? A.P[row * A.ldp + (int64_t)k * d + j] : 0.0f;
+          r += sdr; j += sdj;
+          if (j >= d) { j -= d; ++r; }
+        }
       }
       __syncthreads();
+      if (prefetch) {                                    // next stage's loads fly during this stage's compute
+        if (k + 1 < K) issue_loads(r0, k + 1);
+        else if (tile + 1 < t1) issue_loads(r0 + 128, 0);
+      }
       const float* er = et + tid * ldt;
       f2_t dk[MONO_QT / 2];
 #pragma unroll
@@ -109,7 +159,7 @@ score_monomer_kernel(MonoArgs A) {
             if (A.dist_out) A.dist_out[(q0 + ql) * A.N + row] = dv[h];
             if (dv[h] < thr[ql]) {
               const int slot = atomicAdd(&cnt[ql], 1);
-              kbase[(int64_t)ql * TOPK_STRIDE + slot] = pack_key(dv[h], (uint32_t)row);
+              kbase[(int64_t)ql * MONO_KSTRIDE + slot] = pack_key(dv[h], (uint32_t)row);
             }
           }
         }
@@ -119,14 +169,14 @@ score_monomer_kernel(MonoArgs A) {
     for (int ql = wid; ql < nq; ql += MONO_THREADS / 32) {
       const int n = cnt[ql];
       if (n > TOPK_TRIGGER) {
-        const int nk = warp_compact(kbase + (int64_t)ql * TOPK_STRIDE, n, A.kk, scratch + wid * TOPK_CAP, lane, &thr[ql]);
+        const int nk = warp_compact(kbase + (int64_t)ql * MONO_KSTRIDE, n, A.kk, scratch + wid * TOPK_CAP, lane, &thr[ql]);
         if (lane == 0) cnt[ql] = nk;
       }
     }
   }
   __syncthreads();
   for (int ql = wid; ql < nq; ql += MONO_THREADS / 32) {
-    const int nk = warp_compact(kbase + (int64_t)ql * TOPK_STRIDE, cnt[ql], A.kk, scratch + wid * TOPK_CAP, lane, nullptr);
+    const int nk = warp_compact(kbase + (int64_t)ql * MONO_KSTRIDE, cnt[ql], A.kk, scratch + wid * TOPK_CAP, lane, nullptr);
     if (lane == 0) A.counts[(int64_t)part * A.Q + q0 + ql] = nk;
   }
 }
@@ -140,7 +190,7 @@ merge_plain_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ coun
   __shared__ tkey_t s_thr;
   const int t = threadIdx.x;
   const int64_t q = blockIdx.x;
-  const int fill = block_merge_topkk(keys, counts, parts, Q, q, kk, s, &s_fill, &s_thr);
+  const int fill = block_merge_topkk(keys, counts, parts, Q, q, kk, s, &s_fill, &s_thr, MONO_KSTRIDE);
   for (int i = t; i < k; i += MRG_THREADS) {
     if (i < fill) {
       top_val[q * k + i] = ord2f((uint32_t)(s[i] >> 32));
@@ -165,7 +215,11 @@ static MonoPlan mono_plan(int64_t Q, int64_t N) {
   p.tiles = (N + 127) / 128;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  int64_t parts = p.nqt > 0 ? (4 * (int64_t)sms) / p.nqt : 1;   // a multiple of the SM count in flight
+  // 28..90 KB of shared memory per CTA: 2..8 CTAs are resident per SM, and only resident warps hide the
+  // staging latency -- 8 CTAs per SM in flight (measured: 4 per SM left 76 % of the warp slots empty)
+  const char* e = getenv("CFL_MONO_CTAS_PER_SM");
+  const int per_sm = e ? atoi(e) : 8;
+  int64_t parts = p.nqt > 0 ? ((per_sm > 0 ? per_sm : 8) * (int64_t)sms) / p.nqt : 1;
   if (parts > p.tiles) parts = p.tiles;
   if (parts < 1) parts = 1;
   p.parts = (int)parts;
@@ -182,7 +236,7 @@ size_t cfl_score_topk_monomer_workspace_bytes(int64_t Q, int K, int d, int64_t N
   (void)K; (void)d; (void)k;
   if (Q <= 0) return 4096;
   MonoPlan p = mono_plan(Q, N > 0 ? N : 1);
-  return align_up((size_t)p.parts * Q * TOPK_STRIDE * sizeof(tkey_t), 256) +
+  return align_up((size_t)p.parts * Q * MONO_KSTRIDE * sizeof(tkey_t), 256) +
          align_up((size_t)p.parts * Q * sizeof(int), 256) + 1024;
 }
 
@@ -202,7 +256,7 @@ int cfl_score_topk_monomer(const float* Aq, int64_t lda, const float* Wq, int64_
   CFL_REQUIRE(Aq && Wq && top_val && top_idx, CFL_ERR_INVALID, "score_topk_monomer: NULL argument");
   CFL_REQUIRE(N == 0 || Pc, CFL_ERR_INVALID, "score_topk_monomer: NULL catalog");
   MonoPlan plan = mono_plan(Q, N > 0 ? N : 1);
-  const size_t keys_bytes = align_up((size_t)plan.parts * Q * TOPK_STRIDE * sizeof(tkey_t), 256);
+  const size_t keys_bytes = align_up((size_t)plan.parts * Q * MONO_KSTRIDE * sizeof(tkey_t), 256);
   const size_t need = keys_bytes + align_up((size_t)plan.parts * Q * sizeof(int), 256);
   CFL_REQUIRE(ws && ws_bytes >= need, CFL_ERR_WORKSPACE, "score_topk_monomer: workspace too small (%zu < %zu)",
               ws_bytes, need);
@@ -214,10 +268,17 @@ int cfl_score_topk_monomer(const float* Aq, int64_t lda, const float* Wq, int64_
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
   } else {
     const size_t smem = mono_smem_bytes(K, d);
-    CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool vec2 = d % 2 == 0 && ldp % 2 == 0 && ((uintptr_t)Pc & 7u) == 0 && !getenv("CFL_MONO_NO_VEC");
     dim3 grid(plan.parts, plan.nqt);
-    timer_record(0, cs);
-    score_monomer_kernel<<<grid, MONO_THREADS, smem, cs>>>(a);
+    if (vec2) {
+      CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      timer_record(0, cs);
+      score_monomer_kernel<true><<<grid, MONO_THREADS, smem, cs>>>(a);
+    } else {
+      CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      timer_record(0, cs);
+      score_monomer_kernel<false><<<grid, MONO_THREADS, smem, cs>>>(a);
+    }
     timer_record(1, cs);
     CFL_LAUNCH_CHECK();
   }

@@ -151,14 +151,14 @@ __device__ __forceinline__ void mrg_compact(tkey_t* s, int* s_fill, tkey_t* s_th
 // returns the number of keys kept (<= kk), sorted ascending in s[0..)
 __device__ __forceinline__ int block_merge_topkk(const tkey_t* __restrict__ keys, const int* __restrict__ counts,
                                                  int parts, int64_t Q, int64_t q, int kk, tkey_t* s, int* s_fill,
-                                                 tkey_t* s_thr) {
+                                                 tkey_t* s_thr, int stride = TOPK_STRIDE) {
   const int t = threadIdx.x;
   if (t == 0) { *s_fill = 0; *s_thr = CFL_KEY_INF; }
   __syncthreads();
   for (int p = 0; p < parts; ++p) {
     int c = counts[(int64_t)p * Q + q];
-    if (c > TOPK_STRIDE) c = TOPK_STRIDE;                    // an over-full lower-bound buffer (flagged for redo)
-    const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
+    if (c > stride) c = stride;                              // an over-full lower-bound buffer (flagged for redo)
+    const tkey_t* src = keys + ((int64_t)p * Q + q) * stride;
     for (int base = 0; base < c; base += MRG_THREADS) {
       // every thread must take the same branch: read the fill level between two barriers, before
       // any thread of this round can append

@@ -210,6 +210,14 @@ int cfl_rank_counts(int mode, const float* Pq, int64_t Q, int K, int d, int64_t 
                     const float* E, int64_t N, int64_t lde, const float* pos_dist, int J,
                     int64_t* counts, void* stream);
 
+/* The same counts over a DENSE distance matrix dense[Q, ldn] (first N columns), e.g. the dist_out of
+ * cfl_score_topk: the tensor-core route for pcd -- the Gram-form distances of every (query, row) are written
+ * once and counted at HBM speed; thresholds read from the same matrix (pos_dist[q,j] = dense[q, pos]) keep the
+ * counts self-consistent (they are exact for the Gram-form fp32 values, which carry the 3xTF32 error of
+ * cfl_score_topk's un-rescored distances instead of the direct form's). */
+int cfl_dense_rank_counts(const float* dense, int64_t Q, int64_t N, int64_t ldn, const float* pos_dist, int J,
+                          int64_t* counts, void* stream);
+
 /* TF-1.x Adam (cfl/models/cfl.py:1083-1085): lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
  * p -= lr_t*m/(sqrt(v)+eps).  grad_scale multiplies g first (1/world for DP averaging). */
 int cfl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step,

@@ -266,3 +266,50 @@ def test_catalog_index_auc_per_query_planted_positives(nat):
     wu, wp, wn = O.per_query_auc(D, pos)
     want = np.array(wu) / (2.0 * np.array(wp) * np.array(wn))
     np.testing.assert_allclose(r.auc.cpu().numpy(), want, atol=2.0 / (J * (N - J)))   # at most a near-tie flip or two
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Q,N,J", [(1, 1, 1), (7, 1000, 8), (33, 4097, 9), (5, 70001, 20), (3, 513, 32)])
+def test_dense_rank_counts_exact_on_tied_values(nat, Q, N, J):
+    rng = np.random.default_rng(Q + N + J)
+    D = np.round(rng.gamma(2.0, size=(Q, N)), 1).astype(np.float32)          # many exact ties
+    pos = _planted(rng, Q, N, min(J, N), pad=N > 40)
+    want_cnt, t = _counts_from_dense(D, pos)
+    got = nat.dense_rank_counts(dev(D), dev(t))
+    assert (got.cpu().numpy() == want_cnt).all()
+    # a strided view (leading dimension > N) counts only the first N columns
+    big = torch.full((Q, N + 13), -1.0, device="cuda")
+    big[:, :N] = dev(D)
+    assert torch.equal(nat.dense_rank_counts(big[:, :N], dev(t)), got)
+
+
+@pytest.mark.gpu
+def test_catalog_index_auc_per_query_gram_route(nat):
+    """The tensor-core route (dense Gram-form distances + HBM-speed counting) against the direct route and the
+    fp64 oracle: same AUC up to near-tie flips inside the Gram error band; counts self-consistent."""
+    from cfl.ranking import CatalogIndex, EncoderWeights
+    rng = np.random.default_rng(634)
+    F, K, d, N, Q, J = 64, 3, 64, 30000, 48, 8
+    w = EncoderWeights(V0=dev(O.xavier_uniform(rng, F, d)), Vp=dev(O.xavier_uniform(rng, F, K * d)),
+                       g0=torch.ones(d).cuda(), gp=torch.ones(K * d).cuda(), b0=torch.zeros(d).cuda(),
+                       bp=torch.zeros(K * d).cuda())
+    X = np.maximum(rng.normal(size=(N, F)), 0).astype(np.float32)
+    index = CatalogIndex.from_features(w, dev(X))
+    xq = dev(X[:Q])
+    pos = rng.permutation(np.arange(Q, N))[:Q * J].reshape(Q, J).astype(np.int64)
+    pos[::5, -1] = -1
+    a = index.auc_per_query(xq, torch.as_tensor(pos), method="direct")
+    b = index.auc_per_query(xq, torch.as_tensor(pos), method="gram")
+    assert (b.counts[..., 1][torch.as_tensor(pos >= 0).cuda()] >= 1).all()
+    Pq = index.project_queries(xq)
+    D = O.all_pairs_dist(Pq.cpu().numpy().astype(np.float64), index.E.cpu().numpy().astype(np.float64))
+    wu, wp, wn = O.per_query_auc(D, pos)
+    want = np.array(wu) / (2.0 * np.array(wp) * np.array(wn))
+    tol = 4.0 / (J * (N - J))                                   # a few near-tie flips
+    np.testing.assert_allclose(a.auc.cpu().numpy(), want, atol=tol)
+    np.testing.assert_allclose(b.auc.cpu().numpy(), want, atol=tol)
+    np.testing.assert_allclose(b.pos_dist.cpu().numpy(), a.pos_dist.cpu().numpy(), rtol=1e-4, equal_nan=True)
+    # chunked sweep = one sweep
+    from cfl import ranking
+    c = ranking._auc_per_query_gram(Pq, index.E, index.mu, index.image, torch.as_tensor(pos), 0, N, None, 1, q_chunk=7)
+    assert torch.equal(c.counts, b.counts)
