@@ -19,7 +19,6 @@ namespace cfl {
 constexpr int MONO_QT = 16;        // queries per CTA (8 packed pairs per thread)
 constexpr int MONO_THREADS = 128;  // one thread per catalog row of a tile
 constexpr int MONO_KSTRIDE = TOPK_CAP;   // keys per (part, query) buffer: the adaptive mode never holds more than 512
-constexpr int MONO_PF = 16;        // float2 staging loads a thread keeps in flight across the compute phase (d <= 32)
 
 struct MonoArgs {
   int K, d;
@@ -34,10 +33,6 @@ struct MonoArgs {
   int64_t tiles;
 };
 
-// VEC2: d, ldp even and the catalog 8-byte aligned -> prototype tiles are staged with 64-bit loads, and for
-// d <= 32 the loads of the NEXT prototype (or the next tile's first one) are issued before the compute phase
-// of the current one and parked in registers, so their latency hides behind the FP work.
-template <bool VEC2>
 __global__ void __launch_bounds__(MONO_THREADS)
 score_monomer_kernel(MonoArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -66,25 +61,11 @@ score_monomer_kernel(MonoArgs A) {
   const int64_t t0 = A.tiles * part / A.parts;
   const int64_t t1 = A.tiles * (part + 1) / A.parts;
   tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * MONO_KSTRIDE;
-  // staging walk: element i = r*dv + j of a [128][dv] prototype tile (dv = d floats, or d/2 float2), advanced
-  // by 128 without divisions
-  const int dv = VEC2 ? d / 2 : d;
-  const int sr0 = tid / dv, sj0 = tid % dv, sdr = MONO_THREADS / dv, sdj = MONO_THREADS % dv;
-  const bool prefetch = VEC2 && dv <= MONO_PF;             // 128*dv/128 = dv loads per thread and stage
-  float2 pf[MONO_PF];
-  auto issue_loads = [&](int64_t r0, int k) {
-    int r = sr0, j = sj0;
-#pragma unroll
-    for (int m = 0; m < MONO_PF; ++m) {
-      if (m < dv) {
-        const int64_t row = r0 + r;
-        pf[m] = row < A.N ? *(const float2*)(A.P + row * A.ldp + (int64_t)k * d + 2 * j) : make_float2(0.0f, 0.0f);
-        r += sdr; j += sdj;
-        if (j >= dv) { j -= dv; ++r; }
-      }
-    }
-  };
-  if (prefetch && t0 < t1) issue_loads(t0 * 128, 0);
+  // staging: LPR lanes walk one catalog row (its d floats of prototype k are contiguous: coalesced), a warp
+  // covers 32/LPR rows per step and the 4 warps interleave; only pointer increments in the loop
+  const int lpr = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
+  const int rstep = (MONO_THREADS / 32) * (32 / lpr);      // rows the CTA stages per step
+  const int srow = wid * (32 / lpr) + lane / lpr, scol = lane % lpr;
 
   for (int64_t tile = t0; tile < t1; ++tile) {
     const int64_t r0 = tile * 128;
@@ -93,39 +74,18 @@ score_monomer_kernel(MonoArgs A) {
     for (int p = 0; p < MONO_QT / 2; ++p) acc[p] = pk2(0.0f, 0.0f);
     for (int k = 0; k < K; ++k) {
       __syncthreads();                                   // queries loaded / previous prototype consumed
-      if (prefetch) {
-        int r = sr0, j = sj0;
-#pragma unroll
-        for (int m = 0; m < MONO_PF; ++m) {
-          if (m < dv) {
-            et[r * ldt + 2 * j] = pf[m].x;
-            et[r * ldt + 2 * j + 1] = pf[m].y;
-            r += sdr; j += sdj;
-            if (j >= dv) { j -= dv; ++r; }
-          }
-        }
-      } else if (VEC2) {
-        for (int i = tid, r = sr0, j = sj0; i < 128 * dv; i += MONO_THREADS) {
-          const int64_t row = r0 + r;
-          const float2 v = row < A.N ? *(const float2*)(A.P + row * A.ldp + (int64_t)k * d + 2 * j) : make_float2(0.0f, 0.0f);
-          et[r * ldt + 2 * j] = v.x;
-          et[r * ldt + 2 * j + 1] = v.y;
-          r += sdr; j += sdj;
-          if (j >= dv) { j -= dv; ++r; }
-        }
-      } else {
-        for (int i = tid, r = sr0, j = sj0; i < 128 * d; i += MONO_THREADS) {
-          const int64_t row = r0 + r;
-          et[r * ldt + j] = row < A.N ? A.P[row * A.ldp + (int64_t)k * d + j] : 0.0f;
-          r += sdr; j += sdj;
-          if (j >= d) { j -= d; ++r; }
+      {
+        const float* src = A.P + (r0 + srow) * A.ldp + (int64_t)k * d;
+        float* dst = et + srow * ldt;
+        const int64_t sstep = (int64_t)rstep * A.ldp;
+        int64_t rows_left = A.N - r0 - srow;               // > 0: this row exists
+#pragma unroll 4
+        for (int r = srow; r < 128; r += rstep) {
+          for (int j = scol; j < d; j += lpr) dst[j] = rows_left > 0 ? src[j] : 0.0f;
+          src += sstep; dst += rstep * ldt; rows_left -= rstep;
         }
       }
       __syncthreads();
-      if (prefetch) {                                    // next stage's loads fly during this stage's compute
-        if (k + 1 < K) issue_loads(r0, k + 1);
-        else if (tile + 1 < t1) issue_loads(r0 + 128, 0);
-      }
       const float* er = et + tid * ldt;
       f2_t dk[MONO_QT / 2];
 #pragma unroll
@@ -209,17 +169,22 @@ static size_t mono_smem_bytes(int K, int d) {
 
 struct MonoPlan { int nqt, parts; int64_t tiles; };
 
-static MonoPlan mono_plan(int64_t Q, int64_t N) {
+// One wave: the grid is sized to the CTAs that are RESIDENT at once (72 registers x 128 threads -> 7 per SM;
+// 228 KB of shared memory per SM, 1 KB reserved per CTA), because only resident warps hide the staging latency
+// and a second, partial wave would idle most SMs (measured: 4 CTAs per SM left 76 % of the warp slots empty,
+// 8 per SM ran 1.1 waves).
+static MonoPlan mono_plan(int64_t Q, int64_t N, int K, int d) {
   MonoPlan p;
   p.nqt = (int)((Q + MONO_QT - 1) / MONO_QT);
   p.tiles = (N + 127) / 128;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
-  // 28..90 KB of shared memory per CTA: 2..8 CTAs are resident per SM, and only resident warps hide the
-  // staging latency -- 8 CTAs per SM in flight (measured: 4 per SM left 76 % of the warp slots empty)
+  int64_t resident = (228 * 1024) / (int64_t)(mono_smem_bytes(K, d) + 1024);
+  if (resident > 7) resident = 7;                      // 72 registers x 128 threads
+  if (resident < 1) resident = 1;
   const char* e = getenv("CFL_MONO_CTAS_PER_SM");
-  const int per_sm = e ? atoi(e) : 8;
-  int64_t parts = p.nqt > 0 ? ((per_sm > 0 ? per_sm : 8) * (int64_t)sms) / p.nqt : 1;
+  if (e && atoi(e) > 0) resident = atoi(e);
+  int64_t parts = p.nqt > 0 ? (resident * sms) / p.nqt : 1;
   if (parts > p.tiles) parts = p.tiles;
   if (parts < 1) parts = 1;
   p.parts = (int)parts;
@@ -233,9 +198,9 @@ using namespace cfl;
 extern "C" {
 
 size_t cfl_score_topk_monomer_workspace_bytes(int64_t Q, int K, int d, int64_t N, int k) {
-  (void)K; (void)d; (void)k;
+  (void)k;
   if (Q <= 0) return 4096;
-  MonoPlan p = mono_plan(Q, N > 0 ? N : 1);
+  MonoPlan p = mono_plan(Q, N > 0 ? N : 1, K, d);
   return align_up((size_t)p.parts * Q * MONO_KSTRIDE * sizeof(tkey_t), 256) +
          align_up((size_t)p.parts * Q * sizeof(int), 256) + 1024;
 }
@@ -255,7 +220,7 @@ int cfl_score_topk_monomer(const float* Aq, int64_t lda, const float* Wq, int64_
   if (Q == 0) return CFL_OK;
   CFL_REQUIRE(Aq && Wq && top_val && top_idx, CFL_ERR_INVALID, "score_topk_monomer: NULL argument");
   CFL_REQUIRE(N == 0 || Pc, CFL_ERR_INVALID, "score_topk_monomer: NULL catalog");
-  MonoPlan plan = mono_plan(Q, N > 0 ? N : 1);
+  MonoPlan plan = mono_plan(Q, N > 0 ? N : 1, K, d);
   const size_t keys_bytes = align_up((size_t)plan.parts * Q * MONO_KSTRIDE * sizeof(tkey_t), 256);
   const size_t need = keys_bytes + align_up((size_t)plan.parts * Q * sizeof(int), 256);
   CFL_REQUIRE(ws && ws_bytes >= need, CFL_ERR_WORKSPACE, "score_topk_monomer: workspace too small (%zu < %zu)",
@@ -268,17 +233,10 @@ int cfl_score_topk_monomer(const float* Aq, int64_t lda, const float* Wq, int64_
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
   } else {
     const size_t smem = mono_smem_bytes(K, d);
-    const bool vec2 = d % 2 == 0 && ldp % 2 == 0 && ((uintptr_t)Pc & 7u) == 0 && !getenv("CFL_MONO_NO_VEC");
+    CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(plan.parts, plan.nqt);
-    if (vec2) {
-      CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      timer_record(0, cs);
-      score_monomer_kernel<true><<<grid, MONO_THREADS, smem, cs>>>(a);
-    } else {
-      CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      timer_record(0, cs);
-      score_monomer_kernel<false><<<grid, MONO_THREADS, smem, cs>>>(a);
-    }
+    timer_record(0, cs);
+    score_monomer_kernel<<<grid, MONO_THREADS, smem, cs>>>(a);
     timer_record(1, cs);
     CFL_LAUNCH_CHECK();
   }
