@@ -33,6 +33,9 @@ struct MonoArgs {
   int64_t tiles;
 };
 
+// VW = floats per staging load: 4 / 2 when d and ldp are multiples of it and the catalog is aligned to it (128- /
+// 64-bit loads: the element walk costs address arithmetic per load, so wider loads cut the overhead), else 1.
+template <int VW>
 __global__ void __launch_bounds__(MONO_THREADS)
 score_monomer_kernel(MonoArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -61,11 +64,10 @@ score_monomer_kernel(MonoArgs A) {
   const int64_t t0 = A.tiles * part / A.parts;
   const int64_t t1 = A.tiles * (part + 1) / A.parts;
   tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * MONO_KSTRIDE;
-  // staging: LPR lanes walk one catalog row (its d floats of prototype k are contiguous: coalesced), a warp
-  // covers 32/LPR rows per step and the 4 warps interleave; only pointer increments in the loop
-  const int lpr = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
-  const int rstep = (MONO_THREADS / 32) * (32 / lpr);      // rows the CTA stages per step
-  const int srow = wid * (32 / lpr) + lane / lpr, scol = lane % lpr;
+  // staging walk: element i = r*dv + j of a [128][dv] prototype tile (dv = d / VW vector loads per row), advanced
+  // by 128 without divisions
+  const int dv = d / VW;
+  const int sr0 = tid / dv, sj0 = tid % dv, sdr = MONO_THREADS / dv, sdj = MONO_THREADS % dv;
 
   for (int64_t tile = t0; tile < t1; ++tile) {
     const int64_t r0 = tile * 128;
@@ -74,16 +76,21 @@ score_monomer_kernel(MonoArgs A) {
     for (int p = 0; p < MONO_QT / 2; ++p) acc[p] = pk2(0.0f, 0.0f);
     for (int k = 0; k < K; ++k) {
       __syncthreads();                                   // queries loaded / previous prototype consumed
-      {
-        const float* src = A.P + (r0 + srow) * A.ldp + (int64_t)k * d;
-        float* dst = et + srow * ldt;
-        const int64_t sstep = (int64_t)rstep * A.ldp;
-        int64_t rows_left = A.N - r0 - srow;               // > 0: this row exists
-#pragma unroll 4
-        for (int r = srow; r < 128; r += rstep) {
-          for (int j = scol; j < d; j += lpr) dst[j] = rows_left > 0 ? src[j] : 0.0f;
-          src += sstep; dst += rstep * ldt; rows_left -= rstep;
+      for (int i = tid, r = sr0, j = sj0; i < 128 * dv; i += MONO_THREADS) {
+        const int64_t row = r0 + r;
+        const float* src = A.P + row * A.ldp + (int64_t)k * d + VW * j;
+        float* dst = et + r * ldt + VW * j;
+        if (VW == 4) {
+          const float4 v = row < A.N ? *(const float4*)src : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        } else if (VW == 2) {
+          const float2 v = row < A.N ? *(const float2*)src : make_float2(0.0f, 0.0f);
+          dst[0] = v.x; dst[1] = v.y;
+        } else {
+          dst[0] = row < A.N ? *src : 0.0f;
         }
+        r += sdr; j += sdj;
+        if (j >= dv) { j -= dv; ++r; }
       }
       __syncthreads();
       const float* er = et + tid * ldt;
@@ -169,7 +176,7 @@ static size_t mono_smem_bytes(int K, int d) {
 
 struct MonoPlan { int nqt, parts; int64_t tiles; };
 
-// One wave: the grid is sized to the CTAs that are RESIDENT at once (72 registers x 128 threads -> 7 per SM;
+// One wave: the grid is sized to the CTAs that are RESIDENT at once (64 registers x 128 threads -> 8 per SM;
 // 228 KB of shared memory per SM, 1 KB reserved per CTA), because only resident warps hide the staging latency
 // and a second, partial wave would idle most SMs (measured: 4 CTAs per SM left 76 % of the warp slots empty,
 // 8 per SM ran 1.1 waves).
@@ -180,7 +187,7 @@ static MonoPlan mono_plan(int64_t Q, int64_t N, int K, int d) {
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   int64_t resident = (228 * 1024) / (int64_t)(mono_smem_bytes(K, d) + 1024);
-  if (resident > 7) resident = 7;                      // 72 registers x 128 threads
+  if (resident > 8) resident = 8;                      // 64 registers x 128 threads
   if (resident < 1) resident = 1;
   const char* e = getenv("CFL_MONO_CTAS_PER_SM");
   if (e && atoi(e) > 0) resident = atoi(e);
@@ -233,10 +240,20 @@ int cfl_score_topk_monomer(const float* Aq, int64_t lda, const float* Wq, int64_
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
   } else {
     const size_t smem = mono_smem_bytes(K, d);
-    CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char* ev = getenv("CFL_MONO_VW");
+    const int vmax = ev ? atoi(ev) : 4;
+    int vw = 1;
+    if (vmax >= 4 && d % 4 == 0 && ldp % 4 == 0 && ((uintptr_t)Pc & 15u) == 0) vw = 4;
+    else if (vmax >= 2 && d % 2 == 0 && ldp % 2 == 0 && ((uintptr_t)Pc & 7u) == 0) vw = 2;
     dim3 grid(plan.parts, plan.nqt);
-    timer_record(0, cs);
-    score_monomer_kernel<<<grid, MONO_THREADS, smem, cs>>>(a);
+#define CFL_MONO_CASE(VV)                                                                                          \
+  case VV:                                                                                                         \
+    CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    timer_record(0, cs);                                                                                           \
+    score_monomer_kernel<VV><<<grid, MONO_THREADS, smem, cs>>>(a);                                                 \
+    break;
+    switch (vw) { CFL_MONO_CASE(4) CFL_MONO_CASE(2) default: CFL_MONO_CASE(1) }
+#undef CFL_MONO_CASE
     timer_record(1, cs);
     CFL_LAUNCH_CHECK();
   }
