@@ -21,7 +21,7 @@ xq = [bench.synth_features(bench.Q, dev, bench.SEED + 7 + i) for i in range(4)]
 Pq = [index.project_queries(x) for x in xq]
 
 
-def run(reps=12):
+def run(reps=24):
     for i in range(3): index.rank_local(Pq[i % 4], bench.TOPK)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -34,7 +34,9 @@ def run(reps=12):
 ref = [index.rank_local(p, bench.TOPK) for p in Pq]
 base = run()
 print(json.dumps(dict(knobs="default", ms=round(base, 4))), flush=True)
-for stride, mult in itertools.product((12, 16, 24, 32), (3, 4, 6)):
+GRID = [tuple(int(v) for v in x.split(':')) for x in os.environ.get('CFL_KNOB_GRID', '').split(',') if x] or \
+    list(itertools.product((12, 16, 24, 32), (3, 4, 6)))
+for stride, mult in GRID:
     os.environ["CFL_SCORE_SAMPLE_STRIDE"] = str(stride)
     os.environ["CFL_SCORE_OPT_MULT"] = str(mult)
     same = all(torch.equal(index.rank_local(p, bench.TOPK)[1], r[1]) for p, r in zip(Pq, ref))
