@@ -36,6 +36,8 @@ def test_workspace_queries_do_not_need_a_gpu():
     assert lib.cfl_project_bwd_workspace_bytes(100, 4096, 80) >= 4096 * 80 * 4
     assert lib.cfl_auc_workspace_bytes(10, 1 << 20) >= 2 * 4 * (1 << 20)
     assert lib.cfl_score_topk_workspace_bytes(1024, 3, 64, 1 << 20, 100) > 0
+    mono = lib.cfl_score_topk_monomer_workspace_bytes(1024, 4, 20, 1 << 20, 100)
+    assert 1024 * 512 * 8 <= mono <= 256 << 20         # >= one 512-key buffer per query, one wave of parts at most
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -47,6 +49,21 @@ def test_compute_calls_fail_loudly_without_a_gpu():
     assert b"device" in lib.cfl_last_error().lower()
     with pytest.raises(_native.CflNativeError):
         _native.project_fwd(torch.zeros(2, 4), torch.zeros(4, 3))   # CPU tensors are rejected
+    # the entry points added for monomer ranking and the per-query AUC: same rule
+    assert lib.cfl_score_topk_monomer(None, 4, None, 1, 2, 4, None, 8, 8, 1, 0, None, None, None, None, 0, None) == -5
+    assert lib.cfl_pair_dist_rows(0, None, 1, 2, 4, 8, None, None, 8, 4, None, 1, None, None) == -5
+    assert lib.cfl_rank_counts(0, None, 1, 2, 4, 8, None, None, 8, 4, None, 1, None, None) == -5
+    assert lib.cfl_dense_rank_counts(None, 1, 8, 8, None, 1, None, None) == -5
+    a, w, P = torch.zeros(2, 4), torch.full((2, 3), 1 / 3), torch.zeros(5, 3, 4)
+    for call in (lambda: _native.score_topk_monomer(a, w, P, 2),
+                 lambda: _native.pair_dist_rows("monomer", a, P, torch.zeros(2, 1, dtype=torch.int64), w=w),
+                 lambda: _native.rank_counts("pcd", torch.zeros(2, 3, 4), torch.zeros(5, 4), torch.zeros(2, 1)),
+                 lambda: _native.dense_rank_counts(torch.zeros(2, 5), torch.zeros(2, 1))):
+        with pytest.raises(_native.CflNativeError):
+            call()
+    from cfl import ranking
+    with pytest.raises(_native.CflNativeError):
+        ranking.MonomerCatalogIndex(ranking.EncoderWeights(V0=torch.zeros(8, 4), Vp=torch.zeros(8, 12)), torch.zeros(5, 12))
 
 
 def test_missing_library_is_an_error_not_a_fallback(monkeypatch):
