@@ -77,7 +77,88 @@ struct RcArgs {
   int64_t tiles;
 };
 
-template <int K, bool MONO>
+// Four queries per pass through a catalog row: every shared-memory load of the row serves four distance
+// evaluations and the query operands arrive as one 128-bit broadcast load (the first version issued two
+// 32-bit loads per FMA and sat at 66 % of the LSU pipe).  Per query the operation sequence is exactly that of
+// pcd_direct / monomer_direct above, so the values -- and the counts -- are bit-identical to theirs.
+template <int K>
+__device__ __forceinline__ void pcd_direct4(const float* __restrict__ er, const float4* __restrict__ q4, int d,
+                                            float (&dist)[4]) {
+  float dk[4][K];
+  float mn[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+    for (int j = 0; j < d; ++j) {
+      const float e = er[j];
+      const float4 p = q4[(k * d + j) * 2];
+      float df;
+      df = e - p.x; acc[0] = fmaf(df, df, acc[0]);
+      df = e - p.y; acc[1] = fmaf(df, df, acc[1]);
+      df = e - p.z; acc[2] = fmaf(df, df, acc[2]);
+      df = e - p.w; acc[3] = fmaf(df, df, acc[3]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { dk[c][k] = acc[c]; mn[c] = fminf(mn[c], acc[c]); }
+  }
+  if (K == 1) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dist[c] = dk[c][0];
+    return;
+  }
+  float inv[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { dk[c][k] = expf(mn[c] - dk[c][k]); sum += dk[c][k]; }
+    inv[c] = 1.0f / sum;
+    dist[c] = 0.0f;
+  }
+#pragma unroll 2
+  for (int j = 0; j < d; ++j) {
+    const float e = er[j];
+    float m[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float4 p = q4[(k * d + j) * 2];
+      m[0] = fmaf(dk[0][k] * inv[0], p.x, m[0]);
+      m[1] = fmaf(dk[1][k] * inv[1], p.y, m[1]);
+      m[2] = fmaf(dk[2][k] * inv[2], p.z, m[2]);
+      m[3] = fmaf(dk[3][k] * inv[3], p.w, m[3]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { const float r = e - m[c]; dist[c] = fmaf(r, r, dist[c]); }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void monomer_direct4(const float* __restrict__ er, const float4* __restrict__ a4,
+                                                const float* __restrict__ w /* [4][K] */, int d, float (&dist)[4]) {
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float dk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+    for (int j = 0; j < d; ++j) {
+      const float ne = -er[k * d + j];
+      const float4 a = a4[j * 2];
+      float df;
+      df = a.x + ne; dk[0] = fmaf(df, df, dk[0]);
+      df = a.y + ne; dk[1] = fmaf(df, df, dk[1]);
+      df = a.z + ne; dk[2] = fmaf(df, df, dk[2]);
+      df = a.w + ne; dk[3] = fmaf(df, df, dk[3]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = fmaf(w[c * K + k], dk[c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dist[c] = acc[c];
+}
+
+// VW = floats per staging load (4 when the row length, the row stride and the base pointer allow 128-bit loads).
+template <int K, bool MONO, int VW>
 __global__ void __launch_bounds__(RC_THREADS)
 rank_count_kernel(RcArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -85,9 +166,9 @@ rank_count_kernel(RcArgs A) {
   const int ew = MONO ? K * d : d;            // floats per catalog row
   const int qw = MONO ? d : K * d;            // floats per query
   const int ldt = ew + 1;
-  float* et = (float*)smem_raw;                               // [128][ew+1]
-  float* qs = et + 128 * ldt;                                 // [QT][qw]
-  float* ws = qs + RC_QT * qw;                                // [QT][K] (monomer)
+  float4* q4 = (float4*)smem_raw;                             // [qw][2]: element i of queries 0-3 | 4-7 (zero padded)
+  float* et = (float*)(q4 + 2 * qw);                          // [128][ew+1]
+  float* ws = et + 128 * ldt;                                 // [QT][K] (monomer)
   float* thr = ws + RC_QT * K;                                // [QT][J]
   int* cnt = (int*)(thr + RC_QT * J);                         // [4 warps][QT][J][2]
 
@@ -95,44 +176,55 @@ rank_count_kernel(RcArgs A) {
   const int part = blockIdx.x;
   const int64_t q0 = (int64_t)blockIdx.y * RC_QT;
   const int nq = (int)((A.Q - q0 < RC_QT) ? (A.Q - q0) : RC_QT);
-  for (int i = tid; i < nq * qw; i += RC_THREADS) qs[i] = A.Pq[(q0 + i / qw) * A.ldq + i % qw];
-  if (MONO) for (int i = tid; i < nq * K; i += RC_THREADS) ws[i] = A.Wq[q0 * K + i];
+  for (int i = tid; i < RC_QT * qw; i += RC_THREADS) {
+    const int ql = i / qw, e = i % qw;
+    ((float*)q4)[e * RC_QT + ql] = ql < nq ? A.Pq[(q0 + ql) * A.ldq + e] : 0.0f;
+  }
+  if (MONO) for (int i = tid; i < RC_QT * K; i += RC_THREADS) ws[i] = i < nq * K ? A.Wq[q0 * K + i] : 0.0f;
   for (int i = tid; i < nq * J; i += RC_THREADS) thr[i] = A.thr[q0 * J + i];
   for (int i = tid; i < (RC_THREADS / 32) * RC_QT * J * 2; i += RC_THREADS) cnt[i] = 0;
   int* mycnt = cnt + wid * RC_QT * J * 2;
   const int64_t t0 = A.tiles * part / A.parts;
   const int64_t t1 = A.tiles * (part + 1) / A.parts;
-  const int sr0 = tid / ew, sj0 = tid % ew, sdr = RC_THREADS / ew, sdj = RC_THREADS % ew;
+  const int dv = ew / VW;
+  const int sr0 = tid / dv, sj0 = tid % dv, sdr = RC_THREADS / dv, sdj = RC_THREADS % dv;
 
   for (int64_t tile = t0; tile < t1; ++tile) {
     const int64_t r0 = tile * 128;
     __syncthreads();
-    for (int i = tid, r = sr0, j = sj0; i < 128 * ew; i += RC_THREADS) {
+    for (int i = tid, r = sr0, j = sj0; i < 128 * dv; i += RC_THREADS) {
       const int64_t row = r0 + r;
-      et[r * ldt + j] = row < A.N ? A.E[row * A.lde + j] : 0.0f;
+      const float* src = A.E + row * A.lde + VW * j;
+      float* dst = et + r * ldt + VW * j;
+      if (VW == 4) {
+        const float4 v = row < A.N ? *(const float4*)src : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      } else {
+        dst[0] = row < A.N ? *src : 0.0f;
+      }
       r += sdr; j += sdj;
-      if (j >= ew) { j -= ew; ++r; }
+      if (j >= dv) { j -= dv; ++r; }
     }
     __syncthreads();
     const bool valid = r0 + tid < A.N;
     const float* er = et + tid * ldt;
-    for (int ql = 0; ql < nq; ++ql) {
-      const float* qv = qs + ql * qw;
-      float dist;
-      if (MONO) {
-        const float* wv = ws + ql * K;
-        dist = monomer_direct<K>([&](int k, int j) { return er[k * d + j]; }, [&](int j) { return qv[j]; },
-                                 [&](int k) { return wv[k]; }, d);
-      } else {
-        dist = pcd_direct<K>([&](int j) { return er[j]; }, [&](int k, int j) { return qv[k * d + j]; }, d);
-      }
-      for (int j = 0; j < J; ++j) {
-        const float t = thr[ql * J + j];
-        const unsigned lt = __ballot_sync(0xffffffffu, valid && dist < t);
-        const unsigned eq = __ballot_sync(0xffffffffu, valid && dist == t);
-        if (lane == 0) {
-          mycnt[(ql * J + j) * 2] += __popc(lt);
-          mycnt[(ql * J + j) * 2 + 1] += __popc(eq);
+    for (int qh = 0; qh * 4 < nq; ++qh) {
+      float dist[4];
+      if (MONO) monomer_direct4<K>(er, q4 + qh, ws + qh * 4 * K, d, dist);
+      else      pcd_direct4<K>(er, q4 + qh, d, dist);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int ql = qh * 4 + c;
+        if (ql < nq) {                                         // warp-uniform
+          for (int j = 0; j < J; ++j) {
+            const float t = thr[ql * J + j];
+            const unsigned lt = __ballot_sync(0xffffffffu, valid && dist[c] < t);
+            const unsigned eq = __ballot_sync(0xffffffffu, valid && dist[c] == t);
+            if (lane == 0) {
+              mycnt[(ql * J + j) * 2] += __popc(lt);
+              mycnt[(ql * J + j) * 2 + 1] += __popc(eq);
+            }
+          }
         }
       }
     }
@@ -209,7 +301,7 @@ dense_rank_count_kernel(const float* __restrict__ dense, int64_t N, int64_t ldn,
 
 static size_t rc_smem_bytes(int K, int d, int J, bool mono) {
   const int ew = mono ? K * d : d, qw = mono ? d : K * d;
-  return (size_t)128 * (ew + 1) * 4 + (size_t)RC_QT * qw * 4 + (size_t)RC_QT * K * 4 + (size_t)RC_QT * J * 4 +
+  return (size_t)RC_QT * qw * 4 + (size_t)128 * (ew + 1) * 4 + (size_t)RC_QT * K * 4 + (size_t)RC_QT * J * 4 +
          (size_t)(RC_THREADS / 32) * RC_QT * J * 2 * 4;
 }
 
@@ -220,9 +312,25 @@ static int rc_launch(const RcArgs& a, bool gather, cudaStream_t cs) {
     pair_dist_rows_kernel<K, MONO><<<(unsigned)((n + 127) / 128), 128, 0, cs>>>(a);
   } else {
     const size_t smem = rc_smem_bytes(K, a.d, a.J, MONO);
-    CFL_CUDA(cudaFuncSetAttribute(rank_count_kernel<K, MONO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(a.parts, (unsigned)((a.Q + RC_QT - 1) / RC_QT));
-    rank_count_kernel<K, MONO><<<grid, RC_THREADS, smem, cs>>>(a);
+    const int ew = MONO ? K * a.d : a.d;
+    const bool v4 = ew % 4 == 0 && a.lde % 4 == 0 && ((uintptr_t)a.E & 15u) == 0;
+    auto kern = v4 ? rank_count_kernel<K, MONO, 4> : rank_count_kernel<K, MONO, 1>;
+    CFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // one wave: as many catalog parts as keep every CTA resident at once (only resident warps hide the
+    // shared-memory latency; a partial second wave idles most SMs)
+    int resident = 0;
+    CFL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, RC_THREADS, smem));
+    if (resident < 1) resident = 1;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    const int64_t nqt = (a.Q + RC_QT - 1) / RC_QT;
+    int64_t parts = ((int64_t)resident * sms) / nqt;
+    if (parts > a.tiles) parts = a.tiles;
+    if (parts < 1) parts = 1;
+    RcArgs b = a;
+    b.parts = (int)parts;
+    dim3 grid((unsigned)parts, (unsigned)nqt);
+    kern<<<grid, RC_THREADS, smem, cs>>>(b);
   }
   CFL_LAUNCH_CHECK();
   return CFL_OK;
@@ -295,13 +403,7 @@ int cfl_rank_counts(int mode, const float* Pq, int64_t Q, int K, int d, int64_t 
   a.mode = mode; a.K = K; a.d = d; a.J = J; a.Q = Q; a.N = N; a.ldq = ldq; a.lde = lde;
   a.Pq = Pq; a.Wq = Wq; a.E = E; a.thr = pos_dist; a.counts = (unsigned long long*)counts;
   a.tiles = (N + 127) / 128;
-  int sms = sm_count();
-  if (sms <= 0) sms = 148;
-  const int64_t nqt = (Q + RC_QT - 1) / RC_QT;
-  int64_t parts = (8 * (int64_t)sms) / nqt;          // only resident warps hide the shared-memory latency (ncu: 4/SM left 78 % of the slots empty)
-  if (parts > a.tiles) parts = a.tiles;
-  if (parts < 1) parts = 1;
-  a.parts = (int)parts;
+  a.parts = 1;                                   // set per kernel instance in rc_launch (one wave)
   return rc_dispatch(a, false, cs);
 }
 
