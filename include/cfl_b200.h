@@ -192,7 +192,8 @@ int cfl_auc(const float* pos_scores, int64_t n_pos, const float* neg_scores, int
  * Operands per mode (the pair scorer's roles, cfl/models/base.py:107-146):
  *   pcd / siamese: Pq[Q,K,d] query prototypes (ldq >= K*d), Wq NULL, E[N,d] candidate embeddings;
  *   monomer:       Pq[Q,d] query embeddings (ldq >= d), Wq[Q,K] gate softmax, E[N,K,d] candidate
- *                  prototypes (lde >= K*d).
+ *                  prototypes (lde >= K*d); the 128-row tile of K*d floats per row must fit one CTA's shared
+ *                  memory: K*d <= ~380, else CFL_ERR_UNSUPPORTED.
  * cfl_pair_dist_rows: pos_dist[q,j] = dist(q, row pos_idx[q,j]) for the J labelled positives of each
  *   query; pos_idx is LOCAL to this shard, entries outside [0,N) (e.g. -1: positive lives on another
  *   shard, or padding) give NaN.
