@@ -313,3 +313,19 @@ def test_catalog_index_auc_per_query_gram_route(nat):
     from cfl import ranking
     c = ranking._auc_per_query_gram(Pq, index.E, index.mu, index.image, torch.as_tensor(pos), 0, N, None, 1, q_chunk=7)
     assert torch.equal(c.counts, b.counts)
+
+
+def test_auc_from_rank_counts_random_cases_against_the_exact_auc():
+    """Randomised bookkeeping check (ties among positives, between positives and negatives, padded slots)."""
+    from cfl.ranking import auc_from_rank_counts
+    rng = np.random.default_rng(99)
+    for trial in range(60):
+        Q, N, J = int(rng.integers(1, 6)), int(rng.integers(3, 60)), int(rng.integers(1, 5))
+        J = min(J, N - 1)
+        D = rng.integers(0, 4, size=(Q, N)).astype(np.float32)             # four distinct values: ties everywhere
+        pos = np.stack([rng.choice(N, J, replace=False) for _ in range(Q)]).astype(np.int64)
+        pos[rng.uniform(size=pos.shape) < 0.2] = -1
+        cnt, t = _counts_from_dense(D, pos)
+        auc, two_u, n_pos, n_neg = auc_from_rank_counts(torch.as_tensor(cnt), torch.as_tensor(t), N)
+        wu, wp, wn = O.per_query_auc(D.astype(np.float64), pos)
+        assert two_u.tolist() == wu and n_pos.tolist() == wp and n_neg.tolist() == wn, trial
