@@ -784,6 +784,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   a.cimg = nullptr; a.e2 = nullptr;
   a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
   a.dbg = nullptr; a.redo_tile = nullptr; a.spill = nullptr; a.spill_cnt = nullptr;
+  a.lb_f16 = 0; a.cimg16 = nullptr; a.qimg16 = nullptr; a.cflag16 = nullptr; a.qflag16 = nullptr;
   bool lb_pass = false;
   const float* redo_only = nullptr;
   a.dbg_mode = getenv("CFL_SCORE_DBG_MODE") ? atoi(getenv("CFL_SCORE_DBG_MODE")) : 0;
@@ -805,6 +806,14 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       }
       a.cimg = image;
       a.e2 = (const float*)((const char*)image + (size_t)plan.tiles * (plan.dpad / 8) * 8192);
+      a.cimg16 = (const char*)image + catalog_f16_offset(N, d);
+      a.cflag16 = (const int*)((const char*)a.cimg16 + catalog_f16_bytes(N, d));
+      a.qimg16 = base + o_qimg + score_umma_qimg16_offset(plan, K);
+      a.qflag16 = (const int*)((const char*)a.qimg16 + score_umma_qimg16_bytes(plan, K));
+      {
+        const char* ef = getenv("CFL_SCORE_LB_F16");
+        a.lb_f16 = ef ? atoi(ef) : 0;
+      }
       st = score_umma_pack_queries(a, base + o_qimg, cs);
       if (st != CFL_OK) return st;
       // Long catalog ranges are scored in two passes: a sparse sample pass (every S-th tile,

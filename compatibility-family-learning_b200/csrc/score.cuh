@@ -40,6 +40,15 @@ struct ScoreArgs {
   tkey_t* spill;         // lower-bound pass: [Q, LB_SPILL] keys that did not fit their (part, query) buffer
   int* spill_cnt;        // [Q]
   const int* redo_tile;  // phase 2 redo launch: per query tile, 1 = some query must be redone (else the CTA exits)
+  // fp16 operand planes of the lower-bound pass (same 11-bit significand as tf32, twice the MMA rate): the
+  // catalog plane lives behind |e|^2 in the catalog image, the query plane behind the tf32 query image; each is
+  // followed by a flag word that its pack kernel raises when a value leaves the fp16 range (the kernel then
+  // keeps the tf32 planes).  lb_f16 = 0 disables the path.
+  int lb_f16;
+  const void* cimg16;
+  const void* qimg16;
+  const int* cflag16;
+  const int* qflag16;
   int dbg_mode;          // experiments (CFL_SCORE_DBG_MODE): 1 = epilogue does nothing, 2 = no TMA / no full-barrier waits
   unsigned long long* dbg; // optional counters {groups seen, skipped, selective, full} (CFL_SCORE_DEBUG)
   ScorePlan plan;
@@ -72,6 +81,10 @@ constexpr float CFL_PLANE_REL = 2.0e-4f;     // relative safety margin of the bo
 ScorePlan make_score_plan(int64_t Q, int K, int d, int64_t N, int k, bool umma_ok);
 bool score_umma_supported(int K, int d);
 size_t catalog_image_bytes(int64_t N, int d);
+size_t catalog_f16_offset(int64_t N, int d);     // byte offset of the fp16 plane inside the catalog image
+size_t catalog_f16_bytes(int64_t N, int d);      // plane only; the flag word follows it
+size_t score_umma_qimg16_offset(const ScorePlan& p, int K);
+size_t score_umma_qimg16_bytes(const ScorePlan& p, int K);
 int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const float* mu, void* image,
                         cudaStream_t st);
 size_t score_umma_qimg_bytes(const ScorePlan& p, int K);

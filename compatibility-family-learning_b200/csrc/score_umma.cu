@@ -21,6 +21,7 @@
 //                 into the per-query buffers (topk.cuh).  Accumulators are double-buffered in
 //                 TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
 // Work per score: 2*K*d flops (x3 MMAs); catalog bytes per row per query tile: 8*dpad + 4.
+#include <cuda_fp16.h>
 #include "score.cuh"
 #include "umma.cuh"
 
@@ -57,26 +58,46 @@ bool score_umma_supported(int K, int d) {
   return score_umma_qt(K, d) != 0;
 }
 
-size_t score_umma_qimg_bytes(const ScorePlan& p, int K) {
+// tf32 hi/lo query image, then the fp16 query image [qtile][kstep16][chunk][n][8 halfs], then its flag word
+size_t score_umma_qimg16_offset(const ScorePlan& p, int K) {
   return (size_t)p.nqt * p.dpad * 8 * (size_t)(K * p.qt);
+}
+size_t score_umma_qimg16_bytes(const ScorePlan& p, int K) {
+  const int nks16 = (p.dpad + 15) / 16;
+  return (size_t)p.nqt * nks16 * 2 * (size_t)(K * p.qt) * 16;
+}
+size_t score_umma_qimg_bytes(const ScorePlan& p, int K) {
+  return score_umma_qimg16_offset(p, K) + score_umma_qimg16_bytes(p, K) + 16;
 }
 
 // ---- catalog image ----------------------------------------------------------------------------
 // [tile][kstep][hl][chunk][row 0..127][4 floats]  (8 KB per (tile,kstep)), then e2[tiles*128].
-size_t catalog_image_bytes(int64_t N, int d) {
+// ... then the fp16 plane of the lower-bound pass: [tile][kstep16][chunk 0|1][row 0..127][8 halfs] (4 KB per
+// (tile, 16 columns)), then one flag word (non-zero: a centred value left the fp16 range, plane unusable).
+size_t catalog_f16_offset(int64_t N, int d) {
   const int64_t tiles = (N + 127) / 128;
   const int nks = (d + 7) / 8;
   return (size_t)tiles * nks * SU_ASTAGE + (size_t)tiles * 128 * sizeof(float);
 }
+size_t catalog_f16_bytes(int64_t N, int d) {
+  const int64_t tiles = (N + 127) / 128;
+  return (size_t)tiles * ((d + 15) / 16) * (SU_ASTAGE / 2);
+}
+size_t catalog_image_bytes(int64_t N, int d) {
+  return catalog_f16_offset(N, d) + catalog_f16_bytes(N, d) + 16;
+}
 
 __global__ void __launch_bounds__(128)
 pack_catalog_kernel(const float* __restrict__ E, int64_t N, int d, int64_t lde,
-                    const float* __restrict__ mu, unsigned char* __restrict__ img, float* __restrict__ e2g) {
+                    const float* __restrict__ mu, unsigned char* __restrict__ img, float* __restrict__ e2g,
+                    unsigned char* __restrict__ img16, int* __restrict__ flag16) {
   const int64_t tile = blockIdx.x;
   const int r = threadIdx.x;
   const int64_t row = tile * 128 + r;
   const int nks = (d + 7) / 8;
   float e2 = 0.0f;
+  float vmax = 0.0f;
+  const int nks16 = (d + 15) / 16;
   for (int ks = 0; ks < nks; ++ks) {
     float v[8];
 #pragma unroll
@@ -93,8 +114,19 @@ pack_catalog_kernel(const float* __restrict__ E, int64_t N, int d, int64_t lde,
     *(float4*)(st + ((0 * 2 + 1) * 128 + r) * 16) = h1;
     *(float4*)(st + ((1 * 2 + 0) * 128 + r) * 16) = l0;
     *(float4*)(st + ((1 * 2 + 1) * 128 + r) * 16) = l1;
+    // the same 8 centred values as halfs: chunk (ks & 1) of fp16 K-step ks >> 1
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) { h[jj] = __float2half_rn(v[jj]); vmax = fmaxf(vmax, fabsf(v[jj])); }
+    unsigned char* st16 = img16 + ((size_t)tile * nks16 + (ks >> 1)) * (SU_ASTAGE / 2);
+    *(uint4*)(st16 + ((ks & 1) * 128 + r) * 16) = *(const uint4*)h;
+  }
+  if (nks & 1) {                                             // odd number of 8-column steps: zero the last half K-step
+    unsigned char* st16 = img16 + ((size_t)tile * nks16 + (nks >> 1)) * (SU_ASTAGE / 2);
+    *(uint4*)(st16 + (1 * 128 + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   e2g[row] = e2;
+  if (!(vmax < 60000.0f)) atomicOr(flag16, 1);               // also catches NaN / inf
 }
 
 int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const float* mu, void* image,
@@ -103,7 +135,10 @@ int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const flo
   const int nks = (d + 7) / 8;
   unsigned char* img = (unsigned char*)image;
   float* e2g = (float*)(img + (size_t)tiles * nks * SU_ASTAGE);
-  pack_catalog_kernel<<<(unsigned)tiles, 128, 0, st>>>(E, N, d, lde, mu, img, e2g);
+  unsigned char* img16 = img + catalog_f16_offset(N, d);
+  int* flag16 = (int*)(img16 + catalog_f16_bytes(N, d));
+  CFL_CUDA(cudaMemsetAsync(flag16, 0, 16, st));
+  pack_catalog_kernel<<<(unsigned)tiles, 128, 0, st>>>(E, N, d, lde, mu, img, e2g, img16, flag16);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
 }
@@ -159,9 +194,43 @@ __global__ void pack_queries_kernel(const float* __restrict__ Pc, int64_t Q, int
   }
 }
 
+// fp16 query image of the lower-bound pass: [qtile][kstep16][chunk][row n = k*QT + ql][8 halfs]
+__global__ void pack_queries_f16_kernel(const float* __restrict__ Pc, int64_t Q, int K, int d, int qt, int dpad,
+                                        unsigned char* __restrict__ img16, int* __restrict__ flag16) {
+  const int nc = K * qt;
+  const int nks16 = (dpad + 15) / 16;
+  const int qtile = blockIdx.x;
+  unsigned char* base = img16 + (size_t)qtile * nks16 * 2 * nc * 16;
+  float vmax = 0.0f;
+  for (int e = threadIdx.x; e < nks16 * 2 * nc; e += blockDim.x) {
+    const int n = e % nc;
+    const int c = (e / nc) % 2;
+    const int ks = e / (2 * nc);
+    const int k = n / qt, ql = n % qt;
+    const int64_t q = (int64_t)qtile * qt + ql;
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = ks * 16 + c * 8 + i;
+      const float x = (q < Q && j < d) ? Pc[(q * K + k) * (int64_t)d + j] : 0.0f;
+      vmax = fmaxf(vmax, fabsf(x));
+      h[i] = __float2half_rn(x);
+    }
+    *(uint4*)(base + ((size_t)(ks * 2 + c) * nc + n) * 16) = *(const uint4*)h;
+  }
+  if (!(vmax < 60000.0f)) atomicOr(flag16, 1);
+}
+
 int score_umma_pack_queries(const ScoreArgs& a, void* qimg, cudaStream_t st) {
   pack_queries_kernel<<<a.plan.nqt, 256, 0, st>>>(a.Pc, a.Q, a.K, a.d, a.plan.qt, a.plan.dpad, (float*)qimg);
   CFL_LAUNCH_CHECK();
+  if (a.lb_f16) {
+    unsigned char* img16 = (unsigned char*)qimg + score_umma_qimg16_offset(a.plan, a.K);
+    int* flag16 = (int*)(img16 + score_umma_qimg16_bytes(a.plan, a.K));
+    CFL_CUDA(cudaMemsetAsync(flag16, 0, 16, st));
+    pack_queries_f16_kernel<<<a.plan.nqt, 256, 0, st>>>(a.Pc, a.Q, a.K, a.d, a.plan.qt, a.plan.dpad, img16, flag16);
+    CFL_LAUNCH_CHECK();
+  }
   return CFL_OK;
 }
 
@@ -536,7 +605,11 @@ score_lb_kernel(ScoreArgs A) {
   const int64_t t1 = A.plan.tiles * (part + 1) / A.plan.parts;
   const int ts = A.tile_stride;
   const int ntiles = (int)((t1 - t0 + ts - 1) / ts);
-  const int kss = (nks % 4 == 0) ? 4 : ((nks % 2 == 0) ? 2 : 1);   // K-steps (4 KB hi blocks) per ring stage
+  // fp16 operand planes (same significand as tf32, K = 16 per MMA: half the K-steps, half the operand bytes) unless
+  // a pack kernel flagged a value outside the fp16 range; both planes use 4 KB blocks [chunk][128 rows][16 B]
+  const bool f16 = A.lb_f16 && *A.cflag16 == 0 && *A.qflag16 == 0;
+  const int nkm = f16 ? (dpad + 15) / 16 : nks;             // MMA K-steps per tile
+  const int kss = (nkm % 4 == 0) ? 4 : ((nkm % 2 == 0) ? 2 : 1);   // K-steps (4 KB blocks) per ring stage
   if (A.thr_init != nullptr) {                               // no live query in this tile: nothing to do
     bool live = false;
     for (int i = tid; i < nq; i += SU_THREADS) live |= A.thr_init[q0 + i] > __int_as_float(0xff800000);
@@ -589,21 +662,24 @@ score_lb_kernel(ScoreArgs A) {
       mbar_wait(bfull, 0);
       const uint64_t a_desc = make_smem_desc(0, 128u * 16u, 128u);
       const uint64_t b_desc = make_smem_desc(0, (uint32_t)NC * 16u, 128u);
-      const uint32_t idesc = make_idesc_tf32(128, (uint32_t)NC);
+      const uint32_t idesc = f16 ? make_idesc_f16(128, (uint32_t)NC) : make_idesc_tf32(128, (uint32_t)NC);
       const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_img);
-      const uint32_t b_step = 4u * (uint32_t)NC * 16u;
+      const uint32_t b_step = (f16 ? 2u : 4u) * (uint32_t)NC * 16u;     // tf32 image: [hl][chunk], fp16 image: [chunk]
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
         mbar_wait(&tempty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
-        for (int ks = 0; ks < nks; ks += kss) {
+        for (int ks = 0; ks < nkm; ks += kss) {
           if (!(A.dbg_mode & 2)) mbar_wait(&full[stage], phase);
           tc_fence_after();
-          for (int j = 0; j < kss; ++j)
-            mma_tf32(d_tmem, a_desc + (uint64_t)((a_base + stage * STAGE_BYTES + j * HI_BYTES) >> 4),
-                     b_desc + (uint64_t)((b_base + (ks + j) * b_step) >> 4), idesc, (ks + j) ? 1u : 0u);
+          for (int j = 0; j < kss; ++j) {
+            const uint64_t ad = a_desc + (uint64_t)((a_base + stage * STAGE_BYTES + j * HI_BYTES) >> 4);
+            const uint64_t bd = b_desc + (uint64_t)((b_base + (ks + j) * b_step) >> 4);
+            if (f16) mma_f16(d_tmem, ad, bd, idesc, (ks + j) ? 1u : 0u);
+            else     mma_tf32(d_tmem, ad, bd, idesc, (ks + j) ? 1u : 0u);
+          }
           mma_commit(&empty[stage]);
           if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
         }
@@ -612,8 +688,8 @@ score_lb_kernel(ScoreArgs A) {
     }
   } else if (warp == SU_NEPI + 1) {
     if (elect_one()) {
-      const uint32_t bbytes = (uint32_t)dpad * 8u * (uint32_t)NC;
-      const unsigned char* qsrc = (const unsigned char*)A.qimg + (size_t)qtile * bbytes;
+      const uint32_t bbytes = f16 ? (uint32_t)nkm * 2u * (uint32_t)NC * 16u : (uint32_t)dpad * 8u * (uint32_t)NC;
+      const unsigned char* qsrc = (const unsigned char*)(f16 ? A.qimg16 : A.qimg) + (size_t)qtile * bbytes;
       mbar_arrive_expect_tx(bfull, bbytes);
       for (uint32_t o = 0; o < bbytes; o += 32768u) {
         uint32_t n = bbytes - o < 32768u ? bbytes - o : 32768u;
@@ -621,12 +697,14 @@ score_lb_kernel(ScoreArgs A) {
       }
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ((A.dbg_mode & 2) ? 0 : ntiles); ++t) {
-        const unsigned char* src = (const unsigned char*)A.cimg + (size_t)(t0 + (int64_t)t * ts) * nks * SU_ASTAGE;
-        for (int ks = 0; ks < nks; ks += kss) {
+        // tf32: the hi half of each 8 KB K-step block; fp16: consecutive 4 KB blocks of the fp16 plane
+        const size_t blk = f16 ? (size_t)HI_BYTES : (size_t)SU_ASTAGE;
+        const unsigned char* src = (const unsigned char*)(f16 ? A.cimg16 : A.cimg) + (size_t)(t0 + (int64_t)t * ts) * nkm * blk;
+        for (int ks = 0; ks < nkm; ks += kss) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], (uint32_t)kss * HI_BYTES);
           for (int j = 0; j < kss; ++j)
-            bulk_g2s(a_ring + stage * STAGE_BYTES + j * HI_BYTES, src + (size_t)(ks + j) * SU_ASTAGE, HI_BYTES, &full[stage]);
+            bulk_g2s(a_ring + stage * STAGE_BYTES + j * HI_BYTES, src + (size_t)(ks + j) * blk, HI_BYTES, &full[stage]);
           if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
         }
       }
@@ -640,7 +718,12 @@ score_lb_kernel(ScoreArgs A) {
     float pmax = 0.0f;
     for (int i = 0; i < SU_THREADS / 32; ++i) pmax = fmaxf(pmax, red[i]);
     // 2 u |p|max, |p|max^2 = pmax / log2e
-    const float mfac = 2.0f * CFL_TF32_PRODUCT_U * sqrtf(pmax * CFL_LN2) * 1.0001f;
+    // fp16 operands: the same relative rounding as tf32 (11-bit significand) for normal values, plus an absolute
+    // 2^-25 per element below the normal range (6.1e-5): |dG| <= u |p||e| + 2^-25 (|p|_1 + |e|_1)
+    const float pnorm = sqrtf(pmax * CFL_LN2);
+    const float sub16 = f16 ? 5.97e-8f * sqrtf((float)dpad) : 0.0f;              // 2^-24 sqrt(d): |x|_1 <= sqrt(d) |x|
+    const float mfac = 2.0f * (CFL_TF32_PRODUCT_U * pnorm + sub16) * 1.0001f;
+    const float mabs = 2.0f * sub16 * pnorm * 1.0001f;
     unsigned dbg_seen = 0, dbg_skip = 0, dbg_push = 0;
     float e2_next = (ntiles > 0) ? __ldg(A.e2 + t0 * 128 + lrow) : 0.0f;      // prefetched one tile ahead
     for (int t = 0; t < ntiles; ++t) {
@@ -650,7 +733,7 @@ score_lb_kernel(ScoreArgs A) {
       const float e2 = e2_next;
       if (t + 1 < ntiles) e2_next = __ldg(A.e2 + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
       // |e|^2 lowered by the fp32 evaluation margin and by the single-product error bound
-      const float e2s = fmaf(-mfac, sqrtf(e2), e2 * (1.0f - CFL_PLANE_REL));
+      const float e2s = fmaf(-mfac, sqrtf(e2), e2 * (1.0f - CFL_PLANE_REL)) - mabs;
       const f2_t e2sp = pk2(e2s, e2s);
       mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
