@@ -277,11 +277,11 @@ def run_ours(args):
 
 
 def launches_per_step(world):
-    # colnorm, pack_weights, project_umma, prep_queries, pack_queries, score_umma x2 (passes A/B),
+    # colnorm, pack_weights, project_umma, prep_queries, pack_queries, pack_queries_f16, score_umma x2 (passes A/B),
     # select_threshold x2, score_lb (probe) + probe_classify, score_lb (pass C), rescore_merge, score_umma
     # (redo, exits when nothing failed verification), merge_rescore (redone queries only)
     # (+ topk_merge after the all-gather for N>1)
-    return 15 + (1 if world > 1 else 0)
+    return 16 + (1 if world > 1 else 0)
 
 
 # ------------------------------------------------------------------------------------------
