@@ -218,12 +218,10 @@ def run_ours(args):
     flops = 2.0 * K * D * Q * N_PER_GPU                           # 2*K*d per score
     achieved = flops / (k_ms / 1e3) / 1e12
     tf32_peak = pk["bf16_sus"] / 2.0                              # TF32 dense = bf16/2 (not in MEASURED_PEAKS)
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu
-    # capture of the same command (profiles/r1_09_lower_bound_pass.md); algorithmic bytes = the hi
-    # (tf32) plane of the catalog image + |e|^2, N * (4*d + 4).
-    # (that capture predates the fp16 operand plane of the lower-bound pass: 2 B instead of 4 B per catalog element;
-    # no ncu capture of the fp16 variant exists yet, so traffic is reported as null rather than a stale number)
-    traffic = None
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full
+    # capture of the same kernel on the same workload (profiles/r1_16_lb_f16.md: 132.6 MB read + 10.4 MB written);
+    # algorithmic bytes = the fp16 plane of the catalog image + |e|^2, N * (2*d + 4).
+    traffic = 143.1e6 if (N_PER_GPU, D, K, Q) == (1_000_000, 64, 3, 1024) else None
     # The dominant kernel issues kind::f16 MMAs (fp16 operands, fp32 accumulate), so the tensor peak it is held to is
     # the measured dense 16-bit rate (bf16_tflops_sustained: the kernel is timed inside a long step); the fraction of
     # the TF32 rate, which earlier builds of this kernel (TF32 operands) reported, is kept beside it.
