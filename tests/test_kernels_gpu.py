@@ -426,6 +426,33 @@ def test_score_topk_lower_bound_pass_regimes(nat, monkeypatch, case):
             assert abs(D[r, c_] - wv[r, -1]) <= rtol * 0.5 * max(wv[r, -1], 1.0) + 1e-7
 
 
+def test_score_topk_lower_bound_planes_fp16_equals_tf32_and_range_guard(nat, monkeypatch):
+    """The lower-bound pass reads fp16 operand planes by default (same 11-bit significand as TF32, half the MMA
+    K-steps); CFL_SCORE_LB_F16=0 forces the tf32 hi planes.  Both must return the same bits (every survivor is
+    rescored exactly), and a catalog with a value outside the fp16 range must fall back to the tf32 planes on the
+    device (the pack kernel raises the flag) instead of losing rows to an infinite Gram value."""
+    rng = np.random.default_rng(78)
+    N, Q, K, d = 150000, 70, 3, 64
+    E = rng.normal(size=(N, d)).astype(np.float32)
+    Pq = (E[rng.integers(0, N, Q)][:, None, :] + 0.5 * rng.normal(size=(Q, K, d))).astype(np.float32)
+    E, Pq = dev(E), dev(Pq)
+    mu = nat.col_mean(E)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "2")
+    monkeypatch.setenv("CFL_SCORE_SAMPLE_STRIDE", "8")
+    monkeypatch.setenv("CFL_SCORE_LB_F16", "0")
+    a = nat.score_topk(Pq, E, 100, mu=mu)
+    monkeypatch.setenv("CFL_SCORE_LB_F16", "1")
+    b = nat.score_topk(Pq, E, 100, mu=mu)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    E[4321, 7] = 1.0e6                                    # far outside the fp16 range after centring
+    Pq[3] = E[4321][None, :] + 0.25                        # a query that must find that row first
+    c = nat.score_topk(Pq, E, 100, mu=mu)
+    monkeypatch.setenv("CFL_SCORE_LB_F16", "0")
+    e = nat.score_topk(Pq, E, 100, mu=mu)
+    assert torch.equal(c[1], e[1]) and torch.equal(c[0], e[0])
+    assert int(c[1][3, 0]) == 4321
+
+
 # ---------------------------------------------------------------------------- full-size properties
 def test_full_size_catalog_properties(nat):
     """BASELINE config 3 size (1M-item catalog, K=3, d=64): size-independent properties instead of a
