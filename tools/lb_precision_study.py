@@ -80,8 +80,8 @@ def gram(Pq, E, op_bits, acc_bits=None, kstep=16):
 
 VARIANTS = {
     # name: (operand mantissa bits, accumulator mantissa bits, rigorous u of one Gram value relative to |p||e|)
-    "tf32 operands, fp32 accumulate (shipped)": (10, None, 1.1 * 2.0 ** -10),
-    "fp16 operands, fp32 accumulate": (10, None, 1.1 * 2.0 ** -10),          # same significand as tf32; range is ample
+    "tf32 operands, fp32 accumulate (fallback planes)": (10, None, 1.1 * 2.0 ** -10),
+    "fp16 operands, fp32 accumulate (shipped)": (10, None, 1.1 * 2.0 ** -10),   # same significand as tf32; range is ample
     "bf16 operands, fp32 accumulate": (7, None, 1.1 * 2.0 ** -7),
     "fp16 operands, fp16 accumulate (d/16 roundings)": (10, 10, 1.1 * 2.0 ** -10 + (D // 16) * 2.0 ** -11),
     "bf16 operands, fp16 accumulate": (7, 10, 1.1 * 2.0 ** -7 + (D // 16) * 2.0 ** -11),
