@@ -135,6 +135,22 @@ def case_rank():
     return dict(E=E, Pq=Pq, dist=D, top_val=vals, top_idx=idx, k=np.asarray(k))
 
 
+def case_rank_monomer():
+    """Monomer mode on the cross product (base.py:109-117 on every (source, target) pair) with exact duplicate rows."""
+    rng = np.random.default_rng(639)
+    Q, K, d, N, k = 10, 3, 12, 600, 20
+    Pt = rng.normal(size=(N, K, d)).astype(f32)
+    Pt[7] = Pt[7, 1][None, :]                   # all prototypes of row 7 coincide ...
+    Pt[90] = Pt[7]                              # ... and rows 90, 555 duplicate it: exact ties
+    Pt[555] = Pt[7]
+    a = (Pt[rng.integers(0, N, Q), rng.integers(0, K, Q)] + 0.5 * rng.normal(size=(Q, d))).astype(f32)
+    a[:4] = (Pt[7, 1] + 0.01 * rng.normal(size=(4, d))).astype(f32)
+    w = O.softmax(2.0 * rng.normal(size=(Q, K))).astype(f32)
+    D = O.all_pairs_monomer_dist(a.astype(f64), w.astype(f64), Pt.astype(f64))
+    vals, idx = O.rank_topk(D, k)
+    return dict(a=a, w=w, Pt=Pt, dist=D, top_val=vals, top_idx=idx, k=np.asarray(k))
+
+
 def case_auc():
     rng = np.random.default_rng(638)
     n = 5000
@@ -149,7 +165,7 @@ def case_auc():
 
 
 CASES = dict(pair_pcd=case_pair_pcd, pair_modes=case_pair_modes, loss=case_loss,
-             project=case_project, rank=case_rank, auc=case_auc)
+             project=case_project, rank=case_rank, rank_monomer=case_rank_monomer, auc=case_auc)
 
 if __name__ == "__main__":
     for name, fn in CASES.items():

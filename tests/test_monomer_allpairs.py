@@ -258,3 +258,15 @@ def test_monomer_full_size_catalog_properties(nat):
         dq = (w[q][None, :] * ((a[q][None, None, :] - Pt) ** 2).sum(-1)).sum(-1)
         kth = torch.topk(dq, k, largest=False).values[-1]
         assert abs(float(kth) - float(tv[q, -1])) <= 1e-5 * float(kth)
+
+
+@pytest.mark.gpu
+def test_score_topk_monomer_golden_fixture(nat):
+    """The committed fixture (tests/golden/rank_monomer.npz, frozen oracle output incl. exact duplicate rows)."""
+    g = np.load(os.path.join(GOLDEN, "rank_monomer.npz"))
+    k = int(g["k"])
+    tv, ti = _check(nat, g["a"], g["w"], g["Pt"], k)
+    assert (ti == g["top_idx"]).mean() >= 0.99            # _check already bounds every mismatch to an fp32 near-tie
+    np.testing.assert_allclose(tv, g["top_val"], rtol=RTOL, atol=1e-7)
+    for q in range(4):                          # rows 7 / 90 / 555 are identical: ties -> lower index
+        assert ti[q, :3].tolist() == [7, 90, 555]

@@ -195,7 +195,7 @@ def test_adam_tf_first_step_moves_by_lr():
     np.testing.assert_allclose(p - p1, 1e-3 * np.sign(g), rtol=1e-5)
 
 
-@pytest.mark.parametrize("name", ["pair_pcd", "pair_modes", "loss", "project", "rank", "auc"])
+@pytest.mark.parametrize("name", ["pair_pcd", "pair_modes", "loss", "project", "rank", "rank_monomer", "auc"])
 def test_golden_fixtures_reproduce(name):
     """The committed fixtures (tests/golden/make_golden.py) must be reproduced bit-for-bit
     (fp64) by the oracle -- freezes the oracle against accidental edits."""
