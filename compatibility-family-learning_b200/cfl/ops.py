@@ -115,11 +115,61 @@ def normalizer_v2(input_shape, scale=None, mean=None, norm=None, clip_value_min=
                        in_scale=in_scale)
 
 
+def unnormalize(tensor, scale, shift):
+    """cfl/ops.py:217-218: the inverse of ``normalize`` without its clip: (x - shift) * scale."""
+    return (tensor - shift) * scale
+
+
+def unnormalizer(scale, shift):
+    """cfl/ops.py:221-225."""
+    return lambda tensor: unnormalize(tensor, scale, shift)
+
+
+def unnormalize_v2(tensor, input_shape, scale=None, mean=None, norm=None):
+    """cfl/ops.py:146-190: the inverse of ``normalize_v2`` without its clip: reshape to ``(-1,) + input_shape``,
+    x*norm + mean (per channel when 3 values), then / scale."""
+    as_tuple = lambda v: v if (v is None or isinstance(v, (list, tuple))) else (v,)
+    mean, norm = as_tuple(mean), as_tuple(norm)
+    tensor = tensor.reshape((-1,) + tuple(input_shape))
+    if (mean and len(mean) > 1) or (norm and len(norm) > 1):
+        chans = list(torch.unbind(tensor, dim=-1))
+        if norm:
+            n3 = tuple(norm) * 3 if len(norm) == 1 else tuple(norm)
+            assert len(n3) == 3
+            chans = [c * n if n != 1.0 else c for c, n in zip(chans, n3)]
+        if mean:
+            m3 = tuple(mean) * 3 if len(mean) == 1 else tuple(mean)
+            assert len(m3) == 3
+            chans = [c + m if m != 0.0 else c for c, m in zip(chans, m3)]
+        tensor = torch.stack(chans, dim=-1)
+    else:
+        if norm and norm[0] != 1.0:
+            tensor = tensor * norm[0]
+        if mean and mean[0] != 0.0:
+            tensor = tensor + mean[0]
+    if scale is not None and scale != 1.0:
+        tensor = tensor / scale
+    return tensor
+
+
+def unnormalizer_v2(input_shape, scale=None, mean=None, norm=None):
+    """cfl/ops.py:193-198."""
+    return lambda tensor: unnormalize_v2(tensor, input_shape, scale=scale, mean=mean, norm=norm)
+
+
 def dist_normalizer(input_shape, ae_shape, data_scale, data_mean, data_norm, latent_norm, data_type):
-    """cfl/ops.py:302-349 (the generation-side un-normalisers are out of scope: None)."""
+    """cfl/ops.py:302-349 -> (data_normalizer, data_unnormalizer, ae_normalizer, ae_unnormalizer,
+    latent_normalizer)."""
     clip_values = {"sigmoid": (0.0, 1.0), "tanh": (-1.0, 1.0), "relu": (0.0, None), "linear": (None, None)}
     lo, hi = clip_values[data_type]
     data_normalizer = normalizer_v2(input_shape, scale=data_scale, mean=data_mean, norm=data_norm,
                                     clip_value_min=lo, clip_value_max=hi)
     latent_normalizer = normalizer_v2(None, norm=latent_norm) if latent_norm else None
-    return data_normalizer, None, data_normalizer, None, latent_normalizer
+    data_unnormalizer = unnormalizer_v2(input_shape, scale=data_scale, mean=data_mean, norm=data_norm)
+    if ae_shape is not None and tuple(ae_shape) != tuple(input_shape):
+        ae_normalizer = normalizer_v2(ae_shape, scale=data_scale, mean=data_mean, norm=data_norm,
+                                      clip_value_min=lo, clip_value_max=hi)
+        ae_unnormalizer = unnormalizer_v2(ae_shape, scale=data_scale, mean=data_mean, norm=data_norm)
+    else:
+        ae_normalizer, ae_unnormalizer = data_normalizer, data_unnormalizer
+    return data_normalizer, data_unnormalizer, ae_normalizer, ae_unnormalizer, latent_normalizer

@@ -204,3 +204,26 @@ def test_sharded_pair_auc_world2_gloo_equals_single_process(tmp_path):
     pos, neg = _pair_scores()
     want = _auc_counts_double(torch.as_tensor(pos), torch.as_tensor(neg)).tolist()
     assert got["a"].tolist() == want and got["b"].tolist() == want
+
+
+def test_unnormalisers_invert_the_normalisers():
+    """cfl/ops.py:146-198,217-225: unnormalize(_v2) undo normalize(_v2) (no clip), also per channel."""
+    from cfl import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(6, 4, 4, 3, generator=g, dtype=torch.float64) * 255
+    kw = dict(scale=1 / 255.0, mean=(0.4, 0.5, 0.6), norm=(0.2, 0.3, 0.25))
+    y = ops.normalize_v2(x, (4, 4, 3), **kw)
+    assert y.shape == (6, 48)
+    back = ops.unnormalizer_v2((4, 4, 3), **kw)(y)
+    assert back.shape == x.shape
+    np.testing.assert_allclose(back.numpy(), x.numpy(), rtol=1e-12, atol=1e-9)
+    y1 = ops.normalize_v2(x[..., 0], (4, 4), scale=2.0, mean=0.5, norm=31.9098)
+    np.testing.assert_allclose(ops.unnormalize_v2(y1, (4, 4), scale=2.0, mean=0.5, norm=31.9098).numpy(), x[..., 0].numpy(),
+                               rtol=1e-12)
+    z = ops.normalize(x, 58.388599, 0.25)
+    np.testing.assert_allclose(ops.unnormalizer(58.388599, 0.25)(z).numpy(), x.numpy(), rtol=1e-12, atol=1e-9)
+    dn, dun, an, aun, ln = ops.dist_normalizer((4, 4, 3), (2, 2, 3), 1 / 255.0, None, (0.5,), 7.0, "linear")
+    np.testing.assert_allclose(dun(dn(x)).numpy(), x.numpy(), rtol=1e-12, atol=1e-9)
+    assert an is not dn and aun is not dun and ln is not None
+    dn2, dun2, an2, aun2, ln2 = ops.dist_normalizer((4,), None, None, None, 31.9098, None, "linear")
+    assert an2 is dn2 and aun2 is dun2 and ln2 is None
