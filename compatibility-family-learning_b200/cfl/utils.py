@@ -11,6 +11,14 @@ from argparse import Namespace
 import torch
 
 
+def log_args(args):
+    """cfl/utils.py:20-22: one warning-level log line per flag, sorted by name."""
+    import logging
+    logger = logging.getLogger(__name__)
+    for name, value in sorted(vars(args).items()):
+        logger.warning("%s = %r", name, value)
+
+
 def reduce_product(xs):
     """cfl/utils.py:25-29."""
     s = 1
