@@ -227,3 +227,74 @@ def test_unnormalisers_invert_the_normalisers():
     assert an is not dn and aun is not dun and ln is not None
     dn2, dun2, an2, aun2, ln2 = ops.dist_normalizer((4,), None, None, None, 31.9098, None, "linear")
     assert an2 is dn2 and aun2 is dun2 and ln2 is None
+
+
+# ---------------------------------------------------------------------------------------------
+def _mono_doubles(nat):
+    """Oracle-backed stand-ins for the kernels the monomer ranking path calls (CPU, test only)."""
+    def project_fwd(x, V, g=None, bias=None, weight_norm=True, in_scale=1.0, act=None, want_pre=False, **kw):
+        y, pre = O.fc_weight_norm(x.numpy().astype(np.float64) * in_scale, V.numpy().astype(np.float64),
+                                  None if g is None else g.numpy().astype(np.float64),
+                                  None if bias is None else bias.numpy().astype(np.float64), act, return_pre=True)[:2]
+        return torch.as_tensor(y, dtype=torch.float32), torch.as_tensor(pre, dtype=torch.float32), None
+
+    def score_topk_monomer(a, w, P, k, idx_base=0, want_dense=False):
+        D = O.all_pairs_monomer_dist(a.numpy().astype(np.float64), w.numpy().astype(np.float64), P.numpy().astype(np.float64))
+        v, i = O.rank_topk(D, min(k, P.shape[0]))
+        return torch.as_tensor(v, dtype=torch.float32), torch.as_tensor(i + idx_base)
+
+    def topk_merge(vals, idx):
+        R, Q, k = vals.shape
+        v = vals.permute(1, 0, 2).reshape(Q, R * k).numpy()
+        i = idx.permute(1, 0, 2).reshape(Q, R * k).numpy()
+        order = np.lexsort((i, v), axis=1)[:, :k]
+        return torch.as_tensor(np.take_along_axis(v, order, 1)), torch.as_tensor(np.take_along_axis(i, order, 1))
+
+    nat.project_fwd, nat.score_topk_monomer, nat.topk_merge = project_fwd, score_topk_monomer, topk_merge
+
+
+def _mono_case():
+    rng = np.random.default_rng(31)
+    N, F, K, d, Q, k = 300, 10, 3, 5, 8, 15
+    X = rng.normal(size=(N, F)).astype(np.float32)
+    return X, O.xavier_uniform(rng, F, d), O.xavier_uniform(rng, F, K * d), O.xavier_uniform(rng, d, K), K, d, Q, k
+
+
+def _mono_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "compatibility-family-learning_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cfl import ranking
+    _mono_doubles(ranking.nat)
+    X, V0, Vp, Vg, K, d, Q, k = _mono_case()
+    t = torch.as_tensor
+    w = ranking.EncoderWeights(V0=t(V0), Vp=t(Vp), g0=torch.ones(d), gp=torch.ones(K * d), Vg=t(Vg), gg=torch.ones(K), act="tanh")
+    lo, hi = ranking.shard_bounds(len(X), world, rank)
+    P = ranking.nat.project_fwd(t(X[lo:hi]), w.Vp, w.gp, None, True, 1.0, "tanh")[0]
+    idx = ranking.MonomerCatalogIndex.__new__(ranking.MonomerCatalogIndex)     # bypass the CUDA-only check of __init__
+    idx.w, idx.P, idx.idx_base, idx.n_total, idx.group, idx.theta = w, P.view(-1, K, d), lo, len(X), None, 1.0
+    tv, ti = idx.rank(t(X[:Q]), k)
+    if rank == 1:
+        np.savez(os.path.join(out_dir, "m.npz"), tv=tv.numpy(), ti=ti.numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_monomer_ranking_world2_gloo_matches_single_process(tmp_path):
+    """MonomerCatalogIndex: target prototypes sharded over 2 ranks + all_gather + merge == the whole catalog; the
+    query side (embedding + gate softmax of the pre-activation embedding, base.py:94-105) follows the oracle."""
+    port = 35500 + os.getpid() % 2000
+    mp.spawn(_mono_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "m.npz")
+    X, V0, Vp, Vg, K, d, Q, k = _mono_case()
+    f = lambda a: a.astype(np.float64)
+    params = {"outputs": (f(V0), np.ones(d), None), "prototype_outputs": (f(Vp), np.ones(K * d), None),
+              "monomer_outputs": (f(Vg), np.ones(K), None)}
+    S = O.build_prototypes(f(X[:Q]), params, "monomer", K, d, "tanh")
+    Tt = O.build_prototypes(f(X), params, "monomer", K, d, "tanh")
+    D = O.all_pairs_monomer_dist(S["activations"], S["monomer_activations"], Tt["prototype_activations"])
+    wv, wi = O.rank_topk(D, k)
+    assert (got["ti"] == wi).all()
+    np.testing.assert_allclose(got["tv"], wv, rtol=1e-5)
