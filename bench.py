@@ -247,7 +247,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         # the CPU arm is timed on rank 0 at N=1 only (torchrun pins OMP threads and the other ranks spin)
-        cpu = cpu_baseline_sample(target_s=12.0) if world == 1 else None
+        cpu = cpu_baseline_sample(target_s=12.0) if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": "query x candidate scores/sec (fused soft-min scoring + top-100)",
             "value": value, "unit": "scores/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -381,6 +381,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU arm (kernel experiments only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

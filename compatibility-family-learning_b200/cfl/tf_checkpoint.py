@@ -257,18 +257,38 @@ def write_tf_checkpoint(prefix: str, tensors: Dict[str, np.ndarray]) -> None:
 
 
 # ---- model <-> checkpoint -------------------------------------------------------------------------------------
-def tf_to_state_dict(tensors: Dict[str, np.ndarray], beta1: float = 0.9):
-    """TF variable names are the ones our models register (tests/test_reference_golden.py); Adam's
-    slot variables keep their TF names (``<var>/Adam``, ``<var>/Adam_1``); the step comes from
-    ``beta1_power`` = beta1^(t+1) as tf.train.AdamOptimizer stores it after t updates."""
+def adam_step_from_powers(tensors: Dict[str, np.ndarray], beta1: float = 0.9, beta2: float = 0.999):
+    """Number of Adam updates t behind a TF checkpoint, from the float32 accumulators tf.train.AdamOptimizer
+    stores (``beta_power = beta^(t+1)`` after t updates).  ``beta2_power`` is tried first: 0.999^t stays a
+    normal float32 up to t ~ 87 000, whereas 0.9^t underflows to exactly 0 near t ~ 1000, so ``beta1_power``
+    alone cannot date a realistically trained model.  Returns None when neither accumulator is usable."""
     import math
+    for suffix, beta in (("beta2_power", beta2), ("beta1_power", beta1)):
+        if not 0.0 < beta < 1.0:
+            continue
+        for k, v in tensors.items():
+            if k.split("/")[-1] == suffix or k.endswith(suffix):
+                x = float(np.asarray(v).reshape(-1)[0])
+                if 1e-37 < x < 1.0:                               # normal float32 range: log is accurate to ~1e-7 relative
+                    return max(0, int(round(math.log(x) / math.log(beta))) - 1)
+    return None
+
+
+def tf_to_state_dict(tensors: Dict[str, np.ndarray], beta1: float = 0.9, beta2: float = 0.999):
+    """TF variable names are the ones our models register (tests/test_reference_golden.py); Adam's
+    slot variables keep their TF names (``<var>/Adam``, ``<var>/Adam_1``); the step comes from the
+    ``beta*_power`` accumulators (see ``adam_step_from_powers``).  When it cannot be recovered the slots
+    are still loaded but a warning says that the bias correction restarts at step 0."""
+    import warnings
     import torch
     sd = {k: torch.from_numpy(np.asarray(v, dtype=np.float32)) for k, v in tensors.items()
-          if not k.endswith("_power") and "ExponentialMovingAverage" not in k}
-    for k, v in tensors.items():
-        if k.endswith("beta1_power") and 0.0 < float(v) < 1.0 and 0.0 < beta1 < 1.0:
-            sd["__step__"] = torch.tensor(max(0, int(round(math.log(float(v)) / math.log(beta1))) - 1))
-            break
+          if not k.endswith("_power") and not k.endswith("_power_1") and "ExponentialMovingAverage" not in k}
+    step = adam_step_from_powers(tensors, beta1, beta2)
+    if step is not None:
+        sd["__step__"] = torch.tensor(step)
+    elif any(k.endswith("/Adam") for k in tensors):
+        warnings.warn("TF checkpoint: Adam step not recoverable from beta1_power / beta2_power (underflowed or absent); "
+                      "the moments are restored but the bias correction restarts at step 0")
     return sd
 
 

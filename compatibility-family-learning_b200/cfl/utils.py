@@ -108,7 +108,8 @@ class Saver(object):
         if not os.path.exists(save_path + self.SUFFIX) and os.path.exists(save_path + ".index"):
             # a checkpoint written by the reference's tf.train.Saver (V2 tensor bundle)
             from .tf_checkpoint import load_tf_checkpoint, tf_to_state_dict
-            sd = tf_to_state_dict(load_tf_checkpoint(save_path), beta1=getattr(sess.model, "beta1", 0.9))
+            sd = tf_to_state_dict(load_tf_checkpoint(save_path), beta1=getattr(sess.model, "beta1", 0.9),
+                                  beta2=getattr(sess.model, "beta2", 0.999))
         else:
             sd = torch.load(save_path + self.SUFFIX, map_location="cpu")
         if trainable_only:          # assign_from_checkpoint_fn(trainable_variables(), ignore_missing_vars=True)
@@ -117,8 +118,15 @@ class Saver(object):
 
 
 def export_tf_checkpoint(model, prefix):
-    """Write the model's variables (and Adam slots) as a TensorFlow V2 checkpoint that the reference's
-    ``saver.restore`` can read (cfl/utils.py:465-497)."""
+    """Write the model's variables (and Adam slots, ``beta1_power`` / ``beta2_power``) as a TensorFlow V2 checkpoint.
+
+    What the reference can do with it (cfl/utils.py:465-497): a ``Dist`` graph (one optimiser, no moving averages)
+    restores it with its plain ``tf.train.Saver().restore``.  A ``CFL`` graph also declares the EMA(0.99) shadow
+    variables of its statistics (cfl/models/cfl.py:528,903-949 -- their names contain TF's auto-numbered op names, which
+    cannot be reproduced without TensorFlow) and, without ``--use-threshold``, a second optimiser's ``beta*_power_1``:
+    those are NOT in the export, so a CFL graph must read it through the reference's own pre-weights route,
+    ``assign_from_checkpoint_fn(trainable_variables(), ignore_missing_vars=True)`` (utils.py:481-490), or a Saver with a
+    restricted ``var_list``.  No TF-written file has been read by, and no export handed to, a real TensorFlow here."""
     from .tf_checkpoint import state_dict_to_tf, write_tf_checkpoint
     write_tf_checkpoint(prefix, state_dict_to_tf(model.state_dict(), getattr(model, "beta1", 0.9),
                                                  getattr(model, "beta2", 0.999)))

@@ -49,7 +49,8 @@ struct ScoreArgs {
   const void* qimg16;
   const int* cflag16;
   const int* qflag16;
-  int dbg_mode;          // experiments (CFL_SCORE_DBG_MODE): 1 = epilogue does nothing, 2 = no TMA / no full-barrier waits
+  int dbg_mode;          // experiments (CFL_SCORE_DBG_MODE bits): 1 = epilogue does nothing, 2 = no TMA / no full-barrier
+                         // waits, 4 = lower-bound epilogue only reads TMEM, 8 = TMEM reads + bound, no votes / pushes
   unsigned long long* dbg; // optional counters {groups seen, skipped, selective, full} (CFL_SCORE_DEBUG)
   ScorePlan plan;
 };

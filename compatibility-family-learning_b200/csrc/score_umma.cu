@@ -754,6 +754,7 @@ score_lb_kernel(ScoreArgs A) {
           tg[i] = t4.x; tg[i + 1] = t4.y; tg[i + 2] = t4.z; tg[i + 3] = t4.w;
         }
         tmem_ld_wait();
+        if (A.dbg_mode & 4) continue;                          // experiment: the epilogue only reads TMEM
         float lb[GQ];
         bool nd = false;
 #pragma unroll
@@ -769,6 +770,7 @@ score_lb_kernel(ScoreArgs A) {
           nd |= (lb[2 * pi] < tg[2 * pi]) | (lb[2 * pi + 1] < tg[2 * pi + 1]);
         }
         ++dbg_seen;
+        if (A.dbg_mode & 8) { dbg_skip += nd ? 1u : 0u; continue; }   // experiment: TMEM reads + bound, no votes / pushes
         if (!__any_sync(0xffffffffu, nd && valid)) { ++dbg_skip; continue; }
         uint32_t nb = 0;
 #pragma unroll

@@ -36,3 +36,17 @@ def test_device_arm_does_not_fall_back_to_the_cpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "scores/s" not in r.stdout
+
+
+def test_smoke_tie_check_accepts_fp32_ties_and_rejects_real_differences():
+    """The index-set check of __graft_entry__.smoke(): a swap inside an fp32 tie at the k-th distance passes
+    (and leaves smoke()'s helpers callable), a swap with a clearly worse candidate fails."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    D = np.array([[0.1, 0.2, 0.3, 0.3 * (1 + 1e-7), 0.9]])
+    want_idx, want_val = np.array([[0, 1, 2]]), np.array([[0.1, 0.2, 0.3]])
+    ge.check_topk_sets(D, want_idx, want_val, np.array([[0, 1, 3]]))          # tie: candidate 3 for 2
+    ge.check_topk_sets(D, want_idx, want_val, np.array([[0, 1, 2]]))
+    with pytest.raises(AssertionError):
+        ge.check_topk_sets(D, want_idx, want_val, np.array([[0, 1, 4]]))

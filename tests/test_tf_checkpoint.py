@@ -101,3 +101,21 @@ def test_saver_restores_reference_style_checkpoints(tmp_path):
     for k in m.sd:
         if k != "__step__":
             assert torch.equal(m2.sd[k], m.sd[k]), k
+
+
+def test_adam_step_survives_beta1_power_underflow():
+    """float32 0.9^t is exactly 0 from t ~ 1000 on; the step must then come from beta2_power."""
+    import warnings
+    import numpy as np
+    from cfl import tf_checkpoint as T
+    for t in (0, 7, 999, 5000, 60000):
+        tensors = {"beta1_power": np.float32(0.9) ** np.float32(t + 1), "beta2_power": np.float32(0.999 ** (t + 1)),
+                   "Dist/Encoder/latent_outputs/fully_connected/weights": np.zeros((2, 2), np.float32),
+                   "Dist/Encoder/latent_outputs/fully_connected/weights/Adam": np.zeros((2, 2), np.float32)}
+        sd = T.tf_to_state_dict(tensors)
+        got = int(sd["__step__"])
+        assert abs(got - t) <= max(1, int(2e-4 * t)), (t, got)   # float32 log resolution
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        sd = T.tf_to_state_dict({"beta1_power": np.float32(0.0), "x/Adam": np.zeros(2, np.float32)})
+        assert "__step__" not in sd and any("not recoverable" in str(x.message) for x in w)
