@@ -366,6 +366,7 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
     for (int p = 0; p < parts; ++p) {
       s_pref[p] = acc;
       int c = counts[(int64_t)p * Q + q];
+      if (c < 0) { over = 1; c = 0; }                          // the filter pass declined (fp16 range): exact redo
       // (keys beyond a full part buffer went to the query's spill list; only ITS overflow loses keys)
       acc += c > TOPK_STRIDE ? TOPK_STRIDE : c;
     }
@@ -784,7 +785,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   a.cimg = nullptr; a.e2 = nullptr;
   a.phase = 0; a.tile_stride = 1; a.thr_init = nullptr;
   a.dbg = nullptr; a.redo_tile = nullptr; a.spill = nullptr; a.spill_cnt = nullptr;
-  a.lb_f16 = 0; a.cimg16 = nullptr; a.qimg16 = nullptr; a.cflag16 = nullptr; a.qflag16 = nullptr;
+  a.cimg16 = nullptr; a.qimg16 = nullptr; a.cflag16 = nullptr; a.qflag16 = nullptr; a.lbrow = nullptr; a.lbq = nullptr;
   bool lb_pass = false;
   const float* redo_only = nullptr;
   a.dbg_mode = getenv("CFL_SCORE_DBG_MODE") ? atoi(getenv("CFL_SCORE_DBG_MODE")) : 0;
@@ -808,12 +809,10 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       a.e2 = (const float*)((const char*)image + (size_t)plan.tiles * (plan.dpad / 8) * 8192);
       a.cimg16 = (const char*)image + catalog_f16_offset(N, d);
       a.cflag16 = (const int*)((const char*)a.cimg16 + catalog_f16_bytes(N, d));
+      a.lbrow = (const float2*)((const char*)image + catalog_lbrow_offset(N, d));
       a.qimg16 = base + o_qimg + score_umma_qimg16_offset(plan, K);
       a.qflag16 = (const int*)((const char*)a.qimg16 + score_umma_qimg16_bytes(plan, K));
-      {
-        const char* ef = getenv("CFL_SCORE_LB_F16");
-        a.lb_f16 = ef ? atoi(ef) : 1;      // on: identical results, pass C -6.5 % (tools/lb_f16_ab.py); 0 keeps the tf32 planes
-      }
+      a.lbq = (const float*)((const char*)a.qflag16 + 16);
       st = score_umma_pack_queries(a, base + o_qimg, cs);
       if (st != CFL_OK) return st;
       // Long catalog ranges are scored in two passes: a sparse sample pass (every S-th tile,
@@ -881,6 +880,10 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         // low-dimensional embedding that the bound stops rejecting (measured: K=8 survivors overflow
         // at d=20..64), so those shapes keep the exact filter (optimistic threshold + exact counts)
         lb_pass = !getenv("CFL_SCORE_NO_LB") && (K <= 4 || getenv("CFL_SCORE_FORCE_LB"));
+        if (lb_pass) {
+          st = score_lb_prep_queries(a, cs);
+          if (st != CFL_OK) return st;
+        }
         if (lb_pass && !getenv("CFL_SCORE_NO_PROBE")) {
           int probe_stride = (int)((tpp + 3) / 4);           // about 4 tiles per part
           if (probe_stride < 1) probe_stride = 1;

@@ -40,15 +40,18 @@ struct ScoreArgs {
   tkey_t* spill;         // lower-bound pass: [Q, LB_SPILL] keys that did not fit their (part, query) buffer
   int* spill_cnt;        // [Q]
   const int* redo_tile;  // phase 2 redo launch: per query tile, 1 = some query must be redone (else the CTA exits)
-  // fp16 operand planes of the lower-bound pass (same 11-bit significand as tf32, twice the MMA rate): the
-  // catalog plane lives behind |e|^2 in the catalog image, the query plane behind the tf32 query image; each is
-  // followed by a flag word that its pack kernel raises when a value leaves the fp16 range (the kernel then
-  // keeps the tf32 planes).  lb_f16 = 0 disables the path.
-  int lb_f16;
+  // Lower-bound pass (score_lb_kernel): fp16 operand planes (same 11-bit significand as tf32, twice the MMA rate).
+  // The catalog plane lives behind |e|^2 in the catalog image, followed by a flag word that the pack kernel raises
+  // when a centred value leaves the fp16 range, and by lbrow = (|e|^2, |e|) per row.  The query side is the
+  // lower-bound image of prep_lb_kernel (2a and an orthonormal basis of the prototypes' affine hull per query),
+  // its flag word, and lbq = (|a|^2 rounded down, |a| rounded up) per query.  A raised flag makes the kernel hand
+  // its queries to the exact redo pass (counts = -1).
   const void* cimg16;
   const void* qimg16;
   const int* cflag16;
   const int* qflag16;
+  const float2* lbrow;
+  const float* lbq;
   int dbg_mode;          // experiments (CFL_SCORE_DBG_MODE bits): 1 = epilogue does nothing, 2 = no TMA / no full-barrier
                          // waits, 4 = lower-bound epilogue only reads TMEM, 8 = TMEM reads + bound, no votes / pushes
   unsigned long long* dbg; // optional counters {groups seen, skipped, selective, full} (CFL_SCORE_DEBUG)
@@ -84,12 +87,14 @@ bool score_umma_supported(int K, int d);
 size_t catalog_image_bytes(int64_t N, int d);
 size_t catalog_f16_offset(int64_t N, int d);     // byte offset of the fp16 plane inside the catalog image
 size_t catalog_f16_bytes(int64_t N, int d);      // plane only; the flag word follows it
+size_t catalog_lbrow_offset(int64_t N, int d);   // byte offset of lbrow[tiles*128] (float2) inside the catalog image
 size_t score_umma_qimg16_offset(const ScorePlan& p, int K);
 size_t score_umma_qimg16_bytes(const ScorePlan& p, int K);
 int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const float* mu, void* image,
                         cudaStream_t st);
 size_t score_umma_qimg_bytes(const ScorePlan& p, int K);
 int score_umma_pack_queries(const ScoreArgs& a, void* qimg, cudaStream_t st);
+int score_lb_prep_queries(const ScoreArgs& a, cudaStream_t st);   // lower-bound image + lbq of the query batch
 int score_umma_launch(const ScoreArgs& a, cudaStream_t st);
 int score_lb_launch(const ScoreArgs& a, cudaStream_t st);
 int score_umma_qt(int K, int d);

@@ -58,7 +58,8 @@ bool score_umma_supported(int K, int d) {
   return score_umma_qt(K, d) != 0;
 }
 
-// tf32 hi/lo query image, then the fp16 query image [qtile][kstep16][chunk][n][8 halfs], then its flag word
+// tf32 hi/lo query image, then the fp16 lower-bound image [qtile][kstep16][chunk][n][8 halfs] (prep_lb_kernel), its
+// flag word and lbq
 size_t score_umma_qimg16_offset(const ScorePlan& p, int K) {
   return (size_t)p.nqt * p.dpad * 8 * (size_t)(K * p.qt);
 }
@@ -66,8 +67,8 @@ size_t score_umma_qimg16_bytes(const ScorePlan& p, int K) {
   const int nks16 = (p.dpad + 15) / 16;
   return (size_t)p.nqt * nks16 * 2 * (size_t)(K * p.qt) * 16;
 }
-size_t score_umma_qimg_bytes(const ScorePlan& p, int K) {
-  return score_umma_qimg16_offset(p, K) + score_umma_qimg16_bytes(p, K) + 16;
+size_t score_umma_qimg_bytes(const ScorePlan& p, int K) {      // ... + flag word + lbq[2 per query slot]
+  return score_umma_qimg16_offset(p, K) + score_umma_qimg16_bytes(p, K) + 16 + (size_t)p.nqt * p.qt * 2 * sizeof(float);
 }
 
 // ---- catalog image ----------------------------------------------------------------------------
@@ -83,14 +84,20 @@ size_t catalog_f16_bytes(int64_t N, int d) {
   const int64_t tiles = (N + 127) / 128;
   return (size_t)tiles * ((d + 15) / 16) * (SU_ASTAGE / 2);
 }
-size_t catalog_image_bytes(int64_t N, int d) {
+// ... then lbrow[tiles*128] float2 = (|e - mu|^2, |e - mu|) per row, (+inf, 0) for the padding rows of the last tile:
+// what the lower-bound pass needs per row (its margin has a term in |e|), one 8-byte load per row and tile.
+size_t catalog_lbrow_offset(int64_t N, int d) {
   return catalog_f16_offset(N, d) + catalog_f16_bytes(N, d) + 16;
+}
+size_t catalog_image_bytes(int64_t N, int d) {
+  const int64_t tiles = (N + 127) / 128;
+  return catalog_lbrow_offset(N, d) + (size_t)tiles * 128 * sizeof(float2);
 }
 
 __global__ void __launch_bounds__(128)
 pack_catalog_kernel(const float* __restrict__ E, int64_t N, int d, int64_t lde,
                     const float* __restrict__ mu, unsigned char* __restrict__ img, float* __restrict__ e2g,
-                    unsigned char* __restrict__ img16, int* __restrict__ flag16) {
+                    unsigned char* __restrict__ img16, int* __restrict__ flag16, float2* __restrict__ lbrow) {
   const int64_t tile = blockIdx.x;
   const int r = threadIdx.x;
   const int64_t row = tile * 128 + r;
@@ -126,6 +133,7 @@ pack_catalog_kernel(const float* __restrict__ E, int64_t N, int d, int64_t lde,
     *(uint4*)(st16 + (1 * 128 + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   e2g[row] = e2;
+  lbrow[row] = (row < N) ? make_float2(e2, sqrtf(e2)) : make_float2(__int_as_float(0x7f800000), 0.0f);
   if (!(vmax < 60000.0f)) atomicOr(flag16, 1);               // also catches NaN / inf
 }
 
@@ -138,7 +146,8 @@ int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const flo
   unsigned char* img16 = img + catalog_f16_offset(N, d);
   int* flag16 = (int*)(img16 + catalog_f16_bytes(N, d));
   CFL_CUDA(cudaMemsetAsync(flag16, 0, 16, st));
-  pack_catalog_kernel<<<(unsigned)tiles, 128, 0, st>>>(E, N, d, lde, mu, img, e2g, img16, flag16);
+  float2* lbrow = (float2*)(img + catalog_lbrow_offset(N, d));
+  pack_catalog_kernel<<<(unsigned)tiles, 128, 0, st>>>(E, N, d, lde, mu, img, e2g, img16, flag16, lbrow);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
 }
@@ -194,43 +203,9 @@ __global__ void pack_queries_kernel(const float* __restrict__ Pc, int64_t Q, int
   }
 }
 
-// fp16 query image of the lower-bound pass: [qtile][kstep16][chunk][row n = k*QT + ql][8 halfs]
-__global__ void pack_queries_f16_kernel(const float* __restrict__ Pc, int64_t Q, int K, int d, int qt, int dpad,
-                                        unsigned char* __restrict__ img16, int* __restrict__ flag16) {
-  const int nc = K * qt;
-  const int nks16 = (dpad + 15) / 16;
-  const int qtile = blockIdx.x;
-  unsigned char* base = img16 + (size_t)qtile * nks16 * 2 * nc * 16;
-  float vmax = 0.0f;
-  for (int e = threadIdx.x; e < nks16 * 2 * nc; e += blockDim.x) {
-    const int n = e % nc;
-    const int c = (e / nc) % 2;
-    const int ks = e / (2 * nc);
-    const int k = n / qt, ql = n % qt;
-    const int64_t q = (int64_t)qtile * qt + ql;
-    __align__(16) __half h[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = ks * 16 + c * 8 + i;
-      const float x = (q < Q && j < d) ? Pc[(q * K + k) * (int64_t)d + j] : 0.0f;
-      vmax = fmaxf(vmax, fabsf(x));
-      h[i] = __float2half_rn(x);
-    }
-    *(uint4*)(base + ((size_t)(ks * 2 + c) * nc + n) * 16) = *(const uint4*)h;
-  }
-  if (!(vmax < 60000.0f)) atomicOr(flag16, 1);
-}
-
 int score_umma_pack_queries(const ScoreArgs& a, void* qimg, cudaStream_t st) {
   pack_queries_kernel<<<a.plan.nqt, 256, 0, st>>>(a.Pc, a.Q, a.K, a.d, a.plan.qt, a.plan.dpad, (float*)qimg);
   CFL_LAUNCH_CHECK();
-  if (a.lb_f16) {
-    unsigned char* img16 = (unsigned char*)qimg + score_umma_qimg16_offset(a.plan, a.K);
-    int* flag16 = (int*)(img16 + score_umma_qimg16_bytes(a.plan, a.K));
-    CFL_CUDA(cudaMemsetAsync(flag16, 0, 16, st));
-    pack_queries_f16_kernel<<<a.plan.nqt, 256, 0, st>>>(a.Pc, a.Q, a.K, a.d, a.plan.qt, a.plan.dpad, img16, flag16);
-    CFL_LAUNCH_CHECK();
-  }
   return CFL_OK;
 }
 
@@ -560,35 +535,157 @@ score_umma_kernel(ScoreArgs A) {
 }
 
 // =====================================================================================================
-// Lower-bound filter pass (phase 3).  Same images, ring and TMEM double buffer as score_umma_kernel, but
-//  * ONE TF32 MMA per K-step (hi x hi planes only; only the hi half of every catalog K-step block is
-//    copied), so the accumulators are swept 8x per tile instead of 24x -- the tensor memory port that
-//    MMA accumulation and the epilogue's tcgen05.ld share is what bounds the 3xTF32 kernel;
-//  * the epilogue never evaluates the soft-min: it pushes every (row, query) whose affine-hull lower
-//    bound, lowered by a rigorous bound on the single-product rounding error, is under the threshold.
-//    dist = |e - sum s_k p_k|^2 with s in the simplex, so an error delta_k on the Gram values moves it
-//    by at most 2 max_k |delta_k| <= 2 u |p|max |e|, u = 2^-10 (two RN tf32 roundings per product);
-//  * no compaction, no barriers: an over-full key buffer is only counted (counts > TOPK_STRIDE) and
-//    the query is redone by the exact kernel.
-// The survivors are rescored exactly by rescore_merge_kernel (score.cu).
+// Lower-bound filter pass (phase 3): the dominant launch of a long-catalog call.
+//
+// dist(e, q) = |e - sum_k s_k p_k|^2 with s in the simplex, hence dist >= the squared distance from e to the AFFINE
+// HULL of the query's prototypes.  With a = the point of that hull closest to the origin (the catalog mean: both
+// sides are centred) and u_1..u_{K-1} an orthonormal basis of span{p_j - p_0}, a is orthogonal to every u_j and
+//     hull distance^2 = |e|^2 - 2 e.a + |a|^2 - sum_j (e.u_j)^2 .
+// The tensor cores produce, per (row, query), the K inner products e.(2a), e.u_1 .. e.u_{K-1} -- ONE fp16 MMA per
+// 16 dimensions (kind::f16, fp32 accumulators in TMEM; fp16 carries tf32's 11-bit significand) -- and the epilogue
+// decides "bound <= threshold" as
+//     e.(2a) + sum_j (e.u_j)^2  >  e2s(row) + cq(query)
+// i.e. K-1 packed FP32x2 FMAs, one packed add and two compares per query PAIR; nothing else is evaluated, nothing
+// is voted on, and a passing (row, query) is appended by its own lane.  The soft-min never runs here: every
+// survivor is rescored exactly by rescore_merge_kernel (score.cu), which also verifies the optimistic threshold.
+//
+// Rigour.  e2s = |e|^2 lowered by a bound on everything the single-product evaluation can lose:
+//   * operands rounded to fp16: |d(e.x)| <= u |e||x| + 2^-25 (|e|_1 + |x|_1) (subnormals), u = 1.1 * 2^-10 -- the 0.1
+//     covers the fp32 accumulation inside the tensor core, measured at <= 1.6 * 2^-24 |e||x| (tools/tmem_probe.cu,
+//     profiles/r2_01_tmem_probe.md);
+//   * sum_j C_j^2 >= sum_j c_j^2 - 2 sqrt(K-1) |e| eta,  eta = the bound above with |x| = 1, because sum c_j^2 <= |e|^2;
+//   * the fp32 evaluation of both sides (CFL_PLANE_REL |e|^2 and 4K ulp terms).
+// cq = |a|^2 - threshold is rounded down.  A value outside the fp16 range (flag words raised by the pack kernels)
+// sends the CTA's queries to the exact redo pass (counts = -1).
 constexpr float CFL_TF32_PRODUCT_U = 1.1f / 1024.0f;
+__host__ __device__ constexpr int lb_gq(int K) { return K <= 2 ? 16 : (K <= 4 ? 8 : 4); }
+
+// fp16 lower-bound image: [qtile][kstep16][chunk][row n][8 halfs] with n = g*(GQ*K) + k*GQ + i for the query
+// ql = g*GQ + i of the tile: the K columns of a query GROUP are contiguous in TMEM (one run of tcgen05.ld), and the
+// two queries of a pair sit in adjacent columns = adjacent registers = one FP32x2 operand.  Row k = 0 holds 2a,
+// rows k >= 1 the basis vectors.  One warp per query slot, fp64 (modified Gram-Schmidt, every vector
+// re-orthogonalised: "twice is enough").
+__global__ void __launch_bounds__(128)
+prep_lb_kernel(const float* __restrict__ Pc, int64_t Q, int K, int d, int qt, int nqt, int dpad,
+               unsigned char* __restrict__ img16, int* __restrict__ flag16, float* __restrict__ lbq) {
+  __shared__ double su[4][CFL_MAX_K - 1][128];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t slot = (int64_t)blockIdx.x * 4 + w;
+  if (slot >= (int64_t)nqt * qt) return;
+  const int GQ = lb_gq(K), NC = K * qt, nks16 = (dpad + 15) / 16;
+  const int qtile = (int)(slot / qt), ql = (int)(slot % qt);
+  const int g = ql / GQ, gi = ql % GQ;
+  unsigned char* base = img16 + (size_t)qtile * nks16 * 2 * NC * 16;
+  auto store = [&](int k, int j, double x) {
+    const int n = g * (GQ * K) + k * GQ + gi;
+    *(__half*)(base + ((size_t)((j >> 4) * 2 + ((j >> 3) & 1)) * NC + n) * 16 + (j & 7) * 2) = __float2half_rn((float)x);
+  };
+  if (slot >= Q) {                                             // padding queries of the last tile: zero rows
+    for (int k = 0; k < K; ++k)
+      for (int j = lane; j < nks16 * 16; j += 32) store(k, j, 0.0);
+    return;
+  }
+  const float* pq = Pc + slot * (int64_t)K * d;
+  double p0[4], a[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) { const int j = lane + 32 * m; p0[m] = (j < d) ? (double)pq[j] : 0.0; a[m] = p0[m]; }
+  for (int k = 1; k < K; ++k) {
+    double v[4];
+    double n0 = 0.0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { const int j = lane + 32 * m; v[m] = (j < d) ? (double)pq[k * d + j] - p0[m] : 0.0; n0 += v[m] * v[m]; }
+    n0 = warp_sum(n0);
+    double nrm = 0.0;
+    for (int pass = 0; pass < 3; ++pass) {                     // pass 2 re-orthogonalises the NORMALISED vector
+      for (int i = 1; i < k; ++i) {
+        double c = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) c += v[m] * su[w][i - 1][lane + 32 * m];
+        c = warp_sum(c);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) v[m] -= c * su[w][i - 1][lane + 32 * m];
+      }
+      if (pass >= 1) {
+        nrm = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) nrm += v[m] * v[m];
+        nrm = warp_sum(nrm);
+        const double inv = (nrm > 1e-280) ? rsqrt(nrm) : 0.0;  // p_k - p_0 exactly inside the previous span: no new direction
+#pragma unroll
+        for (int m = 0; m < 4; ++m) v[m] *= inv;
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) su[w][k - 1][lane + 32 * m] = v[m];
+    __syncwarp();
+    (void)n0;
+  }
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 1; i < K; ++i) {
+      double c = 0.0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) c += a[m] * su[w][i - 1][lane + 32 * m];
+      c = warp_sum(c);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) a[m] -= c * su[w][i - 1][lane + 32 * m];
+    }
+  double a2 = 0.0, vmax = 0.0;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) { a2 += a[m] * a[m]; vmax = fmax(vmax, fabs(2.0 * a[m])); }
+  a2 = warp_sum(a2);
+  for (int m = 0; m < 4; ++m) {
+    const int j = lane + 32 * m;
+    if (j >= nks16 * 16) continue;
+    store(0, j, j < d ? 2.0 * a[m] : 0.0);
+    for (int k = 1; k < K; ++k) store(k, j, j < d ? su[w][k - 1][j] : 0.0);
+  }
+  if (!(vmax < 60000.0)) atomicOr(flag16, 1);                  // also catches NaN / inf
+  if (lane == 0) {
+    lbq[2 * slot] = __double2float_rd(a2);
+    lbq[2 * slot + 1] = __double2float_ru(sqrt(a2));
+  }
+}
+
+int score_lb_prep_queries(const ScoreArgs& a, cudaStream_t st) {
+  unsigned char* img16 = (unsigned char*)const_cast<void*>(a.qimg16);
+  int* flag16 = const_cast<int*>(a.qflag16);
+  CFL_CUDA(cudaMemsetAsync(flag16, 0, 16, st));
+  const int64_t slots = (int64_t)a.plan.nqt * a.plan.qt;
+  prep_lb_kernel<<<(unsigned)((slots + 3) / 4), 128, 0, st>>>(a.Pc, a.Q, a.K, a.d, a.plan.qt, a.plan.nqt, a.plan.dpad,
+                                                             img16, flag16, const_cast<float*>(a.lbq));
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+// NCOLS consecutive TMEM columns of this warp's 32 lanes -> registers, as a run of x16 / x8 / x4 loads
+template <int NCOLS, int OFF = 0>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NCOLS]) {
+  if constexpr (NCOLS - OFF >= 16) {
+    tmem_ld16(taddr + OFF, *reinterpret_cast<float(*)[16]>(&v[OFF]));
+    tmem_ld_cols<NCOLS, OFF + 16>(taddr, v);
+  } else if constexpr (NCOLS - OFF >= 8) {
+    tmem_ld8(taddr + OFF, *reinterpret_cast<float(*)[8]>(&v[OFF]));
+    tmem_ld_cols<NCOLS, OFF + 8>(taddr, v);
+  } else if constexpr (NCOLS - OFF >= 4) {
+    tmem_ld4(taddr + OFF, *reinterpret_cast<float(*)[4]>(&v[OFF]));
+    tmem_ld_cols<NCOLS, OFF + 4>(taddr, v);
+  }
+}
 
 template <int K>
 __global__ void __launch_bounds__(SU_THREADS, 1)
 score_lb_kernel(ScoreArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int GQ = K <= 2 ? 16 : (K <= 4 ? 8 : 4);
-  constexpr int PBS = qplane_stride(K);
+  constexpr int GQ = lb_gq(K);
+  constexpr int GC = GQ * K;                                   // TMEM columns of one query group
   const int QT = A.plan.qt;
   const int NC = K * QT;
   const int dpad = A.plan.dpad;
-  const int nks = dpad / 8;
   const SuLayout L = su_layout(K, QT, dpad);
   unsigned char* b_img = smem + L.b_img;
   unsigned char* a_ring = smem + L.a_ring;
   float* red = (float*)(smem + L.scratch);
-  float* qpl = (float*)(smem + L.qpl);
-  float* thr = (float*)(smem + L.thr);
+  float* cq = (float*)(smem + L.thr);
   int* cnt = (int*)(smem + L.cnt);
   uint64_t* full = (uint64_t*)(smem + L.bars);
   uint64_t* empty = full + SU_NSTAGE;
@@ -605,12 +702,13 @@ score_lb_kernel(ScoreArgs A) {
   const int64_t t1 = A.plan.tiles * (part + 1) / A.plan.parts;
   const int ts = A.tile_stride;
   const int ntiles = (int)((t1 - t0 + ts - 1) / ts);
-  // fp16 operand planes (same significand as tf32, K = 16 per MMA: half the K-steps, half the operand bytes) unless
-  // a pack kernel flagged a value outside the fp16 range; both planes use 4 KB blocks [chunk][128 rows][16 B]
-  const bool f16 = A.lb_f16 && *A.cflag16 == 0 && *A.qflag16 == 0;
-  const int nkm = f16 ? (dpad + 15) / 16 : nks;             // MMA K-steps per tile
+  const int nkm = (dpad + 15) / 16;                            // MMA K-steps (16 halfs) per tile
   const int kss = (nkm % 4 == 0) ? 4 : ((nkm % 2 == 0) ? 2 : 1);   // K-steps (4 KB blocks) per ring stage
-  if (A.thr_init != nullptr) {                               // no live query in this tile: nothing to do
+  if (*A.cflag16 != 0 || *A.qflag16 != 0) {                    // a value outside the fp16 range: exact redo pass
+    for (int ql = tid; ql < nq; ql += SU_THREADS) A.counts[(int64_t)part * A.Q + q0 + ql] = -1;
+    return;
+  }
+  if (A.thr_init != nullptr) {                                 // no live query in this tile: nothing to do
     bool live = false;
     for (int i = tid; i < nq; i += SU_THREADS) live |= A.thr_init[q0 + i] > __int_as_float(0xff800000);
     if (!__syncthreads_or(live)) {
@@ -618,7 +716,7 @@ score_lb_kernel(ScoreArgs A) {
       return;
     }
   }
-  constexpr uint32_t HI_BYTES = SU_ASTAGE / 2;                     // [chunk][128 rows][16 B]
+  constexpr uint32_t BLK = SU_ASTAGE / 2;                      // one K-step of the fp16 plane: [chunk][128 rows][16 B]
   constexpr uint32_t STAGE_BYTES = 2 * SU_ASTAGE;
 
   uint32_t ncols = 32;
@@ -627,29 +725,28 @@ score_lb_kernel(ScoreArgs A) {
     if (lane == 0) {
       for (int s = 0; s < SU_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-      mbar_init(&tempty[0], SU_EPI_THREADS); mbar_init(&tempty[1], SU_EPI_THREADS);
+      mbar_init(&tempty[0], SU_NEPI); mbar_init(&tempty[1], SU_NEPI);   // one arrival per epilogue WARP
       mbar_init(bfull, 1);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, ncols);
   }
-  for (int i = tid; i < QT * PBS; i += SU_THREADS) {
-    const int ql = i / PBS, j = i % PBS;
-    qpl[((ql >> 1) * PBS + j) * 2 + (ql & 1)] = (ql < nq) ? A.qplane[(q0 + ql) * PBS + j] : 0.0f;
-  }
-  // largest prototype norm of the tile (qpar[k] = log2e |p_k|^2): one margin factor for the whole CTA
-  float pm = 0.0f;
-  for (int i = tid; i < nq * K; i += SU_THREADS) pm = fmaxf(pm, A.qpar[(q0 + i / K) * qpar_stride(K) + i % K]);
-  pm = warp_max(pm);
-  if (lane == 0) red[warp] = pm;
+  // largest |a| of the tile: one margin factor for the whole CTA
+  float am = 0.0f;
+  for (int i = tid; i < nq; i += SU_THREADS) am = fmaxf(am, A.lbq[2 * (q0 + i) + 1]);
+  am = warp_max(am);
+  if (lane == 0) red[warp] = am;
+  // cq = |a|^2 - threshold, rounded down; padding / dead queries get +inf (never pass), no threshold -inf (always)
   for (int i = tid; i < QT; i += SU_THREADS) {
-    float th = __int_as_float(0xff800000);
+    float c = __int_as_float(0x7f800000);
     if (i < nq) {
       const float tau = A.thr_init ? A.thr_init[q0 + i] : __int_as_float(0x7f800000);
-      th = (tau < 3.0e38f) ? nextafterf(tau, 3.4e38f) : tau;
+      const float a2 = A.lbq[2 * (q0 + i)];
+      if (tau > 3.0e38f) c = __int_as_float(0xff800000);
+      else if (tau > -3.0e38f) c = __fsub_rd(a2, nextafterf(tau, 3.4e38f)) - 5.0e-7f * (a2 + fabsf(tau));
     }
-    thr[i] = th;
+    cq[i] = c;
     cnt[i] = 0;
   }
   tc_fence_before();
@@ -658,13 +755,14 @@ score_lb_kernel(ScoreArgs A) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == SU_NEPI) {
+    // ================================ MMA issuer (one lane) =================================
     if (elect_one()) {
       mbar_wait(bfull, 0);
       const uint64_t a_desc = make_smem_desc(0, 128u * 16u, 128u);
       const uint64_t b_desc = make_smem_desc(0, (uint32_t)NC * 16u, 128u);
-      const uint32_t idesc = f16 ? make_idesc_f16(128, (uint32_t)NC) : make_idesc_tf32(128, (uint32_t)NC);
+      const uint32_t idesc = make_idesc_f16(128, (uint32_t)NC);
       const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_img);
-      const uint32_t b_step = (f16 ? 2u : 4u) * (uint32_t)NC * 16u;     // tf32 image: [hl][chunk], fp16 image: [chunk]
+      const uint32_t b_step = 2u * (uint32_t)NC * 16u;
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
@@ -675,10 +773,9 @@ score_lb_kernel(ScoreArgs A) {
           if (!(A.dbg_mode & 2)) mbar_wait(&full[stage], phase);
           tc_fence_after();
           for (int j = 0; j < kss; ++j) {
-            const uint64_t ad = a_desc + (uint64_t)((a_base + stage * STAGE_BYTES + j * HI_BYTES) >> 4);
+            const uint64_t ad = a_desc + (uint64_t)((a_base + stage * STAGE_BYTES + j * BLK) >> 4);
             const uint64_t bd = b_desc + (uint64_t)((b_base + (ks + j) * b_step) >> 4);
-            if (f16) mma_f16(d_tmem, ad, bd, idesc, (ks + j) ? 1u : 0u);
-            else     mma_tf32(d_tmem, ad, bd, idesc, (ks + j) ? 1u : 0u);
+            mma_f16(d_tmem, ad, bd, idesc, (ks + j) ? 1u : 0u);
           }
           mma_commit(&empty[stage]);
           if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
@@ -687,135 +784,104 @@ score_lb_kernel(ScoreArgs A) {
       }
     }
   } else if (warp == SU_NEPI + 1) {
+    // ================================ TMA producer (one lane) ===============================
     if (elect_one()) {
-      const uint32_t bbytes = f16 ? (uint32_t)nkm * 2u * (uint32_t)NC * 16u : (uint32_t)dpad * 8u * (uint32_t)NC;
-      const unsigned char* qsrc = (const unsigned char*)(f16 ? A.qimg16 : A.qimg) + (size_t)qtile * bbytes;
+      const uint32_t bbytes = (uint32_t)nkm * 2u * (uint32_t)NC * 16u;
+      const unsigned char* qsrc = (const unsigned char*)A.qimg16 + (size_t)qtile * bbytes;
       mbar_arrive_expect_tx(bfull, bbytes);
       for (uint32_t o = 0; o < bbytes; o += 32768u) {
-        uint32_t n = bbytes - o < 32768u ? bbytes - o : 32768u;
+        const uint32_t n = bbytes - o < 32768u ? bbytes - o : 32768u;
         bulk_g2s(b_img + o, qsrc + o, n, bfull);
       }
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ((A.dbg_mode & 2) ? 0 : ntiles); ++t) {
-        // tf32: the hi half of each 8 KB K-step block; fp16: consecutive 4 KB blocks of the fp16 plane
-        const size_t blk = f16 ? (size_t)HI_BYTES : (size_t)SU_ASTAGE;
-        const unsigned char* src = (const unsigned char*)(f16 ? A.cimg16 : A.cimg) + (size_t)(t0 + (int64_t)t * ts) * nkm * blk;
+        const unsigned char* src = (const unsigned char*)A.cimg16 + (size_t)(t0 + (int64_t)t * ts) * nkm * BLK;
         for (int ks = 0; ks < nkm; ks += kss) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)kss * HI_BYTES);
-          for (int j = 0; j < kss; ++j)
-            bulk_g2s(a_ring + stage * STAGE_BYTES + j * HI_BYTES, src + (size_t)(ks + j) * blk, HI_BYTES, &full[stage]);
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)kss * BLK);
+          bulk_g2s(a_ring + stage * STAGE_BYTES, src + (size_t)ks * BLK, (uint32_t)kss * BLK, &full[stage]);
           if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else {
-    constexpr int WPQ = SU_NEPI / 4;
+    // ======================================= epilogue ========================================
+    constexpr int WPQ = SU_NEPI / 4;                           // warps per TMEM lane quarter
     const int lq = warp & 3, sub = warp >> 2;
     const int lrow = lq * 32 + lane;
-    const uint32_t lane_lt = (1u << lane) - 1u;
+    const int ngroups = (nq + GQ - 1) / GQ;
     tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
-    float pmax = 0.0f;
-    for (int i = 0; i < SU_THREADS / 32; ++i) pmax = fmaxf(pmax, red[i]);
-    // 2 u |p|max, |p|max^2 = pmax / log2e
-    // fp16 operands: the same relative rounding as tf32 (11-bit significand) for normal values, plus an absolute
-    // 2^-25 per element below the normal range (6.1e-5): |dG| <= u |p||e| + 2^-25 (|p|_1 + |e|_1)
-    const float pnorm = sqrtf(pmax * CFL_LN2);
-    const float sub16 = f16 ? 5.97e-8f * sqrtf((float)dpad) : 0.0f;              // 2^-24 sqrt(d): |x|_1 <= sqrt(d) |x|
-    const float mfac = 2.0f * (CFL_TF32_PRODUCT_U * pnorm + sub16) * 1.0001f;
-    const float mabs = 2.0f * sub16 * pnorm * 1.0001f;
-    unsigned dbg_seen = 0, dbg_skip = 0, dbg_push = 0;
-    float e2_next = (ntiles > 0) ? __ldg(A.e2 + t0 * 128 + lrow) : 0.0f;      // prefetched one tile ahead
+    float amax = 0.0f;
+    for (int i = 0; i < SU_THREADS / 32; ++i) amax = fmaxf(amax, red[i]);
+    const float s16 = 5.97e-8f * sqrtf((float)(nkm * 16));    // 2^-24 sqrt(d): twice the subnormal term
+    const float rk = sqrtf((float)(K - 1));
+    const float ulp = (float)(4 * K) * 5.97e-8f;
+    const float c_e2 = 1.0f - CFL_PLANE_REL - (2.0f * rk * (CFL_TF32_PRODUCT_U + s16) + ulp) * 1.0001f;
+    const float c_sq = ((2.0f * CFL_TF32_PRODUCT_U + 2.0f * ulp) * amax + 2.0f * s16 * (1.0f + rk)) * 1.0001f;
+    const float c_abs = 2.0f * s16 * amax * 1.0001f;
+    float2 er_next = (ntiles > 0) ? __ldg(A.lbrow + t0 * 128 + lrow) : make_float2(0.f, 0.f);   // one tile ahead
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
-      const int64_t row = (t0 + (int64_t)t * ts) * 128 + lrow;
-      const bool valid = row < A.N;
-      const float e2 = e2_next;
-      if (t + 1 < ntiles) e2_next = __ldg(A.e2 + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
-      // |e|^2 lowered by the fp32 evaluation margin and by the single-product error bound
-      const float e2s = fmaf(-mfac, sqrtf(e2), e2 * (1.0f - CFL_PLANE_REL)) - mabs;
+      const uint32_t row = (uint32_t)((t0 + (int64_t)t * ts) * 128 + lrow);
+      const float2 er = er_next;
+      if (t + 1 < ntiles) er_next = __ldg(A.lbrow + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
+      // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
+      const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
       const f2_t e2sp = pk2(e2s, e2s);
       mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
-      if (A.dbg_mode & 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); continue; }
-      for (int g = sub; g * GQ < nq; g += WPQ) {
-        float gk[K][GQ];
+      if (!(A.dbg_mode & 1)) {
+        for (int g = sub; g < ngroups; g += WPQ) {
+          float v[GC];
+          tmem_ld_cols<GC>(taddr + (uint32_t)(g * GC), v);
+          float cg[GQ];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if constexpr (GQ == 16)     tmem_ld16(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
-          else if constexpr (GQ == 8) tmem_ld8(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
-          else                        tmem_ld4(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
-        }
-        float tg[GQ];
+          for (int i = 0; i < GQ; i += 4) {
+            const float4 c4 = *(const float4*)(cq + g * GQ + i);
+            cg[i] = c4.x; cg[i + 1] = c4.y; cg[i + 2] = c4.z; cg[i + 3] = c4.w;
+          }
+          tmem_ld_wait();
+          if (A.dbg_mode & 4) continue;                        // experiment: the epilogue only reads TMEM
+          float lhs[GQ], rhs[GQ];
+          bool anyp = false;
 #pragma unroll
-        for (int i = 0; i < GQ; i += 4) {
-          const float4 t4 = *(const float4*)(thr + g * GQ + i);
-          tg[i] = t4.x; tg[i + 1] = t4.y; tg[i + 2] = t4.z; tg[i + 3] = t4.w;
-        }
-        tmem_ld_wait();
-        if (A.dbg_mode & 4) continue;                          // experiment: the epilogue only reads TMEM
-        float lb[GQ];
-        bool nd = false;
+          for (int pi = 0; pi < GQ / 2; ++pi) {
+            f2_t acc = pk2(v[2 * pi], v[2 * pi + 1]);
 #pragma unroll
-        for (int pi = 0; pi < GQ / 2; ++pi) {
-          f2_t pv[PBS];
-          const ulonglong2* src = (const ulonglong2*)(qpl + (g * (GQ / 2) + pi) * PBS * 2);
+            for (int k = 1; k < K; ++k) {
+              const f2_t c = pk2(v[k * GQ + 2 * pi], v[k * GQ + 2 * pi + 1]);
+              acc = fma2(c, c, acc);
+            }
+            upk2(acc, lhs[2 * pi], lhs[2 * pi + 1]);
+            upk2(add2(e2sp, pk2(cg[2 * pi], cg[2 * pi + 1])), rhs[2 * pi], rhs[2 * pi + 1]);
+            anyp |= (lhs[2 * pi] > rhs[2 * pi]) | (lhs[2 * pi + 1] > rhs[2 * pi + 1]);
+          }
+          if (anyp && !(A.dbg_mode & 8)) {                     // rare (a fraction of a percent of the lanes): lane-level appends
+            uint32_t nb = 0;
 #pragma unroll
-          for (int j = 0; j < PBS; j += 2) { const ulonglong2 u = src[j >> 1]; pv[j] = u.x; pv[j + 1] = u.y; }
-          float gA[K], gB[K];
-#pragma unroll
-          for (int k = 0; k < K; ++k) { gA[k] = gk[k][2 * pi]; gB[k] = gk[k][2 * pi + 1]; }
-          plane_bound_pair<K>(gA, gB, e2sp, pv, lb[2 * pi], lb[2 * pi + 1]);
-          nd |= (lb[2 * pi] < tg[2 * pi]) | (lb[2 * pi + 1] < tg[2 * pi + 1]);
-        }
-        ++dbg_seen;
-        if (A.dbg_mode & 8) { dbg_skip += nd ? 1u : 0u; continue; }   // experiment: TMEM reads + bound, no votes / pushes
-        if (!__any_sync(0xffffffffu, nd && valid)) { ++dbg_skip; continue; }
-        uint32_t nb = 0;
-#pragma unroll
-        for (int i = 0; i < GQ; ++i) nb |= (lb[i] < tg[i]) ? (1u << i) : 0u;
-        if (!valid) nb = 0;
-        const uint32_t anyn = __reduce_or_sync(0xffffffffu, nb);
-#pragma unroll
-        for (int i = 0; i < GQ; ++i) {
-          if (anyn & (1u << i)) {                              // warp-uniform
-            const bool pass = (nb >> i) & 1u;
-            const uint32_t m = __ballot_sync(0xffffffffu, pass);
-            const int ql = g * GQ + i;
-            const int leader = __ffs(m) - 1;
-            int basei = 0;
-            if (lane == leader) basei = atomicAdd(&cnt[ql], __popc(m));
-            basei = __shfl_sync(0xffffffffu, basei, leader);
-            const int slot = basei + __popc(m & lane_lt);
-            if (basei + __popc(m) <= TOPK_STRIDE) {                // warp-uniform
-              if (pass) kbase[(int64_t)ql * TOPK_STRIDE + slot] = pack_key(lb[i], (uint32_t)row);
-            } else {                                           // this part's buffer is full: spill list of the query
-              const uint32_t sm = __ballot_sync(0xffffffffu, pass && slot >= TOPK_STRIDE);
-              int sb = 0;
-              if (lane == leader && sm) sb = atomicAdd(&A.spill_cnt[q0 + ql], __popc(sm));
-              sb = __shfl_sync(0xffffffffu, sb, leader);
-              if (pass) {
-                if (slot < TOPK_STRIDE) kbase[(int64_t)ql * TOPK_STRIDE + slot] = pack_key(lb[i], (uint32_t)row);
-                else {
-                  const int sp = sb + __popc(sm & lane_lt);
-                  if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = pack_key(lb[i], (uint32_t)row);
-                }
+            for (int i = 0; i < GQ; ++i) nb |= (lhs[i] > rhs[i]) ? (1u << i) : 0u;
+            const tkey_t key = pack_key(0.0f, row);
+            while (nb) {
+              const int ql = g * GQ + __ffs(nb) - 1;
+              nb &= nb - 1;
+              const int slot = atomicAdd(&cnt[ql], 1);
+              if (slot < TOPK_STRIDE) {
+                kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
+              } else {                                         // this part's buffer is full: spill list of the query
+                const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
+                if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
               }
             }
-            dbg_push += __popc(m);
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[buf]);
-    }
-    if (A.dbg != nullptr && lane == 0) {
-      atomicAdd(&A.dbg[0], (unsigned long long)dbg_seen); atomicAdd(&A.dbg[1], (unsigned long long)dbg_skip);
-      atomicAdd(&A.dbg[2], (unsigned long long)dbg_push);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
     }
     epi_bar_sync();
-    // counts may exceed TOPK_STRIDE: that marks an over-full buffer (verify_counts_kernel redoes the query)
+    // counts may exceed TOPK_STRIDE: the excess went to the query's spill list
     for (int ql = tid; ql < nq; ql += SU_EPI_THREADS) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
   }
   tc_fence_before();

@@ -426,11 +426,11 @@ def test_score_topk_lower_bound_pass_regimes(nat, monkeypatch, case):
             assert abs(D[r, c_] - wv[r, -1]) <= rtol * 0.5 * max(wv[r, -1], 1.0) + 1e-7
 
 
-def test_score_topk_lower_bound_planes_fp16_equals_tf32_and_range_guard(nat, monkeypatch):
-    """The lower-bound pass reads fp16 operand planes by default (same 11-bit significand as TF32, half the MMA
-    K-steps); CFL_SCORE_LB_F16=0 forces the tf32 hi planes.  Both must return the same bits (every survivor is
-    rescored exactly), and a catalog with a value outside the fp16 range must fall back to the tf32 planes on the
-    device (the pack kernel raises the flag) instead of losing rows to an infinite Gram value."""
+def test_score_topk_lower_bound_pass_equals_exact_filter_and_range_guard(nat, monkeypatch):
+    """The lower-bound pass (fp16 single-product MMA + affine-hull bound, every survivor rescored exactly) must
+    return the same bits as the exact 3xTF32 filter pass (CFL_SCORE_NO_LB), and a catalog or query with a value
+    outside the fp16 range must hand its queries to the exact redo pass on the device (the pack kernels raise a
+    flag, the kernel writes counts = -1) instead of losing rows to an infinite Gram value."""
     rng = np.random.default_rng(78)
     N, Q, K, d = 150000, 70, 3, 64
     E = rng.normal(size=(N, d)).astype(np.float32)
@@ -439,15 +439,15 @@ def test_score_topk_lower_bound_planes_fp16_equals_tf32_and_range_guard(nat, mon
     mu = nat.col_mean(E)
     monkeypatch.setenv("CFL_SCORE_MIN_TILES", "2")
     monkeypatch.setenv("CFL_SCORE_SAMPLE_STRIDE", "8")
-    monkeypatch.setenv("CFL_SCORE_LB_F16", "0")
+    monkeypatch.setenv("CFL_SCORE_NO_LB", "1")
     a = nat.score_topk(Pq, E, 100, mu=mu)
-    monkeypatch.setenv("CFL_SCORE_LB_F16", "1")
+    monkeypatch.delenv("CFL_SCORE_NO_LB")
     b = nat.score_topk(Pq, E, 100, mu=mu)
     assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
     E[4321, 7] = 1.0e6                                    # far outside the fp16 range after centring
     Pq[3] = E[4321][None, :] + 0.25                        # a query that must find that row first
     c = nat.score_topk(Pq, E, 100, mu=mu)
-    monkeypatch.setenv("CFL_SCORE_LB_F16", "0")
+    monkeypatch.setenv("CFL_SCORE_NO_LB", "1")
     e = nat.score_topk(Pq, E, 100, mu=mu)
     assert torch.equal(c[1], e[1]) and torch.equal(c[0], e[0])
     assert int(c[1][3, 0]) == 4321
