@@ -52,6 +52,7 @@ SIGNATURES = {
     "cfl_score_topk_packed_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
     "cfl_score_topk_packed": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _i64,
                                      _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cfl_score_topk_stats": (_int, [_i64, _int, _int, _i64, _int, _int, _vp, _sz, _vp, _vp]),
     "cfl_score_topk_monomer_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
     "cfl_score_topk_monomer": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _i64, _i64, _int, _i64,
                                       _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -286,9 +287,10 @@ def catalog_pack(E, K, mu=None):
     return img
 
 
-def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False, image=None):
+def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False, image=None, want_stats=False):
     """Top-k candidates of every query by soft-min distance; exact (rescored) values.
-    ``image`` = catalog_pack(E, K, mu) skips the per-call packing of the catalog."""
+    ``image`` = catalog_pack(E, K, mu) skips the per-call packing of the catalog.  ``want_stats`` appends the int64
+    counters of cfl_score_topk_stats (SCORE_STAT_NAMES) for this call."""
     Pq = _f32c(Pq, "Pq")
     if Pq.dim() == 2:
         Pq = Pq[:, None, :]
@@ -313,7 +315,16 @@ def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False, imag
         _check(lib().cfl_score_topk(MODES[mode], _ptr(Pq2), Q, K, d, ldq, _ptr(E), N, lde, _ptr(mu),
                                     int(k), int(idx_base), _ptr(top_val), _ptr(top_idx), _ptr(dense),
                                     _ptr(ws), ws.numel(), _stream()), "cfl_score_topk")
+    if want_stats:
+        stats = torch.zeros(SCORE_NSTATS, dtype=torch.int64, device=dev)
+        _check(lib().cfl_score_topk_stats(Q, K, d, N, int(k), 1 if image is not None else 0, _ptr(ws), ws.numel(),
+                                          _ptr(stats), _stream()), "cfl_score_topk_stats")
+        return (top_val, top_idx, stats)
     return (top_val, top_idx, dense) if want_dense else (top_val, top_idx)
+
+
+SCORE_NSTATS = 8
+SCORE_STAT_NAMES = ("survivors", "spill_queries", "probe_dropped_queries", "redo_queries", "lower_bound_pass")
 
 
 def score_topk_monomer(a, w, P, k, idx_base=0, want_dense=False):

@@ -114,6 +114,14 @@ class CatalogIndex:
         return nat.score_topk(Pq, self.E, k, mu=self.mu, mode="pcd", idx_base=self.idx_base,
                               image=self.image)
 
+    def rank_local_stats(self, xq: torch.Tensor, k: int = 100):
+        """One local ranking call plus the counters of cfl_score_topk_stats as a dict (survivors of the
+        filter pass, queries that spilled / were dropped by the probe / were redone exactly)."""
+        Pq = self.project_queries(xq)
+        tv, ti, st = nat.score_topk(Pq, self.E, k, mu=self.mu, mode="pcd", idx_base=self.idx_base,
+                                    image=self.image, want_stats=True)
+        return tv, ti, dict(zip(nat.SCORE_STAT_NAMES, st.tolist()))
+
     def rank(self, xq: torch.Tensor, k: int = 100):
         """-> (dist [Q,k] ascending, index [Q,k] int64 global).  score = theta+ - dist."""
         Pq = self.project_queries(xq)

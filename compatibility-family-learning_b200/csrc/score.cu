@@ -466,7 +466,14 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
     const int redo = (s_over || !proven) ? 1 : 0;
     s_redo = redo;
     thr_redo[q] = redo ? tau[q] : __int_as_float(0xff800000);
-    if (redo) { redo_tile[q / qt] = 1; if (dbg) atomicAdd(&dbg[3], 1ull); }
+    if (redo) redo_tile[q / qt] = 1;
+    if (dbg) {                                               // statistics of the call (cfl_score_topk_stats)
+      atomicAdd(&dbg[0], (unsigned long long)total);
+      if (spill_cnt[q] > 0) atomicAdd(&dbg[1], 1ull);
+      if (!(tau_opt[q] > __int_as_float(0xff800000))) atomicAdd(&dbg[2], 1ull);
+      if (redo) atomicAdd(&dbg[3], 1ull);
+      if (q == 0) dbg[4] = 1ull;
+    }
   }
   __syncthreads();
   if (s_redo) return;
@@ -681,7 +688,10 @@ __global__ void verify_counts_kernel(const int* __restrict__ counts, int parts, 
   const bool redo = over || (tot < kk && tau_opt[q] < tau[q]);
   thr_redo[q] = redo ? tau[q] : __int_as_float(0xff800000);
   if (redo) redo_tile[q / qt] = 1;
-  if (redo && dbg) atomicAdd(&dbg[3], 1ull);
+  if (dbg) {
+    atomicAdd(&dbg[0], (unsigned long long)tot);
+    if (redo) atomicAdd(&dbg[3], 1ull);
+  }
 }
 
 // ---- cross-rank merge: rank-based merge of R sorted lists --------------------------------
@@ -719,6 +729,42 @@ topk_merge_kernel(const float* __restrict__ vals, const int64_t* __restrict__ id
 
 using namespace cfl;
 
+// Tuning knobs of cfl_score_topk (DESIGN.md "Experiment knobs"): read from the environment in ONE place per call.
+// Results never depend on them.  The ones that switch work off for timing experiments (CFL_SCORE_DBG_MODE) or force a
+// path outside its validated range (CFL_SCORE_FORCE_LB) are honoured only under CFL_EXPERIMENTS=1.
+struct ScoreKnobs {
+  int sample_stride = 32;     // tools/knob_sweep.py: 32 beats 16 by 7 % on the C3 step (the sample pass halves; r_opt = 16)
+  int64_t min_tiles = 128;    // tiles per part below which one adaptive exact pass is used
+  int opt_mult = 4;           // optimistic threshold = ceil(opt_mult * kk / stride)-th best of the sample
+  bool no_cascade = false, no_optimistic = false, no_lb = false, no_probe = false, force_lb = false;
+  int dbg_mode = 0;
+};
+static ScoreKnobs read_knobs() {
+  ScoreKnobs k;
+  const char* e;
+  if ((e = getenv("CFL_SCORE_SAMPLE_STRIDE"))) k.sample_stride = atoi(e);
+  if ((e = getenv("CFL_SCORE_MIN_TILES"))) k.min_tiles = atoll(e);
+  if ((e = getenv("CFL_SCORE_OPT_MULT"))) k.opt_mult = atoi(e);
+  k.no_cascade = getenv("CFL_SCORE_NO_CASCADE") != nullptr;
+  k.no_optimistic = getenv("CFL_SCORE_NO_OPTIMISTIC") != nullptr;
+  k.no_lb = getenv("CFL_SCORE_NO_LB") != nullptr;
+  k.no_probe = getenv("CFL_SCORE_NO_PROBE") != nullptr;
+  if ((e = getenv("CFL_EXPERIMENTS")) && atoi(e) != 0) {
+    k.force_lb = getenv("CFL_SCORE_FORCE_LB") != nullptr;
+    if ((e = getenv("CFL_SCORE_DBG_MODE"))) k.dbg_mode = atoi(e);
+  }
+  return k;
+}
+static bool score_two_pass(const ScoreKnobs& kn, const ScorePlan& plan, bool dense) {
+  return kn.sample_stride > 1 && !dense && plan.tiles / plan.parts >= kn.min_tiles;
+}
+static bool score_lb_pass(const ScoreKnobs& kn, int K) {
+  // the affine hull of K prototypes has K-1 dimensions: for K > 4 it swallows so much of a low-dimensional embedding
+  // that the bound stops rejecting (measured: K=8 survivors overflow at d=20..64), so those shapes keep the exact
+  // filter (optimistic threshold + exact counts)
+  return !kn.no_lb && (K <= 4 || kn.force_lb);
+}
+
 static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePlan& p, bool own_image,
                               size_t* o_pc, size_t* o_qpar, size_t* o_qimg, size_t* o_keys, size_t* o_cnt,
                               size_t* o_cimg) {
@@ -733,6 +779,8 @@ static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePla
   off = align_up(off + (size_t)(3 * Q + p.nqt + 4) * sizeof(float), 256);
   // lower-bound pass: per-query spill list for keys that do not fit their (part, query) buffer + counters
   if (p.impl) off = align_up(off + (size_t)Q * LB_SPILL * sizeof(tkey_t) + (size_t)Q * sizeof(int), 256);
+  // statistics of the call (cfl_score_topk_stats): CFL_SCORE_NSTATS 64-bit counters
+  if (p.impl) off = align_up(off + CFL_SCORE_NSTATS * sizeof(unsigned long long), 256);
   return off + 1024;
 }
 
@@ -788,10 +836,8 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   a.cimg16 = nullptr; a.qimg16 = nullptr; a.cflag16 = nullptr; a.qflag16 = nullptr; a.lbrow = nullptr; a.lbq = nullptr;
   bool lb_pass = false;
   const float* redo_only = nullptr;
-  a.dbg_mode = getenv("CFL_SCORE_DBG_MODE") ? atoi(getenv("CFL_SCORE_DBG_MODE")) : 0;
-  static unsigned long long* dbg_dev = nullptr;
-  const bool dbg_on = getenv("CFL_SCORE_DEBUG") != nullptr;
-  if (dbg_on && !dbg_dev) CFL_CUDA(cudaMalloc(&dbg_dev, 4 * sizeof(unsigned long long)));
+  const ScoreKnobs kn = read_knobs();
+  a.dbg_mode = kn.dbg_mode;
   a.plan = plan;
   if (N == 0) {
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
@@ -818,11 +864,8 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       // Long catalog ranges are scored in two passes: a sparse sample pass (every S-th tile,
       // running thresholds) whose merged kk-th best distance bounds the final threshold, then the
       // full pass that only filters against that fixed bound (no barriers, no compaction).
-      const char* es = getenv("CFL_SCORE_SAMPLE_STRIDE");
-      const char* em = getenv("CFL_SCORE_MIN_TILES");
-      const int sstride = es ? atoi(es) : 32;   // tools/knob_sweep.py: 32 beats 16 by 7 % on the C3 step (the sample pass halves; r_opt = 16)
-      const int64_t min_tiles = em ? atoll(em) : 128;
-      const bool two_pass = sstride > 1 && !dist_out && plan.tiles / plan.parts >= min_tiles;
+      const int sstride = kn.sample_stride;
+      const bool two_pass = score_two_pass(kn, plan, dist_out != nullptr);
       float* tau = (float*)(base + align_up(o_cimg + ((image == (const void*)(base + o_cimg)) ? catalog_image_bytes(N, d) : 0), 1024));
       if (!two_pass) timer_record(0, cs);
       const size_t sel_smem = ((size_t)plan.parts + 1 + SEL_SMEM_KEYS) * sizeof(uint32_t);
@@ -835,7 +878,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         const int64_t tiles_b = (tpp + sstride - 1) / sstride;
         int64_t tiles_a = ((int64_t)plan.kk * tiles_b + 384 * (int64_t)plan.parts - 1) / (384 * (int64_t)plan.parts);
         if (tiles_a < 1) tiles_a = 1;
-        const bool cascade = tiles_a <= 7 && tiles_a * 128 * plan.parts >= 2 * plan.kk && !getenv("CFL_SCORE_NO_CASCADE");
+        const bool cascade = tiles_a <= 7 && tiles_a * 128 * plan.parts >= 2 * plan.kk && !kn.no_cascade;
         if (cascade) {
           a.phase = 2; a.thr_init = nullptr;                 // +inf thresholds: keep every sampled row
           a.tile_stride = (int)((tpp + tiles_a - 1) / tiles_a);
@@ -863,43 +906,37 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         int* redo_tile = (int*)(tau + 3 * Q);
         a.spill = (tkey_t*)((char*)tau + align_up((size_t)(3 * Q + plan.nqt + 4) * sizeof(float), 256));
         a.spill_cnt = (int*)(a.spill + (size_t)Q * LB_SPILL);
-        const char* eo = getenv("CFL_SCORE_OPT_MULT");
-        const int opt_mult = eo ? atoi(eo) : 4;
-        int r_opt = (int)((opt_mult * (int64_t)plan.kk + sstride - 1) / sstride);
-        if (getenv("CFL_SCORE_NO_OPTIMISTIC")) r_opt = 0;
+        unsigned long long* stats = (unsigned long long*)((char*)a.spill + align_up((size_t)Q * LB_SPILL * sizeof(tkey_t) + (size_t)Q * sizeof(int), 256));
+        CFL_CUDA(cudaMemsetAsync(stats, 0, CFL_SCORE_NSTATS * sizeof(unsigned long long), cs));
+        int r_opt = (int)((kn.opt_mult * (int64_t)plan.kk + sstride - 1) / sstride);
+        if (kn.no_optimistic) r_opt = 0;
         select_threshold_kernel<<<(unsigned)Q, SEL_THREADS, sel_smem, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau,
                                                                             tau_opt, r_opt);
         CFL_LAUNCH_CHECK();
         CFL_CUDA(cudaMemsetAsync(redo_tile, 0, (size_t)plan.nqt * sizeof(int), cs));
         a.phase = 2; a.tile_stride = 1; a.thr_init = tau_opt;
         timer_record(0, cs);                 // bench.py times the dominant launch: the full filter pass
-        if (dbg_on) { CFL_CUDA(cudaMemsetAsync(dbg_dev, 0, 32, cs)); a.dbg = dbg_dev; }
-        // single-product lower-bound filter (survivors rescored exactly by rescore_merge_kernel), or
-        // the exact 3xTF32 filter when disabled
-        // the affine hull of K prototypes has K-1 dimensions: for K > 4 it swallows so much of a
-        // low-dimensional embedding that the bound stops rejecting (measured: K=8 survivors overflow
-        // at d=20..64), so those shapes keep the exact filter (optimistic threshold + exact counts)
-        lb_pass = !getenv("CFL_SCORE_NO_LB") && (K <= 4 || getenv("CFL_SCORE_FORCE_LB"));
+        // single-product lower-bound filter (survivors rescored exactly by rescore_merge_kernel), or the exact 3xTF32
+        // filter when disabled / for K > 4
+        lb_pass = score_lb_pass(kn, K);
         if (lb_pass) {
           st = score_lb_prep_queries(a, cs);
           if (st != CFL_OK) return st;
         }
-        if (lb_pass && !getenv("CFL_SCORE_NO_PROBE")) {
+        if (lb_pass && !kn.no_probe) {
           int probe_stride = (int)((tpp + 3) / 4);           // about 4 tiles per part
           if (probe_stride < 1) probe_stride = 1;
           const int64_t probe_tiles = (tpp + probe_stride - 1) / probe_stride;
-          a.phase = 3; a.tile_stride = probe_stride; a.dbg = nullptr;
+          a.phase = 3; a.tile_stride = probe_stride;
           CFL_CUDA(cudaMemsetAsync(a.spill_cnt, 0, (size_t)Q * sizeof(int), cs));
           st = score_lb_launch(a, cs);
           if (st != CFL_OK) return st;
           // only the pathological regimes (most rows survive) are taken out: 4x the total key capacity
           const float limit = 4.0f * ((float)plan.parts * (float)TOPK_STRIDE + (float)LB_SPILL);
           probe_classify_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, cs>>>(
-              a.counts, plan.parts, Q, (float)tpp / (float)probe_tiles, limit, tau_opt, dbg_on ? dbg_dev : nullptr,
-              a.spill_cnt);
+              a.counts, plan.parts, Q, (float)tpp / (float)probe_tiles, limit, tau_opt, nullptr, a.spill_cnt);
           CFL_LAUNCH_CHECK();
           a.phase = 2; a.tile_stride = 1;
-          if (dbg_on) a.dbg = dbg_dev;
           timer_record(0, cs);
         }
         if (lb_pass) {
@@ -919,7 +956,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
                                   (int)rs_smem));                                                               \
     rescore_merge_kernel<KK><<<(unsigned)Q, MRG_THREADS, rs_smem, cs>>>(                                        \
         a.keys, a.counts, plan.parts, Q, plan.kk, k, Pq, ldq, d, E, lde, idx_base, top_val, top_idx, tau,       \
-        tau_opt, plan.qt, thr_redo, redo_tile, a.dbg, a.spill, a.spill_cnt);                                    \
+        tau_opt, plan.qt, thr_redo, redo_tile, stats, a.spill, a.spill_cnt);                                    \
     break;
           switch (K) {
             CFL_RSC_CASE(1) CFL_RSC_CASE(2) CFL_RSC_CASE(3) CFL_RSC_CASE(4)
@@ -928,9 +965,8 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
 #undef CFL_RSC_CASE
         } else {
           verify_counts_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, cs>>>(a.counts, plan.parts, Q, plan.kk, plan.qt,
-                                                                           tau, tau_opt, thr_redo, redo_tile, a.dbg);
+                                                                           tau, tau_opt, thr_redo, redo_tile, stats);
         }
-        a.dbg = nullptr;
         CFL_LAUNCH_CHECK();
         a.thr_init = thr_redo; a.redo_tile = redo_tile;
         st = score_umma_launch(a, cs);
@@ -942,13 +978,6 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       }
       if (!two_pass) timer_record(1, cs);
       if (st != CFL_OK) return st;
-      if (dbg_on) {
-        unsigned long long h[4];
-        CFL_CUDA(cudaMemcpyAsync(h, dbg_dev, 32, cudaMemcpyDeviceToHost, cs));
-        CFL_CUDA(cudaStreamSynchronize(cs));
-        fprintf(stderr, "[cfl score] filter pass groups: bound tested %llu, skipped %llu, pushed keys %llu, queries redone %llu\n",
-                h[0], h[1], h[2], h[3]);
-      }
     } else {
       timer_record(0, cs);
       switch (K) {
@@ -1012,6 +1041,29 @@ int cfl_score_topk_packed(int mode, const float* Pq, int64_t Q, int K, int d, in
   CFL_REQUIRE(image, CFL_ERR_INVALID, "score_topk_packed: NULL image");
   return score_topk_impl(mode, Pq, Q, K, d, ldq, E, image, N, lde, mu, k, idx_base, top_val, top_idx,
                          dist_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int cfl_score_topk_stats(int64_t Q, int K, int d, int64_t N, int k, int packed, const void* ws, size_t ws_bytes,
+                         unsigned long long* stats_out, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(ws && stats_out && Q > 0 && N > 0, CFL_ERR_INVALID, "score_topk_stats: bad arguments");
+  const bool umma_ok = score_umma_supported(K, d);
+  ScorePlan plan = make_score_plan(Q, K, d, N, k, umma_ok);
+  const ScoreKnobs kn = read_knobs();
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (!umma_ok || !score_two_pass(kn, plan, false)) {         // short catalogs / CUDA-core shapes: one adaptive pass, no statistics
+    CFL_CUDA(cudaMemsetAsync(stats_out, 0, CFL_SCORE_NSTATS * sizeof(unsigned long long), cs));
+    return CFL_OK;
+  }
+  size_t o_pc, o_qpar, o_qimg, o_keys, o_cnt, o_cimg;
+  const size_t need = score_ws_layout(Q, K, d, N, plan, packed == 0, &o_pc, &o_qpar, &o_qimg, &o_keys, &o_cnt, &o_cimg);
+  CFL_REQUIRE(ws_bytes >= need, CFL_ERR_WORKSPACE, "score_topk_stats: workspace too small (%zu < %zu)", ws_bytes, need);
+  const char* tau = (const char*)ws + align_up(o_cimg + (packed == 0 ? catalog_image_bytes(N, d) : 0), 1024);
+  const char* spill = tau + align_up((size_t)(3 * Q + plan.nqt + 4) * sizeof(float), 256);
+  const char* stats = spill + align_up((size_t)Q * LB_SPILL * sizeof(tkey_t) + (size_t)Q * sizeof(int), 256);
+  CFL_CUDA(cudaMemcpyAsync(stats_out, stats, CFL_SCORE_NSTATS * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, cs));
+  return CFL_OK;
 }
 
 int cfl_topk_merge(const float* vals, const int64_t* idx, int R, int64_t Q, int k, float* top_val,

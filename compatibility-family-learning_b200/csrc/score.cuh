@@ -53,7 +53,8 @@ struct ScoreArgs {
   const float2* lbrow;
   const float* lbq;
   int dbg_mode;          // experiments (CFL_SCORE_DBG_MODE bits): 1 = epilogue does nothing, 2 = no TMA / no full-barrier
-                         // waits, 4 = lower-bound epilogue only reads TMEM, 8 = TMEM reads + bound, no votes / pushes
+                         // waits, 4 = lower-bound epilogue only reads TMEM, 8 = TMEM reads + bound, no pushes, 16 = MMA issue does
+                         // not wait for the epilogue (honoured only under CFL_EXPERIMENTS=1)
   unsigned long long* dbg; // optional counters {groups seen, skipped, selective, full} (CFL_SCORE_DEBUG)
   ScorePlan plan;
 };

@@ -152,6 +152,17 @@ int cfl_score_topk_packed(int mode, const float* Pq, int64_t Q, int K, int d, in
                           float* top_val, int64_t* top_idx, float* dist_out,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* Statistics of the LAST cfl_score_topk / cfl_score_topk_packed call that used workspace `ws` with this shape
+ * (packed = 1 for the _packed entry point): CFL_SCORE_NSTATS unsigned 64-bit counters copied to device memory
+ * `stats_out` on `stream`: [0] keys that survived the full filter pass, summed over queries (each is rescored
+ * exactly), [1] queries that used their spill list, [2] queries the probe took out of the lower-bound pass,
+ * [3] queries redone by the exact kernel under the safe threshold, [4] 1 when the lower-bound pass ran.  All zero
+ * for catalogs short enough for the single adaptive pass.  (bench.py prints them so that a regression to the slow
+ * paths is visible; no reference call site.) */
+#define CFL_SCORE_NSTATS 8
+int cfl_score_topk_stats(int64_t Q, int K, int d, int64_t N, int k, int packed, const void* ws, size_t ws_bytes,
+                         unsigned long long* stats_out, void* stream);
+
 /* Monomer mode on the cross product (SURVEY App. A.6 applied to DistBase.build_dist, monomer branch,
  * cfl/models/base.py:109-117; gate cfl/models/base.py:94-105).  The roles follow the reference:
  *   Aq[Q,d]  = act(e0) of the SOURCE (query) items,  Wq[Q,K] = their gate softmax (dense, row-major),
