@@ -806,10 +806,16 @@ score_lb_kernel(ScoreArgs A) {
     }
   } else {
     // ======================================= epilogue ========================================
+    // Per tile a warp owns the query groups g = sub, sub + WPQ, ... of its TMEM lane quarter.  It reads RG groups
+    // per round into registers; as soon as the LAST round's tcgen05.ld has completed it releases the accumulator
+    // buffer (the MMA of tile t+2 never waits for CUDA-core work), evaluates the bound from registers and only
+    // then appends the rare survivors.
     constexpr int WPQ = SU_NEPI / 4;                           // warps per TMEM lane quarter
+    constexpr int RG = (GC <= 24) ? 2 : 1;                     // groups held in registers at once (<= 48 accumulators)
     const int lq = warp & 3, sub = warp >> 2;
     const int lrow = lq * 32 + lane;
     const int ngroups = (nq + GQ - 1) / GQ;
+    const int my_groups = ngroups > sub ? (ngroups - sub + WPQ - 1) / WPQ : 0;
     tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
     float amax = 0.0f;
     for (int i = 0; i < SU_THREADS / 32; ++i) amax = fmaxf(amax, red[i]);
@@ -831,54 +837,77 @@ score_lb_kernel(ScoreArgs A) {
       mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
-      if (!(A.dbg_mode & 1)) {
-        for (int g = sub; g < ngroups; g += WPQ) {
-          float v[GC];
-          tmem_ld_cols<GC>(taddr + (uint32_t)(g * GC), v);
+      bool released = false;
+      for (int r0 = 0; r0 < my_groups && !(A.dbg_mode & 1); r0 += RG) {
+        float v[RG][GC];
+#pragma unroll
+        for (int r = 0; r < RG; ++r)
+          if (r0 + r < my_groups) tmem_ld_cols<GC>(taddr + (uint32_t)((sub + (r0 + r) * WPQ) * GC), v[r]);
+        tmem_ld_wait();
+        if (r0 + RG >= my_groups) {                            // last round: the accumulators are in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+          released = true;
+        }
+        if (A.dbg_mode & 4) continue;                          // experiment: the epilogue only reads TMEM
+        uint32_t nb[RG];
+#pragma unroll
+        for (int r = 0; r < RG; ++r) {
+          nb[r] = 0;
+          if (r0 + r >= my_groups) continue;
+          const int g = sub + (r0 + r) * WPQ;
           float cg[GQ];
 #pragma unroll
           for (int i = 0; i < GQ; i += 4) {
             const float4 c4 = *(const float4*)(cq + g * GQ + i);
             cg[i] = c4.x; cg[i + 1] = c4.y; cg[i + 2] = c4.z; cg[i + 3] = c4.w;
           }
-          tmem_ld_wait();
-          if (A.dbg_mode & 4) continue;                        // experiment: the epilogue only reads TMEM
           float lhs[GQ], rhs[GQ];
           bool anyp = false;
 #pragma unroll
           for (int pi = 0; pi < GQ / 2; ++pi) {
-            f2_t acc = pk2(v[2 * pi], v[2 * pi + 1]);
+            f2_t acc = pk2(v[r][2 * pi], v[r][2 * pi + 1]);
 #pragma unroll
             for (int k = 1; k < K; ++k) {
-              const f2_t c = pk2(v[k * GQ + 2 * pi], v[k * GQ + 2 * pi + 1]);
+              const f2_t c = pk2(v[r][k * GQ + 2 * pi], v[r][k * GQ + 2 * pi + 1]);
               acc = fma2(c, c, acc);
             }
             upk2(acc, lhs[2 * pi], lhs[2 * pi + 1]);
             upk2(add2(e2sp, pk2(cg[2 * pi], cg[2 * pi + 1])), rhs[2 * pi], rhs[2 * pi + 1]);
             anyp |= (lhs[2 * pi] > rhs[2 * pi]) | (lhs[2 * pi + 1] > rhs[2 * pi + 1]);
           }
-          if (anyp && !(A.dbg_mode & 8)) {                     // rare (a fraction of a percent of the lanes): lane-level appends
-            uint32_t nb = 0;
+          if (anyp) {                                          // rare: which queries of the group
 #pragma unroll
-            for (int i = 0; i < GQ; ++i) nb |= (lhs[i] > rhs[i]) ? (1u << i) : 0u;
-            const tkey_t key = pack_key(0.0f, row);
-            while (nb) {
-              const int ql = g * GQ + __ffs(nb) - 1;
-              nb &= nb - 1;
-              const int slot = atomicAdd(&cnt[ql], 1);
-              if (slot < TOPK_STRIDE) {
-                kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
-              } else {                                         // this part's buffer is full: spill list of the query
-                const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
-                if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
-              }
+            for (int i = 0; i < GQ; ++i) nb[r] |= (lhs[i] > rhs[i]) ? (1u << i) : 0u;
+          }
+        }
+        if (A.dbg_mode & 8) continue;                          // experiment: no appends
+        // survivors (a fraction of a percent of the lanes) are appended by their own lane
+#pragma unroll
+        for (int r = 0; r < RG; ++r) {
+          uint32_t m = nb[r];
+          if (m == 0) continue;
+          const int g = sub + (r0 + r) * WPQ;
+          const tkey_t key = pack_key(0.0f, row);
+          while (m) {
+            const int ql = g * GQ + __ffs(m) - 1;
+            m &= m - 1;
+            const int slot = atomicAdd(&cnt[ql], 1);
+            if (slot < TOPK_STRIDE) {
+              kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
+            } else {                                           // this part's buffer is full: spill list of the query
+              const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
+              if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (!released) {                                         // a warp without a group in this tile (short query tile)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+      }
     }
     epi_bar_sync();
     // counts may exceed TOPK_STRIDE: the excess went to the query's spill list

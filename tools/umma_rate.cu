@@ -1,0 +1,99 @@
+// tcgen05.mma.kind::f16 issue-rate probe: clk per MMA (M = 128, K = 16) for N in {64..256}, operands in shared memory in
+// (a) the K-major SWIZZLE_NONE layout the scoring kernels use, (b) K-major SWIZZLE_128B; free-running issue from one
+// thread per CTA, one CTA per SM, data = whatever shared memory holds (timing only).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I compatibility-family-learning_b200/csrc \
+//             tools/umma_rate.cu -o compatibility-family-learning_b200/build/umma_rate
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "umma.cuh"
+
+using namespace cfl::umma;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;            // SBO = 8 rows x 128 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+
+// mode 0: SWIZZLE_NONE, 4 K-steps per "tile" each with its own 4 KB A block and 2*N*16 B block (as score_lb_kernel)
+// mode 1: SWIZZLE_128B, 4 K-steps = 32-byte advances inside one 128 B row
+// nbuf: accumulator buffers cycled per tile (1 or 2); tf32: kind::tf32 with K = 8 instead
+__global__ void __launch_bounds__(128, 1)
+rate_kernel(int N, int mode, int tiles, int nbuf, int tf32, unsigned long long* cyc) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = slot;
+  if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t a_base = smem_u32(smem), b_base = a_base + 65536;
+      const uint32_t idesc = tf32 ? make_idesc_tf32(128, (uint32_t)N) : make_idesc_f16(128, (uint32_t)N);
+      const long long t0 = clock64();
+      for (int t = 0; t < tiles; ++t) {
+        const uint32_t d_tmem = tb + (uint32_t)((t % nbuf) * N);
+        const uint32_t a_t = a_base + (uint32_t)((t & 3) * 16384);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint64_t ad, bd;
+          if (mode == 0) {
+            ad = make_smem_desc(a_t + ks * 4096, 128u * 16u, 128u);
+            bd = make_smem_desc(b_base + ks * (2u * N * 16u), (uint32_t)N * 16u, 128u);
+          } else {
+            ad = desc_sw128(a_t + ks * 32);
+            bd = desc_sw128(b_base + ks * 32);
+          }
+          if (tf32) mma_tf32(d_tmem, ad, bd, idesc, ks ? 1u : 0u);
+          else mma_f16(d_tmem, ad, bd, idesc, ks ? 1u : 0u);
+        }
+      }
+      mma_commit(&bar);
+      mbar_wait(&bar, 0);
+      const long long t1 = clock64();
+      cyc[blockIdx.x] = (unsigned long long)(t1 - t0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+int main() {
+  const int grid = 148, tiles = 2000;
+  unsigned long long* cyc;
+  CK(cudaMalloc(&cyc, grid * 8));
+  const int smem = 65536 + 32768 + 1024;
+  CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int tf32 = 0; tf32 < 2; ++tf32)
+    for (int mode = 0; mode < 2; ++mode)
+      for (int nbuf = 1; nbuf <= 2; ++nbuf)
+        for (int N : {64, 96, 128, 192, 256}) {
+          if (nbuf * N > 512) continue;
+          rate_kernel<<<grid, 128, smem>>>(N, mode, tiles, nbuf, tf32, cyc);
+          CK(cudaDeviceSynchronize());
+          rate_kernel<<<grid, 128, smem>>>(N, mode, tiles, nbuf, tf32, cyc);
+          CK(cudaDeviceSynchronize());
+          std::vector<unsigned long long> h(grid);
+          CK(cudaMemcpy(h.data(), cyc, grid * 8, cudaMemcpyDeviceToHost));
+          unsigned long long mx = 0; for (auto c : h) mx = c > mx ? c : mx;
+          const double per = (double)mx / (tiles * 4.0);
+          const double kk = tf32 ? 8.0 : 16.0;
+          printf("%s %-12s nbuf=%d N=%3d : %6.1f clk/MMA  (nominal %5.1f)  %6.0f flop/clk/SM  operand bytes/clk %5.1f\n",
+                 tf32 ? "tf32" : "f16 ", mode ? "SWIZZLE_128B" : "SWIZZLE_NONE", nbuf, N, per, 128.0 * N / 256.0,
+                 2.0 * 128 * N * kk / per, (128.0 + N) * 32.0 / per);
+        }
+  return 0;
+}
