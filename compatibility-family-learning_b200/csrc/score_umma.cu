@@ -544,8 +544,8 @@ score_umma_kernel(ScoreArgs A) {
 // The tensor cores produce, per (row, query), the K inner products e.(2a), e.u_1 .. e.u_{K-1} -- ONE fp16 MMA per
 // 16 dimensions (kind::f16, fp32 accumulators in TMEM; fp16 carries tf32's 11-bit significand) -- and the epilogue
 // decides "bound <= threshold" as
-//     e.(2a) + sum_j (e.u_j)^2  >  e2s(row) + cq(query)
-// i.e. K-1 packed FP32x2 FMAs, one packed add and two compares per query PAIR; nothing else is evaluated, nothing
+//     e.(2a) - cq(query) + sum_j (e.u_j)^2  >  e2s(row)
+// i.e. K-1 packed FP32x2 FMAs and one packed add per query PAIR, then a 3-input max tree and ONE compare per group; nothing else is evaluated, nothing
 // is voted on, and a passing (row, query) is appended by its own lane.  The soft-min never runs here: every
 // survivor is rescored exactly by rescore_merge_kernel (score.cu), which also verifies the optimistic threshold.
 //
@@ -558,6 +558,15 @@ score_umma_kernel(ScoreArgs A) {
 // cq = |a|^2 - threshold is rounded down.  A value outside the fp16 range (flag words raised by the pack kernels)
 // sends the CTA's queries to the exact redo pass (counts = -1).
 constexpr float CFL_TF32_PRODUCT_U = 1.1f / 1024.0f;
+#ifdef CFL_LB_TRACE
+// timing trace of CTA (0,0) (tools/lb_trace.py; builds with CFL_NVCC_EXTRA=-DCFL_LB_TRACE only): per tile
+// [0] MMA warp before the tempty wait, [1] after it, [2] after issuing the tile's MMAs, [3] epilogue warp 0 before the
+// tfull wait, [4] after it, [5] accumulators in registers, [6] bound evaluated / appends done
+__device__ unsigned long long g_lb_trace[8 * 4096];
+#define LB_TRACE(slot, tile) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (tile) < 4096) g_lb_trace[(tile) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define LB_TRACE(slot, tile) do { } while (0)
+#endif
 __host__ __device__ constexpr int lb_gq(int K) { return K <= 2 ? 16 : (K <= 4 ? 8 : 4); }
 
 // fp16 lower-bound image: [qtile][kstep16][chunk][row n][8 halfs] with n = g*(GQ*K) + k*GQ + i for the query
@@ -672,7 +681,9 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NCOLS]) 
   }
 }
 
-template <int K>
+// GPW > 0: every epilogue warp owns exactly GPW query groups per tile (QT / GQ == 4 GPW): straight-line epilogue.
+// GPW = 0: any tile shape (generic loop).
+template <int K, int GPW>
 __global__ void __launch_bounds__(SU_THREADS, 1)
 score_lb_kernel(ScoreArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -685,7 +696,7 @@ score_lb_kernel(ScoreArgs A) {
   unsigned char* b_img = smem + L.b_img;
   unsigned char* a_ring = smem + L.a_ring;
   float* red = (float*)(smem + L.scratch);
-  float* cq = (float*)(smem + L.thr);
+  float* ncq = (float*)(smem + L.thr);                         // -cq per query of the tile
   int* cnt = (int*)(smem + L.cnt);
   uint64_t* full = (uint64_t*)(smem + L.bars);
   uint64_t* empty = full + SU_NSTAGE;
@@ -737,7 +748,8 @@ score_lb_kernel(ScoreArgs A) {
   for (int i = tid; i < nq; i += SU_THREADS) am = fmaxf(am, A.lbq[2 * (q0 + i) + 1]);
   am = warp_max(am);
   if (lane == 0) red[warp] = am;
-  // cq = |a|^2 - threshold, rounded down; padding / dead queries get +inf (never pass), no threshold -inf (always)
+  // cq = |a|^2 - threshold, rounded down (stored negated); padding / dead queries get +inf (never pass), no threshold
+  // -inf (always pass)
   for (int i = tid; i < QT; i += SU_THREADS) {
     float c = __int_as_float(0x7f800000);
     if (i < nq) {
@@ -746,7 +758,7 @@ score_lb_kernel(ScoreArgs A) {
       if (tau > 3.0e38f) c = __int_as_float(0xff800000);
       else if (tau > -3.0e38f) c = __fsub_rd(a2, nextafterf(tau, 3.4e38f)) - 5.0e-7f * (a2 + fabsf(tau));
     }
-    cq[i] = c;
+    ncq[i] = -c;
     cnt[i] = 0;
   }
   tc_fence_before();
@@ -763,16 +775,34 @@ score_lb_kernel(ScoreArgs A) {
       const uint32_t idesc = make_idesc_f16(128, (uint32_t)NC);
       const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_img);
       const uint32_t b_step = 2u * (uint32_t)NC * 16u;
+      // tcgen05.mma issue blocks while the tensor pipe's queue is full, so a wait placed between two tiles is paid
+      // in full (mbarrier.try_wait costs ~130 clk even when the phase is complete).  The waits for the NEXT ring
+      // stage / accumulator buffer are therefore issued one MMA early, while the previous MMAs still execute.
       int stage = 0; uint32_t phase = 0;
+      const int nsteps = nkm / kss;                            // ring stages per tile
+      if (ntiles > 0) {
+        mbar_wait(&tempty[0], 1u);
+        if (!(A.dbg_mode & 2)) mbar_wait(&full[0], 0u);
+        tc_fence_after();
+      }
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
-        if (!(A.dbg_mode & 16)) mbar_wait(&tempty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);   // 16: MMA free-running (timing only)
-        tc_fence_after();
+        LB_TRACE(0, t);
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
-        for (int ks = 0; ks < nkm; ks += kss) {
-          if (!(A.dbg_mode & 2)) mbar_wait(&full[stage], phase);
-          tc_fence_after();
+        for (int sidx = 0; sidx < nsteps; ++sidx) {
+          const int ks = sidx * kss;
           for (int j = 0; j < kss; ++j) {
+            if (j == kss - 1) {                                // look ahead: barriers of the next stage (and tile)
+              LB_TRACE(1, t);
+              int nstage = stage + 1; uint32_t nphase = phase;
+              if (nstage == SU_NSTAGE) { nstage = 0; nphase ^= 1u; }
+              const bool last = sidx == nsteps - 1;
+              if (!last || t + 1 < ntiles) {
+                if (last && !(A.dbg_mode & 16)) mbar_wait(&tempty[buf ^ 1], ((uint32_t)((t + 1) >> 1) & 1u) ^ 1u);
+                if (!(A.dbg_mode & 2)) mbar_wait(&full[nstage], nphase);
+                tc_fence_after();
+              }
+            }
             const uint64_t ad = a_desc + (uint64_t)((a_base + stage * STAGE_BYTES + j * BLK) >> 4);
             const uint64_t bd = b_desc + (uint64_t)((b_base + (ks + j) * b_step) >> 4);
             mma_f16(d_tmem, ad, bd, idesc, (ks + j) ? 1u : 0u);
@@ -781,6 +811,7 @@ score_lb_kernel(ScoreArgs A) {
           if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
         }
         mma_commit(&tfull[buf]);
+        LB_TRACE(2, t);
       }
     }
   } else if (warp == SU_NEPI + 1) {
@@ -833,10 +864,73 @@ score_lb_kernel(ScoreArgs A) {
       if (t + 1 < ntiles) er_next = __ldg(A.lbrow + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
       // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
       const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
-      const f2_t e2sp = pk2(e2s, e2s);
+      if (tid == 0) LB_TRACE(3, t);
       mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
+      if (tid == 0) LB_TRACE(4, t);
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
+      if constexpr (GPW > 0) {
+        // ---- straight-line path: all of the warp's accumulators -> registers, release, evaluate ----
+        float v[GPW][GC], tq[GPW][GQ];
+        if (!(A.dbg_mode & 1)) {
+#pragma unroll
+          for (int r = 0; r < GPW; ++r) tmem_ld_cols<GC>(taddr + (uint32_t)((sub + r * WPQ) * GC), v[r]);
+#pragma unroll
+          for (int r = 0; r < GPW; ++r)
+#pragma unroll
+            for (int i = 0; i < GQ; i += 4) {
+              const float4 c4 = *(const float4*)(ncq + (sub + r * WPQ) * GQ + i);
+              tq[r][i] = c4.x; tq[r][i + 1] = c4.y; tq[r][i + 2] = c4.z; tq[r][i + 3] = c4.w;
+            }
+          tmem_ld_wait();
+        }
+        if (tid == 0) LB_TRACE(5, t);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (!(A.dbg_mode & 5)) {
+          // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
+#pragma unroll
+          for (int r = 0; r < GPW; ++r)
+#pragma unroll
+            for (int pi = 0; pi < GQ / 2; ++pi) {
+              f2_t acc = add2(pk2(v[r][2 * pi], v[r][2 * pi + 1]), pk2(tq[r][2 * pi], tq[r][2 * pi + 1]));
+#pragma unroll
+              for (int k = 1; k < K; ++k) {
+                const f2_t c = pk2(v[r][k * GQ + 2 * pi], v[r][k * GQ + 2 * pi + 1]);
+                acc = fma2(c, c, acc);
+              }
+              upk2(acc, tq[r][2 * pi], tq[r][2 * pi + 1]);
+            }
+          float m = tq[0][0];
+#pragma unroll
+          for (int r = 0; r < GPW; ++r)
+#pragma unroll
+            for (int i = (r == 0 ? 1 : 0); i < GQ; i += 2) m = (i + 1 < GQ) ? max3(m, tq[r][i], tq[r][i + 1]) : fmaxf(m, tq[r][i]);
+          if (m > e2s && !(A.dbg_mode & 8)) {                  // rare (a fraction of a percent of the lanes): lane-level appends
+            const tkey_t key = pack_key(0.0f, row);
+#pragma unroll
+            for (int r = 0; r < GPW; ++r) {
+              uint32_t nb = 0;
+#pragma unroll
+              for (int i = 0; i < GQ; ++i) nb |= (tq[r][i] > e2s) ? (1u << i) : 0u;
+              while (nb) {
+                const int ql = (sub + r * WPQ) * GQ + __ffs(nb) - 1;
+                nb &= nb - 1;
+                const int slot = atomicAdd(&cnt[ql], 1);
+                if (slot < TOPK_STRIDE) {
+                  kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
+                } else {                                       // this part's buffer is full: spill list of the query
+                  const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
+                  if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
+                }
+              }
+            }
+          }
+        }
+        if (tid == 0) LB_TRACE(6, t);
+        continue;
+      }
       bool released = false;
       for (int r0 = 0; r0 < my_groups && !(A.dbg_mode & 1); r0 += RG) {
         float v[RG][GC];
@@ -844,6 +938,7 @@ score_lb_kernel(ScoreArgs A) {
         for (int r = 0; r < RG; ++r)
           if (r0 + r < my_groups) tmem_ld_cols<GC>(taddr + (uint32_t)((sub + (r0 + r) * WPQ) * GC), v[r]);
         tmem_ld_wait();
+        if (tid == 0) LB_TRACE(5, t);
         if (r0 + RG >= my_groups) {                            // last round: the accumulators are in registers
           tc_fence_before();
           __syncwarp();
@@ -851,58 +946,51 @@ score_lb_kernel(ScoreArgs A) {
           released = true;
         }
         if (A.dbg_mode & 4) continue;                          // experiment: the epilogue only reads TMEM
-        uint32_t nb[RG];
 #pragma unroll
         for (int r = 0; r < RG; ++r) {
-          nb[r] = 0;
           if (r0 + r >= my_groups) continue;
           const int g = sub + (r0 + r) * WPQ;
-          float cg[GQ];
+          float t[GQ];
 #pragma unroll
           for (int i = 0; i < GQ; i += 4) {
-            const float4 c4 = *(const float4*)(cq + g * GQ + i);
-            cg[i] = c4.x; cg[i + 1] = c4.y; cg[i + 2] = c4.z; cg[i + 3] = c4.w;
+            const float4 c4 = *(const float4*)(ncq + g * GQ + i);
+            t[i] = c4.x; t[i + 1] = c4.y; t[i + 2] = c4.z; t[i + 3] = c4.w;
           }
-          float lhs[GQ], rhs[GQ];
-          bool anyp = false;
+          // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
 #pragma unroll
           for (int pi = 0; pi < GQ / 2; ++pi) {
-            f2_t acc = pk2(v[r][2 * pi], v[r][2 * pi + 1]);
+            f2_t acc = add2(pk2(v[r][2 * pi], v[r][2 * pi + 1]), pk2(t[2 * pi], t[2 * pi + 1]));
 #pragma unroll
             for (int k = 1; k < K; ++k) {
               const f2_t c = pk2(v[r][k * GQ + 2 * pi], v[r][k * GQ + 2 * pi + 1]);
               acc = fma2(c, c, acc);
             }
-            upk2(acc, lhs[2 * pi], lhs[2 * pi + 1]);
-            upk2(add2(e2sp, pk2(cg[2 * pi], cg[2 * pi + 1])), rhs[2 * pi], rhs[2 * pi + 1]);
-            anyp |= (lhs[2 * pi] > rhs[2 * pi]) | (lhs[2 * pi + 1] > rhs[2 * pi + 1]);
+            upk2(acc, t[2 * pi], t[2 * pi + 1]);
           }
-          if (anyp) {                                          // rare: which queries of the group
+          float m = max3(t[0], t[1], t[2]);
 #pragma unroll
-            for (int i = 0; i < GQ; ++i) nb[r] |= (lhs[i] > rhs[i]) ? (1u << i) : 0u;
-          }
-        }
-        if (A.dbg_mode & 8) continue;                          // experiment: no appends
-        // survivors (a fraction of a percent of the lanes) are appended by their own lane
+          for (int i = 3; i + 1 < GQ; i += 2) m = max3(m, t[i], t[i + 1]);
+          if constexpr (GQ % 2 == 0) m = fmaxf(m, t[GQ - 1]);
+          if (m > e2s && !(A.dbg_mode & 8)) {                  // rare (a fraction of a percent of the lanes): lane-level appends
+            uint32_t nb = 0;
 #pragma unroll
-        for (int r = 0; r < RG; ++r) {
-          uint32_t m = nb[r];
-          if (m == 0) continue;
-          const int g = sub + (r0 + r) * WPQ;
-          const tkey_t key = pack_key(0.0f, row);
-          while (m) {
-            const int ql = g * GQ + __ffs(m) - 1;
-            m &= m - 1;
-            const int slot = atomicAdd(&cnt[ql], 1);
-            if (slot < TOPK_STRIDE) {
-              kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
-            } else {                                           // this part's buffer is full: spill list of the query
-              const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
-              if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
+            for (int i = 0; i < GQ; ++i) nb |= (t[i] > e2s) ? (1u << i) : 0u;
+            const tkey_t key = pack_key(0.0f, row);
+            while (nb) {
+              const int ql = g * GQ + __ffs(nb) - 1;
+              nb &= nb - 1;
+              const int slot = atomicAdd(&cnt[ql], 1);
+              if (slot < TOPK_STRIDE) {
+                kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
+              } else {                                         // this part's buffer is full: spill list of the query
+                const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
+                if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
+              }
             }
           }
         }
       }
+      if (tid == 0) LB_TRACE(6, t);
       if (!released) {                                         // a warp without a group in this tile (short query tile)
         tc_fence_before();
         __syncwarp();
@@ -918,16 +1006,29 @@ score_lb_kernel(ScoreArgs A) {
   if (warp == SU_NEPI) tmem_dealloc(tmem_base, ncols);
 }
 
-template <int K>
-static int launch_lb(const ScoreArgs& a, cudaStream_t st) {
+template <int K, int GPW>
+static int launch_lb_gpw(const ScoreArgs& a, cudaStream_t st) {
   SuLayout L = su_layout(K, a.plan.qt, a.plan.dpad);
   size_t smem = L.total + 1024;
-  CFL_CUDA(cudaFuncSetAttribute(score_lb_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CFL_CUDA(cudaFuncSetAttribute(score_lb_kernel<K, GPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(a.plan.parts, a.plan.nqt);
-  score_lb_kernel<K><<<grid, SU_THREADS, smem, st>>>(a);
+  score_lb_kernel<K, GPW><<<grid, SU_THREADS, smem, st>>>(a);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
 }
+template <int K>
+static int launch_lb(const ScoreArgs& a, cudaStream_t st) {
+  const int groups = a.plan.qt / lb_gq(K);
+  if (a.plan.qt % lb_gq(K) == 0 && groups == (SU_NEPI / 4) * 2 && 2 * lb_gq(K) * K <= 48) return launch_lb_gpw<K, 2>(a, st);
+  if (a.plan.qt % lb_gq(K) == 0 && groups == (SU_NEPI / 4) * 1) return launch_lb_gpw<K, 1>(a, st);
+  return launch_lb_gpw<K, 0>(a, st);
+}
+
+#ifdef CFL_LB_TRACE
+extern "C" int cfl_lb_trace_read(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_lb_trace, (size_t)n * sizeof(unsigned long long));
+}
+#endif
 
 int score_lb_launch(const ScoreArgs& a, cudaStream_t st) {
   switch (a.K) {
