@@ -681,8 +681,11 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NCOLS]) 
   }
 }
 
-// GPW > 0: every epilogue warp owns exactly GPW query groups per tile (QT / GQ == 4 GPW): straight-line epilogue.
-// GPW = 0: any tile shape (generic loop).
+// GPW > 0 ("team mode", QT / GQ == 2 GPW): the epilogue warps form two teams of 8 (two per TMEM lane quarter); team b
+// serves the tiles t = b (mod 2), i.e. always accumulator buffer b.  A warp owns GPW query groups of its quarter, reads
+// them in rounds of RG groups (<= 48 accumulator registers), releases the buffer as soon as the last round's
+// tcgen05.ld has completed and has two tile times for its chain (barrier wake-up, TMEM latency, bound, appends), so the
+// jitter of the rare appends no longer stalls the MMA.  GPW = 0: any tile shape, every warp serves every tile.
 template <int K, int GPW>
 __global__ void __launch_bounds__(SU_THREADS, 1)
 score_lb_kernel(ScoreArgs A) {
@@ -736,7 +739,8 @@ score_lb_kernel(ScoreArgs A) {
     if (lane == 0) {
       for (int s = 0; s < SU_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-      mbar_init(&tempty[0], SU_NEPI); mbar_init(&tempty[1], SU_NEPI);   // one arrival per epilogue WARP
+      mbar_init(&tempty[0], GPW > 0 ? SU_NEPI / 2 : SU_NEPI);           // one arrival per epilogue WARP (of the team)
+      mbar_init(&tempty[1], GPW > 0 ? SU_NEPI / 2 : SU_NEPI);
       mbar_init(bfull, 1);
       fence_barrier_init();
     }
@@ -856,42 +860,47 @@ score_lb_kernel(ScoreArgs A) {
     const float c_e2 = 1.0f - CFL_PLANE_REL - (2.0f * rk * (CFL_TF32_PRODUCT_U + s16) + ulp) * 1.0001f;
     const float c_sq = ((2.0f * CFL_TF32_PRODUCT_U + 2.0f * ulp) * amax + 2.0f * s16 * (1.0f + rk)) * 1.0001f;
     const float c_abs = 2.0f * s16 * amax * 1.0001f;
-    float2 er_next = (ntiles > 0) ? __ldg(A.lbrow + t0 * 128 + lrow) : make_float2(0.f, 0.f);   // one tile ahead
-    for (int t = 0; t < ntiles; ++t) {
-      const int buf = t & 1;
-      const uint32_t row = (uint32_t)((t0 + (int64_t)t * ts) * 128 + lrow);
-      const float2 er = er_next;
-      if (t + 1 < ntiles) er_next = __ldg(A.lbrow + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
-      // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
-      const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
-      if (tid == 0) LB_TRACE(3, t);
-      mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
-      tc_fence_after();
-      if (tid == 0) LB_TRACE(4, t);
+    if constexpr (GPW > 0) {
+      // ---------------------------------- team mode ----------------------------------
+      const int team = sub >> 1, sub2 = sub & 1;
+      const int buf = team;
       const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
-      if constexpr (GPW > 0) {
-        // ---- straight-line path: all of the warp's accumulators -> registers, release, evaluate ----
-        float v[GPW][GC], tq[GPW][GQ];
-        if (!(A.dbg_mode & 1)) {
+      float2 er_nx = (team < ntiles) ? __ldg(A.lbrow + (t0 + (int64_t)team * ts) * 128 + lrow) : make_float2(0.f, 0.f);
+      for (int t = team; t < ntiles; t += 2) {
+        const uint32_t row = (uint32_t)((t0 + (int64_t)t * ts) * 128 + lrow);
+        const float2 er = er_nx;
+        if (t + 2 < ntiles) er_nx = __ldg(A.lbrow + (t0 + (int64_t)(t + 2) * ts) * 128 + lrow);
+        // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
+        const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
+        if (tid == 0) LB_TRACE(3, t);
+        mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
+        tc_fence_after();
+        if (tid == 0) LB_TRACE(4, t);
 #pragma unroll
-          for (int r = 0; r < GPW; ++r) tmem_ld_cols<GC>(taddr + (uint32_t)((sub + r * WPQ) * GC), v[r]);
+        for (int r0 = 0; r0 < GPW; r0 += RG) {
+          float v[RG][GC], tq[RG][GQ];
+          if (!(A.dbg_mode & 1)) {
 #pragma unroll
-          for (int r = 0; r < GPW; ++r)
+            for (int r = 0; r < RG; ++r) tmem_ld_cols<GC>(taddr + (uint32_t)((sub2 + 2 * (r0 + r)) * GC), v[r]);
 #pragma unroll
-            for (int i = 0; i < GQ; i += 4) {
-              const float4 c4 = *(const float4*)(ncq + (sub + r * WPQ) * GQ + i);
-              tq[r][i] = c4.x; tq[r][i + 1] = c4.y; tq[r][i + 2] = c4.z; tq[r][i + 3] = c4.w;
-            }
-          tmem_ld_wait();
-        }
-        if (tid == 0) LB_TRACE(5, t);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
-        if (!(A.dbg_mode & 5)) {
+            for (int r = 0; r < RG; ++r)
+#pragma unroll
+              for (int i = 0; i < GQ; i += 4) {
+                const float4 c4 = *(const float4*)(ncq + (sub2 + 2 * (r0 + r)) * GQ + i);
+                tq[r][i] = c4.x; tq[r][i + 1] = c4.y; tq[r][i + 2] = c4.z; tq[r][i + 3] = c4.w;
+              }
+            tmem_ld_wait();
+          }
+          if (r0 + RG >= GPW) {                                // last round: the tile's accumulators are in registers
+            if (tid == 0) LB_TRACE(5, t);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+          }
+          if (A.dbg_mode & 5) continue;
           // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
 #pragma unroll
-          for (int r = 0; r < GPW; ++r)
+          for (int r = 0; r < RG; ++r)
 #pragma unroll
             for (int pi = 0; pi < GQ / 2; ++pi) {
               f2_t acc = add2(pk2(v[r][2 * pi], v[r][2 * pi + 1]), pk2(tq[r][2 * pi], tq[r][2 * pi + 1]));
@@ -904,18 +913,18 @@ score_lb_kernel(ScoreArgs A) {
             }
           float m = tq[0][0];
 #pragma unroll
-          for (int r = 0; r < GPW; ++r)
+          for (int r = 0; r < RG; ++r)
 #pragma unroll
             for (int i = (r == 0 ? 1 : 0); i < GQ; i += 2) m = (i + 1 < GQ) ? max3(m, tq[r][i], tq[r][i + 1]) : fmaxf(m, tq[r][i]);
-          if (m > e2s && !(A.dbg_mode & 8)) {                  // rare (a fraction of a percent of the lanes): lane-level appends
+          if (m > e2s && !(A.dbg_mode & 8)) {                  // rare (about a lane per warp and tile): lane-level appends
             const tkey_t key = pack_key(0.0f, row);
 #pragma unroll
-            for (int r = 0; r < GPW; ++r) {
+            for (int r = 0; r < RG; ++r) {
               uint32_t nb = 0;
 #pragma unroll
               for (int i = 0; i < GQ; ++i) nb |= (tq[r][i] > e2s) ? (1u << i) : 0u;
               while (nb) {
-                const int ql = (sub + r * WPQ) * GQ + __ffs(nb) - 1;
+                const int ql = (sub2 + 2 * (r0 + r)) * GQ + __ffs(nb) - 1;
                 nb &= nb - 1;
                 const int slot = atomicAdd(&cnt[ql], 1);
                 if (slot < TOPK_STRIDE) {
@@ -929,8 +938,19 @@ score_lb_kernel(ScoreArgs A) {
           }
         }
         if (tid == 0) LB_TRACE(6, t);
-        continue;
       }
+    } else {
+    float2 er_next = (ntiles > 0) ? __ldg(A.lbrow + t0 * 128 + lrow) : make_float2(0.f, 0.f);   // one tile ahead
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t row = (uint32_t)((t0 + (int64_t)t * ts) * 128 + lrow);
+      const float2 er = er_next;
+      if (t + 1 < ntiles) er_next = __ldg(A.lbrow + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
+      // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
+      const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
+      mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
       bool released = false;
       for (int r0 = 0; r0 < my_groups && !(A.dbg_mode & 1); r0 += RG) {
         float v[RG][GC];
@@ -938,7 +958,6 @@ score_lb_kernel(ScoreArgs A) {
         for (int r = 0; r < RG; ++r)
           if (r0 + r < my_groups) tmem_ld_cols<GC>(taddr + (uint32_t)((sub + (r0 + r) * WPQ) * GC), v[r]);
         tmem_ld_wait();
-        if (tid == 0) LB_TRACE(5, t);
         if (r0 + RG >= my_groups) {                            // last round: the accumulators are in registers
           tc_fence_before();
           __syncwarp();
@@ -990,12 +1009,12 @@ score_lb_kernel(ScoreArgs A) {
           }
         }
       }
-      if (tid == 0) LB_TRACE(6, t);
       if (!released) {                                         // a warp without a group in this tile (short query tile)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
       }
+    }
     }
     epi_bar_sync();
     // counts may exceed TOPK_STRIDE: the excess went to the query's spill list
@@ -1018,9 +1037,11 @@ static int launch_lb_gpw(const ScoreArgs& a, cudaStream_t st) {
 }
 template <int K>
 static int launch_lb(const ScoreArgs& a, cudaStream_t st) {
-  const int groups = a.plan.qt / lb_gq(K);
-  if (a.plan.qt % lb_gq(K) == 0 && groups == (SU_NEPI / 4) * 2 && 2 * lb_gq(K) * K <= 48) return launch_lb_gpw<K, 2>(a, st);
-  if (a.plan.qt % lb_gq(K) == 0 && groups == (SU_NEPI / 4) * 1) return launch_lb_gpw<K, 1>(a, st);
+  constexpr int GQ = lb_gq(K);
+  constexpr int RG = (GQ * K <= 24) ? 2 : 1;
+  const int groups = a.plan.qt / GQ;
+  if (a.plan.qt % GQ == 0 && groups == 8 && 4 % RG == 0) return launch_lb_gpw<K, 4>(a, st);
+  if (a.plan.qt % GQ == 0 && groups == 4 && 2 % RG == 0) return launch_lb_gpw<K, 2>(a, st);
   return launch_lb_gpw<K, 0>(a, st);
 }
 
