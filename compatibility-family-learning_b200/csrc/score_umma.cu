@@ -771,17 +771,19 @@ score_lb_kernel(ScoreArgs A) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == SU_NEPI) {
-    // ================================ MMA issuer (one lane) =================================
-    if (elect_one()) {
+    // ============================ MMA issuer (whole warp, one elected lane issues) ============================
+    // The loop is warp-uniform so that descriptors and addresses stay in uniform registers: one thread running
+    // ~30 dependent instructions per MMA (address arithmetic, R2UR moves) cannot keep the tensor pipe's queue full.
+    // The barrier waits for the NEXT ring stage / accumulator buffer are issued one MMA early, while the previous
+    // MMAs still execute (mbarrier.try_wait costs ~130 clk even when the phase is complete).
+    {
       mbar_wait(bfull, 0);
-      const uint64_t a_desc = make_smem_desc(0, 128u * 16u, 128u);
-      const uint64_t b_desc = make_smem_desc(0, (uint32_t)NC * 16u, 128u);
+      const uint64_t a_desc = make_smem_desc(smem_u32(a_ring), 128u * 16u, 128u);
+      const uint64_t b_desc = make_smem_desc(smem_u32(b_img), (uint32_t)NC * 16u, 128u);
+      const uint32_t a_lo0 = (uint32_t)a_desc, a_hi = (uint32_t)(a_desc >> 32);
+      const uint32_t b_lo0 = (uint32_t)b_desc, b_hi = (uint32_t)(b_desc >> 32);
       const uint32_t idesc = make_idesc_f16(128, (uint32_t)NC);
-      const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_img);
-      const uint32_t b_step = 2u * (uint32_t)NC * 16u;
-      // tcgen05.mma issue blocks while the tensor pipe's queue is full, so a wait placed between two tiles is paid
-      // in full (mbarrier.try_wait costs ~130 clk even when the phase is complete).  The waits for the NEXT ring
-      // stage / accumulator buffer are therefore issued one MMA early, while the previous MMAs still execute.
+      const uint32_t b_step16 = 2u * (uint32_t)NC;             // (2 chunks * NC rows * 16 B) >> 4
       int stage = 0; uint32_t phase = 0;
       const int nsteps = nkm / kss;                            // ring stages per tile
       if (ntiles > 0) {
@@ -791,13 +793,13 @@ score_lb_kernel(ScoreArgs A) {
       }
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
-        LB_TRACE(0, t);
+        if (lane == 0) LB_TRACE(0, t);
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
+        uint32_t b_lo = b_lo0;
         for (int sidx = 0; sidx < nsteps; ++sidx) {
-          const int ks = sidx * kss;
+          uint32_t a_lo = a_lo0 + (uint32_t)stage * (STAGE_BYTES >> 4);
           for (int j = 0; j < kss; ++j) {
             if (j == kss - 1) {                                // look ahead: barriers of the next stage (and tile)
-              LB_TRACE(1, t);
               int nstage = stage + 1; uint32_t nphase = phase;
               if (nstage == SU_NSTAGE) { nstage = 0; nphase ^= 1u; }
               const bool last = sidx == nsteps - 1;
@@ -807,15 +809,15 @@ score_lb_kernel(ScoreArgs A) {
                 tc_fence_after();
               }
             }
-            const uint64_t ad = a_desc + (uint64_t)((a_base + stage * STAGE_BYTES + j * BLK) >> 4);
-            const uint64_t bd = b_desc + (uint64_t)((b_base + (ks + j) * b_step) >> 4);
-            mma_f16(d_tmem, ad, bd, idesc, (ks + j) ? 1u : 0u);
+            if (elect_one()) mma_f16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, (sidx | j) ? 1u : 0u);
+            a_lo += BLK >> 4;
+            b_lo += b_step16;
           }
-          mma_commit(&empty[stage]);
+          if (elect_one()) mma_commit(&empty[stage]);
           if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
         }
-        mma_commit(&tfull[buf]);
-        LB_TRACE(2, t);
+        if (elect_one()) mma_commit(&tfull[buf]);
+        if (lane == 0) LB_TRACE(2, t);
       }
     }
   } else if (warp == SU_NEPI + 1) {

@@ -71,7 +71,58 @@ rate_kernel(int N, int mode, int tiles, int nbuf, int tf32, unsigned long long* 
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// issue timeline of 12 back-to-back MMAs from an idle pipe: clock after every issue, then after completion
+__global__ void __launch_bounds__(128, 1)
+issue_kernel(int N, unsigned long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = slot;
+  if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t a_base = smem_u32(smem), b_base = a_base + 65536;
+      const uint32_t idesc = make_idesc_f16(128, (uint32_t)N);
+      unsigned long long ts[16];
+      ts[0] = clock64();
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const uint64_t ad = make_smem_desc(a_base + (i & 3) * 4096, 128u * 16u, 128u);
+        const uint64_t bd = make_smem_desc(b_base + (i & 3) * (2u * N * 16u), (uint32_t)N * 16u, 128u);
+        mma_f16(tb + (uint32_t)((i & 1) * N), ad, bd, idesc, 0u);
+        ts[i + 1] = clock64();
+      }
+      mma_commit(&bar);
+      ts[13] = clock64();
+      mbar_wait(&bar, 0);
+      ts[14] = clock64();
+      for (int i = 0; i < 15; ++i) out[i] = ts[i] - ts[0];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 int main() {
+  {
+    unsigned long long* o; CK(cudaMalloc(&o, 16 * 8));
+    CK(cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 32768 + 1024));
+    for (int rep = 0; rep < 2; ++rep) {
+      issue_kernel<<<1, 128, 65536 + 32768 + 1024>>>(192, o);
+      CK(cudaDeviceSynchronize());
+    }
+    unsigned long long h[16]; CK(cudaMemcpy(h, o, sizeof(h), cudaMemcpyDeviceToHost));
+    printf("issue timeline N=192 (clk after issue of MMA 1..12, after commit, after completion):");
+    for (int i = 1; i < 15; ++i) printf(" %llu", h[i]);
+    printf("\n");
+  }
+
   const int grid = 148, tiles = 2000;
   unsigned long long* cyc;
   CK(cudaMalloc(&cyc, grid * 8));
