@@ -767,13 +767,17 @@ static bool score_lb_pass(const ScoreKnobs& kn, int K) {
 
 static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePlan& p, bool own_image,
                               size_t* o_pc, size_t* o_qpar, size_t* o_qimg, size_t* o_keys, size_t* o_cnt,
-                              size_t* o_cimg) {
+                              size_t* o_cimg, size_t* o_lbimg = nullptr) {
   size_t off = 0;
+  const LbPlan lb = p.impl ? make_lb_plan(Q, K, d, p.tiles) : LbPlan{0, 0, 0, 0};
+  const int kparts = p.parts > lb.parts ? p.parts : lb.parts;          // key buffers serve both tilings
   *o_pc = off;   off = align_up(off + (size_t)Q * K * d * 4, 256);
   *o_qpar = off; off = align_up(off + (size_t)Q * (qpar_stride(K) + qplane_stride(K)) * 4, 256);
   *o_qimg = off; off = align_up(off + (p.impl ? score_umma_qimg_bytes(p, K) : 0), 1024);
-  *o_keys = off; off = align_up(off + (size_t)p.parts * Q * TOPK_STRIDE * sizeof(tkey_t), 256);
-  *o_cnt = off;  off = align_up(off + (size_t)p.parts * Q * sizeof(int), 1024);
+  if (o_lbimg) *o_lbimg = off;
+  off = align_up(off + (p.impl ? score_lb_qimg_bytes(lb, K, d) : 0), 1024);
+  *o_keys = off; off = align_up(off + (size_t)kparts * Q * TOPK_STRIDE * sizeof(tkey_t), 256);
+  *o_cnt = off;  off = align_up(off + (size_t)kparts * Q * sizeof(int), 1024);
   *o_cimg = off; off = align_up(off + ((p.impl && own_image) ? catalog_image_bytes(N, d) : 0), 1024);
   // tau[Q], tau_opt[Q], thr_redo[Q], redo flags per query tile: live right after (see `tau` below)
   off = align_up(off + (size_t)(3 * Q + p.nqt + 4) * sizeof(float), 256);
@@ -820,8 +824,9 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   bool umma_ok = N > 0 && score_umma_supported(K, d);
   CFL_REQUIRE(!image || umma_ok, CFL_ERR_UNSUPPORTED, "score_topk_packed: shape K=%d d=%d has no tcgen05 tiling", K, d);
   ScorePlan plan = make_score_plan(Q, K, d, N > 0 ? N : 1, k, umma_ok);
-  size_t o_pc, o_qpar, o_qimg, o_keys, o_cnt, o_cimg;
-  size_t need = score_ws_layout(Q, K, d, N, plan, image == nullptr, &o_pc, &o_qpar, &o_qimg, &o_keys, &o_cnt, &o_cimg);
+  size_t o_pc, o_qpar, o_qimg, o_keys, o_cnt, o_cimg, o_lbimg;
+  size_t need = score_ws_layout(Q, K, d, N, plan, image == nullptr, &o_pc, &o_qpar, &o_qimg, &o_keys, &o_cnt, &o_cimg,
+                                &o_lbimg);
   CFL_REQUIRE(ws && ws_bytes >= need, CFL_ERR_WORKSPACE, "score_topk: workspace too small (%zu < %zu)",
               ws_bytes, need);
   char* base = (char*)ws;
@@ -839,6 +844,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   const ScoreKnobs kn = read_knobs();
   a.dbg_mode = kn.dbg_mode;
   a.plan = plan;
+  a.lb = plan.impl ? make_lb_plan(Q, K, d, plan.tiles) : LbPlan{0, 0, 0, 0};
   if (N == 0) {
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
   } else {
@@ -856,8 +862,8 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       a.cimg16 = (const char*)image + catalog_f16_offset(N, d);
       a.cflag16 = (const int*)((const char*)a.cimg16 + catalog_f16_bytes(N, d));
       a.lbrow = (const float2*)((const char*)image + catalog_lbrow_offset(N, d));
-      a.qimg16 = base + o_qimg + score_umma_qimg16_offset(plan, K);
-      a.qflag16 = (const int*)((const char*)a.qimg16 + score_umma_qimg16_bytes(plan, K));
+      a.qimg16 = base + o_lbimg;
+      a.qflag16 = (const int*)((const char*)a.qimg16 + (size_t)a.lb.nqt * ((d + 15) / 16) * 2 * (size_t)(K * a.lb.qt) * 16);
       a.lbq = (const float*)((const char*)a.qflag16 + 16);
       st = score_umma_pack_queries(a, base + o_qimg, cs);
       if (st != CFL_OK) return st;
@@ -924,17 +930,18 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
           if (st != CFL_OK) return st;
         }
         if (lb_pass && !kn.no_probe) {
-          int probe_stride = (int)((tpp + 3) / 4);           // about 4 tiles per part
+          const int64_t tpp_lb = plan.tiles / a.lb.parts;    // the lower-bound pass has its own catalog parts
+          int probe_stride = (int)((tpp_lb + 3) / 4);        // about 4 tiles per part
           if (probe_stride < 1) probe_stride = 1;
-          const int64_t probe_tiles = (tpp + probe_stride - 1) / probe_stride;
+          const int64_t probe_tiles = (tpp_lb + probe_stride - 1) / probe_stride;
           a.phase = 3; a.tile_stride = probe_stride;
           CFL_CUDA(cudaMemsetAsync(a.spill_cnt, 0, (size_t)Q * sizeof(int), cs));
           st = score_lb_launch(a, cs);
           if (st != CFL_OK) return st;
           // only the pathological regimes (most rows survive) are taken out: 4x the total key capacity
-          const float limit = 4.0f * ((float)plan.parts * (float)TOPK_STRIDE + (float)LB_SPILL);
+          const float limit = 4.0f * ((float)a.lb.parts * (float)TOPK_STRIDE + (float)LB_SPILL);
           probe_classify_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, cs>>>(
-              a.counts, plan.parts, Q, (float)tpp / (float)probe_tiles, limit, tau_opt, nullptr, a.spill_cnt);
+              a.counts, a.lb.parts, Q, (float)tpp_lb / (float)probe_tiles, limit, tau_opt, nullptr, a.spill_cnt);
           CFL_LAUNCH_CHECK();
           a.phase = 2; a.tile_stride = 1;
           timer_record(0, cs);
@@ -949,13 +956,13 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         if (lb_pass) {
           // exact rescoring of every survivor + verification; flagged queries are redone below
           const int dp = (d + RSC_CH - 1) / RSC_CH * RSC_CH;
-          const size_t rs_smem = ((size_t)K * dp + (size_t)(MRG_THREADS / 32) * 32 * RSC_LD + plan.parts + 2 + 4) * sizeof(float);
+          const size_t rs_smem = ((size_t)K * dp + (size_t)(MRG_THREADS / 32) * 32 * RSC_LD + a.lb.parts + 2 + 4) * sizeof(float);
 #define CFL_RSC_CASE(KK)                                                                                        \
   case KK:                                                                                                      \
     CFL_CUDA(cudaFuncSetAttribute(rescore_merge_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                   (int)rs_smem));                                                               \
     rescore_merge_kernel<KK><<<(unsigned)Q, MRG_THREADS, rs_smem, cs>>>(                                        \
-        a.keys, a.counts, plan.parts, Q, plan.kk, k, Pq, ldq, d, E, lde, idx_base, top_val, top_idx, tau,       \
+        a.keys, a.counts, a.lb.parts, Q, plan.kk, k, Pq, ldq, d, E, lde, idx_base, top_val, top_idx, tau,       \
         tau_opt, plan.qt, thr_redo, redo_tile, stats, a.spill, a.spill_cnt);                                    \
     break;
           switch (K) {

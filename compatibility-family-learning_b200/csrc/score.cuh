@@ -18,6 +18,11 @@ struct ScorePlan {
   int dpad;        // d rounded up to 8 (MMA K granularity for tf32)
 };
 
+// Tiling of the lower-bound pass (score_lb.cu): its own query tile, catalog parts and TMEM buffering.
+struct LbPlan {
+  int qt, nqt, parts, nbuf;
+};
+
 struct ScoreArgs {
   int mode, K, d;
   int64_t Q, N, lde;
@@ -57,6 +62,7 @@ struct ScoreArgs {
                          // not wait for the epilogue (honoured only under CFL_EXPERIMENTS=1)
   unsigned long long* dbg; // optional counters {groups seen, skipped, selective, full} (CFL_SCORE_DEBUG)
   ScorePlan plan;
+  LbPlan lb;
 };
 
 // Per-query parameter block (floats), padded to a multiple of 4 so it loads as float4:
@@ -89,8 +95,8 @@ size_t catalog_image_bytes(int64_t N, int d);
 size_t catalog_f16_offset(int64_t N, int d);     // byte offset of the fp16 plane inside the catalog image
 size_t catalog_f16_bytes(int64_t N, int d);      // plane only; the flag word follows it
 size_t catalog_lbrow_offset(int64_t N, int d);   // byte offset of lbrow[tiles*128] (float2) inside the catalog image
-size_t score_umma_qimg16_offset(const ScorePlan& p, int K);
-size_t score_umma_qimg16_bytes(const ScorePlan& p, int K);
+LbPlan make_lb_plan(int64_t Q, int K, int d, int64_t tiles);
+size_t score_lb_qimg_bytes(const LbPlan& p, int K, int d);   // lower-bound image + flag word + lbq
 int catalog_pack_launch(const float* E, int64_t N, int d, int64_t lde, const float* mu, void* image,
                         cudaStream_t st);
 size_t score_umma_qimg_bytes(const ScorePlan& p, int K);

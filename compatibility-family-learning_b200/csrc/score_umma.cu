@@ -58,17 +58,8 @@ bool score_umma_supported(int K, int d) {
   return score_umma_qt(K, d) != 0;
 }
 
-// tf32 hi/lo query image, then the fp16 lower-bound image [qtile][kstep16][chunk][n][8 halfs] (prep_lb_kernel), its
-// flag word and lbq
-size_t score_umma_qimg16_offset(const ScorePlan& p, int K) {
+size_t score_umma_qimg_bytes(const ScorePlan& p, int K) {      // tf32 hi/lo query image
   return (size_t)p.nqt * p.dpad * 8 * (size_t)(K * p.qt);
-}
-size_t score_umma_qimg16_bytes(const ScorePlan& p, int K) {
-  const int nks16 = (p.dpad + 15) / 16;
-  return (size_t)p.nqt * nks16 * 2 * (size_t)(K * p.qt) * 16;
-}
-size_t score_umma_qimg_bytes(const ScorePlan& p, int K) {      // ... + flag word + lbq[2 per query slot]
-  return score_umma_qimg16_offset(p, K) + score_umma_qimg16_bytes(p, K) + 16 + (size_t)p.nqt * p.qt * 2 * sizeof(float);
 }
 
 // ---- catalog image ----------------------------------------------------------------------------
@@ -532,540 +523,6 @@ score_umma_kernel(ScoreArgs A) {
   tc_fence_before();
   __syncthreads();
   if (warp == SU_NEPI) tmem_dealloc(tmem_base, ncols);
-}
-
-// =====================================================================================================
-// Lower-bound filter pass (phase 3): the dominant launch of a long-catalog call.
-//
-// dist(e, q) = |e - sum_k s_k p_k|^2 with s in the simplex, hence dist >= the squared distance from e to the AFFINE
-// HULL of the query's prototypes.  With a = the point of that hull closest to the origin (the catalog mean: both
-// sides are centred) and u_1..u_{K-1} an orthonormal basis of span{p_j - p_0}, a is orthogonal to every u_j and
-//     hull distance^2 = |e|^2 - 2 e.a + |a|^2 - sum_j (e.u_j)^2 .
-// The tensor cores produce, per (row, query), the K inner products e.(2a), e.u_1 .. e.u_{K-1} -- ONE fp16 MMA per
-// 16 dimensions (kind::f16, fp32 accumulators in TMEM; fp16 carries tf32's 11-bit significand) -- and the epilogue
-// decides "bound <= threshold" as
-//     e.(2a) - cq(query) + sum_j (e.u_j)^2  >  e2s(row)
-// i.e. K-1 packed FP32x2 FMAs and one packed add per query PAIR, then a 3-input max tree and ONE compare per group; nothing else is evaluated, nothing
-// is voted on, and a passing (row, query) is appended by its own lane.  The soft-min never runs here: every
-// survivor is rescored exactly by rescore_merge_kernel (score.cu), which also verifies the optimistic threshold.
-//
-// Rigour.  e2s = |e|^2 lowered by a bound on everything the single-product evaluation can lose:
-//   * operands rounded to fp16: |d(e.x)| <= u |e||x| + 2^-25 (|e|_1 + |x|_1) (subnormals), u = 1.1 * 2^-10 -- the 0.1
-//     covers the fp32 accumulation inside the tensor core, measured at <= 1.6 * 2^-24 |e||x| (tools/tmem_probe.cu,
-//     profiles/r2_01_tmem_probe.md);
-//   * sum_j C_j^2 >= sum_j c_j^2 - 2 sqrt(K-1) |e| eta,  eta = the bound above with |x| = 1, because sum c_j^2 <= |e|^2;
-//   * the fp32 evaluation of both sides (CFL_PLANE_REL |e|^2 and 4K ulp terms).
-// cq = |a|^2 - threshold is rounded down.  A value outside the fp16 range (flag words raised by the pack kernels)
-// sends the CTA's queries to the exact redo pass (counts = -1).
-constexpr float CFL_TF32_PRODUCT_U = 1.1f / 1024.0f;
-#ifdef CFL_LB_TRACE
-// timing trace of CTA (0,0) (tools/lb_trace.py; builds with CFL_NVCC_EXTRA=-DCFL_LB_TRACE only): per tile
-// [0] MMA warp before the tempty wait, [1] after it, [2] after issuing the tile's MMAs, [3] epilogue warp 0 before the
-// tfull wait, [4] after it, [5] accumulators in registers, [6] bound evaluated / appends done
-__device__ unsigned long long g_lb_trace[8 * 4096];
-#define LB_TRACE(slot, tile) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (tile) < 4096) g_lb_trace[(tile) * 8 + (slot)] = clock64(); } while (0)
-#else
-#define LB_TRACE(slot, tile) do { } while (0)
-#endif
-__host__ __device__ constexpr int lb_gq(int K) { return K <= 2 ? 16 : (K <= 4 ? 8 : 4); }
-
-// fp16 lower-bound image: [qtile][kstep16][chunk][row n][8 halfs] with n = g*(GQ*K) + k*GQ + i for the query
-// ql = g*GQ + i of the tile: the K columns of a query GROUP are contiguous in TMEM (one run of tcgen05.ld), and the
-// two queries of a pair sit in adjacent columns = adjacent registers = one FP32x2 operand.  Row k = 0 holds 2a,
-// rows k >= 1 the basis vectors.  One warp per query slot, fp64 (modified Gram-Schmidt, every vector
-// re-orthogonalised: "twice is enough").
-__global__ void __launch_bounds__(128)
-prep_lb_kernel(const float* __restrict__ Pc, int64_t Q, int K, int d, int qt, int nqt, int dpad,
-               unsigned char* __restrict__ img16, int* __restrict__ flag16, float* __restrict__ lbq) {
-  __shared__ double su[4][CFL_MAX_K - 1][128];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t slot = (int64_t)blockIdx.x * 4 + w;
-  if (slot >= (int64_t)nqt * qt) return;
-  const int GQ = lb_gq(K), NC = K * qt, nks16 = (dpad + 15) / 16;
-  const int qtile = (int)(slot / qt), ql = (int)(slot % qt);
-  const int g = ql / GQ, gi = ql % GQ;
-  unsigned char* base = img16 + (size_t)qtile * nks16 * 2 * NC * 16;
-  auto store = [&](int k, int j, double x) {
-    const int n = g * (GQ * K) + k * GQ + gi;
-    *(__half*)(base + ((size_t)((j >> 4) * 2 + ((j >> 3) & 1)) * NC + n) * 16 + (j & 7) * 2) = __float2half_rn((float)x);
-  };
-  if (slot >= Q) {                                             // padding queries of the last tile: zero rows
-    for (int k = 0; k < K; ++k)
-      for (int j = lane; j < nks16 * 16; j += 32) store(k, j, 0.0);
-    return;
-  }
-  const float* pq = Pc + slot * (int64_t)K * d;
-  double p0[4], a[4];
-#pragma unroll
-  for (int m = 0; m < 4; ++m) { const int j = lane + 32 * m; p0[m] = (j < d) ? (double)pq[j] : 0.0; a[m] = p0[m]; }
-  for (int k = 1; k < K; ++k) {
-    double v[4];
-    double n0 = 0.0;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) { const int j = lane + 32 * m; v[m] = (j < d) ? (double)pq[k * d + j] - p0[m] : 0.0; n0 += v[m] * v[m]; }
-    n0 = warp_sum(n0);
-    double nrm = 0.0;
-    for (int pass = 0; pass < 3; ++pass) {                     // pass 2 re-orthogonalises the NORMALISED vector
-      for (int i = 1; i < k; ++i) {
-        double c = 0.0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) c += v[m] * su[w][i - 1][lane + 32 * m];
-        c = warp_sum(c);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) v[m] -= c * su[w][i - 1][lane + 32 * m];
-      }
-      if (pass >= 1) {
-        nrm = 0.0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) nrm += v[m] * v[m];
-        nrm = warp_sum(nrm);
-        const double inv = (nrm > 1e-280) ? rsqrt(nrm) : 0.0;  // p_k - p_0 exactly inside the previous span: no new direction
-#pragma unroll
-        for (int m = 0; m < 4; ++m) v[m] *= inv;
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m) su[w][k - 1][lane + 32 * m] = v[m];
-    __syncwarp();
-    (void)n0;
-  }
-  for (int pass = 0; pass < 2; ++pass)
-    for (int i = 1; i < K; ++i) {
-      double c = 0.0;
-#pragma unroll
-      for (int m = 0; m < 4; ++m) c += a[m] * su[w][i - 1][lane + 32 * m];
-      c = warp_sum(c);
-#pragma unroll
-      for (int m = 0; m < 4; ++m) a[m] -= c * su[w][i - 1][lane + 32 * m];
-    }
-  double a2 = 0.0, vmax = 0.0;
-#pragma unroll
-  for (int m = 0; m < 4; ++m) { a2 += a[m] * a[m]; vmax = fmax(vmax, fabs(2.0 * a[m])); }
-  a2 = warp_sum(a2);
-  for (int m = 0; m < 4; ++m) {
-    const int j = lane + 32 * m;
-    if (j >= nks16 * 16) continue;
-    store(0, j, j < d ? 2.0 * a[m] : 0.0);
-    for (int k = 1; k < K; ++k) store(k, j, j < d ? su[w][k - 1][j] : 0.0);
-  }
-  if (!(vmax < 60000.0)) atomicOr(flag16, 1);                  // also catches NaN / inf
-  if (lane == 0) {
-    lbq[2 * slot] = __double2float_rd(a2);
-    lbq[2 * slot + 1] = __double2float_ru(sqrt(a2));
-  }
-}
-
-int score_lb_prep_queries(const ScoreArgs& a, cudaStream_t st) {
-  unsigned char* img16 = (unsigned char*)const_cast<void*>(a.qimg16);
-  int* flag16 = const_cast<int*>(a.qflag16);
-  CFL_CUDA(cudaMemsetAsync(flag16, 0, 16, st));
-  const int64_t slots = (int64_t)a.plan.nqt * a.plan.qt;
-  prep_lb_kernel<<<(unsigned)((slots + 3) / 4), 128, 0, st>>>(a.Pc, a.Q, a.K, a.d, a.plan.qt, a.plan.nqt, a.plan.dpad,
-                                                             img16, flag16, const_cast<float*>(a.lbq));
-  CFL_LAUNCH_CHECK();
-  return CFL_OK;
-}
-
-// NCOLS consecutive TMEM columns of this warp's 32 lanes -> registers, as a run of x16 / x8 / x4 loads
-template <int NCOLS, int OFF = 0>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NCOLS]) {
-  if constexpr (NCOLS - OFF >= 16) {
-    tmem_ld16(taddr + OFF, *reinterpret_cast<float(*)[16]>(&v[OFF]));
-    tmem_ld_cols<NCOLS, OFF + 16>(taddr, v);
-  } else if constexpr (NCOLS - OFF >= 8) {
-    tmem_ld8(taddr + OFF, *reinterpret_cast<float(*)[8]>(&v[OFF]));
-    tmem_ld_cols<NCOLS, OFF + 8>(taddr, v);
-  } else if constexpr (NCOLS - OFF >= 4) {
-    tmem_ld4(taddr + OFF, *reinterpret_cast<float(*)[4]>(&v[OFF]));
-    tmem_ld_cols<NCOLS, OFF + 4>(taddr, v);
-  }
-}
-
-// GPW > 0 ("team mode", QT / GQ == 2 GPW): the epilogue warps form two teams of 8 (two per TMEM lane quarter); team b
-// serves the tiles t = b (mod 2), i.e. always accumulator buffer b.  A warp owns GPW query groups of its quarter, reads
-// them in rounds of RG groups (<= 48 accumulator registers), releases the buffer as soon as the last round's
-// tcgen05.ld has completed and has two tile times for its chain (barrier wake-up, TMEM latency, bound, appends), so the
-// jitter of the rare appends no longer stalls the MMA.  GPW = 0: any tile shape, every warp serves every tile.
-template <int K, int GPW>
-__global__ void __launch_bounds__(SU_THREADS, 1)
-score_lb_kernel(ScoreArgs A) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int GQ = lb_gq(K);
-  constexpr int GC = GQ * K;                                   // TMEM columns of one query group
-  const int QT = A.plan.qt;
-  const int NC = K * QT;
-  const int dpad = A.plan.dpad;
-  const SuLayout L = su_layout(K, QT, dpad);
-  unsigned char* b_img = smem + L.b_img;
-  unsigned char* a_ring = smem + L.a_ring;
-  float* red = (float*)(smem + L.scratch);
-  float* ncq = (float*)(smem + L.thr);                         // -cq per query of the tile
-  int* cnt = (int*)(smem + L.cnt);
-  uint64_t* full = (uint64_t*)(smem + L.bars);
-  uint64_t* empty = full + SU_NSTAGE;
-  uint64_t* tfull = empty + SU_NSTAGE;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* bfull = tempty + 2;
-  uint32_t* tmem_slot = (uint32_t*)(smem + L.tmem_slot);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int part = blockIdx.x, qtile = blockIdx.y;
-  const int64_t q0 = (int64_t)qtile * QT;
-  const int nq = (int)((A.Q - q0 < QT) ? (A.Q - q0) : QT);
-  const int64_t t0 = A.plan.tiles * part / A.plan.parts;
-  const int64_t t1 = A.plan.tiles * (part + 1) / A.plan.parts;
-  const int ts = A.tile_stride;
-  const int ntiles = (int)((t1 - t0 + ts - 1) / ts);
-  const int nkm = (dpad + 15) / 16;                            // MMA K-steps (16 halfs) per tile
-  const int kss = (nkm % 4 == 0) ? 4 : ((nkm % 2 == 0) ? 2 : 1);   // K-steps (4 KB blocks) per ring stage
-  if (*A.cflag16 != 0 || *A.qflag16 != 0) {                    // a value outside the fp16 range: exact redo pass
-    for (int ql = tid; ql < nq; ql += SU_THREADS) A.counts[(int64_t)part * A.Q + q0 + ql] = -1;
-    return;
-  }
-  if (A.thr_init != nullptr) {                                 // no live query in this tile: nothing to do
-    bool live = false;
-    for (int i = tid; i < nq; i += SU_THREADS) live |= A.thr_init[q0 + i] > __int_as_float(0xff800000);
-    if (!__syncthreads_or(live)) {
-      for (int ql = tid; ql < nq; ql += SU_THREADS) A.counts[(int64_t)part * A.Q + q0 + ql] = 0;
-      return;
-    }
-  }
-  constexpr uint32_t BLK = SU_ASTAGE / 2;                      // one K-step of the fp16 plane: [chunk][128 rows][16 B]
-  constexpr uint32_t STAGE_BYTES = 2 * SU_ASTAGE;
-
-  uint32_t ncols = 32;
-  while ((int)ncols < 2 * NC) ncols <<= 1;
-  if (warp == SU_NEPI) {
-    if (lane == 0) {
-      for (int s = 0; s < SU_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-      mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-      mbar_init(&tempty[0], GPW > 0 ? SU_NEPI / 2 : SU_NEPI);           // one arrival per epilogue WARP (of the team)
-      mbar_init(&tempty[1], GPW > 0 ? SU_NEPI / 2 : SU_NEPI);
-      mbar_init(bfull, 1);
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_slot, ncols);
-  }
-  // largest |a| of the tile: one margin factor for the whole CTA
-  float am = 0.0f;
-  for (int i = tid; i < nq; i += SU_THREADS) am = fmaxf(am, A.lbq[2 * (q0 + i) + 1]);
-  am = warp_max(am);
-  if (lane == 0) red[warp] = am;
-  // cq = |a|^2 - threshold, rounded down (stored negated); padding / dead queries get +inf (never pass), no threshold
-  // -inf (always pass)
-  for (int i = tid; i < QT; i += SU_THREADS) {
-    float c = __int_as_float(0x7f800000);
-    if (i < nq) {
-      const float tau = A.thr_init ? A.thr_init[q0 + i] : __int_as_float(0x7f800000);
-      const float a2 = A.lbq[2 * (q0 + i)];
-      if (tau > 3.0e38f) c = __int_as_float(0xff800000);
-      else if (tau > -3.0e38f) c = __fsub_rd(a2, nextafterf(tau, 3.4e38f)) - 5.0e-7f * (a2 + fabsf(tau));
-    }
-    ncq[i] = -c;
-    cnt[i] = 0;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == SU_NEPI) {
-    // ============================ MMA issuer (whole warp, one elected lane issues) ============================
-    // The loop is warp-uniform so that descriptors and addresses stay in uniform registers: one thread running
-    // ~30 dependent instructions per MMA (address arithmetic, R2UR moves) cannot keep the tensor pipe's queue full.
-    // The barrier waits for the NEXT ring stage / accumulator buffer are issued one MMA early, while the previous
-    // MMAs still execute (mbarrier.try_wait costs ~130 clk even when the phase is complete).
-    {
-      mbar_wait(bfull, 0);
-      const uint64_t a_desc = make_smem_desc(smem_u32(a_ring), 128u * 16u, 128u);
-      const uint64_t b_desc = make_smem_desc(smem_u32(b_img), (uint32_t)NC * 16u, 128u);
-      const uint32_t a_lo0 = (uint32_t)a_desc, a_hi = (uint32_t)(a_desc >> 32);
-      const uint32_t b_lo0 = (uint32_t)b_desc, b_hi = (uint32_t)(b_desc >> 32);
-      const uint32_t idesc = make_idesc_f16(128, (uint32_t)NC);
-      const uint32_t b_step16 = 2u * (uint32_t)NC;             // (2 chunks * NC rows * 16 B) >> 4
-      int stage = 0; uint32_t phase = 0;
-      const int nsteps = nkm / kss;                            // ring stages per tile
-      if (ntiles > 0) {
-        mbar_wait(&tempty[0], 1u);
-        if (!(A.dbg_mode & 2)) mbar_wait(&full[0], 0u);
-        tc_fence_after();
-      }
-      for (int t = 0; t < ntiles; ++t) {
-        const int buf = t & 1;
-        if (lane == 0) LB_TRACE(0, t);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
-        uint32_t b_lo = b_lo0;
-        for (int sidx = 0; sidx < nsteps; ++sidx) {
-          uint32_t a_lo = a_lo0 + (uint32_t)stage * (STAGE_BYTES >> 4);
-          for (int j = 0; j < kss; ++j) {
-            if (j == kss - 1) {                                // look ahead: barriers of the next stage (and tile)
-              int nstage = stage + 1; uint32_t nphase = phase;
-              if (nstage == SU_NSTAGE) { nstage = 0; nphase ^= 1u; }
-              const bool last = sidx == nsteps - 1;
-              if (!last || t + 1 < ntiles) {
-                if (last && !(A.dbg_mode & 16)) mbar_wait(&tempty[buf ^ 1], ((uint32_t)((t + 1) >> 1) & 1u) ^ 1u);
-                if (!(A.dbg_mode & 2)) mbar_wait(&full[nstage], nphase);
-                tc_fence_after();
-              }
-            }
-            if (elect_one()) mma_f16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, (sidx | j) ? 1u : 0u);
-            a_lo += BLK >> 4;
-            b_lo += b_step16;
-          }
-          if (elect_one()) mma_commit(&empty[stage]);
-          if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
-        }
-        if (elect_one()) mma_commit(&tfull[buf]);
-        if (lane == 0) LB_TRACE(2, t);
-      }
-    }
-  } else if (warp == SU_NEPI + 1) {
-    // ================================ TMA producer (one lane) ===============================
-    if (elect_one()) {
-      const uint32_t bbytes = (uint32_t)nkm * 2u * (uint32_t)NC * 16u;
-      const unsigned char* qsrc = (const unsigned char*)A.qimg16 + (size_t)qtile * bbytes;
-      mbar_arrive_expect_tx(bfull, bbytes);
-      for (uint32_t o = 0; o < bbytes; o += 32768u) {
-        const uint32_t n = bbytes - o < 32768u ? bbytes - o : 32768u;
-        bulk_g2s(b_img + o, qsrc + o, n, bfull);
-      }
-      int stage = 0; uint32_t phase = 0;
-      for (int t = 0; t < ((A.dbg_mode & 2) ? 0 : ntiles); ++t) {
-        const unsigned char* src = (const unsigned char*)A.cimg16 + (size_t)(t0 + (int64_t)t * ts) * nkm * BLK;
-        for (int ks = 0; ks < nkm; ks += kss) {
-          mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)kss * BLK);
-          bulk_g2s(a_ring + stage * STAGE_BYTES, src + (size_t)ks * BLK, (uint32_t)kss * BLK, &full[stage]);
-          if (++stage == SU_NSTAGE) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else {
-    // ======================================= epilogue ========================================
-    // Per tile a warp owns the query groups g = sub, sub + WPQ, ... of its TMEM lane quarter.  It reads RG groups
-    // per round into registers; as soon as the LAST round's tcgen05.ld has completed it releases the accumulator
-    // buffer (the MMA of tile t+2 never waits for CUDA-core work), evaluates the bound from registers and only
-    // then appends the rare survivors.
-    constexpr int WPQ = SU_NEPI / 4;                           // warps per TMEM lane quarter
-    constexpr int RG = (GC <= 24) ? 2 : 1;                     // groups held in registers at once (<= 48 accumulators)
-    const int lq = warp & 3, sub = warp >> 2;
-    const int lrow = lq * 32 + lane;
-    const int ngroups = (nq + GQ - 1) / GQ;
-    const int my_groups = ngroups > sub ? (ngroups - sub + WPQ - 1) / WPQ : 0;
-    tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
-    float amax = 0.0f;
-    for (int i = 0; i < SU_THREADS / 32; ++i) amax = fmaxf(amax, red[i]);
-    const float s16 = 5.97e-8f * sqrtf((float)(nkm * 16));    // 2^-24 sqrt(d): twice the subnormal term
-    const float rk = sqrtf((float)(K - 1));
-    const float ulp = (float)(4 * K) * 5.97e-8f;
-    const float c_e2 = 1.0f - CFL_PLANE_REL - (2.0f * rk * (CFL_TF32_PRODUCT_U + s16) + ulp) * 1.0001f;
-    const float c_sq = ((2.0f * CFL_TF32_PRODUCT_U + 2.0f * ulp) * amax + 2.0f * s16 * (1.0f + rk)) * 1.0001f;
-    const float c_abs = 2.0f * s16 * amax * 1.0001f;
-    if constexpr (GPW > 0) {
-      // ---------------------------------- team mode ----------------------------------
-      const int team = sub >> 1, sub2 = sub & 1;
-      const int buf = team;
-      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
-      float2 er_nx = (team < ntiles) ? __ldg(A.lbrow + (t0 + (int64_t)team * ts) * 128 + lrow) : make_float2(0.f, 0.f);
-      for (int t = team; t < ntiles; t += 2) {
-        const uint32_t row = (uint32_t)((t0 + (int64_t)t * ts) * 128 + lrow);
-        const float2 er = er_nx;
-        if (t + 2 < ntiles) er_nx = __ldg(A.lbrow + (t0 + (int64_t)(t + 2) * ts) * 128 + lrow);
-        // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
-        const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
-        if (tid == 0) LB_TRACE(3, t);
-        mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
-        tc_fence_after();
-        if (tid == 0) LB_TRACE(4, t);
-#pragma unroll
-        for (int r0 = 0; r0 < GPW; r0 += RG) {
-          float v[RG][GC], tq[RG][GQ];
-          if (!(A.dbg_mode & 1)) {
-#pragma unroll
-            for (int r = 0; r < RG; ++r) tmem_ld_cols<GC>(taddr + (uint32_t)((sub2 + 2 * (r0 + r)) * GC), v[r]);
-#pragma unroll
-            for (int r = 0; r < RG; ++r)
-#pragma unroll
-              for (int i = 0; i < GQ; i += 4) {
-                const float4 c4 = *(const float4*)(ncq + (sub2 + 2 * (r0 + r)) * GQ + i);
-                tq[r][i] = c4.x; tq[r][i + 1] = c4.y; tq[r][i + 2] = c4.z; tq[r][i + 3] = c4.w;
-              }
-            tmem_ld_wait();
-          }
-          if (r0 + RG >= GPW) {                                // last round: the tile's accumulators are in registers
-            if (tid == 0) LB_TRACE(5, t);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
-          }
-          if (A.dbg_mode & 5) continue;
-          // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
-#pragma unroll
-          for (int r = 0; r < RG; ++r)
-#pragma unroll
-            for (int pi = 0; pi < GQ / 2; ++pi) {
-              f2_t acc = add2(pk2(v[r][2 * pi], v[r][2 * pi + 1]), pk2(tq[r][2 * pi], tq[r][2 * pi + 1]));
-#pragma unroll
-              for (int k = 1; k < K; ++k) {
-                const f2_t c = pk2(v[r][k * GQ + 2 * pi], v[r][k * GQ + 2 * pi + 1]);
-                acc = fma2(c, c, acc);
-              }
-              upk2(acc, tq[r][2 * pi], tq[r][2 * pi + 1]);
-            }
-          float m = tq[0][0];
-#pragma unroll
-          for (int r = 0; r < RG; ++r)
-#pragma unroll
-            for (int i = (r == 0 ? 1 : 0); i < GQ; i += 2) m = (i + 1 < GQ) ? max3(m, tq[r][i], tq[r][i + 1]) : fmaxf(m, tq[r][i]);
-          if (m > e2s && !(A.dbg_mode & 8)) {                  // rare (about a lane per warp and tile): lane-level appends
-            const tkey_t key = pack_key(0.0f, row);
-#pragma unroll
-            for (int r = 0; r < RG; ++r) {
-              uint32_t nb = 0;
-#pragma unroll
-              for (int i = 0; i < GQ; ++i) nb |= (tq[r][i] > e2s) ? (1u << i) : 0u;
-              while (nb) {
-                const int ql = (sub2 + 2 * (r0 + r)) * GQ + __ffs(nb) - 1;
-                nb &= nb - 1;
-                const int slot = atomicAdd(&cnt[ql], 1);
-                if (slot < TOPK_STRIDE) {
-                  kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
-                } else {                                       // this part's buffer is full: spill list of the query
-                  const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
-                  if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
-                }
-              }
-            }
-          }
-        }
-        if (tid == 0) LB_TRACE(6, t);
-      }
-    } else {
-    float2 er_next = (ntiles > 0) ? __ldg(A.lbrow + t0 * 128 + lrow) : make_float2(0.f, 0.f);   // one tile ahead
-    for (int t = 0; t < ntiles; ++t) {
-      const int buf = t & 1;
-      const uint32_t row = (uint32_t)((t0 + (int64_t)t * ts) * 128 + lrow);
-      const float2 er = er_next;
-      if (t + 1 < ntiles) er_next = __ldg(A.lbrow + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
-      // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
-      const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
-      mbar_wait(&tfull[buf], (uint32_t)(t >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
-      bool released = false;
-      for (int r0 = 0; r0 < my_groups && !(A.dbg_mode & 1); r0 += RG) {
-        float v[RG][GC];
-#pragma unroll
-        for (int r = 0; r < RG; ++r)
-          if (r0 + r < my_groups) tmem_ld_cols<GC>(taddr + (uint32_t)((sub + (r0 + r) * WPQ) * GC), v[r]);
-        tmem_ld_wait();
-        if (r0 + RG >= my_groups) {                            // last round: the accumulators are in registers
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[buf]);
-          released = true;
-        }
-        if (A.dbg_mode & 4) continue;                          // experiment: the epilogue only reads TMEM
-#pragma unroll
-        for (int r = 0; r < RG; ++r) {
-          if (r0 + r >= my_groups) continue;
-          const int g = sub + (r0 + r) * WPQ;
-          float t[GQ];
-#pragma unroll
-          for (int i = 0; i < GQ; i += 4) {
-            const float4 c4 = *(const float4*)(ncq + g * GQ + i);
-            t[i] = c4.x; t[i + 1] = c4.y; t[i + 2] = c4.z; t[i + 3] = c4.w;
-          }
-          // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
-#pragma unroll
-          for (int pi = 0; pi < GQ / 2; ++pi) {
-            f2_t acc = add2(pk2(v[r][2 * pi], v[r][2 * pi + 1]), pk2(t[2 * pi], t[2 * pi + 1]));
-#pragma unroll
-            for (int k = 1; k < K; ++k) {
-              const f2_t c = pk2(v[r][k * GQ + 2 * pi], v[r][k * GQ + 2 * pi + 1]);
-              acc = fma2(c, c, acc);
-            }
-            upk2(acc, t[2 * pi], t[2 * pi + 1]);
-          }
-          float m = max3(t[0], t[1], t[2]);
-#pragma unroll
-          for (int i = 3; i + 1 < GQ; i += 2) m = max3(m, t[i], t[i + 1]);
-          if constexpr (GQ % 2 == 0) m = fmaxf(m, t[GQ - 1]);
-          if (m > e2s && !(A.dbg_mode & 8)) {                  // rare (a fraction of a percent of the lanes): lane-level appends
-            uint32_t nb = 0;
-#pragma unroll
-            for (int i = 0; i < GQ; ++i) nb |= (t[i] > e2s) ? (1u << i) : 0u;
-            const tkey_t key = pack_key(0.0f, row);
-            while (nb) {
-              const int ql = g * GQ + __ffs(nb) - 1;
-              nb &= nb - 1;
-              const int slot = atomicAdd(&cnt[ql], 1);
-              if (slot < TOPK_STRIDE) {
-                kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
-              } else {                                         // this part's buffer is full: spill list of the query
-                const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
-                if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
-              }
-            }
-          }
-        }
-      }
-      if (!released) {                                         // a warp without a group in this tile (short query tile)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
-      }
-    }
-    }
-    epi_bar_sync();
-    // counts may exceed TOPK_STRIDE: the excess went to the query's spill list
-    for (int ql = tid; ql < nq; ql += SU_EPI_THREADS) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == SU_NEPI) tmem_dealloc(tmem_base, ncols);
-}
-
-template <int K, int GPW>
-static int launch_lb_gpw(const ScoreArgs& a, cudaStream_t st) {
-  SuLayout L = su_layout(K, a.plan.qt, a.plan.dpad);
-  size_t smem = L.total + 1024;
-  CFL_CUDA(cudaFuncSetAttribute(score_lb_kernel<K, GPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(a.plan.parts, a.plan.nqt);
-  score_lb_kernel<K, GPW><<<grid, SU_THREADS, smem, st>>>(a);
-  CFL_LAUNCH_CHECK();
-  return CFL_OK;
-}
-template <int K>
-static int launch_lb(const ScoreArgs& a, cudaStream_t st) {
-  constexpr int GQ = lb_gq(K);
-  constexpr int RG = (GQ * K <= 24) ? 2 : 1;
-  const int groups = a.plan.qt / GQ;
-  if (a.plan.qt % GQ == 0 && groups == 8 && 4 % RG == 0) return launch_lb_gpw<K, 4>(a, st);
-  if (a.plan.qt % GQ == 0 && groups == 4 && 2 % RG == 0) return launch_lb_gpw<K, 2>(a, st);
-  return launch_lb_gpw<K, 0>(a, st);
-}
-
-#ifdef CFL_LB_TRACE
-extern "C" int cfl_lb_trace_read(unsigned long long* host, int n) {
-  return (int)cudaMemcpyFromSymbol(host, g_lb_trace, (size_t)n * sizeof(unsigned long long));
-}
-#endif
-
-int score_lb_launch(const ScoreArgs& a, cudaStream_t st) {
-  switch (a.K) {
-    case 1: return launch_lb<1>(a, st);
-    case 2: return launch_lb<2>(a, st);
-    case 3: return launch_lb<3>(a, st);
-    case 4: return launch_lb<4>(a, st);
-    case 5: return launch_lb<5>(a, st);
-    case 6: return launch_lb<6>(a, st);
-    case 7: return launch_lb<7>(a, st);
-    case 8: return launch_lb<8>(a, st);
-  }
-  set_error("score_lb: K=%d unsupported", a.K);
-  return CFL_ERR_UNSUPPORTED;
 }
 
 template <int K>
