@@ -223,6 +223,51 @@ __host__ __device__ inline LbLayout lb_layout(int K, int qt, int nkm) {
   return L;
 }
 
+template <int KSS>
+__device__ __forceinline__ void lb_mma_loop(const ScoreArgs& A, uint32_t a_base, uint32_t b_base, uint32_t tmem_base, int NC,
+                                            int NBUF, int nkm, int ntiles, uint64_t* full, uint64_t* empty,
+                                            uint64_t* tfull, uint64_t* tempty) {
+  const uint32_t idesc = make_idesc_f16(128, (uint32_t)NC);
+  const uint32_t b_step = 2u * (uint32_t)NC * 16u;            // bytes per K-step of the query image
+  const int nsteps = nkm / KSS;                                // ring stages per tile
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
+  int stage = 0; uint32_t phase = 0;
+  int buf = 0; uint32_t bphase = 0;                            // accumulator buffer of tile t and the parity of its use count
+  if (ntiles > 0) {
+    mbar_wait_addr(tempty0, 1u);
+    if (!(A.dbg_mode & 2)) mbar_wait_addr(full0, 0u);
+    tc_fence_after();
+  }
+  for (int t = 0; t < ntiles; ++t) {
+    LB_TRACE(0, t);
+    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
+    int nbuf_i = buf + 1; uint32_t nbphase = bphase;
+    if (nbuf_i == NBUF) { nbuf_i = 0; nbphase ^= 1u; }
+    for (int sidx = 0; sidx < nsteps; ++sidx) {
+      const uint32_t a_st = a_base + (uint32_t)stage * LB_STAGE;
+      const uint32_t b_st = b_base + (uint32_t)(sidx * KSS) * b_step;
+      int nstage = stage + 1; uint32_t nphase = phase;
+      if (nstage == LB_NSTAGE) { nstage = 0; nphase ^= 1u; }
+      const bool last = sidx == nsteps - 1;
+#pragma unroll
+      for (int j = 0; j < KSS; ++j) {
+        if (j == KSS - 1 && (!last || t + 1 < ntiles)) {       // look ahead: barriers of the next stage (and tile)
+          if (last && !(A.dbg_mode & 16)) mbar_wait_addr(tempty0 + (uint32_t)nbuf_i * 8u, nbphase ^ 1u);
+          if (!(A.dbg_mode & 2)) mbar_wait_addr(full0 + (uint32_t)nstage * 8u, nphase);
+          tc_fence_after();
+        }
+        mma_f16(d_tmem, make_smem_desc(a_st + (uint32_t)j * LB_BLK, 128u * 16u, 128u),
+                make_smem_desc(b_st + (uint32_t)j * b_step, (uint32_t)NC * 16u, 128u), idesc, (sidx | j) ? 1u : 0u);
+      }
+      mma_commit_addr(empty0 + (uint32_t)stage * 8u);
+      stage = nstage; phase = nphase;
+    }
+    mma_commit_addr(tfull0 + (uint32_t)buf * 8u);
+    LB_TRACE(2, t);
+    buf = nbuf_i; bphase = nbphase;
+  }
+}
+
 template <int K>
 __global__ void __launch_bounds__(LB_THREADS, 1)
 score_lb_kernel(ScoreArgs A) {
@@ -302,53 +347,20 @@ score_lb_kernel(ScoreArgs A) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == LB_NEPI) {
-    // ============================ MMA issuer (whole warp, one elected lane issues) ============================
-    // Warp-uniform loop: descriptors stay 32-bit low words that advance by a constant per MMA.  The barrier waits
-    // for the NEXT ring stage / accumulator buffer are issued one MMA early, while the queued MMAs still execute.
-    mbar_wait(bfull, 0);
-    const uint64_t a_desc = make_smem_desc(smem_u32(a_ring), 128u * 16u, 128u);
-    const uint64_t b_desc = make_smem_desc(smem_u32(b_img), (uint32_t)NC * 16u, 128u);
-    const uint32_t a_lo0 = (uint32_t)a_desc, a_hi = (uint32_t)(a_desc >> 32);
-    const uint32_t b_lo0 = (uint32_t)b_desc, b_hi = (uint32_t)(b_desc >> 32);
-    const uint32_t idesc = make_idesc_f16(128, (uint32_t)NC);
-    const uint32_t b_step16 = 2u * (uint32_t)NC;               // (2 chunks * NC rows * 16 B) >> 4
-    int stage = 0; uint32_t phase = 0;
-    const int nsteps = nkm / kss;                              // ring stages per tile
-    int buf = 0; uint32_t bphase = 0;                          // accumulator buffer of tile t and its use count parity
-    if (ntiles > 0) {
-      mbar_wait(&tempty[0], 1u);
-      if (!(A.dbg_mode & 2)) mbar_wait(&full[0], 0u);
-      tc_fence_after();
-    }
-    for (int t = 0; t < ntiles; ++t) {
-      if (lane == 0) LB_TRACE(0, t);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
-      int nbuf_i = buf + 1; uint32_t nbphase = bphase;
-      if (nbuf_i == NBUF) { nbuf_i = 0; nbphase ^= 1u; }
-      uint32_t b_lo = b_lo0;
-      for (int sidx = 0; sidx < nsteps; ++sidx) {
-        uint32_t a_lo = a_lo0 + (uint32_t)stage * (LB_STAGE >> 4);
-        for (int j = 0; j < kss; ++j) {
-          if (j == kss - 1) {                                  // look ahead: barriers of the next stage (and tile)
-            int nstage = stage + 1; uint32_t nphase = phase;
-            if (nstage == LB_NSTAGE) { nstage = 0; nphase ^= 1u; }
-            const bool last = sidx == nsteps - 1;
-            if (!last || t + 1 < ntiles) {
-              if (last && !(A.dbg_mode & 16)) mbar_wait(&tempty[nbuf_i], nbphase ^ 1u);
-              if (!(A.dbg_mode & 2)) mbar_wait(&full[nstage], nphase);
-              tc_fence_after();
-            }
-          }
-          if (elect_one()) mma_f16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, (sidx | j) ? 1u : 0u);
-          a_lo += LB_BLK >> 4;
-          b_lo += b_step16;
-        }
-        if (elect_one()) mma_commit(&empty[stage]);
-        if (++stage == LB_NSTAGE) { stage = 0; phase ^= 1u; }
+    // ================================ MMA issuer (one elected lane) =================================
+    // One thread issues; what limits it is the latency of its OWN instruction stream (a dependent SASS instruction
+    // costs ~5 clk when a single thread runs): ~25 instructions of address arithmetic and R2UR moves per MMA make the
+    // issue slower than the tensor pipe (tools/umma_rate.cu).  The loop is therefore written so that ptxas keeps every
+    // operand in uniform registers: all values derive from kernel parameters and shared-memory addresses, the K-steps
+    // of a ring stage are unrolled at compile time, and the barrier waits for the NEXT stage / accumulator buffer are
+    // issued before the stage's last MMA, while the queued MMAs still execute.
+    if (elect_one()) {
+      mbar_wait(bfull, 0);
+      switch (kss) {
+        case 4: lb_mma_loop<4>(A, smem_u32(a_ring), smem_u32(b_img), tmem_base, NC, NBUF, nkm, ntiles, full, empty, tfull, tempty); break;
+        case 2: lb_mma_loop<2>(A, smem_u32(a_ring), smem_u32(b_img), tmem_base, NC, NBUF, nkm, ntiles, full, empty, tfull, tempty); break;
+        default: lb_mma_loop<1>(A, smem_u32(a_ring), smem_u32(b_img), tmem_base, NC, NBUF, nkm, ntiles, full, empty, tfull, tempty); break;
       }
-      if (elect_one()) mma_commit(&tfull[buf]);
-      if (lane == 0) LB_TRACE(2, t);
-      buf = nbuf_i; bphase = nbphase;
     }
   } else if (warp == LB_NEPI + 1) {
     // ================================ TMA producer (one lane) ===============================

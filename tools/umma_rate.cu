@@ -109,7 +109,92 @@ issue_kernel(int N, unsigned long long* out) {
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// The MMA warp's loop of a scoring kernel, piece by piece: 4 MMAs per tile, then
+//   bit 0: tcgen05.commit to a "stage empty" barrier      bit 1: tcgen05.commit to the tile's "tfull" barrier
+//   bit 2: an epilogue warp waits on tfull and arrives on tempty; the MMA warp waits on tempty before re-using the
+//          accumulator buffer (nbuf buffers)              bit 3: that wait is issued before the tile's LAST MMA
+//   bit 4: whole-warp loop with an elected lane per instruction (else one elected thread runs the loop)
+__global__ void __launch_bounds__(128, 1)
+loop_kernel(int N, int tiles, int nbuf, int what, unsigned long long* cyc) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bars[16];
+  __shared__ uint32_t slot;
+  uint64_t* tfull = bars; uint64_t* tempty = bars + 4; uint64_t* sempty = bars + 8; uint64_t* done = bars + 12;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 1); mbar_init(&sempty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = slot;
+  const uint32_t a_base = smem_u32(smem), b_base = a_base + 65536;
+  const uint32_t idesc = make_idesc_f16(128, (uint32_t)N);
+  const uint64_t a_desc = make_smem_desc(a_base, 128u * 16u, 128u), b_desc = make_smem_desc(b_base, (uint32_t)N * 16u, 128u);
+  const uint32_t a_lo0 = (uint32_t)a_desc, a_hi = (uint32_t)(a_desc >> 32), b_lo0 = (uint32_t)b_desc, b_hi = (uint32_t)(b_desc >> 32);
+  if (warp == 1) {
+    const bool whole = what & 16;
+    if (whole || elect_one()) {
+      const long long t0 = clock64();
+      int buf = 0; uint32_t bph = 0;
+      for (int t = 0; t < tiles; ++t) {
+        const uint32_t d_tmem = tb + (uint32_t)(buf * N);
+        int nb = buf + 1; uint32_t nph = bph; if (nb == nbuf) { nb = 0; nph ^= 1u; }
+        if ((what & 4) && !(what & 8)) { mbar_wait(&tempty[buf], bph ^ 1u); tc_fence_after(); }
+        uint32_t a_lo = a_lo0 + (uint32_t)(t & 3) * 1024u, b_lo = b_lo0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          if ((what & 12) == 12 && ks == 3 && t + 1 < tiles) { mbar_wait(&tempty[nb], nph ^ 1u); tc_fence_after(); }
+          if (!whole || elect_one()) mma_f16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, ks ? 1u : 0u);
+          a_lo += 256u; b_lo += 2u * (uint32_t)N;
+        }
+        if (what & 1) { if (!whole || elect_one()) mma_commit(&sempty[t & 3]); }
+        if (what & 2) { if (!whole || elect_one()) mma_commit(&tfull[buf]); }
+        buf = nb; bph = nph;
+      }
+      if (!whole || elect_one()) mma_commit(done);
+      mbar_wait(done, 0);
+      const long long t1 = clock64();
+      if (lane == 0 || !whole) cyc[blockIdx.x] = (unsigned long long)(t1 - t0);
+    }
+  } else if (warp == 2 && (what & 4)) {
+    int buf = 0; uint32_t bph = 0;
+    for (int t = 0; t < tiles; ++t) {
+      mbar_wait(&tfull[buf], bph);
+      tc_fence_after();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (++buf == nbuf) { buf = 0; bph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 int main() {
+  {
+    unsigned long long* c; CK(cudaMalloc(&c, 148 * 8));
+    const int sm = 65536 + 32768 + 1024;
+    CK(cudaFuncSetAttribute(loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    struct { int what; const char* name; } cases[] = {
+      {0, "MMAs only"}, {1, "+ commit(stage)"}, {3, "+ commit(stage) + commit(tfull)"},
+      {7, "+ hand-shake with an epilogue warp, wait at tile start"}, {15, "+ hand-shake, wait before the last MMA"},
+      {16 + 3, "whole-warp loop: commits"}, {16 + 7, "whole-warp loop: hand-shake, wait at tile start"},
+      {16 + 15, "whole-warp loop: hand-shake, wait before the last MMA"}};
+    for (int N : {144, 192})
+      for (int nbuf = 2; nbuf <= (N == 144 ? 3 : 2); ++nbuf)
+        for (auto& cs : cases) {
+          for (int rep = 0; rep < 2; ++rep) { loop_kernel<<<148, 128, sm>>>(N, 1000, nbuf, cs.what, c); CK(cudaDeviceSynchronize()); }
+          unsigned long long h[148]; CK(cudaMemcpy(h, c, sizeof(h), cudaMemcpyDeviceToHost));
+          unsigned long long mx = 0; for (auto x : h) mx = x > mx ? x : mx;
+          printf("loop N=%d nbuf=%d %-58s: %6.0f clk/tile (MMA law %3.0f)\n", N, nbuf, cs.name, (double)mx / 1000.0, 4 * (43.0 + N / 2.0));
+        }
+  }
   {
     unsigned long long* o; CK(cudaMalloc(&o, 16 * 8));
     CK(cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 32768 + 1024));
