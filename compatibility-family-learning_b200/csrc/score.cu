@@ -769,7 +769,7 @@ static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePla
                               size_t* o_pc, size_t* o_qpar, size_t* o_qimg, size_t* o_keys, size_t* o_cnt,
                               size_t* o_cimg, size_t* o_lbimg = nullptr) {
   size_t off = 0;
-  const LbPlan lb = p.impl ? make_lb_plan(Q, K, d, p.tiles) : LbPlan{0, 0, 0, 0};
+  const LbPlan lb = p.impl ? make_lb_plan(Q, K, d, p.tiles) : LbPlan{0, 0, 0, 0, 0};
   const int kparts = p.parts > lb.parts ? p.parts : lb.parts;          // key buffers serve both tilings
   *o_pc = off;   off = align_up(off + (size_t)Q * K * d * 4, 256);
   *o_qpar = off; off = align_up(off + (size_t)Q * (qpar_stride(K) + qplane_stride(K)) * 4, 256);
@@ -844,7 +844,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   const ScoreKnobs kn = read_knobs();
   a.dbg_mode = kn.dbg_mode;
   a.plan = plan;
-  a.lb = plan.impl ? make_lb_plan(Q, K, d, plan.tiles) : LbPlan{0, 0, 0, 0};
+  a.lb = plan.impl ? make_lb_plan(Q, K, d, plan.tiles) : LbPlan{0, 0, 0, 0, 0};
   if (N == 0) {
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
   } else {
@@ -863,7 +863,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       a.cflag16 = (const int*)((const char*)a.cimg16 + catalog_f16_bytes(N, d));
       a.lbrow = (const float2*)((const char*)image + catalog_lbrow_offset(N, d));
       a.qimg16 = base + o_lbimg;
-      a.qflag16 = (const int*)((const char*)a.qimg16 + (size_t)a.lb.nqt * ((d + 15) / 16) * 2 * (size_t)(K * a.lb.qt) * 16);
+      a.qflag16 = (const int*)((const char*)a.qimg16 + (size_t)a.lb.nqt * a.lb.sub * a.lb.qt * ((d + 15) / 16) * 2 * K * 16);
       a.lbq = (const float*)((const char*)a.qflag16 + 16);
       st = score_umma_pack_queries(a, base + o_qimg, cs);
       if (st != CFL_OK) return st;

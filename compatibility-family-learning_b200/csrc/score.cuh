@@ -20,7 +20,11 @@ struct ScorePlan {
 
 // Tiling of the lower-bound pass (score_lb.cu): its own query tile, catalog parts and TMEM buffering.
 struct LbPlan {
-  int qt, nqt, parts, nbuf;
+  int qt;      // queries per accumulator buffer (sub-tile): K*qt TMEM columns
+  int sub;     // sub-tiles per CTA: every catalog tile in shared memory is multiplied with `sub` query images
+  int nqt;     // CTAs along the query axis = ceil(Q / (qt*sub))
+  int parts;   // catalog parts (CTAs along the catalog axis)
+  int nbuf;    // TMEM accumulator buffers
 };
 
 struct ScoreArgs {

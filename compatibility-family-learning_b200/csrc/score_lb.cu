@@ -55,43 +55,47 @@ __device__ unsigned long long g_lb_trace[8 * 4096];
 #endif
 __host__ __device__ constexpr int lb_gq(int K) { return K <= 2 ? 16 : (K <= 4 ? 8 : 4); }
 
-// Tiling of the pass: qt queries per CTA (a multiple of the group size GQ, K*qt a multiple of 16 and <= 256), nbuf
-// accumulator buffers of K*qt TMEM columns, parts = catalog ranges so that parts * nqt ~ the SM count.
+// Tiling of the pass.  A CTA keeps `sub` query images of qt queries each resident (K*qt TMEM columns per accumulator
+// buffer, a multiple of 16 and <= 256) and multiplies every catalog tile it streams with all of them, so the catalog
+// plane is fetched from L2 once per qt*sub queries: with one image per CTA the pass is bound by the L2 -> SM traffic
+// of the re-read plane (measured ~20 B/clk/SM with every SM streaming), not by the tensor pipe.  parts = catalog
+// ranges so that parts * nqt ~ the SM count.  Cost model (clk per CTA): tiles * max(sub * tensor, L2) from the
+// measured laws tensor = nkm * (43 + N/2), L2 = tile bytes / 20.
 LbPlan make_lb_plan(int64_t Q, int K, int d, int64_t tiles) {
-  LbPlan p;
+  LbPlan best{0, 0, 0, 0, 0};
   const int GQ = lb_gq(K);
   const int nkm = (d + 15) / 16;
-  int best = 0;
+  int sms = sm_count(); if (sms <= 0) sms = 148;
   double best_cost = 1e30;
   for (int qt = GQ; K * qt <= 256; qt += GQ) {
     const int nc = K * qt;
     if (nc % 16 != 0) continue;
     const int nbuf = 512 / nc > LB_MAXBUF ? LB_MAXBUF : 512 / nc;
-    const double tile_clk = nkm * (43.0 + nc / 2.0);            // tensor work per tile (measured law)
+    const double tile_clk = nkm * (43.0 + nc / 2.0);            // tensor work per (catalog tile, sub-tile)
     if (nbuf < 2) continue;
     if (nbuf < 3 && tile_clk < 1000.0) continue;                // short tiles need a third buffer to hide the hand-shake
-    const int64_t nqt = (Q + qt - 1) / qt;
-    int sms = sm_count(); if (sms <= 0) sms = 148;
-    int64_t parts = sms / nqt; if (parts < 1) parts = 1; if (parts > tiles) parts = tiles;
-    const double waves = (double)((tiles + parts - 1) / parts);  // tiles per CTA (one wave when parts * nqt <= SMs)
-    const double rounds = (double)((nqt * parts + sms - 1) / sms);
-    const double cost = waves * rounds * tile_clk;
-    if (cost < best_cost * 0.999) { best_cost = cost; best = qt; }
+    for (int sub = 1; sub <= 4; ++sub) {
+      const size_t smem = (size_t)sub * nkm * 2 * nc * 16 + (size_t)LB_NSTAGE * LB_STAGE + 4096;
+      if (smem > 200 * 1024) break;
+      const int64_t nqt = (Q + (int64_t)qt * sub - 1) / ((int64_t)qt * sub);
+      int64_t parts = sms / nqt; if (parts < 1) parts = 1; if (parts > tiles) parts = tiles;
+      const double per_cta = (double)((tiles + parts - 1) / parts);
+      const double rounds = (double)((nqt * parts + sms - 1) / sms);
+      const double l2_clk = nkm * 4096.0 / 20.0;
+      const double step = sub * tile_clk > l2_clk ? sub * tile_clk : l2_clk;
+      const double cost = per_cta * rounds * step;
+      if (cost < best_cost * 0.999) { best_cost = cost; best = LbPlan{qt, sub, (int)nqt, (int)parts, nbuf}; }
+      if ((int64_t)qt * sub >= Q) break;
+    }
   }
-  if (best == 0) best = GQ;
-  p.qt = best;
-  p.nqt = (int)((Q + best - 1) / best);
-  int sms = sm_count(); if (sms <= 0) sms = 148;
-  int64_t parts = sms / p.nqt; if (parts < 1) parts = 1; if (parts > tiles) parts = tiles;
-  p.parts = (int)parts;
-  const int nc = K * best;
-  p.nbuf = 512 / nc > LB_MAXBUF ? LB_MAXBUF : 512 / nc;
-  return p;
+  if (best.qt == 0) best = LbPlan{GQ, 1, (int)((Q + GQ - 1) / GQ), 1, 2};
+  return best;
 }
 
-size_t score_lb_qimg_bytes(const LbPlan& p, int K, int d) {      // image + flag word + lbq[2 per query slot]
+size_t score_lb_qimg_bytes(const LbPlan& p, int K, int d) {      // images + flag word + lbq[2 per query slot]
   const int nks16 = (d + 15) / 16;
-  return (size_t)p.nqt * nks16 * 2 * (size_t)(K * p.qt) * 16 + 16 + (size_t)p.nqt * p.qt * 2 * sizeof(float);
+  const size_t slots = (size_t)p.nqt * p.sub * p.qt;
+  return slots * nks16 * 2 * K * 16 + 16 + slots * 2 * sizeof(float);
 }
 
 // fp16 lower-bound image: [qtile][kstep16][chunk][row n][8 halfs] with n = g*(GQ*K) + k*GQ + i for the query
@@ -184,8 +188,8 @@ int score_lb_prep_queries(const ScoreArgs& a, cudaStream_t st) {
   unsigned char* img16 = (unsigned char*)const_cast<void*>(a.qimg16);
   int* flag16 = const_cast<int*>(a.qflag16);
   CFL_CUDA(cudaMemsetAsync(flag16, 0, 16, st));
-  const int64_t slots = (int64_t)a.lb.nqt * a.lb.qt;
-  prep_lb_kernel<<<(unsigned)((slots + 3) / 4), 128, 0, st>>>(a.Pc, a.Q, a.K, a.d, a.lb.qt, a.lb.nqt, a.plan.dpad,
+  const int64_t slots = (int64_t)a.lb.nqt * a.lb.sub * a.lb.qt;   // one image per sub-tile of qt queries
+  prep_lb_kernel<<<(unsigned)((slots + 3) / 4), 128, 0, st>>>(a.Pc, a.Q, a.K, a.d, a.lb.qt, a.lb.nqt * a.lb.sub, a.plan.dpad,
                                                              img16, flag16, const_cast<float*>(a.lbq));
   CFL_LAUNCH_CHECK();
   return CFL_OK;
@@ -209,13 +213,13 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NCOLS]) 
 struct LbLayout {
   uint32_t b_img, a_ring, ncq, cnt, red, bars, tmem_slot, total;
 };
-__host__ __device__ inline LbLayout lb_layout(int K, int qt, int nkm) {
+__host__ __device__ inline LbLayout lb_layout(int K, int qt, int sub, int nkm) {
   LbLayout L;
   uint32_t off = 0;
-  L.b_img = off;   off += (uint32_t)nkm * 2u * (uint32_t)(K * qt) * 16u;  off = (off + 1023u) & ~1023u;
+  L.b_img = off;   off += (uint32_t)sub * (uint32_t)nkm * 2u * (uint32_t)(K * qt) * 16u;  off = (off + 1023u) & ~1023u;
   L.a_ring = off;  off += LB_NSTAGE * LB_STAGE;
-  L.ncq = off;     off += (uint32_t)qt * 4u;                              off = (off + 15u) & ~15u;
-  L.cnt = off;     off += (uint32_t)qt * 4u;                              off = (off + 15u) & ~15u;
+  L.ncq = off;     off += (uint32_t)(qt * sub) * 4u;                      off = (off + 15u) & ~15u;
+  L.cnt = off;     off += (uint32_t)(qt * sub) * 4u;                      off = (off + 15u) & ~15u;
   L.red = off;     off += 32u * 4u;
   L.bars = off;    off += (2u * LB_NSTAGE + 2u * LB_MAXBUF + 1u) * 8u;
   L.tmem_slot = off; off += 16u;
@@ -223,16 +227,19 @@ __host__ __device__ inline LbLayout lb_layout(int K, int qt, int nkm) {
   return L;
 }
 
+// Sequence of "steps" u = (catalog tile t, sub-tile s): accumulator buffer u mod NBUF, A = the tile's ring stage(s),
+// B = query image s.  A ring stage is handed back to the TMA producer after its LAST sub-tile.
 template <int KSS>
 __device__ __forceinline__ void lb_mma_loop(const ScoreArgs& A, uint32_t a_base, uint32_t b_base, uint32_t tmem_base, int NC,
-                                            int NBUF, int nkm, int ntiles, uint64_t* full, uint64_t* empty,
+                                            int NBUF, int SUB, int nkm, int ntiles, uint64_t* full, uint64_t* empty,
                                             uint64_t* tfull, uint64_t* tempty) {
   const uint32_t idesc = make_idesc_f16(128, (uint32_t)NC);
-  const uint32_t b_step = 2u * (uint32_t)NC * 16u;            // bytes per K-step of the query image
-  const int nsteps = nkm / KSS;                                // ring stages per tile
+  const uint32_t b_step = 2u * (uint32_t)NC * 16u;            // bytes per K-step of a query image
+  const uint32_t b_img = (uint32_t)nkm * b_step;               // bytes per query image
+  const int nsteps = nkm / KSS;                                // ring stages per catalog tile
   const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
-  int stage = 0; uint32_t phase = 0;
-  int buf = 0; uint32_t bphase = 0;                            // accumulator buffer of tile t and the parity of its use count
+  int stage0 = 0; uint32_t phase0 = 0;                         // first ring stage of tile t
+  int buf = 0; uint32_t bphase = 0;                            // accumulator buffer of the step and the parity of its use count
   if (ntiles > 0) {
     mbar_wait_addr(tempty0, 1u);
     if (!(A.dbg_mode & 2)) mbar_wait_addr(full0, 0u);
@@ -240,31 +247,40 @@ __device__ __forceinline__ void lb_mma_loop(const ScoreArgs& A, uint32_t a_base,
   }
   for (int t = 0; t < ntiles; ++t) {
     LB_TRACE(0, t);
-    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
-    int nbuf_i = buf + 1; uint32_t nbphase = bphase;
-    if (nbuf_i == NBUF) { nbuf_i = 0; nbphase ^= 1u; }
-    for (int sidx = 0; sidx < nsteps; ++sidx) {
-      const uint32_t a_st = a_base + (uint32_t)stage * LB_STAGE;
-      const uint32_t b_st = b_base + (uint32_t)(sidx * KSS) * b_step;
-      int nstage = stage + 1; uint32_t nphase = phase;
-      if (nstage == LB_NSTAGE) { nstage = 0; nphase ^= 1u; }
-      const bool last = sidx == nsteps - 1;
+    for (int sq = 0; sq < SUB; ++sq) {
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NC);
+      int nbuf_i = buf + 1; uint32_t nbphase = bphase;
+      if (nbuf_i == NBUF) { nbuf_i = 0; nbphase ^= 1u; }
+      const bool last_sub = sq == SUB - 1;
+      int stage = stage0; uint32_t phase = phase0;
+      for (int sidx = 0; sidx < nsteps; ++sidx) {
+        const uint32_t a_st = a_base + (uint32_t)stage * LB_STAGE;
+        const uint32_t b_st = b_base + (uint32_t)sq * b_img + (uint32_t)(sidx * KSS) * b_step;
+        int nstage = stage + 1; uint32_t nphase = phase;
+        if (nstage == LB_NSTAGE) { nstage = 0; nphase ^= 1u; }
+        const bool last = sidx == nsteps - 1;
 #pragma unroll
-      for (int j = 0; j < KSS; ++j) {
-        if (j == KSS - 1 && (!last || t + 1 < ntiles)) {       // look ahead: barriers of the next stage (and tile)
-          if (last && !(A.dbg_mode & 16)) mbar_wait_addr(tempty0 + (uint32_t)nbuf_i * 8u, nbphase ^ 1u);
-          if (!(A.dbg_mode & 2)) mbar_wait_addr(full0 + (uint32_t)nstage * 8u, nphase);
-          tc_fence_after();
+        for (int j = 0; j < KSS; ++j) {
+          if (j == KSS - 1) {                                  // look ahead: barriers of the next stage / step
+            bool fence = false;
+            if (last && (!last_sub || t + 1 < ntiles) && !(A.dbg_mode & 16)) { mbar_wait_addr(tempty0 + (uint32_t)nbuf_i * 8u, nbphase ^ 1u); fence = true; }
+            // the next stage holds catalog data not yet waited for: the tile's further stages during its first
+            // sub-tile, the next tile's first stage after the last sub-tile
+            const bool need_full = last ? (last_sub && t + 1 < ntiles) : (sq == 0);
+            if (need_full && !(A.dbg_mode & 2)) { mbar_wait_addr(full0 + (uint32_t)nstage * 8u, nphase); fence = true; }
+            if (fence) tc_fence_after();
+          }
+          mma_f16(d_tmem, make_smem_desc(a_st + (uint32_t)j * LB_BLK, 128u * 16u, 128u),
+                  make_smem_desc(b_st + (uint32_t)j * b_step, (uint32_t)NC * 16u, 128u), idesc, (sidx | j) ? 1u : 0u);
         }
-        mma_f16(d_tmem, make_smem_desc(a_st + (uint32_t)j * LB_BLK, 128u * 16u, 128u),
-                make_smem_desc(b_st + (uint32_t)j * b_step, (uint32_t)NC * 16u, 128u), idesc, (sidx | j) ? 1u : 0u);
+        if (last_sub) mma_commit_addr(empty0 + (uint32_t)stage * 8u);
+        stage = nstage; phase = nphase;
       }
-      mma_commit_addr(empty0 + (uint32_t)stage * 8u);
-      stage = nstage; phase = nphase;
+      mma_commit_addr(tfull0 + (uint32_t)buf * 8u);
+      buf = nbuf_i; bphase = nbphase;
+      if (last_sub) { stage0 = stage; phase0 = phase; }
     }
-    mma_commit_addr(tfull0 + (uint32_t)buf * 8u);
     LB_TRACE(2, t);
-    buf = nbuf_i; bphase = nbphase;
   }
 }
 
@@ -275,12 +291,14 @@ score_lb_kernel(ScoreArgs A) {
   constexpr int GQ = lb_gq(K);
   constexpr int GC = GQ * K;                                   // TMEM columns of one query group
   constexpr int WPQ = LB_NEPI / 4;                             // warps per TMEM lane quarter
-  const int QT = A.lb.qt;
+  const int QT = A.lb.qt;                                      // queries per sub-tile (one accumulator buffer)
+  const int SUB = A.lb.sub;                                    // sub-tiles (query images) of this CTA
+  const int QC = QT * SUB;                                     // queries per CTA
   const int NC = K * QT;
   const int NBUF = A.lb.nbuf;
   const int nkm = (A.plan.dpad + 15) / 16;                     // MMA K-steps (16 halfs) per tile
   const int kss = (nkm % 4 == 0) ? 4 : ((nkm % 2 == 0) ? 2 : 1);   // K-steps (4 KB blocks) per ring stage
-  const LbLayout L = lb_layout(K, QT, nkm);
+  const LbLayout L = lb_layout(K, QT, SUB, nkm);
   unsigned char* b_img = smem + L.b_img;
   unsigned char* a_ring = smem + L.a_ring;
   float* ncq = (float*)(smem + L.ncq);                         // -cq per query of the tile
@@ -295,8 +313,8 @@ score_lb_kernel(ScoreArgs A) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int part = blockIdx.x, qtile = blockIdx.y;
-  const int64_t q0 = (int64_t)qtile * QT;
-  const int nq = (int)((A.Q - q0 < QT) ? (A.Q - q0) : QT);
+  const int64_t q0 = (int64_t)qtile * QC;
+  const int nq = (int)((A.Q - q0 < QC) ? (A.Q - q0) : QC);
   const int64_t t0 = A.plan.tiles * part / A.lb.parts;
   const int64_t t1 = A.plan.tiles * (part + 1) / A.lb.parts;
   const int ts = A.tile_stride;
@@ -330,7 +348,7 @@ score_lb_kernel(ScoreArgs A) {
   if (lane == 0) red[warp] = am;
   // cq = |a|^2 - threshold, rounded down (stored negated); padding / dead queries get +inf (never pass), no threshold
   // -inf (always pass)
-  for (int i = tid; i < QT; i += LB_THREADS) {
+  for (int i = tid; i < QC; i += LB_THREADS) {
     float c = __int_as_float(0x7f800000);
     if (i < nq) {
       const float tau = A.thr_init ? A.thr_init[q0 + i] : __int_as_float(0x7f800000);
@@ -357,15 +375,15 @@ score_lb_kernel(ScoreArgs A) {
     if (elect_one()) {
       mbar_wait(bfull, 0);
       switch (kss) {
-        case 4: lb_mma_loop<4>(A, smem_u32(a_ring), smem_u32(b_img), tmem_base, NC, NBUF, nkm, ntiles, full, empty, tfull, tempty); break;
-        case 2: lb_mma_loop<2>(A, smem_u32(a_ring), smem_u32(b_img), tmem_base, NC, NBUF, nkm, ntiles, full, empty, tfull, tempty); break;
-        default: lb_mma_loop<1>(A, smem_u32(a_ring), smem_u32(b_img), tmem_base, NC, NBUF, nkm, ntiles, full, empty, tfull, tempty); break;
+        case 4: lb_mma_loop<4>(A, smem_u32(a_ring), smem_u32(b_img), tmem_base, NC, NBUF, SUB, nkm, ntiles, full, empty, tfull, tempty); break;
+        case 2: lb_mma_loop<2>(A, smem_u32(a_ring), smem_u32(b_img), tmem_base, NC, NBUF, SUB, nkm, ntiles, full, empty, tfull, tempty); break;
+        default: lb_mma_loop<1>(A, smem_u32(a_ring), smem_u32(b_img), tmem_base, NC, NBUF, SUB, nkm, ntiles, full, empty, tfull, tempty); break;
       }
     }
   } else if (warp == LB_NEPI + 1) {
     // ================================ TMA producer (one lane) ===============================
     if (elect_one()) {
-      const uint32_t bbytes = (uint32_t)nkm * 2u * (uint32_t)NC * 16u;
+      const uint32_t bbytes = (uint32_t)SUB * (uint32_t)nkm * 2u * (uint32_t)NC * 16u;   // SUB consecutive query images
       const unsigned char* qsrc = (const unsigned char*)A.qimg16 + (size_t)qtile * bbytes;
       mbar_arrive_expect_tx(bfull, bbytes);
       for (uint32_t o = 0; o < bbytes; o += 32768u) {
@@ -391,7 +409,6 @@ score_lb_kernel(ScoreArgs A) {
     // as the warp's LAST group of the tile is in registers.
     const int lq = warp & 3, sub = warp >> 2;
     const int lrow = lq * 32 + lane;
-    const int ngroups = (nq + GQ - 1) / GQ;
     tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
     float amax = 0.0f;
     for (int i = 0; i < LB_THREADS / 32; ++i) amax = fmaxf(amax, red[i]);
@@ -403,75 +420,80 @@ score_lb_kernel(ScoreArgs A) {
     const float c_abs = 2.0f * s16 * amax * 1.0001f;
     float2 er_next = (ntiles > 0) ? __ldg(A.lbrow + t0 * 128 + lrow) : make_float2(0.f, 0.f);   // one tile ahead
     int buf = 0; uint32_t bphase = 0;
+    int rot = sub;                                             // (sub - step) mod WPQ: first group of this warp in the step
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t row = (uint32_t)((t0 + (int64_t)t * ts) * 128 + lrow);
       const float2 er = er_next;
       if (t + 1 < ntiles) er_next = __ldg(A.lbrow + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
       // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
       const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
-      if (tid == 0) LB_TRACE(3, t);
-      mbar_wait(&tfull[buf], bphase);
-      tc_fence_after();
-      if (tid == 0) LB_TRACE(4, t);
-      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
-      bool released = false;
-      for (int g = (sub + WPQ - (t & (WPQ - 1))) & (WPQ - 1); g < ngroups && !(A.dbg_mode & 1); g += WPQ) {
-        float v[GC], tq[GQ];
-        tmem_ld_cols<GC>(taddr + (uint32_t)(g * GC), v);
+      const tkey_t key = pack_key(0.0f, row);
+      for (int sq = 0; sq < SUB; ++sq) {
+        const int qb = sq * QT;                                // first query of the sub-tile within the CTA's queries
+        const int ngroups = nq > qb ? ((nq - qb < QT ? nq - qb : QT) + GQ - 1) / GQ : 0;
+        if (tid == 0 && sq == 0) LB_TRACE(3, t);
+        mbar_wait(&tfull[buf], bphase);
+        tc_fence_after();
+        if (tid == 0 && sq == 0) LB_TRACE(4, t);
+        const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
+        bool released = false;
+        for (int g = rot; g < ngroups && !(A.dbg_mode & 1); g += WPQ) {
+          float v[GC], tq[GQ];
+          tmem_ld_cols<GC>(taddr + (uint32_t)(g * GC), v);
 #pragma unroll
-        for (int i = 0; i < GQ; i += 4) {
-          const float4 c4 = *(const float4*)(ncq + g * GQ + i);
-          tq[i] = c4.x; tq[i + 1] = c4.y; tq[i + 2] = c4.z; tq[i + 3] = c4.w;
-        }
-        tmem_ld_wait();
-        if (g + WPQ >= ngroups) {                              // the warp's last group of this tile is in registers
-          if (tid == 0) LB_TRACE(5, t);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[buf]);
-          released = true;
-        }
-        if (A.dbg_mode & 4) continue;                          // experiment: the epilogue only reads TMEM
-        // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
-#pragma unroll
-        for (int pi = 0; pi < GQ / 2; ++pi) {
-          f2_t acc = add2(pk2(v[2 * pi], v[2 * pi + 1]), pk2(tq[2 * pi], tq[2 * pi + 1]));
-#pragma unroll
-          for (int k = 1; k < K; ++k) {
-            const f2_t c = pk2(v[k * GQ + 2 * pi], v[k * GQ + 2 * pi + 1]);
-            acc = fma2(c, c, acc);
+          for (int i = 0; i < GQ; i += 4) {
+            const float4 c4 = *(const float4*)(ncq + qb + g * GQ + i);
+            tq[i] = c4.x; tq[i + 1] = c4.y; tq[i + 2] = c4.z; tq[i + 3] = c4.w;
           }
-          upk2(acc, tq[2 * pi], tq[2 * pi + 1]);
-        }
-        float m = max3(tq[0], tq[1], tq[2]);
+          tmem_ld_wait();
+          if (g + WPQ >= ngroups) {                            // the warp's last group of this step is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+            released = true;
+          }
+          if (A.dbg_mode & 4) continue;                        // experiment: the epilogue only reads TMEM
+          // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
 #pragma unroll
-        for (int i = 3; i + 1 < GQ; i += 2) m = max3(m, tq[i], tq[i + 1]);
-        m = fmaxf(m, tq[GQ - 1]);
-        if (m > e2s && !(A.dbg_mode & 8)) {                    // rare (about a lane per warp and tile): lane-level appends
-          uint32_t nb = 0;
+          for (int pi = 0; pi < GQ / 2; ++pi) {
+            f2_t acc = add2(pk2(v[2 * pi], v[2 * pi + 1]), pk2(tq[2 * pi], tq[2 * pi + 1]));
 #pragma unroll
-          for (int i = 0; i < GQ; ++i) nb |= (tq[i] > e2s) ? (1u << i) : 0u;
-          const tkey_t key = pack_key(0.0f, row);
-          while (nb) {
-            const int ql = g * GQ + __ffs(nb) - 1;
-            nb &= nb - 1;
-            const int slot = atomicAdd(&cnt[ql], 1);
-            if (slot < TOPK_STRIDE) {
-              kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
-            } else {                                           // this part's buffer is full: spill list of the query
-              const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
-              if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
+            for (int k = 1; k < K; ++k) {
+              const f2_t c = pk2(v[k * GQ + 2 * pi], v[k * GQ + 2 * pi + 1]);
+              acc = fma2(c, c, acc);
+            }
+            upk2(acc, tq[2 * pi], tq[2 * pi + 1]);
+          }
+          float m = max3(tq[0], tq[1], tq[2]);
+#pragma unroll
+          for (int i = 3; i + 1 < GQ; i += 2) m = max3(m, tq[i], tq[i + 1]);
+          m = fmaxf(m, tq[GQ - 1]);
+          if (m > e2s && !(A.dbg_mode & 8)) {                  // rare (about a lane per warp and step): lane-level appends
+            uint32_t nb = 0;
+#pragma unroll
+            for (int i = 0; i < GQ; ++i) nb |= (tq[i] > e2s) ? (1u << i) : 0u;
+            while (nb) {
+              const int ql = qb + g * GQ + __ffs(nb) - 1;
+              nb &= nb - 1;
+              const int slot = atomicAdd(&cnt[ql], 1);
+              if (slot < TOPK_STRIDE) {
+                kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
+              } else {                                         // this part's buffer is full: spill list of the query
+                const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
+                if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
+              }
             }
           }
         }
+        if (!released) {                                       // no group for this warp in this step
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+        if (++buf == NBUF) { buf = 0; bphase ^= 1u; }
+        rot = (rot + WPQ - 1) & (WPQ - 1);
       }
       if (tid == 0) LB_TRACE(6, t);
-      if (!released) {                                         // no group for this warp in this tile
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
-      }
-      if (++buf == NBUF) { buf = 0; bphase ^= 1u; }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(LB_NEPI * 32) : "memory");
     // counts may exceed TOPK_STRIDE: the excess went to the query's spill list
@@ -484,7 +506,7 @@ score_lb_kernel(ScoreArgs A) {
 
 template <int K>
 static int launch_lb(const ScoreArgs& a, cudaStream_t st) {
-  const LbLayout L = lb_layout(K, a.lb.qt, (a.plan.dpad + 15) / 16);
+  const LbLayout L = lb_layout(K, a.lb.qt, a.lb.sub, (a.plan.dpad + 15) / 16);
   const size_t smem = L.total + 1024;                          // slack for the alignment of the dynamic segment
   CFL_CUDA(cudaFuncSetAttribute(score_lb_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(a.lb.parts, a.lb.nqt);
