@@ -53,42 +53,40 @@ __device__ unsigned long long g_lb_trace[8 * 4096];
 #else
 #define LB_TRACE(slot, tile) do { } while (0)
 #endif
-__host__ __device__ constexpr int lb_gq(int K) { return K <= 2 ? 16 : (K <= 4 ? 8 : 4); }
+// A sub-tile holds 4 query groups of GQ queries: epilogue warp `sub` of every TMEM lane quarter owns group `sub`, i.e.
+// K*GQ <= 48 accumulator columns per (row, step) in registers.  K*4*GQ = 192 TMEM columns per buffer where K divides 48.
+__host__ __device__ constexpr int lb_gq(int K) {
+  return K == 1 ? 48 : K == 2 ? 24 : K == 3 ? 16 : K == 4 ? 12 : K == 5 ? 8 : K == 6 ? 8 : K == 7 ? 4 : 6;
+}
 
-// Tiling of the pass.  A CTA keeps `sub` query images of qt queries each resident (K*qt TMEM columns per accumulator
-// buffer, a multiple of 16 and <= 256) and multiplies every catalog tile it streams with all of them, so the catalog
+// Tiling of the pass.  A sub-tile = 4 groups of lb_gq(K) queries = one accumulator buffer of K*qt TMEM columns.  A CTA
+// keeps `sub` query images resident and multiplies every catalog tile it streams with all of them, so the catalog
 // plane is fetched from L2 once per qt*sub queries: with one image per CTA the pass is bound by the L2 -> SM traffic
 // of the re-read plane (measured ~20 B/clk/SM with every SM streaming), not by the tensor pipe.  parts = catalog
 // ranges so that parts * nqt ~ the SM count.  Cost model (clk per CTA): tiles * max(sub * tensor, L2) from the
 // measured laws tensor = nkm * (43 + N/2), L2 = tile bytes / 20.
 LbPlan make_lb_plan(int64_t Q, int K, int d, int64_t tiles) {
-  LbPlan best{0, 0, 0, 0, 0};
-  const int GQ = lb_gq(K);
+  const int qt = 4 * lb_gq(K);
+  const int nc = K * qt;
   const int nkm = (d + 15) / 16;
+  const int nbuf = 512 / nc > LB_MAXBUF ? LB_MAXBUF : 512 / nc;
   int sms = sm_count(); if (sms <= 0) sms = 148;
+  const double tile_clk = nkm * (43.0 + nc / 2.0);              // tensor work per (catalog tile, sub-tile)
+  const double l2_clk = nkm * 4096.0 / 20.0;
+  LbPlan best{qt, 1, (int)((Q + qt - 1) / qt), 1, nbuf};
   double best_cost = 1e30;
-  for (int qt = GQ; K * qt <= 256; qt += GQ) {
-    const int nc = K * qt;
-    if (nc % 16 != 0) continue;
-    const int nbuf = 512 / nc > LB_MAXBUF ? LB_MAXBUF : 512 / nc;
-    const double tile_clk = nkm * (43.0 + nc / 2.0);            // tensor work per (catalog tile, sub-tile)
-    if (nbuf < 2) continue;
-    if (nbuf < 3 && tile_clk < 1000.0) continue;                // short tiles need a third buffer to hide the hand-shake
-    for (int sub = 1; sub <= 4; ++sub) {
-      const size_t smem = (size_t)sub * nkm * 2 * nc * 16 + (size_t)LB_NSTAGE * LB_STAGE + 4096;
-      if (smem > 200 * 1024) break;
-      const int64_t nqt = (Q + (int64_t)qt * sub - 1) / ((int64_t)qt * sub);
-      int64_t parts = sms / nqt; if (parts < 1) parts = 1; if (parts > tiles) parts = tiles;
-      const double per_cta = (double)((tiles + parts - 1) / parts);
-      const double rounds = (double)((nqt * parts + sms - 1) / sms);
-      const double l2_clk = nkm * 4096.0 / 20.0;
-      const double step = sub * tile_clk > l2_clk ? sub * tile_clk : l2_clk;
-      const double cost = per_cta * rounds * step;
-      if (cost < best_cost * 0.999) { best_cost = cost; best = LbPlan{qt, sub, (int)nqt, (int)parts, nbuf}; }
-      if ((int64_t)qt * sub >= Q) break;
-    }
+  for (int sub = 1; sub <= 4; ++sub) {
+    const size_t smem = (size_t)sub * nkm * 2 * nc * 16 + (size_t)LB_NSTAGE * LB_STAGE + 8192;
+    if (smem > 200 * 1024) break;
+    const int64_t nqt = (Q + (int64_t)qt * sub - 1) / ((int64_t)qt * sub);
+    int64_t parts = sms / nqt; if (parts < 1) parts = 1; if (parts > tiles) parts = tiles;
+    const double per_cta = (double)((tiles + parts - 1) / parts);
+    const double rounds = (double)((nqt * parts + sms - 1) / sms);
+    const double step = sub * tile_clk > l2_clk ? sub * tile_clk : l2_clk;
+    const double cost = per_cta * rounds * step;
+    if (cost < best_cost * 0.999) { best_cost = cost; best = LbPlan{qt, sub, (int)nqt, (int)parts, nbuf}; }
+    if ((int64_t)qt * sub >= Q) break;
   }
-  if (best.qt == 0) best = LbPlan{GQ, 1, (int)((Q + GQ - 1) / GQ), 1, 2};
   return best;
 }
 
@@ -290,7 +288,6 @@ score_lb_kernel(ScoreArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int GQ = lb_gq(K);
   constexpr int GC = GQ * K;                                   // TMEM columns of one query group
-  constexpr int WPQ = LB_NEPI / 4;                             // warps per TMEM lane quarter
   const int QT = A.lb.qt;                                      // queries per sub-tile (one accumulator buffer)
   const int SUB = A.lb.sub;                                    // sub-tiles (query images) of this CTA
   const int QC = QT * SUB;                                     // queries per CTA
@@ -403,10 +400,10 @@ score_lb_kernel(ScoreArgs A) {
     }
   } else {
     // ======================================= epilogue ========================================
-    // Warp (lane quarter lq, sub) owns, in tile t, the query groups g with (g + t) mod WPQ == sub (rotating, so that
-    // group counts that are not a multiple of WPQ balance over tiles).  Per group: accumulators -> registers
-    // (tcgen05.ld), -cq from shared memory, bound, rare lane-level appends; the accumulator buffer is released as soon
-    // as the warp's LAST group of the tile is in registers.
+    // Warp (lane quarter lq, sub) owns query group `sub` of every sub-tile: per step it waits for the accumulators,
+    // moves its K*GQ columns to registers (tcgen05.ld), releases the buffer at once (the MMA of step u + NBUF never
+    // waits for CUDA-core work), then evaluates the bound: K-1 packed FMAs + one packed add per query pair, a 3-input
+    // max tree, ONE compare; the rare survivors are appended by their own lane.
     const int lq = warp & 3, sub = warp >> 2;
     const int lrow = lq * 32 + lane;
     tkey_t* kbase = A.keys + ((int64_t)part * A.Q + q0) * TOPK_STRIDE;
@@ -419,79 +416,67 @@ score_lb_kernel(ScoreArgs A) {
     const float c_sq = ((2.0f * CFL_TF32_PRODUCT_U + 2.0f * ulp) * amax + 2.0f * s16 * (1.0f + rk)) * 1.0001f;
     const float c_abs = 2.0f * s16 * amax * 1.0001f;
     float2 er_next = (ntiles > 0) ? __ldg(A.lbrow + t0 * 128 + lrow) : make_float2(0.f, 0.f);   // one tile ahead
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(sub * GC);
+    const float* ncq_w = ncq + sub * GQ;
     int buf = 0; uint32_t bphase = 0;
-    int rot = sub;                                             // (sub - step) mod WPQ: first group of this warp in the step
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t row = (uint32_t)((t0 + (int64_t)t * ts) * 128 + lrow);
       const float2 er = er_next;
       if (t + 1 < ntiles) er_next = __ldg(A.lbrow + (t0 + (int64_t)(t + 1) * ts) * 128 + lrow);
       // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
       const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
-      const tkey_t key = pack_key(0.0f, row);
       for (int sq = 0; sq < SUB; ++sq) {
-        const int qb = sq * QT;                                // first query of the sub-tile within the CTA's queries
-        const int ngroups = nq > qb ? ((nq - qb < QT ? nq - qb : QT) + GQ - 1) / GQ : 0;
         if (tid == 0 && sq == 0) LB_TRACE(3, t);
         mbar_wait(&tfull[buf], bphase);
         tc_fence_after();
         if (tid == 0 && sq == 0) LB_TRACE(4, t);
-        const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * NC);
-        bool released = false;
-        for (int g = rot; g < ngroups && !(A.dbg_mode & 1); g += WPQ) {
-          float v[GC], tq[GQ];
-          tmem_ld_cols<GC>(taddr + (uint32_t)(g * GC), v);
-#pragma unroll
-          for (int i = 0; i < GQ; i += 4) {
-            const float4 c4 = *(const float4*)(ncq + qb + g * GQ + i);
-            tq[i] = c4.x; tq[i + 1] = c4.y; tq[i + 2] = c4.z; tq[i + 3] = c4.w;
-          }
+        float v[GC];
+        if (!(A.dbg_mode & 1)) {
+          tmem_ld_cols<GC>(taddr0 + (uint32_t)(buf * NC), v);
           tmem_ld_wait();
-          if (g + WPQ >= ngroups) {                            // the warp's last group of this step is in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
-            released = true;
-          }
-          if (A.dbg_mode & 4) continue;                        // experiment: the epilogue only reads TMEM
-          // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
-#pragma unroll
-          for (int pi = 0; pi < GQ / 2; ++pi) {
-            f2_t acc = add2(pk2(v[2 * pi], v[2 * pi + 1]), pk2(tq[2 * pi], tq[2 * pi + 1]));
-#pragma unroll
-            for (int k = 1; k < K; ++k) {
-              const f2_t c = pk2(v[k * GQ + 2 * pi], v[k * GQ + 2 * pi + 1]);
-              acc = fma2(c, c, acc);
-            }
-            upk2(acc, tq[2 * pi], tq[2 * pi + 1]);
-          }
-          float m = max3(tq[0], tq[1], tq[2]);
-#pragma unroll
-          for (int i = 3; i + 1 < GQ; i += 2) m = max3(m, tq[i], tq[i + 1]);
-          m = fmaxf(m, tq[GQ - 1]);
-          if (m > e2s && !(A.dbg_mode & 8)) {                  // rare (about a lane per warp and step): lane-level appends
-            uint32_t nb = 0;
-#pragma unroll
-            for (int i = 0; i < GQ; ++i) nb |= (tq[i] > e2s) ? (1u << i) : 0u;
-            while (nb) {
-              const int ql = qb + g * GQ + __ffs(nb) - 1;
-              nb &= nb - 1;
-              const int slot = atomicAdd(&cnt[ql], 1);
-              if (slot < TOPK_STRIDE) {
-                kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
-              } else {                                         // this part's buffer is full: spill list of the query
-                const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
-                if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
-              }
-            }
-          }
         }
-        if (!released) {                                       // no group for this warp in this step
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[buf]);
-        }
+        if (tid == 0 && sq == 0) LB_TRACE(5, t);
+        tc_fence_before();                                     // the accumulators are in registers: release the buffer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
         if (++buf == NBUF) { buf = 0; bphase ^= 1u; }
-        rot = (rot + WPQ - 1) & (WPQ - 1);
+        if (A.dbg_mode & 5) continue;                          // experiments: no epilogue work / TMEM reads only
+        // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
+        // (evaluated in place: v[i], i < GQ, becomes t_i)
+        const float2* ncq2 = (const float2*)(ncq_w + sq * QT);
+#pragma unroll
+        for (int pi = 0; pi < GQ / 2; ++pi) {
+          const float2 c2 = ncq2[pi];
+          f2_t acc = add2(pk2(v[2 * pi], v[2 * pi + 1]), pk2(c2.x, c2.y));
+#pragma unroll
+          for (int k = 1; k < K; ++k) {
+            const f2_t c = pk2(v[k * GQ + 2 * pi], v[k * GQ + 2 * pi + 1]);
+            acc = fma2(c, c, acc);
+          }
+          upk2(acc, v[2 * pi], v[2 * pi + 1]);
+        }
+        float m = max3(v[0], v[1], v[2]);
+#pragma unroll
+        for (int i = 3; i + 1 < GQ; i += 2) m = max3(m, v[i], v[i + 1]);
+        m = fmaxf(m, v[GQ - 1]);
+        if (m > e2s && !(A.dbg_mode & 8)) {                    // rare (about a lane per warp and step): lane-level appends
+          unsigned long long nb = 0;
+#pragma unroll
+          for (int i = 0; i < GQ; ++i) nb |= (v[i] > e2s) ? (1ull << i) : 0ull;
+          const tkey_t key = pack_key(0.0f, row);
+          while (nb) {
+            const int ql = sq * QT + sub * GQ + __ffsll((long long)nb) - 1;
+            nb &= nb - 1;
+            if (ql >= nq) continue;                            // padding queries never pass (ncq = -inf); belt and braces
+            const int slot = atomicAdd(&cnt[ql], 1);
+            if (slot < TOPK_STRIDE) {
+              kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
+            } else {                                           // this part's buffer is full: spill list of the query
+              const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
+              if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
+            }
+          }
+        }
       }
       if (tid == 0) LB_TRACE(6, t);
     }
