@@ -208,8 +208,9 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NCOLS]) 
   }
 }
 
+constexpr int LB_WQ = 64;                            // entries of a warp's survivor queue (16 B each)
 struct LbLayout {
-  uint32_t b_img, a_ring, ncq, cnt, red, bars, tmem_slot, total;
+  uint32_t b_img, a_ring, ncq, cnt, red, wq, bars, tmem_slot, total;
 };
 __host__ __device__ inline LbLayout lb_layout(int K, int qt, int sub, int nkm) {
   LbLayout L;
@@ -219,10 +220,36 @@ __host__ __device__ inline LbLayout lb_layout(int K, int qt, int sub, int nkm) {
   L.ncq = off;     off += (uint32_t)(qt * sub) * 4u;                      off = (off + 15u) & ~15u;
   L.cnt = off;     off += (uint32_t)(qt * sub) * 4u;                      off = (off + 15u) & ~15u;
   L.red = off;     off += 32u * 4u;
+  L.wq = off;      off += (uint32_t)LB_NEPI * LB_WQ * 16u;
   L.bars = off;    off += (2u * LB_NSTAGE + 2u * LB_MAXBUF + 1u) * 8u;
   L.tmem_slot = off; off += 16u;
   L.total = off;
   return L;
+}
+
+// Appends the entries of a warp's survivor queue to the per-(part, query) key buffers (warp-uniform call): lane e takes
+// entry e, one shared-memory atomic + one 8-byte store per surviving (row, query).
+__device__ __forceinline__ void lb_flush_queue(const uint4* wq, int fill, int lane, int QT, int g0, int nq, int* cnt,
+                                               tkey_t* kbase, tkey_t* spill, int* spill_cnt, int64_t q0) {
+  __syncwarp();
+  for (int e = lane; e < fill; e += 32) {
+    const uint4 en = wq[e];
+    unsigned long long nb = ((unsigned long long)en.w << 32) | en.z;
+    const tkey_t key = pack_key(0.0f, en.x);
+    while (nb) {
+      const int ql = (int)en.y * QT + g0 + __ffsll((long long)nb) - 1;
+      nb &= nb - 1;
+      if (ql >= nq) continue;                                  // padding queries never pass (ncq = -inf); belt and braces
+      const int slot = atomicAdd(&cnt[ql], 1);
+      if (slot < TOPK_STRIDE) {
+        kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
+      } else {                                                 // this part's buffer is full: spill list of the query
+        const int sp = atomicAdd(&spill_cnt[q0 + ql], 1);
+        if (sp < LB_SPILL) spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // Sequence of "steps" u = (catalog tile t, sub-tile s): accumulator buffer u mod NBUF, A = the tile's ring stage(s),
@@ -418,6 +445,8 @@ score_lb_kernel(ScoreArgs A) {
     float2 er_next = (ntiles > 0) ? __ldg(A.lbrow + t0 * 128 + lrow) : make_float2(0.f, 0.f);   // one tile ahead
     const uint32_t taddr0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(sub * GC);
     const float* ncq_w = ncq + sub * GQ;
+    uint4* wq = (uint4*)(smem + L.wq) + warp * LB_WQ;
+    int wq_fill = 0;
     int buf = 0; uint32_t bphase = 0;
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t row = (uint32_t)((t0 + (int64_t)t * ts) * 128 + lrow);
@@ -455,31 +484,43 @@ score_lb_kernel(ScoreArgs A) {
           }
           upk2(acc, v[2 * pi], v[2 * pi + 1]);
         }
-        float m = max3(v[0], v[1], v[2]);
+        // max over the group as a two-level tree of 3-input maxima: the triples' maxima locate the survivors cheaply
+        constexpr int NT3 = (GQ + 2) / 3;
+        float m3[NT3];
 #pragma unroll
-        for (int i = 3; i + 1 < GQ; i += 2) m = max3(m, v[i], v[i + 1]);
-        m = fmaxf(m, v[GQ - 1]);
-        if (m > e2s && !(A.dbg_mode & 8)) {                    // rare (about a lane per warp and step): lane-level appends
-          unsigned long long nb = 0;
+        for (int j = 0; j < NT3; ++j) {
+          const int i0 = 3 * j, i1 = 3 * j + 1 < GQ ? 3 * j + 1 : i0, i2 = 3 * j + 2 < GQ ? 3 * j + 2 : i0;
+          m3[j] = max3(v[i0], v[i1], v[i2]);
+        }
+        float m = m3[0];
 #pragma unroll
-          for (int i = 0; i < GQ; ++i) nb |= (v[i] > e2s) ? (1ull << i) : 0ull;
-          const tkey_t key = pack_key(0.0f, row);
-          while (nb) {
-            const int ql = sq * QT + sub * GQ + __ffsll((long long)nb) - 1;
-            nb &= nb - 1;
-            if (ql >= nq) continue;                            // padding queries never pass (ncq = -inf); belt and braces
-            const int slot = atomicAdd(&cnt[ql], 1);
-            if (slot < TOPK_STRIDE) {
-              kbase[(int64_t)ql * TOPK_STRIDE + slot] = key;
-            } else {                                           // this part's buffer is full: spill list of the query
-              const int sp = atomicAdd(&A.spill_cnt[q0 + ql], 1);
-              if (sp < LB_SPILL) A.spill[(q0 + ql) * (int64_t)LB_SPILL + sp] = key;
-            }
+        for (int j = 1; j < NT3; j += 2) m = (j + 1 < NT3) ? max3(m, m3[j], m3[j + 1]) : fmaxf(m, m3[j]);
+        const bool hit = m > e2s && !(A.dbg_mode & 8);
+        const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+        if (hb != 0) {
+          // Rare per lane (a fraction of a percent), but about every second warp-step has one: the survivors go to
+          // the warp's queue in shared memory -- (row, sub-tile, mask of the group's surviving queries), position by
+          // ballot, no atomics -- and are appended to the per-query key buffers in batches of >= 32 entries, so the
+          // latency of the shared-memory atomics and the dependent global stores is paid once per batch.
+          const int nh = __popc(hb);
+          if (wq_fill + nh > LB_WQ) { lb_flush_queue(wq, wq_fill, lane, QT, sub * GQ, nq, cnt, kbase, A.spill, A.spill_cnt, q0); wq_fill = 0; }
+          if (hit) {
+            unsigned long long nb = 0;
+#pragma unroll
+            for (int j = 0; j < NT3; ++j)
+              if (m3[j] > e2s) {
+#pragma unroll
+                for (int i = 3 * j; i < 3 * j + 3 && i < GQ; ++i) nb |= (v[i] > e2s) ? (1ull << i) : 0ull;
+              }
+            wq[wq_fill + __popc(hb & ((1u << lane) - 1u))] = make_uint4(row, (uint32_t)sq, (uint32_t)nb, (uint32_t)(nb >> 32));
           }
+          wq_fill += nh;
+          __syncwarp();
         }
       }
       if (tid == 0) LB_TRACE(6, t);
     }
+    lb_flush_queue(wq, wq_fill, lane, QT, sub * GQ, nq, cnt, kbase, A.spill, A.spill_cnt, q0);
     asm volatile("bar.sync 1, %0;" ::"n"(LB_NEPI * 32) : "memory");
     // counts may exceed TOPK_STRIDE: the excess went to the query's spill list
     for (int ql = tid; ql < nq; ql += LB_NEPI * 32) A.counts[(int64_t)part * A.Q + q0 + ql] = cnt[ql];
