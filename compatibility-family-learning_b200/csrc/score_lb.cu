@@ -44,6 +44,13 @@ constexpr int LB_NSTAGE = 6;                         // ring stages of up to 4 K
 constexpr uint32_t LB_BLK = 2u * 128u * 16u;         // one K-step of the fp16 catalog plane: [chunk][128 rows][16 B]
 constexpr uint32_t LB_STAGE = 4u * LB_BLK;
 constexpr int LB_MAXBUF = 4;
+// CFL_SCORE_DBG_MODE experiments (tools/passc_probe.py) exist only in builds with CFL_NVCC_EXTRA=-DCFL_LB_EXPERIMENTS: a
+// load of the mode word plus a branch per check sits on the critical path of every step otherwise.
+#ifdef CFL_LB_EXPERIMENTS
+#define LB_DBG(A, bits) (((A).dbg_mode & (bits)) != 0)
+#else
+#define LB_DBG(A, bits) false
+#endif
 #ifdef CFL_LB_TRACE
 // timing trace of CTA (0,0) (tools/lb_trace.py; builds with CFL_NVCC_EXTRA=-DCFL_LB_TRACE only): per tile
 // [0] MMA warp starts the tile, [2] tile issued, [3] epilogue warp 0 before the tfull wait, [4] after it,
@@ -267,7 +274,7 @@ __device__ __forceinline__ void lb_mma_loop(const ScoreArgs& A, uint32_t a_base,
   int buf = 0; uint32_t bphase = 0;                            // accumulator buffer of the step and the parity of its use count
   if (ntiles > 0) {
     mbar_wait_addr(tempty0, 1u);
-    if (!(A.dbg_mode & 2)) mbar_wait_addr(full0, 0u);
+    if (!LB_DBG(A, 2)) mbar_wait_addr(full0, 0u);
     tc_fence_after();
   }
   for (int t = 0; t < ntiles; ++t) {
@@ -288,13 +295,14 @@ __device__ __forceinline__ void lb_mma_loop(const ScoreArgs& A, uint32_t a_base,
         for (int j = 0; j < KSS; ++j) {
           if (j == KSS - 1) {                                  // look ahead: barriers of the next stage / step
             bool fence = false;
-            if (last && (!last_sub || t + 1 < ntiles) && !(A.dbg_mode & 16)) { mbar_wait_addr(tempty0 + (uint32_t)nbuf_i * 8u, nbphase ^ 1u); fence = true; }
+            if (last && (!last_sub || t + 1 < ntiles) && !LB_DBG(A, 16)) { mbar_wait_addr(tempty0 + (uint32_t)nbuf_i * 8u, nbphase ^ 1u); fence = true; }
             // the next stage holds catalog data not yet waited for: the tile's further stages during its first
             // sub-tile, the next tile's first stage after the last sub-tile
             const bool need_full = last ? (last_sub && t + 1 < ntiles) : (sq == 0);
-            if (need_full && !(A.dbg_mode & 2)) { mbar_wait_addr(full0 + (uint32_t)nstage * 8u, nphase); fence = true; }
+            if (need_full && !LB_DBG(A, 2)) { mbar_wait_addr(full0 + (uint32_t)nstage * 8u, nphase); fence = true; }
             if (fence) tc_fence_after();
           }
+          if (!LB_DBG(A, 64))                              // 64: no MMAs at all, only the barrier traffic (timing only)
           mma_f16(d_tmem, make_smem_desc(a_st + (uint32_t)j * LB_BLK, 128u * 16u, 128u),
                   make_smem_desc(b_st + (uint32_t)j * b_step, (uint32_t)NC * 16u, 128u), idesc, (sidx | j) ? 1u : 0u);
         }
@@ -415,7 +423,7 @@ score_lb_kernel(ScoreArgs A) {
         bulk_g2s(b_img + o, qsrc + o, n, bfull);
       }
       int stage = 0; uint32_t phase = 0;
-      for (int t = 0; t < ((A.dbg_mode & 2) ? 0 : ntiles); ++t) {
+      for (int t = 0; t < (LB_DBG(A, 2) ? 0 : ntiles); ++t) {
         const unsigned char* src = (const unsigned char*)A.cimg16 + (size_t)(t0 + (int64_t)t * ts) * nkm * LB_BLK;
         for (int ks = 0; ks < nkm; ks += kss) {
           mbar_wait(&empty[stage], phase ^ 1u);
@@ -455,27 +463,27 @@ score_lb_kernel(ScoreArgs A) {
       // |e|^2 lowered by the error bound of the single-product evaluation; +inf for the padding rows
       const float e2s = fmaf(er.x, c_e2, fmaf(-c_sq, er.y, -c_abs));
       for (int sq = 0; sq < SUB; ++sq) {
-        if (tid == 0 && sq == 0) LB_TRACE(3, t);
+        if (tid == 0) LB_TRACE(3, t * SUB + sq);
         mbar_wait(&tfull[buf], bphase);
         tc_fence_after();
-        if (tid == 0 && sq == 0) LB_TRACE(4, t);
+        if (tid == 0) LB_TRACE(4, t * SUB + sq);
         float v[GC];
-        if (!(A.dbg_mode & 1)) {
+        if (!LB_DBG(A, 1)) {
           tmem_ld_cols<GC>(taddr0 + (uint32_t)(buf * NC), v);
           tmem_ld_wait();
         }
-        if (tid == 0 && sq == 0) LB_TRACE(5, t);
+        if (tid == 0) LB_TRACE(5, t * SUB + sq);
         tc_fence_before();                                     // the accumulators are in registers: release the buffer
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[buf]);
         if (++buf == NBUF) { buf = 0; bphase ^= 1u; }
-        if (A.dbg_mode & 5) continue;                          // experiments: no epilogue work / TMEM reads only
+        if (LB_DBG(A, 5)) continue;                          // experiments: no epilogue work / TMEM reads only
         // t_i = e.(2a) - cq_i + sum_j (e.u_j)^2 ; the (row, query) survives iff t_i > e2s(row)
         // (evaluated in place: v[i], i < GQ, becomes t_i)
         const float2* ncq2 = (const float2*)(ncq_w + sq * QT);
 #pragma unroll
         for (int pi = 0; pi < GQ / 2; ++pi) {
-          const float2 c2 = ncq2[pi];
+          const float2 c2 = LB_DBG(A, 32) ? make_float2(e2s, e2s) : ncq2[pi];   // 32: no shared-memory reads (timing only)
           f2_t acc = add2(pk2(v[2 * pi], v[2 * pi + 1]), pk2(c2.x, c2.y));
 #pragma unroll
           for (int k = 1; k < K; ++k) {
@@ -495,7 +503,8 @@ score_lb_kernel(ScoreArgs A) {
         float m = m3[0];
 #pragma unroll
         for (int j = 1; j < NT3; j += 2) m = (j + 1 < NT3) ? max3(m, m3[j], m3[j + 1]) : fmaxf(m, m3[j]);
-        const bool hit = m > e2s && !(A.dbg_mode & 8);
+        if (tid == 0) LB_TRACE(6, t * SUB + sq);
+        const bool hit = m > e2s && !LB_DBG(A, 8);
         const uint32_t hb = __ballot_sync(0xffffffffu, hit);
         if (hb != 0) {
           // Rare per lane (a fraction of a percent), but about every second warp-step has one: the survivors go to
@@ -517,8 +526,8 @@ score_lb_kernel(ScoreArgs A) {
           wq_fill += nh;
           __syncwarp();
         }
+        if (tid == 0) LB_TRACE(7, t * SUB + sq);
       }
-      if (tid == 0) LB_TRACE(6, t);
     }
     lb_flush_queue(wq, wq_fill, lane, QT, sub * GQ, nq, cnt, kbase, A.spill, A.spill_cnt, q0);
     asm volatile("bar.sync 1, %0;" ::"n"(LB_NEPI * 32) : "memory");

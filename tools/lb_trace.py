@@ -32,17 +32,13 @@ n = 8 * 4096
 buf = (C.c_ulonglong * n)()
 assert nat.lib().cfl_lb_trace_read(buf, n) == 0
 tr = np.frombuffer(buf, dtype=np.uint64).reshape(4096, 8).astype(np.int64)
-T = 860
-tr = tr[:T]
-names = ["mma: wait tempty", "mma: issue", "epi: wait tfull", "epi: tcgen05.ld", "epi: compute+append"]
-d = [tr[:, 1] - tr[:, 0], tr[:, 2] - tr[:, 1], tr[:, 4] - tr[:, 3], tr[:, 5] - tr[:, 4], tr[:, 6] - tr[:, 5]]
-per_tile = np.diff(tr[:, 2])
-print("mode", os.environ.get("CFL_SCORE_DBG_MODE", "0"), "clk per tile (MMA issue to issue): median", int(np.median(per_tile)), "mean", int(per_tile.mean()))
+T = 1100
+tr = tr[20:T]
+names = ["epi: wait tfull", "epi: tcgen05.ld + wait", "epi: release + math", "epi: ballot + hit path", "epi: loop back to next wait"]
+d = [tr[:, 4] - tr[:, 3], tr[:, 5] - tr[:, 4], tr[:, 6] - tr[:, 5], tr[:, 7] - tr[:, 6], tr[1:, 3] - tr[:-1, 7]]
+per = np.diff(tr[:, 4])
+print("mode", os.environ.get("CFL_SCORE_DBG_MODE", "0"), "clk per step (epilogue warp 0, tfull seen to tfull seen): median", int(np.median(per)), "mean", int(per.mean()))
 for nm, x in zip(names, d):
-    x = x[10:]
-    print(f"  {nm:22s} median {int(np.median(x)):6d}  mean {int(x.mean()):6d}  p90 {int(np.percentile(x, 90)):6d}")
-print("  epilogue tile t starts (tfull seen) after MMA issue of tile t by: median", int(np.median((tr[:, 4] - tr[:, 2])[10:])))
-print("  first tiles (relative clk):")
-base = tr[0, 0]
-for t in range(6):
-    print("   ", t, [int(x - base) for x in tr[t, :7]])
+    print(f"  {nm:28s} median {int(np.median(x)):6d}  mean {int(x.mean()):6d}  p90 {int(np.percentile(x, 90)):6d}")
+hitp = tr[:, 7] - tr[:, 6]
+print("  steps with a hit path > 60 clk:", float((hitp > 60).mean()), " mean cost of those:", int(hitp[hitp > 60].mean()) if (hitp > 60).any() else 0)

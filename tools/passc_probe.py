@@ -10,7 +10,7 @@ import bench
 from cfl import _native as nat
 from cfl.ranking import CatalogIndex
 
-os.environ["CFL_EXPERIMENTS"] = "1"
+os.environ["CFL_EXPERIMENTS"] = "1"     # modes other than 0 need a build with CFL_NVCC_EXTRA=-DCFL_LB_EXPERIMENTS
 dev = torch.device("cuda", 0)
 w = bench.synth_weights(dev)
 E = torch.empty(bench.N_PER_GPU, bench.D, device=dev)
