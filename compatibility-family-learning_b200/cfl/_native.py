@@ -68,6 +68,7 @@ SIGNATURES = {
     "cfl_adam_step_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),
     "cfl_set_kernel_timer": (_int, [_vp, _vp]),
     "cfl_selftest_umma": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
+    "cfl_selftest_umma_f16": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
 }
 
 
@@ -472,6 +473,16 @@ def set_kernel_timer(start_event=None, stop_event=None):
         ev.record()                      # forces creation of the underlying cudaEvent_t
     _check(lib().cfl_set_kernel_timer(C.c_void_p(start_event.cuda_event), C.c_void_p(stop_event.cuda_event)),
            "cfl_set_kernel_timer")
+
+
+def selftest_umma_f16(A, Bm):
+    """D[128,N] = fp16(A)[128,Kd] @ fp16(Bm)[N,Kd]^T with ONE kind::f16 MMA per 16 dimensions (test only)."""
+    A = _f32c(A, "A").contiguous()
+    Bm = _f32c(Bm, "Bm").contiguous()
+    N, Kd = Bm.shape
+    D = torch.empty(128, N, dtype=torch.float32, device=A.device)
+    _check(lib().cfl_selftest_umma_f16(_ptr(A), _ptr(Bm), _ptr(D), N, Kd, _stream()), "cfl_selftest_umma_f16")
+    return D
 
 
 def selftest_umma(A, Bm):

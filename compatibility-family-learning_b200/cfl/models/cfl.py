@@ -146,6 +146,10 @@ class CFL(PairModel):
         if self.model_type == "linear":
             return super().train_step(src_pos, dst_pos, src_neg, dst_neg, val_batches)
         # conv: autograd over torch trunk + kernel heads; loss in torch ops (BASELINE config 1: plumbing)
+        if self.caffe_margin or not self.use_threshold:
+            # the linear path implements both (cfl.py:912-921 and the separate theta optimiser of cfl.py:1076-1079);
+            # the conv plumbing does not: refuse instead of silently optimising a different objective
+            raise NotImplementedError("conv model: caffe_margin / use_threshold=False are only implemented for model_type='linear'")
         import torch.nn.functional as TF
         s_pos_src, _, dp, pp = self._conv_forward(self._dev(src_pos), self._dev(dst_pos))
         _, _, dn, pn = self._conv_forward(self._dev(src_neg), self._dev(dst_neg))

@@ -556,6 +556,62 @@ extern "C" int cfl_lb_trace_read(unsigned long long* host, int n) {
 }
 #endif
 
+// ---- self-test of the pass's MMA: D[128, N] = A[128, Kd] B[N, Kd]^T, operands rounded to fp16 (RN), ONE kind::f16 MMA
+// per 16 dimensions, fp32 accumulators: what the error margin of the lower bound (CFL_TF32_PRODUCT_U) is about.
+__global__ void __launch_bounds__(160)
+lb_selftest_kernel(const float* __restrict__ Af, const float* __restrict__ Bf, float* __restrict__ D, int N, int Kd) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int nks = (Kd + 15) / 16;
+  const uint32_t a_step = 2u * 128u * 16u, b_step = 2u * (uint32_t)N * 16u;
+  unsigned char* a_img = smem;
+  unsigned char* b_img = smem + (size_t)nks * a_step;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (tid < 128) {
+    for (int ks = 0; ks < nks; ++ks)
+      for (int c = 0; c < 2; ++c) {
+        __align__(16) __half h[8];
+        for (int i = 0; i < 8; ++i) { const int j = ks * 16 + c * 8 + i; h[i] = __float2half_rn(j < Kd ? Af[(size_t)tid * Kd + j] : 0.0f); }
+        *(uint4*)(a_img + (size_t)ks * a_step + (c * 128 + tid) * 16) = *(const uint4*)h;
+        for (int n = tid; n < N; n += 128) {
+          for (int i = 0; i < 8; ++i) { const int j = ks * 16 + c * 8 + i; h[i] = __float2half_rn(j < Kd ? Bf[(size_t)n * Kd + j] : 0.0f); }
+          *(uint4*)(b_img + (size_t)ks * b_step + ((size_t)c * N + n) * 16) = *(const uint4*)h;
+        }
+      }
+    fence_proxy_async();
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 4) tmem_alloc(&slot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = slot;
+  if (warp == 4) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(128, (uint32_t)N);
+      for (int ks = 0; ks < nks; ++ks)
+        mma_f16(tb, make_smem_desc(smem_u32(a_img) + ks * a_step, 128u * 16u, 128u),
+                make_smem_desc(smem_u32(b_img) + ks * b_step, (uint32_t)N * 16u, 128u), idesc, ks ? 1u : 0u);
+      mma_commit(&bar);
+    }
+  } else {
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 8) {
+      float v[8];
+      tmem_ld8(tb + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      for (int j = 0; j < 8; ++j) D[(size_t)tid * N + c0 + j] = v[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tb, ncols);
+}
+
 int score_lb_launch(const ScoreArgs& a, cudaStream_t st) {
   switch (a.K) {
     case 1: return launch_lb<1>(a, st);
@@ -572,3 +628,18 @@ int score_lb_launch(const ScoreArgs& a, cudaStream_t st) {
 }
 
 }  // namespace cfl
+
+extern "C" int cfl_selftest_umma_f16(const float* A, const float* Bm, float* D, int N, int Kd, void* stream) {
+  using namespace cfl;
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(A && Bm && D, CFL_ERR_INVALID, "selftest_umma_f16: NULL argument");
+  CFL_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, CFL_ERR_INVALID, "selftest_umma_f16: N must be a multiple of 16 in [16,256]");
+  CFL_REQUIRE(Kd >= 1 && Kd <= 128, CFL_ERR_INVALID, "selftest_umma_f16: Kd must be in [1,128]");
+  const int nks = (Kd + 15) / 16;
+  const size_t smem = (size_t)nks * (2 * 128 * 16 + 2 * (size_t)N * 16) + 1024;
+  CFL_CUDA(cudaFuncSetAttribute(lb_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lb_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, Bm, D, N, Kd);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}

@@ -248,6 +248,11 @@ int cfl_set_kernel_timer(void* start_event, void* stop_event);
  * Test-only; used by tests/ to validate descriptors and layouts in isolation. */
 int cfl_selftest_umma(const float* A, const float* Bm, float* D, int N, int Kd, void* stream);
 
+/* Self-test of the lower-bound pass's MMA: operands rounded to fp16, one tcgen05.mma.kind::f16 per 16 dimensions, fp32
+ * accumulators; D[128,N] = A[128,Kd] * B[N,Kd]^T, Kd <= 128.  Test-only: tests/ measures the rounding the error margin
+ * of the bound has to cover (operand rounding + accumulation inside the tensor core). */
+int cfl_selftest_umma_f16(const float* A, const float* Bm, float* D, int N, int Kd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

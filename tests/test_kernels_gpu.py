@@ -453,6 +453,108 @@ def test_score_topk_lower_bound_pass_equals_exact_filter_and_range_guard(nat, mo
     assert int(c[1][3, 0]) == 4321
 
 
+def test_lower_bound_mma_rounding_is_inside_the_margin(nat):
+    """The rigorous margin of the lower-bound pass charges u = 1.1 * 2^-10 |e||x| per Gram value: 2^-10 (+ 2^-22) for
+    the two fp16 operand roundings, the rest for the fp32 accumulation inside the tensor core.  Measured here on the
+    MMA the pass issues (kind::f16, fp32 accumulators): against the exact product of the ROUNDED operands the error
+    must stay below 2^-20 |a||b| (seen: ~1.6 * 2^-24), against the exact product of the unrounded operands below u."""
+    rng = np.random.default_rng(5)
+    for Kd, scale in ((64, 1.0), (128, 1.0), (20, 0.05), (64, 30.0)):
+        A = (rng.normal(size=(128, Kd)) * scale).astype(np.float32)
+        B = (rng.normal(size=(192, Kd)) * scale).astype(np.float32)
+        D = host(nat.selftest_umma_f16(dev(A), dev(B))).astype(np.float64)
+        Ah, Bh = A.astype(np.float16).astype(np.float64), B.astype(np.float16).astype(np.float64)
+        nrm = np.linalg.norm(A.astype(np.float64), axis=1)[:, None] * np.linalg.norm(B.astype(np.float64), axis=1)[None, :]
+        acc_err = np.abs(D - Ah @ Bh.T) / nrm
+        tot_err = np.abs(D - A.astype(np.float64) @ B.astype(np.float64).T) / nrm
+        assert acc_err.max() < 2.0 ** -20, (Kd, scale, acc_err.max())
+        assert tot_err.max() < 1.1 * 2.0 ** -10, (Kd, scale, tot_err.max())
+        assert abs((D - Ah @ Bh.T).mean()) < 1e-6 * nrm.mean()          # no truncation bias
+
+
+@pytest.mark.parametrize("K,d", [(4, 128), (8, 128), (8, 20), (1, 64), (4, 20), (2, 64), (3, 12)])
+def test_large_catalog_cascade_matches_oracle(nat, monkeypatch, K, d):
+    """The path bench.py times (sample passes -> thresholds -> probe -> full filter pass -> exact rescoring ->
+    verification / redo) against the fp64 oracle at the shapes of the C5 sweep: d = 128 (two ring stages per tile,
+    small query tiles), K = 8 (exact 3xTF32 filter on a long catalog), K = 1 (siamese-like), d = 20 / 12 (padded
+    K-steps).  Also: identical bits with the single adaptive pass."""
+    rng = np.random.default_rng(100 * K + d)
+    N, Q = 150_000, 150
+    E = rng.normal(size=(N, d)).astype(np.float32)
+    Pq = (E[rng.integers(0, N, Q)][:, None, :] + 0.5 * rng.normal(size=(Q, K, d))).astype(np.float32)
+    E, Pq = dev(E), dev(Pq)
+    mu = nat.col_mean(E)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "100000000")
+    a = nat.score_topk(Pq, E, 100, mu=mu)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "2")
+    monkeypatch.setenv("CFL_SCORE_SAMPLE_STRIDE", "8")
+    tv, ti, st = nat.score_topk(Pq, E, 100, mu=mu, want_stats=True)
+    assert torch.equal(a[1], ti) and torch.equal(a[0], tv)
+    stats = dict(zip(nat.SCORE_STAT_NAMES, st.tolist()))
+    assert stats["lower_bound_pass"] == (1 if K <= 4 else 0)
+    qs = [0, 37, 74, 111, Q - 1]
+    D = O.all_pairs_dist(host(Pq[qs]).astype(np.float64), host(E).astype(np.float64), block=1)
+    wv, wi = O.rank_topk(D, 100)
+    np.testing.assert_allclose(host(tv[qs]), wv, rtol=1e-4)
+    got = host(ti[qs])
+    for r in range(len(qs)):
+        for c_ in set(got[r].tolist()) ^ set(wi[r].tolist()):
+            assert abs(D[r, c_] - wv[r, -1]) <= 1e-5 * max(wv[r, -1], 1.0) + 1e-7
+
+
+def test_clustered_catalog_cascade_matches_oracle(nat, monkeypatch):
+    """Adversarial catalog for the threshold cascade: 40 tight clusters (sigma 0.02), queries sitting on cluster
+    centres, so that thousands of rows lie within a hair of every threshold, the samples see only a few clusters per
+    tile, and survivors concentrate on a handful of queries' key buffers (spill lists, probe, exact redo)."""
+    rng = np.random.default_rng(4242)
+    N, Q, K, d = 200_000, 128, 3, 64
+    centres = rng.normal(size=(40, d)).astype(np.float32)
+    lab = rng.integers(0, 40, N)
+    E = (centres[lab] + 0.02 * rng.normal(size=(N, d))).astype(np.float32)
+    Pq = (centres[rng.integers(0, 40, Q)][:, None, :] + 0.05 * rng.normal(size=(Q, K, d))).astype(np.float32)
+    E, Pq = dev(E), dev(Pq)
+    mu = nat.col_mean(E)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "100000000")
+    a = nat.score_topk(Pq, E, 100, mu=mu)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "2")
+    monkeypatch.setenv("CFL_SCORE_SAMPLE_STRIDE", "8")
+    tv, ti, st = nat.score_topk(Pq, E, 100, mu=mu, want_stats=True)
+    assert torch.equal(a[1], ti) and torch.equal(a[0], tv)
+    qs = [0, 31, 64, 99, Q - 1]
+    D = O.all_pairs_dist(host(Pq[qs]).astype(np.float64), host(E).astype(np.float64), block=1)
+    wv, wi = O.rank_topk(D, 100)
+    np.testing.assert_allclose(host(tv[qs]), wv, rtol=1e-4)
+    got = host(ti[qs])
+    for r in range(len(qs)):
+        for c_ in set(got[r].tolist()) ^ set(wi[r].tolist()):
+            assert abs(D[r, c_] - wv[r, -1]) <= 1e-5 * max(wv[r, -1], 1.0) + 1e-7
+
+
+def test_bench_shape_matches_oracle_with_default_knobs(nat):
+    """bench.py's own shape -- K = 3, d = 64, 1 M catalog rows, Q = 1024 queries (16 query tiles x 9 catalog parts for
+    the exact kernel, 8 x 18 for the lower-bound pass), every knob at its default -- against the fp64 oracle for one
+    query out of each of eight different query tiles, plus the statistics bench.py prints."""
+    g = torch.Generator(device="cuda").manual_seed(633)
+    N, d, K, Q, k = 1_000_000, 64, 3, 1024, 100
+    E = torch.randn(N, d, generator=g, device="cuda")
+    anchors = torch.randint(0, N, (Q,), generator=g, device="cuda")
+    Pq = E[anchors][:, None, :] + 0.5 * torch.randn(Q, K, d, generator=g, device="cuda")
+    mu = nat.col_mean(E)
+    img = nat.catalog_pack(E, K, mu)
+    tv, ti, st = nat.score_topk(Pq, E, k, mu=mu, image=img, want_stats=True)
+    stats = dict(zip(nat.SCORE_STAT_NAMES, st.tolist()))
+    assert stats["lower_bound_pass"] == 1 and stats["redo_queries"] <= 2 and stats["spill_queries"] == 0
+    assert 100 * Q <= stats["survivors"] <= 4000 * Q
+    qs = [0, 70, 200, 333, 470, 600, 900, 1023]
+    D = O.all_pairs_dist(host(Pq[qs]).astype(np.float64), host(E).astype(np.float64), block=1)
+    wv, wi = O.rank_topk(D, k)
+    np.testing.assert_allclose(host(tv[qs]), wv, rtol=1e-4)
+    got = host(ti[qs])
+    for r in range(len(qs)):
+        for c_ in set(got[r].tolist()) ^ set(wi[r].tolist()):
+            assert abs(D[r, c_] - wv[r, -1]) <= 1e-5 * max(wv[r, -1], 1.0) + 1e-7
+
+
 # ---------------------------------------------------------------------------- full-size properties
 def test_full_size_catalog_properties(nat):
     """BASELINE config 3 size (1M-item catalog, K=3, d=64): size-independent properties instead of a

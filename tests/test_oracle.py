@@ -209,3 +209,24 @@ def test_golden_fixtures_reproduce(name):
     for k in fresh:
         np.testing.assert_allclose(np.asarray(fresh[k]), stored[k], rtol=1e-13, atol=0,
                                    err_msg=f"{name}:{k}")
+
+
+def test_conv2d_weight_norm_oracle_matches_an_independent_convolution():
+    """The conv-trunk oracle (cfl/layers.py:100-187: l2_normalize with eps, SAME padding (1, 2) for 28 -> 14) against
+    torch's float64 conv2d with explicit asymmetric padding."""
+    import torch
+    import torch.nn.functional as TF
+    from oracle import cfl_oracle as O
+    rng = np.random.default_rng(3)
+    x = rng.uniform(size=(3, 28, 28, 1))
+    V1, g1, b1 = rng.normal(size=(5, 5, 1, 8)), rng.uniform(0.5, 1.5, 8), rng.normal(size=8) * 0.1
+    V2, g2, b2 = rng.normal(size=(5, 5, 8, 16)), rng.uniform(0.5, 1.5, 16), rng.normal(size=16) * 0.1
+    got = O.conv_pcd_trunk(x.reshape(3, 784), [(V1, g1, b1), (V2, g2, b2)])
+    t = torch.as_tensor(x).permute(0, 3, 1, 2)
+    for V, g, b in ((V1, g1, b1), (V2, g2, b2)):
+        W = torch.as_tensor(V / np.sqrt(np.maximum((V * V).sum((0, 1, 2), keepdims=True), 1e-12)) * g.reshape(1, 1, 1, -1))
+        t = TF.conv2d(TF.pad(t, (1, 2, 1, 2)), W.permute(3, 2, 0, 1), bias=torch.as_tensor(b), stride=2)
+        t = torch.where(t > 0, t, 0.2 * t)
+    want = t.permute(0, 2, 3, 1).reshape(3, -1).numpy()
+    assert got.shape == (3, 7 * 7 * 16)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
