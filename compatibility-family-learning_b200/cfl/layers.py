@@ -84,7 +84,9 @@ def conv2d_weight_norm(inputs, num_outputs, kernel_size, stride=1, padding="SAME
         ph = max((-(-H // sh) - 1) * sh + kh - H, 0)
         pw = max((-(-Wd // sw) - 1) * sw + kw - Wd, 0)
         x = TF.pad(x, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
-    y = TF.conv2d(x, W.permute(3, 2, 0, 1), bias=b, stride=(sh, sw))
+    # fp32 convolution: cuDNN's TF32 default (10-bit significand) would miss the 1e-4 contract of the path by 10x
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        y = TF.conv2d(x, W.permute(3, 2, 0, 1), bias=b, stride=(sh, sw))
     y = y.permute(0, 2, 3, 1)
     act = _act_name(activation_fn)
     if act == "lrelu":
