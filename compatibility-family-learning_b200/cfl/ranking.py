@@ -129,12 +129,33 @@ class CatalogIndex:
         world = self._world()
         if world == 1:
             return tv, ti
-        Q = tv.shape[0]
-        gv = torch.empty(world * Q, k, dtype=tv.dtype, device=tv.device)     # concatenated along dim 0
-        gi = torch.empty(world * Q, k, dtype=ti.dtype, device=ti.device)
-        torch.distributed.all_gather_into_tensor(gv, tv.contiguous(), group=self.group)
-        torch.distributed.all_gather_into_tensor(gi, ti.contiguous(), group=self.group)
-        return nat.topk_merge(gv.view(world, Q, k), gi.view(world, Q, k))
+        return _gather_merge(tv, ti, self.group, world)
+
+    def rank_async(self, xq: torch.Tensor, k: int = 100):
+        """As ``rank`` for a stream of independent query batches: the local scoring runs on the current stream, the
+        exchange (all-gather + merge kernel) on a side stream, so that batch i's exchange overlaps batch i+1's
+        scoring.  -> (dist, index, event); the tensors are valid once ``event`` has fired (wait for it, or make the
+        consuming stream wait: ``stream.wait_event(event)``)."""
+        Pq = self.project_queries(xq)
+        tv, ti = self.rank_local(Pq, k)
+        dev = tv.device
+        cur = torch.cuda.current_stream(dev)
+        done = torch.cuda.Event()
+        world = self._world()
+        if world == 1:
+            done.record(cur)
+            return tv, ti, done
+        if not hasattr(self, "_xchg"):
+            self._xchg = torch.cuda.Stream(dev)
+        scored = torch.cuda.Event()
+        scored.record(cur)
+        with torch.cuda.stream(self._xchg):
+            self._xchg.wait_event(scored)
+            tv.record_stream(self._xchg)
+            ti.record_stream(self._xchg)
+            mv, mi = _gather_merge(tv, ti, self.group, world)
+            done.record(self._xchg)
+        return mv, mi, done
 
     def rank_host(self, xq_host: torch.Tensor, k: int, out_val: torch.Tensor, out_idx: torch.Tensor):
         """Host-buffer entry point: pinned query features in, pinned results out, nothing blocks.
@@ -163,15 +184,19 @@ class CatalogIndex:
         self._slot_free[s].record(cur)
         tv, ti = self.rank_local(Pq, k)
         world = self._world()
-        if world > 1:
-            Q = tv.shape[0]
-            gv = torch.empty(world * Q, k, dtype=tv.dtype, device=dev)
-            gi = torch.empty(world * Q, k, dtype=ti.dtype, device=dev)
-            torch.distributed.all_gather_into_tensor(gv, tv.contiguous(), group=self.group)
-            torch.distributed.all_gather_into_tensor(gi, ti.contiguous(), group=self.group)
-            tv, ti = nat.topk_merge(gv.view(world, Q, k), gi.view(world, Q, k))
         scored = torch.cuda.Event()
         scored.record(cur)
+        if world > 1:
+            # exchange + merge on their own stream: they overlap the next batch's scoring
+            if not hasattr(self, "_xchg"):
+                self._xchg = torch.cuda.Stream(dev)
+            with torch.cuda.stream(self._xchg):
+                self._xchg.wait_event(scored)
+                tv.record_stream(self._xchg)
+                ti.record_stream(self._xchg)
+                tv, ti = _gather_merge(tv, ti, self.group, world)
+                scored = torch.cuda.Event()
+                scored.record(self._xchg)
         with torch.cuda.stream(self._d2h):
             self._d2h.wait_event(scored)
             out_val.copy_(tv, non_blocking=True)
@@ -293,13 +318,20 @@ def _auc_per_query_gram(Pq, E, mu, image, pos_idx, idx_base, n_total, group, wor
 
 
 def _gather_merge(tv, ti, group, world):
-    """The one exchange step of the sharded ranking: all-gather the per-rank [Q,k] lists, merge."""
+    """The one exchange step of the sharded ranking: ONE all-gather of the per-rank [Q,k] lists -- indices and values
+    packed into a single 12-byte-per-entry record buffer, so the latency-bound collective is paid once, not twice --
+    then the merge kernel."""
     Q, k = tv.shape
-    gv = torch.empty(world * Q, k, dtype=tv.dtype, device=tv.device)
-    gi = torch.empty(world * Q, k, dtype=ti.dtype, device=ti.device)
-    torch.distributed.all_gather_into_tensor(gv, tv.contiguous(), group=group)
-    torch.distributed.all_gather_into_tensor(gi, ti.contiguous(), group=group)
-    return nat.topk_merge(gv.view(world, Q, k), gi.view(world, Q, k))
+    n = Q * k
+    rec = torch.empty(12 * n, dtype=torch.uint8, device=tv.device)
+    rec[:8 * n].view(torch.int64).copy_(ti.reshape(-1))
+    rec[8 * n:].view(torch.float32).copy_(tv.reshape(-1))
+    out = torch.empty(world * 12 * n, dtype=torch.uint8, device=tv.device)
+    torch.distributed.all_gather_into_tensor(out, rec, group=group)
+    out = out.view(world, 12 * n)
+    gi = out[:, :8 * n].contiguous().view(torch.int64).view(world, Q, k)
+    gv = out[:, 8 * n:].contiguous().view(torch.float32).view(world, Q, k)
+    return nat.topk_merge(gv, gi)
 
 
 class MonomerCatalogIndex:
