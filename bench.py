@@ -192,8 +192,8 @@ def c5_line(d, world, rank, device, steps=8):
 
 
 def small_q_line(index, device, q=16, steps=50):
-    """Q = 16 queries against the resident C3 catalog: one adaptive pass of the exact 3xTF32 kernel, bound by streaming
-    the catalog image (8 d + 4 bytes per row) from HBM."""
+    """Q = 16 queries against the resident C3 catalog: the HBM-bound regime.  The timed kernel is the full filter pass
+    (score_lb_kernel), which streams the catalog's fp16 plane + (|e|^2, |e|) per row = 2d + 8 bytes per row once."""
     from cfl import _native as nat
     xq = synth_features(q, device, SEED + 99)
     for _ in range(5):
@@ -211,11 +211,14 @@ def small_q_line(index, device, q=16, steps=50):
     nat.set_kernel_timer(None, None)
     ms = e0.elapsed_time(e1) / steps
     kms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in zip(ks, ke)]))
-    img_bytes = N_PER_GPU * (8 * D + 4)
+    st = index.rank_local_stats(xq, TOPK)[2]
+    plane = N_PER_GPU * (2 * D + 8)
     pk = peaks()
-    return {"queries": q, "ms_per_step": ms, "kernel_ms": kms, "catalog_bytes_per_pass": img_bytes,
-            "catalog_gbs": img_bytes / (kms / 1e3) / 1e9, "hbm_frac": img_bytes / (kms / 1e3) / 1e9 / pk["hbm"],
-            "kernel": "score_umma_kernel<3>, single adaptive pass (3xTF32 planes: 8d+4 B per row)"}
+    return {"queries": q, "ms_per_step": ms, "queries_per_s": q / (ms / 1e3), "kernel_ms": kms,
+            "catalog_bytes_per_pass": plane, "catalog_gbs": plane / (kms / 1e3) / 1e9,
+            "hbm_frac": plane / (kms / 1e3) / 1e9 / pk["hbm"], "lower_bound_pass": st["lower_bound_pass"],
+            "kernel": "score_lb_kernel<3> over the whole catalog (fp16 plane + row norms, read once from HBM); the rest "
+                      "of the step is launch-bound (16 small kernels)"}
 
 
 def run_ours(args):

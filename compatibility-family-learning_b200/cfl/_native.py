@@ -52,7 +52,7 @@ SIGNATURES = {
     "cfl_score_topk_packed_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
     "cfl_score_topk_packed": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _i64,
                                      _vp, _vp, _vp, _vp, _sz, _vp]),
-    "cfl_score_topk_stats": (_int, [_i64, _int, _int, _i64, _int, _int, _vp, _sz, _vp, _vp]),
+    "cfl_score_topk_stats": (_int, [_i64, _int, _int, _i64, _int, _int, _vp, _sz, _vp, _vp, _vp]),
     "cfl_score_topk_monomer_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
     "cfl_score_topk_monomer": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _i64, _i64, _int, _i64,
                                       _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -318,9 +318,10 @@ def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False, imag
                                     _ptr(ws), ws.numel(), _stream()), "cfl_score_topk")
     if want_stats:
         stats = torch.zeros(SCORE_NSTATS, dtype=torch.int64, device=dev)
+        thr = torch.zeros(3, Q, dtype=torch.float32, device=dev) if want_stats == "thresholds" else None
         _check(lib().cfl_score_topk_stats(Q, K, d, N, int(k), 1 if image is not None else 0, _ptr(ws), ws.numel(),
-                                          _ptr(stats), _stream()), "cfl_score_topk_stats")
-        return (top_val, top_idx, stats)
+                                          _ptr(stats), _ptr(thr), _stream()), "cfl_score_topk_stats")
+        return (top_val, top_idx, stats, thr) if thr is not None else (top_val, top_idx, stats)
     return (top_val, top_idx, dense) if want_dense else (top_val, top_idx)
 
 

@@ -553,8 +553,8 @@ sample_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__
 // Same thresholds by radix selection instead of sorting: only the VALUES of the kk-th and r_opt-th
 // smallest distances are needed, so four 8-bit passes over the 32-bit ordered distances (staged in
 // shared memory when they fit) replace the ~20 cooperative sorts of block_merge_topkk.
-constexpr int SEL_THREADS = 256;
-constexpr int SEL_SMEM_KEYS = 12288;
+constexpr int SEL_THREADS = 1024;              // few blocks (one per query) when Q is small: they must be wide
+constexpr int SEL_SMEM_KEYS = 24576;            // 148 parts x kk keys of an adaptive sample pass fit (96 KB)
 
 __device__ __forceinline__ uint32_t radix_select(const uint32_t* __restrict__ sv, const tkey_t* __restrict__ keys,
                                                  const int* __restrict__ s_pref, int parts, int64_t Q, int64_t q,
@@ -734,7 +734,8 @@ using namespace cfl;
 // path outside its validated range (CFL_SCORE_FORCE_LB) are honoured only under CFL_EXPERIMENTS=1.
 struct ScoreKnobs {
   int sample_stride = 32;     // tools/knob_sweep.py: 32 beats 16 by 7 % on the C3 step (the sample pass halves; r_opt = 16)
-  int64_t min_tiles = 128;    // tiles per part below which one adaptive exact pass is used
+  int64_t min_tiles = 16;     // tiles per part below which one adaptive exact pass is used (tools/small_q_probe.py: the
+                              // sampled two-pass path wins from Q = 1 on a 1 M-row catalog)
   int opt_mult = 4;           // optimistic threshold = ceil(opt_mult * kk / stride)-th best of the sample
   bool no_cascade = false, no_optimistic = false, no_lb = false, no_probe = false, force_lb = false;
   int dbg_mode = 0;
@@ -884,7 +885,12 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         const int64_t tiles_b = (tpp + sstride - 1) / sstride;
         int64_t tiles_a = ((int64_t)plan.kk * tiles_b + 384 * (int64_t)plan.parts - 1) / (384 * (int64_t)plan.parts);
         if (tiles_a < 1) tiles_a = 1;
-        const bool cascade = tiles_a <= 7 && tiles_a * 128 * plan.parts >= 2 * plan.kk && !kn.no_cascade;
+        // The cascade needs a pass-B sample several times larger than pass A's: tau_a (kk-th best of pass A) leaves
+        // about kk * |B| / |A| rows of pass B under it, and pass B must find at least kk of them to define the
+        // thresholds (with |B| ~ |A| -- short part ranges, e.g. a few queries on 148 parts -- a seventh of the queries
+        // ended up without thresholds and fell through to the exact redo pass).  Pass A visits up to tiles_a + 1 tiles.
+        const bool cascade = tiles_a <= 7 && tiles_a * 128 * plan.parts >= 2 * plan.kk && tiles_b >= 4 * (tiles_a + 1) &&
+                             !kn.no_cascade;
         if (cascade) {
           a.phase = 2; a.thr_init = nullptr;                 // +inf thresholds: keep every sampled row
           a.tile_stride = (int)((tpp + tiles_a - 1) / tiles_a);
@@ -1051,7 +1057,7 @@ int cfl_score_topk_packed(int mode, const float* Pq, int64_t Q, int K, int d, in
 }
 
 int cfl_score_topk_stats(int64_t Q, int K, int d, int64_t N, int k, int packed, const void* ws, size_t ws_bytes,
-                         unsigned long long* stats_out, void* stream) {
+                         unsigned long long* stats_out, float* thr_out, void* stream) {
   int st = device_check();
   if (st != CFL_OK) return st;
   CFL_REQUIRE(ws && stats_out && Q > 0 && N > 0, CFL_ERR_INVALID, "score_topk_stats: bad arguments");
@@ -1061,6 +1067,7 @@ int cfl_score_topk_stats(int64_t Q, int K, int d, int64_t N, int k, int packed, 
   cudaStream_t cs = (cudaStream_t)stream;
   if (!umma_ok || !score_two_pass(kn, plan, false)) {         // short catalogs / CUDA-core shapes: one adaptive pass, no statistics
     CFL_CUDA(cudaMemsetAsync(stats_out, 0, CFL_SCORE_NSTATS * sizeof(unsigned long long), cs));
+    if (thr_out) CFL_CUDA(cudaMemsetAsync(thr_out, 0, (size_t)3 * Q * sizeof(float), cs));
     return CFL_OK;
   }
   size_t o_pc, o_qpar, o_qimg, o_keys, o_cnt, o_cimg;
@@ -1070,6 +1077,7 @@ int cfl_score_topk_stats(int64_t Q, int K, int d, int64_t N, int k, int packed, 
   const char* spill = tau + align_up((size_t)(3 * Q + plan.nqt + 4) * sizeof(float), 256);
   const char* stats = spill + align_up((size_t)Q * LB_SPILL * sizeof(tkey_t) + (size_t)Q * sizeof(int), 256);
   CFL_CUDA(cudaMemcpyAsync(stats_out, stats, CFL_SCORE_NSTATS * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, cs));
+  if (thr_out) CFL_CUDA(cudaMemcpyAsync(thr_out, tau, (size_t)3 * Q * sizeof(float), cudaMemcpyDeviceToDevice, cs));
   return CFL_OK;
 }
 

@@ -157,11 +157,12 @@ int cfl_score_topk_packed(int mode, const float* Pq, int64_t Q, int K, int d, in
  * `stats_out` on `stream`: [0] keys that survived the full filter pass, summed over queries (each is rescored
  * exactly), [1] queries that used their spill list, [2] queries the probe took out of the lower-bound pass,
  * [3] queries redone by the exact kernel under the safe threshold, [4] 1 when the lower-bound pass ran.  All zero
- * for catalogs short enough for the single adaptive pass.  (bench.py prints them so that a regression to the slow
- * paths is visible; no reference call site.) */
+ * for catalogs short enough for the single adaptive pass.  thr_out (optional, device, 3*Q floats): the per-query
+ * thresholds of that call -- safe threshold tau, optimistic threshold tau_opt, redo threshold (-inf = not redone).
+ * (bench.py prints the counters so that a regression to the slow paths is visible; no reference call site.) */
 #define CFL_SCORE_NSTATS 8
 int cfl_score_topk_stats(int64_t Q, int K, int d, int64_t N, int k, int packed, const void* ws, size_t ws_bytes,
-                         unsigned long long* stats_out, void* stream);
+                         unsigned long long* stats_out, float* thr_out, void* stream);
 
 /* Monomer mode on the cross product (SURVEY App. A.6 applied to DistBase.build_dist, monomer branch,
  * cfl/models/base.py:109-117; gate cfl/models/base.py:94-105).  The roles follow the reference:
