@@ -196,8 +196,12 @@ def small_q_line(index, device, q=16, steps=50):
     (score_lb_kernel), which streams the catalog's fp16 plane + (|e|^2, |e|) per row = 2d + 8 bytes per row once."""
     from cfl import _native as nat
     xq = synth_features(q, device, SEED + 99)
+
+    def local_step():                      # this rank's shard only: no collective (the line is measured on rank 0 alone)
+        return index.rank_local(index.project_queries(xq), TOPK)
+
     for _ in range(5):
-        index.rank(xq, TOPK)
+        local_step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ks, ke = [], []
@@ -205,7 +209,7 @@ def small_q_line(index, device, q=16, steps=50):
     for _ in range(steps):
         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         nat.set_kernel_timer(a_, b_); ks.append(a_); ke.append(b_)
-        index.rank(xq, TOPK)
+        local_step()
     e1.record()
     torch.cuda.synchronize()
     nat.set_kernel_timer(None, None)
