@@ -44,7 +44,7 @@ import torch  # noqa: E402
 F, K, D, N_PER_GPU, Q, TOPK = 1024, 3, 64, 1_000_000, 1024, 100
 DATA_NORM = 31.9098            # experiments/dyadic/run.sh:15
 SEED = 633
-PASS_C_DRAM_BYTES = None       # set from the ncu capture of the current kernel (profiles/r2_02_pass_c.md)
+PASS_C_DRAM_BYTES = 145.0e6    # dram__bytes_read + write of score_lb_kernel<3> on this workload (profiles/r2_02_pass_c.md)
 WORKLOAD = "C3 dyadic all-pairs: F=1024 K=3 d=64, 1M-item catalog per GPU, Q=1024 queries/step, top-100"
 
 
