@@ -56,6 +56,11 @@ SIGNATURES = {
     "cfl_score_topk_monomer_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
     "cfl_score_topk_monomer": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _i64, _i64, _int, _i64,
                                       _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cfl_monomer_pack_bytes": (_sz, [_i64, _int, _int]),
+    "cfl_monomer_pack": (_int, [_vp, _i64, _int, _int, _i64, _vp, _vp, _sz, _vp]),
+    "cfl_score_topk_monomer_packed_workspace_bytes": (_sz, [_i64, _int, _int, _i64, _int]),
+    "cfl_score_topk_monomer_packed": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _vp, _i64, _i64, _vp, _int, _i64,
+                                             _vp, _vp, _vp, _vp, _sz, _vp]),
     "cfl_topk_merge": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
     "cfl_col_mean_workspace_bytes": (_sz, [_i64, _int]),
     "cfl_col_mean": (_int, [_vp, _i64, _int, _i64, _vp, _vp, _sz, _vp]),
@@ -351,6 +356,47 @@ def score_topk_monomer(a, w, P, k, idx_base=0, want_dense=False):
                                         _ptr(top_val), _ptr(top_idx), _ptr(dense), _ptr(ws), ws.numel(), _stream()),
            "cfl_score_topk_monomer")
     return (top_val, top_idx, dense) if want_dense else (top_val, top_idx)
+
+
+def monomer_pack(P, mu=None):
+    """Tensor-core image of a monomer catalog P [N,K,d] (None when K(d+1) > 128: CUDA-core kernel only)."""
+    P = _f32c(P, "P")
+    if P.dim() != 3:
+        raise CflNativeError("monomer_pack: P must be [N,K,d]")
+    N, K, d = P.shape
+    nbytes = lib().cfl_monomer_pack_bytes(N, K, d)
+    if nbytes == 0:
+        return None
+    P2, ldp = _rows(P.reshape(N, K * d), "P")
+    img = torch.empty(nbytes + 1024, dtype=torch.uint8, device=P.device)
+    off = (-img.data_ptr()) % 1024
+    img = img[off:off + nbytes]
+    mu = None if mu is None else _f32c(mu, "mu").contiguous()
+    _check(lib().cfl_monomer_pack(_ptr(P2), N, K, d, ldp, _ptr(mu), _ptr(img), nbytes, _stream()), "cfl_monomer_pack")
+    return img
+
+
+def score_topk_monomer_packed(a, w, P, image, k, mu=None, idx_base=0, want_stats=False):
+    """Monomer top-k through the tensor-core path (image = monomer_pack(P, mu)); values and indices as
+    score_topk_monomer (the survivors are rescored in its arithmetic)."""
+    a, lda = _rows(a, "a")
+    w = _f32c(w, "w").contiguous()
+    P = _f32c(P, "P")
+    N, K, d = P.shape
+    Q = a.shape[0]
+    if a.shape[1] != d or tuple(w.shape) != (Q, K):
+        raise CflNativeError(f"score_topk_monomer_packed: a {tuple(a.shape)}, w {tuple(w.shape)} do not match P {tuple(P.shape)}")
+    P2, ldp = _rows(P.reshape(N, K * d), "P")
+    dev = P.device
+    top_val = torch.empty(Q, k, dtype=torch.float32, device=dev)
+    top_idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    stats = torch.zeros(SCORE_NSTATS, dtype=torch.int64, device=dev) if want_stats else None
+    mu = None if mu is None else _f32c(mu, "mu").contiguous()
+    ws = _ws.get(lib().cfl_score_topk_monomer_packed_workspace_bytes(Q, K, d, N, k), dev)
+    _check(lib().cfl_score_topk_monomer_packed(_ptr(a), lda, _ptr(w), Q, K, d, _ptr(image), _ptr(P2), N, ldp, _ptr(mu),
+                                               int(k), int(idx_base), _ptr(top_val), _ptr(top_idx), _ptr(stats), _ptr(ws),
+                                               ws.numel(), _stream()), "cfl_score_topk_monomer_packed")
+    return (top_val, top_idx, stats) if want_stats else (top_val, top_idx)
 
 
 def topk_merge(vals, idx):

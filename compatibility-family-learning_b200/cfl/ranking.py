@@ -355,6 +355,18 @@ class MonomerCatalogIndex:
         self.n_total = int(n_total if n_total is not None else prototypes.shape[0])
         self.theta = float(theta)
         self.group = group
+        # tensor-core image of the (static) catalog: augmented fp16 vectors centred on the global mean of all prototypes
+        # (None when K(d+1) > 128: the CUDA-core kernel serves those shapes)
+        self.mu = self._global_mean() if self.P.shape[0] else None
+        self.image = nat.monomer_pack(self.P, self.mu) if self.P.shape[0] else None
+
+    def _global_mean(self):
+        s = self.P.double().sum(dim=(0, 1))
+        n = torch.tensor([float(self.P.shape[0] * self.P.shape[1])], dtype=torch.float64, device=self.P.device)
+        if self._world() > 1:
+            torch.distributed.all_reduce(s, group=self.group)
+            torch.distributed.all_reduce(n, group=self.group)
+        return (s / n).float()
 
     @classmethod
     def from_features(cls, weights: EncoderWeights, features: torch.Tensor, idx_base: int = 0,
@@ -387,6 +399,8 @@ class MonomerCatalogIndex:
         return a, torch.softmax(logits, dim=-1)
 
     def rank_local(self, a: torch.Tensor, gate: torch.Tensor, k: int):
+        if self.image is not None:
+            return nat.score_topk_monomer_packed(a, gate, self.P, self.image, k, mu=self.mu, idx_base=self.idx_base)
         return nat.score_topk_monomer(a, gate, self.P, k, idx_base=self.idx_base)
 
     def rank(self, xq: torch.Tensor, k: int = 100):

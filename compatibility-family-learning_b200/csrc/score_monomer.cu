@@ -31,6 +31,8 @@ struct MonoArgs {
   float* dist_out;   // optional dense [Q, N]
   int parts, kk;
   int64_t tiles;
+  int tile_stride;          // visit every tile_stride-th tile of a part (the threshold sample of the tensor-core path)
+  const int* redo_tile;     // optional [ceil(Q / MONO_QT)]: a CTA whose query tile has nothing to redo exits at once
 };
 
 // VW = floats per staging load: 4 / 2 when d and ldp are multiples of it and the catalog is aligned to it (128- /
@@ -50,6 +52,7 @@ score_monomer_kernel(MonoArgs A) {
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int part = blockIdx.x;
+  if (A.redo_tile != nullptr && A.redo_tile[blockIdx.y] == 0) return;
   const int64_t q0 = (int64_t)blockIdx.y * MONO_QT;
   const int nq = (int)((A.Q - q0 < MONO_QT) ? (A.Q - q0) : MONO_QT);
   for (int i = tid; i < MONO_QT * d; i += MONO_THREADS) {
@@ -69,7 +72,7 @@ score_monomer_kernel(MonoArgs A) {
   const int dv = d / VW;
   const int sr0 = tid / dv, sj0 = tid % dv, sdr = MONO_THREADS / dv, sdj = MONO_THREADS % dv;
 
-  for (int64_t tile = t0; tile < t1; ++tile) {
+  for (int64_t tile = t0; tile < t1; tile += A.tile_stride) {
     const int64_t r0 = tile * 128;
     f2_t acc[MONO_QT / 2];
 #pragma unroll
@@ -151,12 +154,15 @@ score_monomer_kernel(MonoArgs A) {
 // Merge of the catalog parts; the keys already carry exact distances.
 __global__ void __launch_bounds__(MRG_THREADS)
 merge_plain_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ counts, int parts, int64_t Q, int kk,
-                   int k, int64_t idx_base, float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
+                   int k, int64_t idx_base, float* __restrict__ top_val, int64_t* __restrict__ top_idx,
+                   const float* __restrict__ only_redo = nullptr) {
   __shared__ tkey_t s[TOPK_CAP];
   __shared__ int s_fill;
   __shared__ tkey_t s_thr;
   const int t = threadIdx.x;
   const int64_t q = blockIdx.x;
+  // second merge of the tensor-core path: only the queries that were redone by this kernel's exact pass
+  if (only_redo != nullptr && !(only_redo[q] > __int_as_float(0xff800000))) return;
   const int fill = block_merge_topkk(keys, counts, parts, Q, q, kk, s, &s_fill, &s_thr, MONO_KSTRIDE);
   for (int i = t; i < k; i += MRG_THREADS) {
     if (i < fill) {
@@ -198,6 +204,44 @@ static MonoPlan mono_plan(int64_t Q, int64_t N, int K, int d) {
   return p;
 }
 
+// Launch of the CUDA-core kernel for the tensor-core path (score_monomer_tc.cu): threshold sample (tile_stride > 1)
+// and exact redo (redo_tile != NULL); keys [parts, Q, MONO_KSTRIDE], counts [parts, Q].
+int mono_exact_launch(const float* Aq, int64_t lda, const float* Wq, int64_t Q, int K, int d, const float* Pc, int64_t N,
+                      int64_t ldp, int kk, int tile_stride, const int* redo_tile, tkey_t* keys, int* counts, int* parts_out,
+                      cudaStream_t cs) {
+  MonoPlan plan = mono_plan(Q, N, K, d);
+  MonoArgs a;
+  a.K = K; a.d = d; a.Q = Q; a.N = N; a.lda = lda; a.ldp = ldp; a.A = Aq; a.W = Wq; a.P = Pc;
+  a.keys = keys; a.counts = counts; a.dist_out = nullptr;
+  a.parts = plan.parts; a.kk = kk; a.tiles = plan.tiles; a.tile_stride = tile_stride; a.redo_tile = redo_tile;
+  *parts_out = plan.parts;
+  const size_t smem = mono_smem_bytes(K, d);
+  int vw = 1;
+  if (d % 4 == 0 && ldp % 4 == 0 && ((uintptr_t)Pc & 15u) == 0) vw = 4;
+  else if (d % 2 == 0 && ldp % 2 == 0 && ((uintptr_t)Pc & 7u) == 0) vw = 2;
+  dim3 grid(plan.parts, plan.nqt);
+  switch (vw) {
+    case 4:
+      CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      score_monomer_kernel<4><<<grid, MONO_THREADS, smem, cs>>>(a); break;
+    case 2:
+      CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      score_monomer_kernel<2><<<grid, MONO_THREADS, smem, cs>>>(a); break;
+    default:
+      CFL_CUDA(cudaFuncSetAttribute(score_monomer_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      score_monomer_kernel<1><<<grid, MONO_THREADS, smem, cs>>>(a); break;
+  }
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+int mono_exact_parts(int64_t Q, int64_t N, int K, int d) { return mono_plan(Q, N, K, d).parts; }
+int mono_merge_launch(const tkey_t* keys, const int* counts, int parts, int64_t Q, int k, int64_t idx_base, float* top_val,
+                      int64_t* top_idx, const float* only_redo, cudaStream_t cs) {
+  merge_plain_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(keys, counts, parts, Q, k, k, idx_base, top_val, top_idx, only_redo);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
 }  // namespace cfl
 
 using namespace cfl;
@@ -235,7 +279,7 @@ int cfl_score_topk_monomer(const float* Aq, int64_t lda, const float* Wq, int64_
   MonoArgs a;
   a.K = K; a.d = d; a.Q = Q; a.N = N; a.lda = lda; a.ldp = ldp; a.A = Aq; a.W = Wq; a.P = Pc;
   a.keys = (tkey_t*)ws; a.counts = (int*)((char*)ws + keys_bytes); a.dist_out = dist_out;
-  a.parts = plan.parts; a.kk = k; a.tiles = plan.tiles;
+  a.parts = plan.parts; a.kk = k; a.tiles = plan.tiles; a.tile_stride = 1; a.redo_tile = nullptr;
   if (N == 0) {
     CFL_CUDA(cudaMemsetAsync(a.counts, 0, (size_t)plan.parts * Q * sizeof(int), cs));
   } else {

@@ -178,6 +178,24 @@ int cfl_score_topk_monomer(const float* Aq, int64_t lda, const float* Wq, int64_
                            float* top_val, int64_t* top_idx, float* dist_out,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* Monomer mode, tensor-core path.  With the augmented vectors v_q = [2 w_qk a_q]_k || [-w_qk]_k and
+ * c'_c = [P'_ck]_k || [|P'_ck|^2]_k (both sides centred on mu) the distance is (sum_k w_qk)|a_q|^2 - v_q.c'_c: ONE Gram
+ * matrix of inner dimension K(d+1) <= 128.  cfl_monomer_pack builds the catalog's fp16 image once (1024-byte aligned,
+ * cfl_monomer_pack_bytes; 0 = no tensor-core path for this shape: use cfl_score_topk_monomer).
+ * cfl_score_topk_monomer_packed: thresholds from the exact CUDA-core kernel on a 1/32 sample of the tiles, the full
+ * pass as a single-product fp16 tcgen05 Gram filter with a rigorous rounding margin, exact fp32 direct-form rescoring
+ * of every survivor (the arithmetic of cfl_score_topk_monomer: identical bits), verification, exact redo of the
+ * queries that fail it.  Outputs as cfl_score_topk_monomer.  stats_out: optional CFL_SCORE_NSTATS counters (device)
+ * as cfl_score_topk_stats.  Pc / mu must be the arrays the image was built from. */
+size_t cfl_monomer_pack_bytes(int64_t N, int K, int d);
+int cfl_monomer_pack(const float* Pc, int64_t N, int K, int d, int64_t ldp, const float* mu, void* image,
+                     size_t image_bytes, void* stream);
+size_t cfl_score_topk_monomer_packed_workspace_bytes(int64_t Q, int K, int d, int64_t N, int k);
+int cfl_score_topk_monomer_packed(const float* Aq, int64_t lda, const float* Wq, int64_t Q, int K, int d,
+                                  const void* image, const float* Pc, int64_t N, int64_t ldp, const float* mu, int k,
+                                  int64_t idx_base, float* top_val, int64_t* top_idx,
+                                  unsigned long long* stats_out, void* ws, size_t ws_bytes, void* stream);
+
 /* Merge R sorted lists per query (the per-rank results after ncclAllGather) into one:
  * vals[R,Q,k], idx[R,Q,k] -> top_val[Q,k], top_idx[Q,k]; order (value, index). */
 int cfl_topk_merge(const float* vals, const int64_t* idx, int R, int64_t Q, int k,

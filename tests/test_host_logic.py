@@ -276,6 +276,7 @@ def _mono_worker(rank, world, port, out_dir):
     P = ranking.nat.project_fwd(t(X[lo:hi]), w.Vp, w.gp, None, True, 1.0, "tanh")[0]
     idx = ranking.MonomerCatalogIndex.__new__(ranking.MonomerCatalogIndex)     # bypass the CUDA-only check of __init__
     idx.w, idx.P, idx.idx_base, idx.n_total, idx.group, idx.theta = w, P.view(-1, K, d), lo, len(X), None, 1.0
+    idx.image, idx.mu = None, idx._global_mean()              # (no tensor-core image on the CPU; the mean is a collective)
     tv, ti = idx.rank(t(X[:Q]), k)
     if rank == 1:
         np.savez(os.path.join(out_dir, "m.npz"), tv=tv.numpy(), ti=ti.numpy())

@@ -270,3 +270,72 @@ def test_score_topk_monomer_golden_fixture(nat):
     np.testing.assert_allclose(tv, g["top_val"], rtol=RTOL, atol=1e-7)
     for q in range(4):                          # rows 7 / 90 / 555 are identical: ties -> lower index
         assert ti[q, :3].tolist() == [7, 90, 555]
+
+
+# ---------------------------------------------------------------------------- tensor-core path
+@pytest.mark.gpu
+@pytest.mark.parametrize("Q,K,d,N,k,clustered", [(70, 4, 20, 150_000, 100, False), (130, 2, 10, 60_000, 100, False),
+                                                  (33, 4, 20, 40_000, 17, True), (9, 1, 64, 30_000, 100, False),
+                                                  (50, 6, 20, 50_000, 100, False), (5, 4, 20, 900, 100, False)])
+def test_score_topk_monomer_packed_equals_the_exact_kernel(nat, Q, K, d, N, k, clustered):
+    """Tensor-core route (Gram filter over the augmented vectors + exact rescoring + verification / redo) == the
+    CUDA-core kernel, bit for bit (values are rescored in its arithmetic), and both match the fp64 oracle."""
+    rng = np.random.default_rng(1000 + Q + K)
+    a, w, Pt = _inputs(rng, Q, K, d, N)
+    if clustered:                              # tight clusters: thousands of rows within a hair of every threshold
+        cen = rng.normal(size=(20, K, d)).astype(np.float32)
+        Pt = (cen[rng.integers(0, 20, N)] + 0.02 * rng.normal(size=(N, K, d))).astype(np.float32)
+        a = (cen[rng.integers(0, 20, Q), 0] + 0.05 * rng.normal(size=(Q, d))).astype(np.float32)
+    Pd = dev(Pt)
+    mu = Pd.reshape(N, K, d).mean(dim=(0, 1))
+    img = nat.monomer_pack(Pd, mu)
+    assert img is not None
+    ev, ei = nat.score_topk_monomer(dev(a), dev(w), Pd, k)
+    tv, ti, st = nat.score_topk_monomer_packed(dev(a), dev(w), Pd, img, k, mu=mu, want_stats=True)
+    assert torch.equal(ei, ti) and torch.equal(ev, tv)
+    stats = dict(zip(nat.SCORE_STAT_NAMES, st.tolist()))
+    assert stats["lower_bound_pass"] == 1
+    if not clustered and N >= 30_000:
+        assert stats["redo_queries"] <= max(1, Q // 20), stats
+    qs = [0, Q // 2, Q - 1]
+    D = O.all_pairs_monomer_dist(a[qs].astype(np.float64), w[qs].astype(np.float64), Pt.astype(np.float64), block=1)
+    wv, wi = O.rank_topk(D, min(k, N))
+    np.testing.assert_allclose(host(tv[qs])[:, :wv.shape[1]], wv, rtol=RTOL)
+
+
+@pytest.mark.gpu
+def test_score_topk_monomer_packed_range_guard_and_large_offset(nat):
+    """A prototype value outside the fp16 range (flag -> every query redone exactly) and an uncentred catalog far
+    from the origin (mu = None: large margins) still return the exact kernel's lists."""
+    rng = np.random.default_rng(77)
+    Q, K, d, N, k = 40, 4, 20, 50_000, 50
+    a, w, Pt = _inputs(rng, Q, K, d, N)
+    Pt = Pt + 10.0
+    a = a + 10.0
+    Pd = dev(Pt)
+    img = nat.monomer_pack(Pd, None)
+    ev, ei = nat.score_topk_monomer(dev(a), dev(w), Pd, k)
+    tv, ti = nat.score_topk_monomer_packed(dev(a), dev(w), Pd, img, k, mu=None)
+    assert torch.equal(ei, ti) and torch.equal(ev, tv)
+    Pd[123, 2, 5] = 3.0e5
+    img = nat.monomer_pack(Pd, None)
+    ev, ei = nat.score_topk_monomer(dev(a), dev(w), Pd, k)
+    tv, ti, st = nat.score_topk_monomer_packed(dev(a), dev(w), Pd, img, k, mu=None, want_stats=True)
+    assert torch.equal(ei, ti) and torch.equal(ev, tv)
+    assert dict(zip(nat.SCORE_STAT_NAMES, st.tolist()))["redo_queries"] == Q
+
+
+@pytest.mark.gpu
+def test_monomer_index_uses_the_tensor_core_path_and_agrees(nat):
+    from cfl.ranking import EncoderWeights, MonomerCatalogIndex
+    rng = np.random.default_rng(5)
+    F, K, d, N, Q = 64, 4, 20, 40_000, 48
+    w = EncoderWeights(V0=dev(O.xavier_uniform(rng, F, d)), Vp=dev(O.xavier_uniform(rng, F, K * d)), g0=torch.ones(d).cuda(),
+                       gp=torch.ones(K * d).cuda(), weight_norm=True, Vg=dev(O.xavier_uniform(rng, d, K)), gg=torch.ones(K).cuda())
+    X = dev(rng.normal(size=(N, F)).astype(np.float32))
+    idx = MonomerCatalogIndex.from_features(w, X)
+    assert idx.image is not None
+    tv, ti = idx.rank(X[:Q], 100)
+    a, gate = idx.project_queries(X[:Q])
+    ev, ei = nat.score_topk_monomer(a, gate, idx.P, 100)
+    assert torch.equal(ti, ei) and torch.equal(tv, ev)
