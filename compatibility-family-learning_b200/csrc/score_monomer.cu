@@ -72,7 +72,8 @@ score_monomer_kernel(MonoArgs A) {
   const int dv = d / VW;
   const int sr0 = tid / dv, sj0 = tid % dv, sdr = MONO_THREADS / dv, sdj = MONO_THREADS % dv;
 
-  for (int64_t tile = t0; tile < t1; tile += A.tile_stride) {
+  // tile_stride > 1: the tiles whose GLOBAL index is a multiple of it (a sample whose density does not depend on the parts)
+  for (int64_t tile = (t0 + A.tile_stride - 1) / A.tile_stride * A.tile_stride; tile < t1; tile += A.tile_stride) {
     const int64_t r0 = tile * 128;
     f2_t acc[MONO_QT / 2];
 #pragma unroll

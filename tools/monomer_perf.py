@@ -45,4 +45,18 @@ for (N, K, d, Q) in CASES:
                           fp32x2_frac=round(2.0 * K * d * scores / (kms / 1e3) / FP32X2_PEAK, 3),
                           catalog_bytes=N * K * d * 4,
                           hbm_frac_single_read=round(N * K * d * 4 / (kms / 1e3) / 1e9 / HBM, 4))), flush=True)
+    mu = P.mean(dim=(0, 1))
+    img = nat.monomer_pack(P, mu)
+    if img is not None:
+        ev, ei = nat.score_topk_monomer(a, w, P, 100)
+        tv, ti, st = nat.score_topk_monomer_packed(a, w, P, img, 100, mu=mu, want_stats=True)
+        same = bool(torch.equal(ev, tv) and torch.equal(ei, ti))
+        ms2, kms2 = timeit(lambda: nat.score_topk_monomer_packed(a, w, P, img, 100, mu=mu))
+        dp = (K * (d + 1) + 15) // 16 * 16
+        print(json.dumps(dict(kernel="score_monomer_packed (tcgen05 Gram filter + exact rescoring)", N=N, K=K, d=d, Q=Q,
+                              ms=round(ms2, 3), filter_kernel_ms=round(kms2, 3), gscores_s=round(scores / ms2 / 1e6, 1),
+                              speedup=round(ms / ms2, 2), identical_to_exact_kernel=same,
+                              survivors_per_query=round(st[0].item() / Q, 1), redo_queries=int(st[3].item()),
+                              filter_tflops=round(2.0 * dp * scores / (kms2 / 1e3) / 1e12, 1),
+                              image_bytes=int(img.numel()))), flush=True)
     del P, a, w
