@@ -1,0 +1,79 @@
+// Standalone driver of the C ABI for compute-sanitizer (python + torch do not survive under the sanitizer on this image):
+// projection -> catalog image -> all-pairs scoring through the sampled two-pass path (exact 3xTF32 kernel, lower-bound
+// tensor-core pass, rescoring, redo) -> monomer tensor-core path -> paired loss forward / backward -> AUC.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I include tools/sanitize_driver.cu \
+//        -o compatibility-family-learning_b200/build/sanitize_driver -L compatibility-family-learning_b200/cfl/_lib -lcfl_b200 \
+//        -Xlinker -rpath -Xlinker '$ORIGIN/../cfl/_lib'
+// Run:   CFL_SCORE_MIN_TILES=2 compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck ./sanitize_driver
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "cfl_b200.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(2); } } while (0)
+#define CF(x) do { int s_ = (x); if (s_ != 0) { printf("cfl error %d (%s) at line %d\n", s_, cfl_last_error(), __LINE__); exit(3); } } while (0)
+
+static float frand() { return (float)rand() / RAND_MAX * 2.0f - 1.0f; }
+template <class T> static T* dalloc(size_t n) { T* p; CK(cudaMalloc(&p, n * sizeof(T) + 1024)); return p; }
+static float* upload(const std::vector<float>& h) { float* p = dalloc<float>(h.size()); CK(cudaMemcpy(p, h.data(), h.size() * 4, cudaMemcpyHostToDevice)); return p; }
+static void* aligned(size_t bytes) { char* p; CK(cudaMalloc(&p, bytes + 2048)); return (void*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023); }
+
+int main() {
+  srand(633);
+  const int K = 3, d = 64, Q = 70, k = 20;
+  const int64_t N = 40000;
+  std::vector<float> hE(N * d), hP((size_t)Q * K * d);
+  for (auto& x : hE) x = frand();
+  for (int q = 0; q < Q; ++q)
+    for (int j = 0; j < K * d; ++j) hP[(size_t)q * K * d + j] = hE[(size_t)(q * 37 % N) * d + j % d] + 0.3f * frand();
+  float *E = upload(hE), *Pq = upload(hP);
+  // catalog mean, image, scoring (two-pass path is forced by CFL_SCORE_MIN_TILES=2 in the environment)
+  float* mu = dalloc<float>(d);
+  void* ws_mean = aligned(cfl_col_mean_workspace_bytes(N, d));
+  CF(cfl_col_mean(E, N, d, d, mu, ws_mean, cfl_col_mean_workspace_bytes(N, d), nullptr));
+  const size_t ib = cfl_catalog_pack_bytes(N, K, d);
+  void* img = aligned(ib);
+  CF(cfl_catalog_pack(E, N, K, d, d, mu, img, ib, nullptr));
+  const size_t wb = cfl_score_topk_packed_workspace_bytes(Q, K, d, N, k);
+  void* ws = aligned(wb);
+  float* tv = dalloc<float>((size_t)Q * k); int64_t* ti = dalloc<int64_t>((size_t)Q * k);
+  for (int rep = 0; rep < 2; ++rep)
+    CF(cfl_score_topk_packed(CFL_PCD, Pq, Q, K, d, (int64_t)K * d, img, E, N, d, mu, k, 0, tv, ti, nullptr, ws, wb, nullptr));
+  unsigned long long* st = dalloc<unsigned long long>(CFL_SCORE_NSTATS);
+  CF(cfl_score_topk_stats(Q, K, d, N, k, 1, ws, wb, st, nullptr, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hv((size_t)Q * k); std::vector<long long> hi((size_t)Q * k); unsigned long long hs[CFL_SCORE_NSTATS];
+  CK(cudaMemcpy(hv.data(), tv, hv.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hi.data(), ti, hi.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hs, st, sizeof(hs), cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int q = 0; q < Q; ++q)
+    for (int i = 1; i < k; ++i) bad += !(hv[(size_t)q * k + i] >= hv[(size_t)q * k + i - 1]) || hi[(size_t)q * k + i] < 0 || hi[(size_t)q * k + i] >= N;
+  printf("pcd: survivors %llu, redo %llu, lower-bound pass %llu, order violations %d, best dist of query 0 = %g (row %lld)\n",
+         hs[0], hs[3], hs[4], bad, hv[0], hi[0]);
+
+  // monomer, tensor-core path
+  const int Km = 4, dm = 20;
+  std::vector<float> hPt((size_t)N * Km * dm), ha((size_t)Q * dm), hw((size_t)Q * Km);
+  for (auto& x : hPt) x = frand();
+  for (int q = 0; q < Q; ++q) {
+    for (int j = 0; j < dm; ++j) ha[(size_t)q * dm + j] = hPt[(size_t)(q * 53 % N) * Km * dm + j] + 0.2f * frand();
+    float s = 0; for (int kk = 0; kk < Km; ++kk) { hw[(size_t)q * Km + kk] = 0.1f + fabsf(frand()); s += hw[(size_t)q * Km + kk]; }
+    for (int kk = 0; kk < Km; ++kk) hw[(size_t)q * Km + kk] /= s;
+  }
+  float *Pt = upload(hPt), *a = upload(ha), *w = upload(hw);
+  const size_t mib = cfl_monomer_pack_bytes(N, Km, dm);
+  void* mimg = aligned(mib);
+  CF(cfl_monomer_pack(Pt, N, Km, dm, (int64_t)Km * dm, nullptr, mimg, mib, nullptr));
+  const size_t mwb = cfl_score_topk_monomer_packed_workspace_bytes(Q, Km, dm, N, k);
+  void* mws = aligned(mwb);
+  CF(cfl_score_topk_monomer_packed(a, dm, w, Q, Km, dm, mimg, Pt, N, (int64_t)Km * dm, nullptr, k, 0, tv, ti, st, mws, mwb, nullptr));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(hs, st, sizeof(hs), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hv.data(), tv, hv.size() * 4, cudaMemcpyDeviceToHost));
+  printf("monomer: survivors %llu, redo %llu, best dist of query 0 = %g\n", hs[0], hs[3], hv[0]);
+  printf("sanitize_driver done\n");
+  return bad ? 1 : 0;
+}
