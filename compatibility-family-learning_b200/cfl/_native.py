@@ -67,6 +67,10 @@ SIGNATURES = {
     "cfl_pair_dist_rows": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _vp, _vp]),
     "cfl_rank_counts": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _vp, _vp]),
     "cfl_dense_rank_counts": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
+    "cfl_rank_counts_packed_workspace_bytes": (_sz, [_i64, _int, _int, _i64]),
+    "cfl_rank_counts_packed": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _int,
+                                      _vp, _vp, _sz, _vp]),
+    "cfl_rank_counts_packed_stats": (_int, [_i64, _int, _int, _i64, _vp, _sz, _vp, _vp]),
     "cfl_auc_workspace_bytes": (_sz, [_i64, _i64]),
     "cfl_auc": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "cfl_adam_step": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _f32, _f32, _f32, _f32, _f32, _vp]),
@@ -460,6 +464,32 @@ def rank_counts(mode, query, catalog, pos_dist, w=None):
     _check(lib().cfl_rank_counts(MODES[mode], _ptr(q2), Q, K, d, ldq, _ptr(w), _ptr(E2), N, lde, _ptr(pos_dist), J,
                                  _ptr(out), _stream()), "cfl_rank_counts")
     return out
+
+
+def rank_counts_packed(query, catalog, image, mu, pos_dist, want_stats=False):
+    """``rank_counts("pcd", ...)`` on the tensor cores: the counts are taken inside the fused scoring kernel's epilogue
+    over the packed catalog ``image`` (``catalog_pack`` of the same catalog / ``mu``), near-ties re-evaluated in the
+    direct form -> the same int64 [Q,J,2] as ``rank_counts``.  want_stats: also a dict of the call's statistics."""
+    q2, Q, K, d, ldq, _, E2, N, lde = _rank_operands("pcd", query, catalog, None)
+    pos_dist = _f32c(pos_dist, "pos_dist").contiguous()
+    if pos_dist.dim() != 2 or pos_dist.shape[0] != Q:
+        raise CflNativeError("rank_counts_packed: pos_dist must be [Q,J]")
+    J = pos_dist.shape[1]
+    out = torch.empty(Q, J, 2, dtype=torch.int64, device=E2.device)
+    mode = MODES["siamese"] if K == 1 else MODES["pcd"]
+    need = lib().cfl_rank_counts_packed_workspace_bytes(Q, K, d, N)
+    ws = _ws.get(need, E2.device)
+    mu = None if mu is None else _f32c(mu, "mu").contiguous()
+    _check(lib().cfl_rank_counts_packed(mode, _ptr(q2), Q, K, d, ldq, _ptr(E2), _ptr(image), N, lde, _ptr(mu),
+                                        _ptr(pos_dist), J, _ptr(out), _ptr(ws), ws.numel(), _stream()),
+           "cfl_rank_counts_packed")
+    if not want_stats:
+        return out
+    raw = (C.c_int64 * 4)()
+    _check(lib().cfl_rank_counts_packed_stats(Q, K, d, N, _ptr(ws), ws.numel(), raw, _stream()),
+           "cfl_rank_counts_packed_stats")
+    return out, dict(records=int(raw[0]), worst_ratio=raw[1] / 1048576.0, beyond_half_band=int(raw[2]),
+                     recounted_queries=int(raw[3]))
 
 
 def dense_rank_counts(dense, pos_dist):

@@ -207,22 +207,23 @@ class CatalogIndex:
             done.record(self._d2h)
         return done
 
-    def auc_per_query(self, xq: torch.Tensor, pos_idx: torch.Tensor, method: str = "direct"):
+    def auc_per_query(self, xq: torch.Tensor, pos_idx: torch.Tensor, method: str = "fused"):
         """All-candidate AUC of every query: ``pos_idx`` [Q,J] int64 = GLOBAL catalog rows of the query's
         labelled positives (unique per query; -1 pads), every other catalog row is a negative.  Exact
         integer rank counts, independent of the sharding.  -> namespace(auc, two_u, n_pos, n_neg, ...).
 
-        ``method="direct"``: fp32 direct-difference distances (the values the ranking reports), CUDA cores.
-        ``method="gram"``: the tensor-core scoring kernel's Gram-form distances written densely once and
-        counted at HBM speed -- ~20x faster; counts are exact for those values, which differ from the direct
-        form by the 3xTF32 Gram error (a few 1e-7 of |e|^2 + |p|^2), so only near-ties can flip."""
+        ``method="fused"`` (default; "gram" is an alias): the counts are taken inside the tensor-core scoring kernel's
+        epilogue (``cfl_rank_counts_packed``) -- no Q x N matrix is ever written; near-ties are re-evaluated in the
+        direct form, so the integers equal the direct route's.
+        ``method="direct"``: every pair in fp32 direct-difference form on the CUDA cores (``cfl_rank_counts``)."""
         Pq = self.project_queries(xq)
         if method == "gram":
-            return _auc_per_query_gram(Pq, self.E, self.mu, self.image, pos_idx, self.idx_base, self.n_total,
-                                       self.group, self._world())
-        if method != "direct":
-            raise ValueError("auc_per_query: method must be 'direct' or 'gram'")
-        return _auc_per_query("pcd", Pq, self.E, None, pos_idx, self.idx_base, self.n_total, self.group, self._world())
+            method = "fused"
+        if method not in ("direct", "fused"):
+            raise ValueError("auc_per_query: method must be 'direct' or 'fused'")
+        packed = (self.image, self.mu) if method == "fused" else None
+        return _auc_per_query("pcd", Pq, self.E, None, pos_idx, self.idx_base, self.n_total, self.group, self._world(),
+                              packed=packed)
 
     def scores(self, dist: torch.Tensor) -> torch.Tensor:
         """Thresholder (blocks.py:21-22): max(theta, 1e-6) - dist."""
@@ -253,8 +254,9 @@ def auc_from_rank_counts(counts: torch.Tensor, pos_dist: torch.Tensor, n_total: 
     return auc, two_u, n_pos, n_neg
 
 
-def _auc_per_query(mode, query, catalog, gate, pos_idx, idx_base, n_total, group, world):
-    """Positives' distances where they live, summed over shards; exact counts per shard, summed."""
+def _auc_per_query(mode, query, catalog, gate, pos_idx, idx_base, n_total, group, world, packed=None):
+    """Positives' distances where they live, summed over shards; exact counts per shard, summed.
+    packed = (catalog image, mu): count on the tensor cores (pcd)."""
     n_local = catalog.shape[0]
     pos_idx = pos_idx.to(catalog.device)
     local = pos_idx - idx_base
@@ -266,51 +268,10 @@ def _auc_per_query(mode, query, catalog, gate, pos_idx, idx_base, n_total, group
         torch.distributed.all_reduce(have, group=group)
         torch.distributed.all_reduce(val, group=group)               # one owner per positive: the sum is its value
         pos_dist = torch.where(have > 0, val, torch.full_like(val, float("nan")))
-    counts = nat.rank_counts(mode, query, catalog, pos_dist, w=gate)
-    if world > 1:
-        torch.distributed.all_reduce(counts, group=group)
-    auc, two_u, n_pos, n_neg = auc_from_rank_counts(counts, pos_dist, n_total)
-    return SimpleNamespace(auc=auc, two_u=two_u, n_pos=n_pos, n_neg=n_neg, counts=counts, pos_dist=pos_dist)
-
-
-def _auc_per_query_gram(Pq, E, mu, image, pos_idx, idx_base, n_total, group, world, q_chunk=None):
-    """pcd on the tensor cores: the Gram-form distance of every (query, row) is written once by the scoring kernel
-    (``dist_out`` of ``cfl_score_topk``), the positives' thresholds are read from that matrix and the counts are
-    taken at HBM speed (``cfl_dense_rank_counts``).  Queries go in chunks that keep the dense block under ~8 GB."""
-    n_local = E.shape[0]
-    Q, J = pos_idx.shape
-    pos_idx = pos_idx.to(E.device)
-    local = pos_idx - idx_base
-    mine = (pos_idx >= 0) & (local >= 0) & (local < n_local)
-    if q_chunk is None:
-        q_chunk = max(1, min(Q, (8 << 30) // max(4 * n_local, 1)))
-    nan = torch.full((Q, J), float("nan"), dtype=torch.float32, device=E.device)
-    pos_dist = nan.clone()
-    counts = torch.empty(Q, J, 2, dtype=torch.int64, device=E.device)
-    chunks = [(lo, min(Q, lo + q_chunk)) for lo in range(0, Q, q_chunk)]
-
-    def dense_of(lo, hi):
-        return nat.score_topk(Pq[lo:hi], E, 1, mu=mu, mode="pcd", image=image, want_dense=True)[2]
-
-    kept = None
-    for lo, hi in chunks:
-        dense = dense_of(lo, hi)
-        t = torch.gather(dense, 1, local[lo:hi].clamp(0, max(n_local - 1, 0))) if n_local else nan[lo:hi]
-        pos_dist[lo:hi] = torch.where(mine[lo:hi], t, nan[lo:hi])
-        if world == 1:
-            counts[lo:hi] = nat.dense_rank_counts(dense, pos_dist[lo:hi])
-        elif len(chunks) == 1:
-            kept = dense
-    if world > 1:
-        # the thresholds of positives owned by other shards arrive now; one owner each -> the sum is the value
-        have = mine.to(torch.int32)
-        val = torch.nan_to_num(pos_dist, nan=0.0)
-        torch.distributed.all_reduce(have, group=group)
-        torch.distributed.all_reduce(val, group=group)
-        pos_dist = torch.where(have > 0, val, nan)
-        for lo, hi in chunks:
-            dense = kept if kept is not None else dense_of(lo, hi)
-            counts[lo:hi] = nat.dense_rank_counts(dense, pos_dist[lo:hi])
+    if packed is not None and n_local > 0:
+        counts = nat.rank_counts_packed(query, catalog, packed[0], packed[1], pos_dist)
+    else:
+        counts = nat.rank_counts(mode, query, catalog, pos_dist, w=gate)
     if world > 1:
         torch.distributed.all_reduce(counts, group=group)
     auc, two_u, n_pos, n_neg = auc_from_rank_counts(counts, pos_dist, n_total)

@@ -18,6 +18,11 @@ int project_fwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float*
                      cudaStream_t st);                       // project_umma.cu
 size_t project_fwd_umma_workspace(int64_t B, int F, int N);  // project_umma.cu
 bool project_fwd_umma_supported(const float* x, int64_t B, int F, int64_t ldx, int N);
+// project_bwd_umma.cu: dV partials on the tensor cores, Cpart[slabs][F][N]
+bool project_bwd_umma_supported(int64_t B, int F, int N);
+int project_bwd_umma_slabs(int64_t B, int F);
+int project_bwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float* dy, int64_t lddy, const float* y,
+                     int64_t ldy, int act, int N, float* Cpart, cudaStream_t st);
 
 // ---- column scaler s_j = g_j / |V_:j| ----------------------------------------------------
 // one block per 32 columns, 8 row slices per block, fixed-order reduction over the slices.
@@ -360,9 +365,11 @@ int cfl_project_fwd(const float* x, int64_t B, int F, int64_t ldx, const float* 
 
 size_t cfl_project_bwd_workspace_bytes(int64_t B, int F, int N) {
   int slabs = bwd_slabs(B);
+  int gslabs = slabs;                                      // the tensor-core dV GEMM cuts the batch its own way
+  if (project_bwd_umma_supported(B, F, N)) gslabs = project_bwd_umma_slabs(B, F);
   return align_up((size_t)N * 3 * sizeof(float), 256) +
          align_up((size_t)slabs * N * 2 * sizeof(double), 256) +
-         align_up((size_t)slabs * F * N * sizeof(float), 256) + 1024;
+         align_up((size_t)gslabs * F * N * sizeof(float), 256) + 1024;
 }
 
 int cfl_project_bwd(const float* x, int64_t B, int F, int64_t ldx, const float* V, int N,
@@ -386,7 +393,9 @@ int cfl_project_bwd(const float* x, int64_t B, int F, int64_t ldx, const float* 
   float* norm = W.take<float>(N);
   float* qn3 = W.take<float>(N);
   double* part = W.take<double>((size_t)slabs * N * 2);
-  float* Cpart = W.take<float>((size_t)slabs * F * N);
+  const bool tc = project_bwd_umma_supported(B, F, N);
+  const int gslabs = tc ? project_bwd_umma_slabs(B, F) : slabs;
+  float* Cpart = W.take<float>((size_t)gslabs * F * N);
   int64_t rps = (B + slabs - 1) / slabs;
   rps = (rps + TK - 1) / TK * TK;
   if (rps < TK) rps = TK;
@@ -400,12 +409,17 @@ int cfl_project_bwd(const float* x, int64_t B, int F, int64_t ldx, const float* 
   colstats_final<<<(N + 127) / 128, 128, 0, cs>>>(part, slabs, N, norm, bias, weight_norm,
                                                  accumulate, reg_c, qn3, dg, dbias, g);
   CFL_LAUNCH_CHECK();
-  dim3 grid((N + TN - 1) / TN, (F + TM - 1) / TM, slabs);
-  project_bwd_gemm<<<grid, 256, 0, cs>>>(x, B, F, ldx, dy, lddy, y, ldy, act, N, rps, Cpart);
-  CFL_LAUNCH_CHECK();
+  if (tc) {
+    st = project_bwd_umma(x, B, F, ldx, dy, lddy, y, ldy, act, N, Cpart, cs);
+    if (st != CFL_OK) return st;
+  } else {
+    dim3 grid((N + TN - 1) / TN, (F + TM - 1) / TM, slabs);
+    project_bwd_gemm<<<grid, 256, 0, cs>>>(x, B, F, ldx, dy, lddy, y, ldy, act, N, rps, Cpart);
+    CFL_LAUNCH_CHECK();
+  }
   int64_t total = (int64_t)F * N;
   project_bwd_final<<<(unsigned)((total + 255) / 256), 256, 0, cs>>>(
-      Cpart, slabs, F, N, V, ldV, weight_norm ? scaler : nullptr, weight_norm ? qn3 : nullptr,
+      Cpart, gslabs, F, N, V, ldV, weight_norm ? scaler : nullptr, weight_norm ? qn3 : nullptr,
       in_scale, reg_c, accumulate, dV);
   CFL_LAUNCH_CHECK();
   return CFL_OK;

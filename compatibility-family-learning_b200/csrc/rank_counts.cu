@@ -11,57 +11,14 @@
 // catalog shards (int64 all-reduce), which makes the AUC independent of the sharding.  The pcd
 // arithmetic is that of merge_rescore_kernel (score.cu), i.e. of the values cfl_score_topk reports;
 // the monomer arithmetic is that of score_monomer_kernel.
-#include "common.cuh"
+#include "score.cuh"
+#include "direct.cuh"
 
 namespace cfl {
 
 constexpr int RC_QT = 8;          // queries per CTA
 constexpr int RC_THREADS = 128;   // one thread per catalog row of a 128-row tile
 constexpr int RC_MAX_J = 32;
-
-// pcd / siamese: e = candidate embedding (target e0), p = the query's K prototypes.
-template <int K, class EAcc, class PAcc>
-__device__ __forceinline__ float pcd_direct(EAcc e, PAcc p, int d) {
-  float dk[K];
-  float mn = 3.0e38f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    float acc = 0.0f;
-#pragma unroll 4
-    for (int j = 0; j < d; ++j) { const float df = e(j) - p(k, j); acc = fmaf(df, df, acc); }
-    dk[k] = acc;
-    mn = fminf(mn, acc);
-  }
-  if (K == 1) return dk[0];
-  float sum = 0.0f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) { dk[k] = expf(mn - dk[k]); sum += dk[k]; }
-  const float inv = 1.0f / sum;
-  float dist = 0.0f;
-#pragma unroll 4
-  for (int j = 0; j < d; ++j) {
-    float m = 0.0f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) m = fmaf(dk[k] * inv, p(k, j), m);
-    const float r = e(j) - m;
-    dist = fmaf(r, r, dist);
-  }
-  return dist;
-}
-
-// monomer: a = the query's embedding, w = its gate softmax, e(k, j) = prototype k of the candidate.
-template <int K, class EAcc, class AAcc, class WAcc>
-__device__ __forceinline__ float monomer_direct(EAcc e, AAcc a, WAcc w, int d) {
-  float acc = 0.0f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    float dk = 0.0f;
-#pragma unroll 4
-    for (int j = 0; j < d; ++j) { const float df = a(j) + (-e(k, j)); dk = fmaf(df, df, dk); }
-    acc = fmaf(w(k), dk, acc);
-  }
-  return acc;
-}
 
 struct RcArgs {
   int mode, K, d, J;
@@ -73,6 +30,7 @@ struct RcArgs {
   const int64_t* pos_idx;  // [Q, J] gather kernel
   float* pos_dist;         // [Q, J] gather kernel output
   unsigned long long* counts;   // [Q, J, 2]
+  const int* only;         // optional [Q]: count only the flagged queries (fallback of cfl_rank_counts_packed)
   int parts;
   int64_t tiles;
 };
@@ -176,6 +134,11 @@ rank_count_kernel(RcArgs A) {
   const int part = blockIdx.x;
   const int64_t q0 = (int64_t)blockIdx.y * RC_QT;
   const int nq = (int)((A.Q - q0 < RC_QT) ? (A.Q - q0) : RC_QT);
+  if (A.only != nullptr) {                                   // restricted recount: leave unless a query here is flagged
+    int flagged = 0;
+    for (int ql = 0; ql < nq; ++ql) flagged |= A.only[q0 + ql];
+    if (!flagged) return;
+  }
   for (int i = tid; i < RC_QT * qw; i += RC_THREADS) {
     const int ql = i / qw, e = i % qw;
     ((float*)q4)[e * RC_QT + ql] = ql < nq ? A.Pq[(q0 + ql) * A.ldq + e] : 0.0f;
@@ -233,6 +196,7 @@ rank_count_kernel(RcArgs A) {
   for (int i = tid; i < nq * J * 2; i += RC_THREADS) {
     unsigned long long s = 0;
     for (int w = 0; w < RC_THREADS / 32; ++w) s += (unsigned long long)cnt[w * RC_QT * J * 2 + i];
+    if (A.only != nullptr && !A.only[q0 + i / (J * 2)]) continue;
     if (s) atomicAdd(&A.counts[q0 * J * 2 + i], s);
   }
 }
@@ -364,6 +328,17 @@ static int rc_check(const char* what, int mode, const float* Pq, int64_t Q, int 
   CFL_REQUIRE(rc_smem_bytes(K, d, J, mono) <= 200 * 1024, CFL_ERR_UNSUPPORTED,
               "%s: K*d = %d too large for the monomer rank-count tile", what, K * d);
   return CFL_OK;
+}
+
+int rank_counts_only_launch(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* E, int64_t N,
+                            int64_t lde, const float* pos_dist, int J, unsigned long long* counts, const int* only,
+                            cudaStream_t st) {
+  RcArgs a = {};
+  a.mode = mode; a.K = K; a.d = d; a.J = J; a.Q = Q; a.N = N; a.ldq = ldq; a.lde = lde;
+  a.Pq = Pq; a.E = E; a.thr = pos_dist; a.counts = counts; a.only = only;
+  a.tiles = (N + 127) / 128;
+  a.parts = 1;
+  return rc_dispatch(a, false, st);
 }
 
 }  // namespace cfl

@@ -142,6 +142,13 @@ __global__ void prep_queries_kernel(const float* __restrict__ Pq, int64_t Q, int
   pl[ci] = (float)(0.5 * alpha + n0 - margin);
 }
 
+int score_prep_queries_launch(const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* mu, float* Pc,
+                              float* qpar, float* qplane, cudaStream_t st) {
+  prep_queries_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, st>>>(Pq, Q, K, d, ldq, mu, Pc, qpar, qplane);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
 // ---- CUDA-core scoring kernel ---------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(SIMT_THREADS)

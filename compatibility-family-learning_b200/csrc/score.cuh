@@ -109,6 +109,13 @@ int score_lb_prep_queries(const ScoreArgs& a, cudaStream_t st);   // lower-bound
 int score_umma_launch(const ScoreArgs& a, cudaStream_t st);
 int score_lb_launch(const ScoreArgs& a, cudaStream_t st);
 int score_umma_qt(int K, int d);
+// query prep shared with the rank-count path (rank_counts_tc.cu): centred prototypes, soft-min and plane-bound blocks
+int score_prep_queries_launch(const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* mu, float* Pc,
+                              float* qpar, float* qplane, cudaStream_t st);
+// rank_counts.cu: the CUDA-core rank count restricted to the queries flagged in only[Q] (adds into counts)
+int rank_counts_only_launch(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* E, int64_t N,
+                            int64_t lde, const float* pos_dist, int J, unsigned long long* counts, const int* only,
+                            cudaStream_t st);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -244,6 +251,58 @@ __device__ __forceinline__ void softmin_pair(const float (&gA)[K], const float (
   // dist = e2 - 2 inv (t1 - inv t2)
   const f2_t v = fma2(ninv, t2, t1);
   upk2(fma2(add2(ninv, ninv), v, e2p), dA, dB);
+}
+
+// softmin_pair that also returns V = sum_k s_k |p_k|^2 - |sum_k s_k p_k|^2, the spread of the prototypes under the
+// soft-min weights: d dist / d(exponent k) = s_k * (-2 (e - m).(p_k - m)), so an error du on the exponents moves dist by
+// at most 2 sqrt(dist * V) |du| -- the sensitivity term of the rank-count rounding band (rank_counts_tc.cu).
+template <int K>
+__device__ __forceinline__ void softmin_pair_var(const float (&gA)[K], const float (&gB)[K], float e2,
+                                                 const f2_t* __restrict__ qp2, float& dA, float& dB, float& vA, float& vB) {
+  const f2_t C2 = pk2(2.0f * CFL_LOG2E, 2.0f * CFL_LOG2E);
+  const f2_t e2p = pk2(e2, e2);
+  f2_t g[K], a[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { g[k] = pk2(gA[k], gB[k]); a[k] = fma2(C2, g[k], qp2[k]); }
+  if (K == 1) {
+    upk2(fma2(pk2(-CFL_LN2, -CFL_LN2), a[0], e2p), dA, dB);
+    vA = 0.0f; vB = 0.0f;
+    return;
+  }
+  float mA, mB;
+  upk2(a[0], mA, mB);
+#pragma unroll
+  for (int k = 1; k < K; ++k) { float x, y; upk2(a[k], x, y); mA = fmaxf(mA, x); mB = fmaxf(mB, y); }
+  const f2_t nm = pk2(-mA, -mB);
+  f2_t w[K];
+  f2_t sum, sp2;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float x, y;
+    upk2(add2(a[k], nm), x, y);
+    w[k] = pk2(fast_ex2(x), fast_ex2(y));
+    sum = (k == 0) ? w[0] : add2(sum, w[k]);
+    sp2 = (k == 0) ? mul2(w[0], qp2[0]) : fma2(w[k], qp2[k], sp2);      // -log2e * sum_k w_k |p_k|^2
+  }
+  float sA, sB;
+  upk2(sum, sA, sB);
+  const f2_t ninv = pk2(fast_rcp(-sA), fast_rcp(-sB));     // -1/sum
+  f2_t t1, t2;
+  int o = K;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    t1 = (k == 0) ? mul2(w[0], g[0]) : fma2(w[k], g[k], t1);
+    f2_t row = mul2(qp2[o], w[k]);                          // diagonal is stored pre-halved
+#pragma unroll
+    for (int l = k + 1; l < K; ++l) row = fma2(qp2[o + l - k], w[l], row);
+    o += K - k;
+    t2 = (k == 0) ? mul2(w[0], row) : fma2(w[k], row, t2);  // half of sum_kl w_k w_l pp_kl
+  }
+  const f2_t v = fma2(ninv, t2, t1);
+  upk2(fma2(add2(ninv, ninv), v, e2p), dA, dB);
+  // V = inv * (ln2 * (-sp2')) ... with sp2 = -log2e * sum w p2:  sum s p2 = ninv * ln2 * sp2;  |m|^2 = 2 inv^2 t2
+  const f2_t m2 = mul2(mul2(ninv, ninv), add2(t2, t2));
+  upk2(fma2(mul2(ninv, pk2(CFL_LN2, CFL_LN2)), sp2, mul2(m2, pk2(-1.0f, -1.0f))), vA, vB);
 }
 
 // Same as softmin_from_gram, reading the pair-interleaved shared-memory block of the tensor-core

@@ -249,6 +249,21 @@ int cfl_rank_counts(int mode, const float* Pq, int64_t Q, int K, int d, int64_t 
 int cfl_dense_rank_counts(const float* dense, int64_t Q, int64_t N, int64_t ldn, const float* pos_dist, int J,
                           int64_t* counts, void* stream);
 
+/* The same counts on the tensor cores, taken inside the fused scoring kernel's epilogue (no Q x N matrix anywhere):
+ * image = cfl_catalog_pack of the same E / mu.  Every (row, query) Gram-form distance is classified against the
+ * thresholds with a rounding band; pairs inside a band (exact ties included) are re-evaluated in the direct form of
+ * cfl_pair_dist_rows, so counts == cfl_rank_counts(...) for pos_dist produced by cfl_pair_dist_rows.  pcd / siamese.
+ * Replaces roc_auc_score over all candidates (cfl/utils.py:267-268); see csrc/rank_counts_tc.cu.
+ * cfl_rank_counts_packed_stats (synchronises the stream): out[CFL_RANK_NSTATS] = {ambiguous records, largest
+ * |Gram - direct| / band in units of 2^-20, records beyond half the band, queries recounted on the CUDA cores}. */
+#define CFL_RANK_NSTATS 4
+size_t cfl_rank_counts_packed_workspace_bytes(int64_t Q, int K, int d, int64_t N);
+int cfl_rank_counts_packed(int mode, const float* Pq, int64_t Q, int K, int d, int64_t ldq, const float* E,
+                           const void* image, int64_t N, int64_t lde, const float* mu, const float* pos_dist, int J,
+                           int64_t* counts, void* ws, size_t ws_bytes, void* stream);
+int cfl_rank_counts_packed_stats(int64_t Q, int K, int d, int64_t N, const void* ws, size_t ws_bytes, int64_t* out,
+                                 void* stream);
+
 /* TF-1.x Adam (cfl/models/cfl.py:1083-1085): lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
  * p -= lr_t*m/(sqrt(v)+eps).  grad_scale multiplies g first (1/world for DP averaging). */
 int cfl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int step,

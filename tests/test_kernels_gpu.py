@@ -183,7 +183,11 @@ def test_project_fwd_shapes(nat, B, F, N):
 
 
 @pytest.mark.parametrize("B,F,N,wn,act", [(100, 512, 80, True, "linear"), (3000, 256, 33, True, "tanh"),
-                                          (64, 100, 20, False, "relu"), (5000, 128, 192, False, None)])
+                                          (64, 100, 20, False, "relu"), (5000, 128, 192, False, None),
+                                          # tensor-core dV GEMM (B >= 256): ragged feature tile, ragged last slab / K-step,
+                                          # every producer layout (N <= 64, <= 128, <= 256), several jobs per CTA
+                                          (4100, 1000, 100, True, "tanh"), (70003, 512, 80, False, "sigmoid"),
+                                          (257, 7, 5, True, "relu"), (40000, 2304, 250, False, None)])
 def test_project_bwd_shapes(nat, B, F, N, wn, act):
     rng = np.random.default_rng(B + F + N)
     x = rng.normal(size=(B, F)).astype(np.float32)

@@ -260,8 +260,10 @@ def test_catalog_index_auc_per_query_planted_positives(nat):
     E = index.E
     for q in range(Q):
         E[torch.as_tensor(pos[q]).cuda()] = Pq[q, rng.integers(0, K, J)] + 0.01 * torch.randn(J, d, device="cuda")
+    index.image = nat.catalog_pack(E, K, index.mu)           # the embeddings changed: repack the catalog image
     r = index.auc_per_query(dev(xq), torch.as_tensor(pos))
     assert (r.auc > 0.999).all()
+    assert torch.equal(r.counts, index.auc_per_query(dev(xq), torch.as_tensor(pos), method="direct").counts)
     D = O.all_pairs_dist(Pq.cpu().numpy().astype(np.float64), E.cpu().numpy().astype(np.float64))
     wu, wp, wn = O.per_query_auc(D, pos)
     want = np.array(wu) / (2.0 * np.array(wp) * np.array(wn))
@@ -284,9 +286,9 @@ def test_dense_rank_counts_exact_on_tied_values(nat, Q, N, J):
 
 
 @pytest.mark.gpu
-def test_catalog_index_auc_per_query_gram_route(nat):
-    """The tensor-core route (dense Gram-form distances + HBM-speed counting) against the direct route and the
-    fp64 oracle: same AUC up to near-tie flips inside the Gram error band; counts self-consistent."""
+def test_catalog_index_auc_per_query_fused_route(nat):
+    """The tensor-core route (counts taken in the scoring kernel's epilogue, near-ties re-evaluated in the direct form)
+    returns the SAME integers as the direct route; both agree with the fp64 oracle up to near-tie flips."""
     from cfl.ranking import CatalogIndex, EncoderWeights
     rng = np.random.default_rng(634)
     F, K, d, N, Q, J = 64, 3, 64, 30000, 48, 8
@@ -299,20 +301,80 @@ def test_catalog_index_auc_per_query_gram_route(nat):
     pos = rng.permutation(np.arange(Q, N))[:Q * J].reshape(Q, J).astype(np.int64)
     pos[::5, -1] = -1
     a = index.auc_per_query(xq, torch.as_tensor(pos), method="direct")
-    b = index.auc_per_query(xq, torch.as_tensor(pos), method="gram")
+    b = index.auc_per_query(xq, torch.as_tensor(pos))                      # default = fused
+    assert torch.equal(a.counts, b.counts)
+    assert torch.equal(torch.nan_to_num(a.pos_dist, nan=-1.0), torch.nan_to_num(b.pos_dist, nan=-1.0))
     assert (b.counts[..., 1][torch.as_tensor(pos >= 0).cuda()] >= 1).all()
     Pq = index.project_queries(xq)
     D = O.all_pairs_dist(Pq.cpu().numpy().astype(np.float64), index.E.cpu().numpy().astype(np.float64))
     wu, wp, wn = O.per_query_auc(D, pos)
     want = np.array(wu) / (2.0 * np.array(wp) * np.array(wn))
-    tol = 4.0 / (J * (N - J))                                   # a few near-tie flips
-    np.testing.assert_allclose(a.auc.cpu().numpy(), want, atol=tol)
-    np.testing.assert_allclose(b.auc.cpu().numpy(), want, atol=tol)
-    np.testing.assert_allclose(b.pos_dist.cpu().numpy(), a.pos_dist.cpu().numpy(), rtol=1e-4, equal_nan=True)
-    # chunked sweep = one sweep
-    from cfl import ranking
-    c = ranking._auc_per_query_gram(Pq, index.E, index.mu, index.image, torch.as_tensor(pos), 0, N, None, 1, q_chunk=7)
-    assert torch.equal(c.counts, b.counts)
+    np.testing.assert_allclose(b.auc.cpu().numpy(), want, atol=4.0 / (J * (N - J)))   # a few near-tie flips vs fp64
+
+
+def _fused_case(rng, K, d, Q, N, J, kind):
+    if kind == "integer":                       # integer-valued inputs: exact ties everywhere, every tie is ambiguous
+        E = rng.integers(-2, 3, size=(N, d)).astype(np.float32)
+        Pq = rng.integers(-2, 3, size=(Q, K, d)).astype(np.float32)
+    else:
+        E = rng.normal(size=(N, d)).astype(np.float32)
+        Pq = (E[rng.integers(0, N, Q)][:, None, :] + 0.5 * rng.normal(size=(Q, K, d))).astype(np.float32)
+        if kind == "offset":                    # a common offset eats mantissa unless the image is centred
+            E += 10.0
+            Pq += 10.0
+        if kind == "far":                       # prototypes far apart: one-hot soft-min
+            Pq *= 4.0
+    pos = _planted(rng, Q, N, J, pad=Q > 4)
+    return E, Pq, pos
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,d,Q,N,J,kind", [
+    (3, 64, 70, 30000, 8, "normal"), (1, 20, 5, 5000, 3, "normal"), (2, 16, 33, 20000, 9, "normal"),
+    (4, 20, 64, 25000, 8, "offset"), (8, 20, 10, 9000, 8, "normal"), (5, 32, 50, 12000, 8, "normal"),
+    (3, 128, 40, 10000, 20, "normal"), (4, 128, 9, 7000, 32, "far"), (2, 8, 20, 3000, 4, "integer"),
+    (3, 12, 130, 129, 2, "integer"), (1, 64, 3, 1, 1, "normal"), (6, 10, 65, 40000, 8, "offset")])
+def test_rank_counts_packed_equals_direct(nat, K, d, Q, N, J, kind):
+    """cfl_rank_counts_packed == cfl_rank_counts, integer for integer (ties, padded slots, ragged tiles, J > 8 in
+    several threshold chunks), and the rounding band has headroom: no ambiguous pair deviated by half of it."""
+    rng = np.random.default_rng(K * 1000 + d + Q + J)
+    E, Pq, pos = _fused_case(rng, K, d, Q, N, min(J, N), kind)
+    Ed, Pd = dev(E), dev(Pq)
+    mu = nat.col_mean(Ed)
+    img = nat.catalog_pack(Ed, K, mu)
+    t = nat.pair_dist_rows("pcd", Pd, Ed, torch.as_tensor(pos).cuda())
+    want = nat.rank_counts("pcd", Pd, Ed, t)
+    got, st = nat.rank_counts_packed(Pd, Ed, img, mu, t, want_stats=True)
+    assert torch.equal(got, want), (st, (got != want).sum().item())
+    assert st["recounted_queries"] == 0
+    if kind != "integer":
+        assert st["worst_ratio"] < 0.5 and st["beyond_half_band"] == 0, st
+    # counts at the fp64 oracle's precision: only near-ties may differ
+    if N <= 30000 and Q <= 70:
+        D = O.all_pairs_dist(Pq.astype(np.float64), E.astype(np.float64))
+        cnt, _ = _counts_from_dense(D, pos)
+        lt = got[..., 0].cpu().numpy()
+        ok = pos >= 0
+        assert np.abs(lt[ok] - cnt[..., 0][ok]).max() <= (N if kind == "integer" else 3)
+
+
+@pytest.mark.gpu
+def test_rank_counts_packed_overflowing_record_list_falls_back(nat, monkeypatch):
+    """A record list that cannot hold the ambiguous pairs flags the affected queries; they are recounted from scratch
+    on the CUDA cores and the integers still equal the direct route's."""
+    monkeypatch.setenv("CFL_EXPERIMENTS", "1")
+    monkeypatch.setenv("CFL_RANK_REC_CAP", "64")
+    rng = np.random.default_rng(77)
+    K, d, Q, N, J = 3, 16, 40, 20000, 8
+    E, Pq, pos = _fused_case(rng, K, d, Q, N, J, "integer")
+    Ed, Pd = dev(E), dev(Pq)
+    mu = nat.col_mean(Ed)
+    img = nat.catalog_pack(Ed, K, mu)
+    t = nat.pair_dist_rows("pcd", Pd, Ed, torch.as_tensor(pos).cuda())
+    want = nat.rank_counts("pcd", Pd, Ed, t)
+    got, st = nat.rank_counts_packed(Pd, Ed, img, mu, t, want_stats=True)
+    assert st["recounted_queries"] > 0
+    assert torch.equal(got, want)
 
 
 def test_auc_from_rank_counts_random_cases_against_the_exact_auc():

@@ -21,6 +21,8 @@ CASES = [("pcd", 1_000_000, 3, 64, 1024, 8), ("pcd", 1_000_000, 4, 20, 1024, 8),
                               ("monomer", 1_000_000, 4, 20, 1024, 8)]
 if os.environ.get("CFL_PERF_ONLY"):
     CASES = [CASES[int(os.environ["CFL_PERF_ONLY"])]]
+if os.environ.get("CFL_PERF_FUSED"):          # only the tensor-core route below
+    CASES = []
 for (mode, N, K, d, Q, J) in CASES:
     pos = torch.randint(0, N, (Q, J), generator=g, device="cuda")
     if mode == "pcd":
@@ -38,18 +40,26 @@ for (mode, N, K, d, Q, J) in CASES:
                           gscores_s=round(Q * N / ms / 1e6, 1))), flush=True)
     del cat, qry
 
-# tensor-core route for pcd: dense Gram-form distances from the scoring kernel + HBM-speed counting
+# tensor-core route for pcd: counts inside the fused scoring kernel's epilogue (cfl_rank_counts_packed) beside the exact
+# scoring pass of the same kernel family (dense-free: top-1 ranking over the same image) as the "scoring time" yardstick
 if not os.environ.get("CFL_PERF_ONLY"):
-    for (N, K, d, Q, J) in [(1_000_000, 3, 64, 1024, 8), (1_000_000, 4, 20, 1024, 8)]:
+    for (N, K, d, Q, J) in [(1_000_000, 3, 64, 1024, 8), (1_000_000, 4, 20, 1024, 8), (1_000_000, 1, 64, 1024, 8),
+                            (1_000_000, 8, 20, 1024, 8), (1_000_000, 3, 64, 1024, 1)]:
         E = torch.randn(N, d, generator=g, device="cuda")
         Pq = E[torch.randint(0, N, (Q,), generator=g, device="cuda")][:, None, :] + 0.5 * torch.randn(Q, K, d, generator=g, device="cuda")
         mu = nat.col_mean(E)
         img = nat.catalog_pack(E, K, mu)
         pos = torch.randint(0, N, (Q, J), generator=g, device="cuda")
-        dense = nat.score_topk(Pq, E, 1, mu=mu, image=img, want_dense=True)[2]
-        t = torch.gather(dense, 1, pos)
-        ms_d = timeit(lambda: nat.score_topk(Pq, E, 1, mu=mu, image=img, want_dense=True))
-        ms_c = timeit(lambda: nat.dense_rank_counts(dense, t))
-        print(json.dumps(dict(kernel="gram_route", N=N, K=K, d=d, Q=Q, J=J, dense_scoring_ms=round(ms_d, 3), count_ms=round(ms_c, 3),
-                              count_hbm_gbs=round(Q * N * 4 / ms_c / 1e6, 1), gscores_s=round(Q * N / (ms_d + ms_c) / 1e6, 1))), flush=True)
-        del E, Pq, dense, img
+        t = nat.pair_dist_rows("pcd", Pq, E, pos)
+        got, st = nat.rank_counts_packed(Pq, E, img, mu, t, want_stats=True)
+        ms = timeit(lambda: nat.rank_counts_packed(Pq, E, img, mu, t))
+        os.environ["CFL_SCORE_NO_LB"] = "1"; os.environ["CFL_SCORE_SAMPLE_STRIDE"] = "1"      # one exact 3xTF32 pass
+        ms_s = timeit(lambda: nat.score_topk(Pq, E, 100, mu=mu, image=img))
+        del os.environ["CFL_SCORE_NO_LB"], os.environ["CFL_SCORE_SAMPLE_STRIDE"]
+        ms_c = timeit(lambda: nat.score_topk(Pq, E, 100, mu=mu, image=img))
+        same = None
+        if os.environ.get("CFL_PERF_CHECK"):
+            same = bool(torch.equal(got, nat.rank_counts("pcd", Pq, E, t)))
+        print(json.dumps(dict(kernel="fused_rank_counts", N=N, K=K, d=d, Q=Q, J=J, ms=round(ms, 3), gscores_s=round(Q * N / ms / 1e6, 1),
+                              exact_scoring_pass_ms=round(ms_s, 3), cascade_top100_ms=round(ms_c, 3), equals_direct=same, **st)), flush=True)
+        del E, Pq, img
