@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
+#include "tmap.cuh"
 
 namespace cfl {
 
@@ -34,9 +35,11 @@ constexpr uint32_t PB_ASTEP = 4u * 128u * 16u;             // [hl][chunk][128 fe
 constexpr int PB_PF = 3;                                   // stages of register prefetch
 
 struct PbArgs {
+  CUtensorMap tmx, tmd, tmy;                               // TMA-staged kernel: x [B, F], dy [B, N], y [B, N]
   const float* x; int64_t B; int F; int64_t ldx;
   const float* dy; int64_t lddy; const float* y; int64_t ldy; int act;
   int N, Npad, nst, nh, rs;
+  int dbg;                                                 // experiments (CFL_EXPERIMENTS=1, CFL_PB_DBG): 1 = loader copies nothing, 2 = producers store nothing
   int64_t slab_rows; int slabs, ftiles;
   float* Cpart;                                            // [slabs][F][N]
 };
@@ -254,16 +257,17 @@ project_bwd_umma_kernel(PbArgs A) {
 
 // ---- variant with the raw tiles staged by the TMA engine ------------------------------------------------------------
 // The register-prefetch kernel above keeps only PF stages of loads in flight per thread (24 KB per SM: latency-bound at
-// ~1/4 of HBM).  Here warp 13 streams the RAW batch-major tiles -- 16 batch rows x 128 features of x (one 512-byte bulk
-// copy per row), the same rows of dy (and y) -- into a deep shared-memory ring (mbarrier expect_tx); the producers then
+// ~1/4 of HBM).  Here warp 13 streams the RAW batch-major tiles -- 16 batch rows x 128 features of x, the same rows of
+// dy (and y) -- into a deep shared-memory ring (mbarrier expect_tx); the producers then
 // transpose out of shared memory: thread (feature f) reads 4 consecutive batch rows at stride 512 B (conflict-free),
-// splits hi/lo and writes the K-major operand chunk as before.  Needs 16-byte aligned rows (x, dy, y; F % 4 == N % 4 == 0);
-// other shapes use the kernel above.
+// splits hi/lo and writes the K-major operand chunk as before.  The tiles are TMA tensor boxes (tmap.cuh: one instruction
+// per tile, ragged edges zero-filled); needs 16-byte aligned bases and leading dimensions % 4 == 0 (x, dy, y), other
+// shapes use the kernel above.
 constexpr int PT_THREADS = 14 * 32;
 
 template <int NBI, bool NEEDY>
 __global__ void __launch_bounds__(PT_THREADS, 1)
-project_bwd_umma_tma_kernel(PbArgs A) {
+project_bwd_umma_tma_kernel(const __grid_constant__ PbArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Npad = A.Npad, NST = A.nst, NH = A.nh, RS = A.rs;
@@ -344,25 +348,25 @@ project_bwd_umma_tma_kernel(PbArgs A) {
   } else if (warp == 13) {
     // ================================ raw-tile loader (one lane) =============================
     if (elect_one()) {
+      tma_prefetch_desc(&A.tmx); tma_prefetch_desc(&A.tmd);
+      if (NEEDY) tma_prefetch_desc(&A.tmy);
       int rs = 0; uint32_t rph = 0;
+      const uint32_t tx = araw + (NEEDY ? 2u : 1u) * braw;       // whole boxes arrive (out-of-range parts as zeros)
       for (int t = 0; t < my_jobs; ++t) {
         const int64_t job = first + (int64_t)t * stride;
         int64_t b0;
         const int rows = job_rows(job, b0);
         const int spj = (rows + PB_ROWS - 1) / PB_ROWS;
-        const int64_t f0 = (job % A.ftiles) * 128;
-        const uint32_t abytes = (uint32_t)((A.F - f0 < 128 ? A.F - f0 : 128) * 4);
-        const uint32_t nbytes = (uint32_t)A.N * 4u;
-        for (int s = 0; s < spj; ++s) {
-          const int nr = rows - s * PB_ROWS < PB_ROWS ? rows - s * PB_ROWS : PB_ROWS;
+        const int f0 = (int)(job % A.ftiles) * 128;
+        int r0 = (int)b0;
+        for (int s = 0; s < spj; ++s, r0 += PB_ROWS) {
           mbar_wait(&rempty[rs], rph ^ 1u);
           unsigned char* dst = raw + (size_t)rs * raw_bytes;
-          mbar_arrive_expect_tx(&rfull[rs], (uint32_t)nr * (abytes + (NEEDY ? 2u : 1u) * nbytes));
-          const int64_t r0 = b0 + (int64_t)s * PB_ROWS;
-          for (int r = 0; r < nr; ++r) {
-            bulk_g2s(dst + r * 512, A.x + (r0 + r) * A.ldx + f0, abytes, &rfull[rs]);
-            bulk_g2s(dst + araw + (size_t)r * Npad * 4, A.dy + (r0 + r) * A.lddy, nbytes, &rfull[rs]);
-            if (NEEDY) bulk_g2s(dst + araw + braw + (size_t)r * Npad * 4, A.y + (r0 + r) * A.ldy, nbytes, &rfull[rs]);
+          mbar_arrive_expect_tx(&rfull[rs], (A.dbg & 1) ? 0u : tx);
+          if (!(A.dbg & 1)) {
+            tma_load_2d(dst, &A.tmx, f0, r0, &rfull[rs]);
+            tma_load_2d(dst + araw, &A.tmd, 0, r0, &rfull[rs]);
+            if (NEEDY) tma_load_2d(dst + araw + braw, &A.tmy, 0, r0, &rfull[rs]);
           }
           if (++rs == RS) { rs = 0; rph ^= 1u; }
         }
@@ -370,21 +374,40 @@ project_bwd_umma_tma_kernel(PbArgs A) {
     }
   } else if (warp >= 4) {
     // ================================ producers: transpose out of the raw ring ================
+    // Everything that does not change from stage to stage is computed once: the thread's read positions in the raw
+    // tiles and its write positions in the operand stage.
     const int p = tid - 128;
     const int fa = p & 127, ca = p >> 7;
+    const int a_rd = ca * 4 * 128 + fa;                          // + (j * 8 + i) * 128
+    const uint32_t a_st = (uint32_t)(ca * 128 + fa) * 16u;       // + j * PB_ASTEP (+ 4096 for lo)
+    int b_rd[NBI], b_r0[NBI];
+    uint32_t b_st[NBI];
+#pragma unroll
+    for (int it = 0; it < NBI; ++it) {
+      const int idx = p + PB_PROD * it;
+      const int n = idx % Npad, ch = idx / Npad;                 // ch = 2 * K-step + chunk
+      b_r0[it] = ch < 2 * PB_KPS ? ch * 4 : -1;
+      b_rd[it] = ch * 4 * Npad + n;                              // + i * Npad
+      b_st[it] = b_off + (uint32_t)(ch >> 1) * bbytes + (uint32_t)((ch & 1) * Npad + n) * 16u;
+    }
+    const uint32_t lo_b = 2u * (uint32_t)Npad * 16u;
     int rs = 0; uint32_t rph = 0;
-    int sidx = 0;
+    int stage = 0; uint32_t phase = 0;
     for (int t = 0; t < my_jobs; ++t) {
-      const int64_t job = first + (int64_t)t * stride;
       int64_t b0;
-      const int rows = job_rows(job, b0);
+      const int rows = job_rows(first + (int64_t)t * stride, b0);
       const int spj = (rows + PB_ROWS - 1) / PB_ROWS;
-      const bool fok = (job % A.ftiles) * 128 + fa < A.F;
-      for (int s = 0; s < spj; ++s, ++sidx) {
-        const int nr = rows - s * PB_ROWS;                       // valid rows of this stage (may exceed 16)
-        const int stage = sidx % NST;
-        const uint32_t phase = (uint32_t)((sidx / NST) & 1);
+      for (int s = 0; s < spj; ++s) {
+        const int nr = rows - s * PB_ROWS;                       // rows of this stage that belong to the slab
         mbar_wait(&rfull[rs], rph);
+        if (A.dbg & 2) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive(&full[stage]);
+          mbar_arrive(&rempty[rs]);
+          if (++rs == RS) { rs = 0; rph ^= 1u; }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+          continue;
+        }
         const float* ar = (const float*)(raw + (size_t)rs * raw_bytes);
         const float* dr = ar + PB_ROWS * 128;
         const float* yr = dr + PB_ROWS * Npad;
@@ -392,52 +415,55 @@ project_bwd_umma_tma_kernel(PbArgs A) {
 #pragma unroll
         for (int j = 0; j < PB_KPS; ++j)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = j * 8 + ca * 4 + i;
-            a[j][i] = (fok && r < nr) ? ar[r * 128 + fa] : 0.0f;
-          }
+          for (int i = 0; i < 4; ++i) a[j][i] = ar[a_rd + (j * 8 + i) * 128];
 #pragma unroll
-        for (int it = 0; it < NBI; ++it) {
-          const int idx = p + PB_PROD * it;
-          const int n = idx % Npad, ch = idx / Npad;
-          const bool nok = ch < 2 * PB_KPS && n < A.N;
+        for (int it = 0; it < NBI; ++it)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int r = ch * 4 + i;
             float gq = 0.0f;
-            if (nok && r < nr) {
-              gq = dr[r * Npad + n];
-              if (NEEDY) gq *= act_grad_from_y(yr[r * Npad + n], A.act);
+            if (b_r0[it] >= 0) {
+              gq = dr[b_rd[it] + i * Npad];
+              if (NEEDY) gq *= act_grad_from_y(yr[b_rd[it] + i * Npad], A.act);
             }
             dd[it][i] = gq;
           }
+        if (nr < PB_ROWS) {                                      // last stage of a slab: its tail rows are another slab's
+#pragma unroll
+          for (int j = 0; j < PB_KPS; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (j * 8 + ca * 4 + i >= nr) a[j][i] = 0.0f;
+#pragma unroll
+          for (int it = 0; it < NBI; ++it)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (b_r0[it] + i >= nr) dd[it][i] = 0.0f;
         }
         mbar_wait(&empty[stage], phase ^ 1u);
         unsigned char* sbase = ring + (size_t)stage * stage_bytes;
 #pragma unroll
         for (int j = 0; j < PB_KPS; ++j) {
           float4 hi, lo;
-          split_tf32x4(make_float4(a[j][0], a[j][1], a[j][2], a[j][3]), hi, lo);
-          unsigned char* dst = sbase + j * PB_ASTEP + (ca * 128 + fa) * 16;
+          split_tf32x4_fast(make_float4(a[j][0], a[j][1], a[j][2], a[j][3]), hi, lo);
+          unsigned char* dst = sbase + j * PB_ASTEP + a_st;
           *(float4*)dst = hi;
           *(float4*)(dst + 2 * 128 * 16) = lo;
         }
 #pragma unroll
         for (int it = 0; it < NBI; ++it) {
-          const int idx = p + PB_PROD * it;
-          const int n = idx % Npad, ch = idx / Npad;
-          if (ch < 2 * PB_KPS) {
+          if (b_r0[it] >= 0) {
             float4 hi, lo;
-            split_tf32x4(make_float4(dd[it][0], dd[it][1], dd[it][2], dd[it][3]), hi, lo);
-            unsigned char* dst = sbase + b_off + (ch >> 1) * bbytes + ((size_t)(ch & 1) * Npad + n) * 16;
+            split_tf32x4_fast(make_float4(dd[it][0], dd[it][1], dd[it][2], dd[it][3]), hi, lo);
+            unsigned char* dst = sbase + b_st[it];
             *(float4*)dst = hi;
-            *(float4*)(dst + 2 * (size_t)Npad * 16) = lo;
+            *(float4*)(dst + lo_b) = lo;
           }
         }
         fence_proxy_async();
         mbar_arrive(&full[stage]);
         mbar_arrive(&rempty[rs]);
         if (++rs == RS) { rs = 0; rph ^= 1u; }
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -548,6 +574,8 @@ int project_bwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float*
   a.N = N; a.Npad = pb_npad(N);
   a.nst = pb_stages(a.Npad);
   a.rs = 0;
+  a.dbg = 0;
+  { const char* e = getenv("CFL_EXPERIMENTS"); if (e && atoi(e) != 0 && (e = getenv("CFL_PB_DBG"))) a.dbg = atoi(e); }
   int nh = 512 / a.Npad - 1;                                  // accumulator sets that fit TMEM, one is the cross terms'
   a.nh = nh > 3 ? 3 : (nh < 1 ? 1 : nh);
   a.slab_rows = project_bwd_umma_slab_rows(B, F);
@@ -561,12 +589,13 @@ int project_bwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float*
   const int grid = (int)(njobs < sms ? njobs : sms);
   const int nbi = (4 * a.Npad + PB_PROD - 1) / PB_PROD;       // B-operand chunks per producer thread and stage
   const bool needy = act != CFL_ACT_LINEAR;
-  const bool aligned = (((uintptr_t)x | (uintptr_t)dy | (needy ? (uintptr_t)y : 0)) & 15u) == 0 && (ldx & 3) == 0 &&
-                       (lddy & 3) == 0 && (!needy || (ldy & 3) == 0) && (F & 3) == 0 && (N & 3) == 0;
-  if (aligned && !getenv("CFL_PROJECT_BWD_NO_TMA")) {
+  if (!getenv("CFL_PROJECT_BWD_NO_TMA")) {
     const size_t stage = (size_t)PB_KPS * (PB_ASTEP + 64u * (size_t)a.Npad);
     const size_t rawb = (size_t)PB_ROWS * 128 * 4 + (needy ? 2 : 1) * (size_t)PB_ROWS * a.Npad * 4;
-    if ((200 * 1024 - 3 * stage) / rawb >= 3) {
+    const bool fits = (200 * 1024 - 3 * stage) / rawb >= 3 && B < ((int64_t)1 << 31);
+    if (fits && make_tmap_2d_f32(&a.tmx, x, (uint64_t)F, (uint64_t)B, (uint64_t)ldx, 128, PB_ROWS) &&
+        make_tmap_2d_f32(&a.tmd, dy, (uint64_t)N, (uint64_t)B, (uint64_t)lddy, (uint32_t)a.Npad, PB_ROWS) &&
+        (!needy || make_tmap_2d_f32(&a.tmy, y, (uint64_t)N, (uint64_t)B, (uint64_t)ldy, (uint32_t)a.Npad, PB_ROWS))) {
       if (nbi <= 1) return pt_launch<1>(a, grid, st);
       if (nbi <= 2) return pt_launch<2>(a, grid, st);
       return pt_launch<4>(a, grid, st);
