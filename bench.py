@@ -20,7 +20,9 @@ Besides the headline line (C3, weak scaling) the same JSON line carries, measure
   "small_q"  Q = 16 queries against the C3 catalog: the HBM-bound regime (catalog GB/s against the measured copy peak);
   "filter"   survivors per query of the full filter pass and the queries that spilled / were redone (a regression to
              the slow paths shows up here);
-  "per_rank" kernel_ms and survivors of every rank (stragglers).
+  "per_rank" kernel_ms and survivors of every rank (stragglers);
+  "auc"      per-query all-candidate AUC (J = 8 positives per query against the whole C3 catalog) with the rank counts
+             taken in the tensor-core scoring kernel's epilogue, beside the CUDA-core route it must equal (N = 1 only).
 """
 from __future__ import annotations
 
@@ -225,6 +227,48 @@ def small_q_line(index, device, q=16, steps=50):
                       "of the step is launch-bound (16 small kernels)"}
 
 
+def auc_line(index, device, j=8, steps=10):
+    """Per-query all-candidate AUC on the resident C3 catalog (J = 8 labelled positives per query, every
+    other catalog row a negative): the rank counts are taken inside the tensor-core scoring kernel's epilogue
+    (cfl_rank_counts_packed); checked once against the CUDA-core direct route (same integers)."""
+    from cfl import _native as nat
+    xq = synth_features(Q, device, SEED + 7)
+    g = torch.Generator(device=device).manual_seed(SEED + 55)
+    pos = torch.randint(0, index.E.shape[0], (Q, j), generator=g, device=device) + index.idx_base
+    fused = index.auc_per_query(xq, pos)
+    direct = index.auc_per_query(xq, pos, method="direct")
+    same = bool(torch.equal(fused.counts, direct.counts))
+    Pq = index.project_queries(xq)
+    _, st = nat.rank_counts_packed(Pq, index.E, index.image, index.mu, fused.pos_dist, want_stats=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ks, ke = [], []
+    e0.record()
+    for _ in range(steps):
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nat.set_kernel_timer(a_, b_); ks.append(a_); ke.append(b_)
+        index.auc_per_query(xq, pos)
+    e1.record()
+    torch.cuda.synchronize()
+    nat.set_kernel_timer(None, None)
+    ms = e0.elapsed_time(e1) / steps
+    kms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in zip(ks, ke)]))
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    index.auc_per_query(xq, pos, method="direct")
+    d1.record()
+    torch.cuda.synchronize()
+    n = index.E.shape[0]
+    return {"workload": f"per-query all-candidate AUC: Q={Q} queries x {n} catalog rows, J={j} positives each",
+            "ms_per_call": ms, "scores_per_s": Q * n / (ms / 1e3), "count_kernels_ms": kms,
+            "count_kernels_tflops": 2.0 * K * D * Q * n / (kms / 1e3) / 1e12,
+            "cuda_core_route_ms": d0.elapsed_time(d1), "counts_equal_cuda_core_route": same,
+            "ambiguous_records": st["records"], "worst_deviation_over_band": round(st["worst_ratio"], 4),
+            "recounted_queries": st["recounted_queries"], "mean_auc": float(torch.nanmean(fused.auc)),
+            "kernel": "rank_count_umma_kernel<3> (3xTF32 tcgen05 Gram + soft-min + packed threshold counters in the "
+                      "epilogue) + rank_fix_kernel (near-ties in fp32 direct form); no Q x N matrix is written"}
+
+
 def run_ours(args):
     from cfl import _native as nat
     from cfl.ranking import CatalogIndex
@@ -375,6 +419,7 @@ def run_ours(args):
                     hbm_gbs=round((traffic or alg_bytes) / (k_ms / 1e3) / 1e9, 1))
 
     small_q = small_q_line(index, device) if (rank == 0 and not args.quick) else None
+    auc = auc_line(index, device) if (world == 1 and not args.quick) else None
     if world > 1:
         torch.distributed.barrier()
     del index, E
@@ -400,7 +445,7 @@ def run_ours(args):
             "filter": {"survivors_per_query": filt["survivors"] / Q, "redo_queries": filt["redo_queries"],
                        "spill_queries": filt["spill_queries"], "probe_dropped_queries": filt["probe_dropped_queries"],
                        "lower_bound_pass": filt["lower_bound_pass"]},
-            "per_rank": per_rank, "small_q": small_q, "c5": c5,
+            "per_rank": per_rank, "small_q": small_q, "auc": auc, "c5": c5,
             "catalog_projection": {"items_per_s": N_PER_GPU / (proj_ms / 1e3), "ms": proj_ms,
                                    "hbm_frac": (N_PER_GPU * (4 * F + 4 * D)) / (proj_ms / 1e3) / 1e9 / pk["hbm"]},
             "setup_s": setup_s,

@@ -317,8 +317,13 @@ project_bwd_umma_tma_kernel(const __grid_constant__ PbArgs A) {
   if (warp == 12) {
     // ================================ MMA issuer (one lane) =================================
     if (elect_one()) {
-      const Step3Desc sd = make_step3((uint32_t)Npad, make_idesc_tf32(128, (uint32_t)Npad));
+      const uint32_t idesc = make_idesc_tf32(128, (uint32_t)Npad);
+      const uint32_t hiw = desc_hi_word(128u);
       const uint32_t ring_u = smem_u32(ring);
+      const uint32_t a_w0 = desc_lo_word(ring_u, 128u * 16u);
+      const uint32_t b_w0 = desc_lo_word(ring_u + b_off, (uint32_t)Npad * 16u);
+      const uint32_t a_lo_d = (2u * 128u * 16u) >> 4, b_lo_d = 2u * (uint32_t)Npad;
+      const uint32_t b_step4 = bbytes >> 4, st4 = stage_bytes >> 4;
       const uint32_t d_lo = tmem_base + (uint32_t)(NH * Npad);
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < my_jobs; ++t) {
@@ -327,17 +332,21 @@ project_bwd_umma_tma_kernel(const __grid_constant__ PbArgs A) {
         const int spj = (rows + PB_ROWS - 1) / PB_ROWS;
         mbar_wait(tempty, ((uint32_t)t & 1u) ^ 1u);
         tc_fence_after();
-        int kidx = 0;
+        uint32_t d_hi = tmem_base; int h = 0;
+        uint32_t seen = 0;
         for (int s = 0; s < spj; ++s) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = ring_u + stage * stage_bytes;
+          uint32_t aw = a_w0 + (uint32_t)stage * st4, bw = b_w0 + (uint32_t)stage * st4;
 #pragma unroll
-          for (int j = 0; j < PB_KPS; ++j, ++kidx) {
-            const uint64_t ao = (uint64_t)((sa + j * PB_ASTEP) >> 4), bo = (uint64_t)((sa + b_off + j * bbytes) >> 4);
-            mma_tf32(d_lo, sd.a_lo + ao, sd.b_hi + bo, sd.idesc, kidx == 0 ? 0u : 1u);
-            mma_tf32(d_lo, sd.a_hi + ao, sd.b_lo + bo, sd.idesc, 1u);
-            mma_tf32(tmem_base + (uint32_t)((kidx % NH) * Npad), sd.a_hi + ao, sd.b_hi + bo, sd.idesc, kidx < NH ? 0u : 1u);
+          for (int j = 0; j < PB_KPS; ++j) {
+            mma_tf32_w(d_lo, aw + a_lo_d, hiw, bw, hiw, idesc, seen ? 1u : 0u);
+            mma_tf32_w(d_lo, aw, hiw, bw + b_lo_d, hiw, idesc, 1u);
+            mma_tf32_w(d_hi, aw, hiw, bw, hiw, idesc, seen >= (uint32_t)NH ? 1u : 0u);
+            aw += PB_ASTEP >> 4; bw += b_step4;
+            if (seen < (uint32_t)NH) ++seen;
+            d_hi += (uint32_t)Npad;
+            if (++h == NH) { h = 0; d_hi = tmem_base; }
           }
           mma_commit(&empty[stage]);
           if (++stage == NST) { stage = 0; phase ^= 1u; }

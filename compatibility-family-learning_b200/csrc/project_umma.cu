@@ -2,6 +2,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
+#include "tmap.cuh"
 
 namespace cfl {
 
@@ -115,11 +116,13 @@ constexpr uint32_t PU_ASTAGE = 4u * PU_APLANE + 64u;          // 8384
 constexpr int PU_PF = 4;
 
 struct PuArgs {
+  CUtensorMap tmx;                                         // TMA-staged kernel: x [B, F], box = 128 rows x 8*kps columns
   const float* x; int64_t B; int F; int64_t ldx;
   const unsigned char* vimg; int N, Npad, nks, nst, kps, nh, nbuf;
   const float* scaler; const float* bias; float in_scale; int act;
   float* y; int64_t ldy; float* pre; float* z;
   int64_t tiles;
+  int rs;                                                  // raw-tile ring stages (TMA-staged kernel)
 };
 
 __global__ void pack_weights_kernel(const float* __restrict__ V, int F, int N, int64_t ldV, int Npad,
@@ -143,6 +146,76 @@ __global__ void pack_weights_kernel(const float* __restrict__ V, int F, int N, i
     ((float4*)img)[step + (size_t)(1 * 2 + c) * Npad + n] = lo;
   }
 }
+
+// Epilogue shared by both projection kernels (warps 0-3): tcgen05.ld 16 columns at a time for the thread's item ->
+// sum of the split accumulators -> in_scale, weight-norm scaler, bias, activation -> y (+ pre, z).
+__device__ __forceinline__ void project_epilogue(const PuArgs& A, int warp, int lane, int my_tiles, int64_t first, int64_t stride,
+                                                 uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty, const float* scs,
+                                                 const float* bis, int NH, int NBUF, int acc_cols, int nks) {
+  const int Npad = A.Npad;
+    // ------------------------------------ epilogue ------------------------------------
+    const int lrow = warp * 32 + lane;
+    const bool vec = ((A.ldy & 3) == 0) && (((uintptr_t)A.y & 15u) == 0) &&
+                     (!A.pre || ((uintptr_t)A.pre & 15u) == 0) && (!A.z || ((uintptr_t)A.z & 15u) == 0);
+    for (int t = 0; t < my_tiles; ++t) {
+      const int buf = t % NBUF;
+      const int64_t row = (first + (int64_t)t * stride) * 128 + lrow;
+      mbar_wait(&tfull[buf], (uint32_t)(t / NBUF) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * acc_cols);
+      const bool two_hi = NH == 2 && nks >= 2;                  // second hi accumulator was written
+      for (int c0 = 0; c0 < Npad; c0 += 16) {
+        float acc[16], part[16];
+        tmem_ld16(taddr + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        if (two_hi) {
+          tmem_ld16(taddr + (uint32_t)(Npad + c0), part);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += part[j];
+        }
+        tmem_ld16(taddr + (uint32_t)(NH * Npad + c0), part);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += part[j];
+        if (row < A.B) {
+          float yv[16], pv[16], zv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            zv[j] = acc[j] * A.in_scale;
+            pv[j] = fmaf(zv[j], scs[c0 + j], bis[c0 + j]);
+            yv[j] = apply_act(pv[j], A.act);
+          }
+          float* yr = A.y + row * A.ldy + c0;
+          if (vec && c0 + 16 <= A.N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *(float4*)(yr + j) = make_float4(yv[j], yv[j + 1], yv[j + 2], yv[j + 3]);
+            if (A.pre) {
+              float* pr = A.pre + row * A.ldy + c0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *(float4*)(pr + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
+            }
+            if (A.z) {
+              float* zr = A.z + row * A.ldy + c0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *(float4*)(zr + j) = make_float4(zv[j], zv[j + 1], zv[j + 2], zv[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (c0 + j < A.N) {
+                yr[j] = yv[j];
+                if (A.pre) A.pre[row * A.ldy + c0 + j] = pv[j];
+                if (A.z) A.z[row * A.ldy + c0 + j] = zv[j];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+  }
 
 __global__ void __launch_bounds__(PU_THREADS, 1)
 project_umma_kernel(PuArgs A) {
@@ -296,68 +369,183 @@ project_umma_kernel(PuArgs A) {
       }
     }
   } else {
-    // ------------------------------------ epilogue ------------------------------------
-    const int lrow = warp * 32 + lane;
-    const bool vec = ((A.ldy & 3) == 0) && (((uintptr_t)A.y & 15u) == 0) &&
-                     (!A.pre || ((uintptr_t)A.pre & 15u) == 0) && (!A.z || ((uintptr_t)A.z & 15u) == 0);
-    for (int t = 0; t < my_tiles; ++t) {
-      const int buf = t % NBUF;
-      const int64_t row = (first + (int64_t)t * stride) * 128 + lrow;
-      mbar_wait(&tfull[buf], (uint32_t)(t / NBUF) & 1u);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * acc_cols);
-      const bool two_hi = NH == 2 && nks >= 2;                  // second hi accumulator was written
-      for (int c0 = 0; c0 < Npad; c0 += 16) {
-        float acc[16], part[16];
-        tmem_ld16(taddr + (uint32_t)c0, acc);
-        tmem_ld_wait();
-        if (two_hi) {
-          tmem_ld16(taddr + (uint32_t)(Npad + c0), part);
-          tmem_ld_wait();
+    project_epilogue(A, warp, lane, my_tiles, first, stride, tmem_base, tfull, tempty, scs, bis, NH, NBUF, acc_cols, nks);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem_base, ncols);
+}
+
+// ---- projection kernel, x staged by the TMA engine ----------------------------------------------------------------------
+// project_umma_kernel above is bound by its producers' own instruction stream (LDG -> registers -> split -> STS with the
+// load latency on the chain: ~2300 clk per 16 KB stage against 900 clk of MMA at N_out = 64, profiles/r2_06).  Here warp 14
+// streams the RAW x tile of a stage (128 items x 8*KPS features, one cp.async.bulk.tensor per stage, rows beyond B and
+// columns beyond F arrive as zeros) into a deep ring, and the producers only re-lay it: each warp reads 512 contiguous bytes
+// (conflict-free LDS.128: 4 items x 8 chunks), splits hi/lo with integer rounding and stores the canonical K-major layout
+// (plane / K-step strides padded so that the 8 (K-step, chunk) targets of a quarter-warp fall into different banks).
+//   warps 0-3 epilogue | 4-11 producers | 12 MMA issue | 13 weight image (bulk copy) | 14 raw x tiles (tensor map)
+constexpr int PT_THREADS = 15 * 32;
+constexpr uint32_t PT_APLANE = 128u * 16u + 64u;             // 2112: chunk planes shifted by 16 banks
+constexpr uint32_t PT_ASTAGE = 4u * PT_APLANE + 16u;         // 8464: K-steps shifted by 4 banks
+
+__global__ void __launch_bounds__(PT_THREADS, 1)
+project_umma_tma_kernel(const __grid_constant__ PuArgs A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Npad = A.Npad, nks = A.nks, NST = A.nst, KPS = A.kps, RS = A.rs;
+  const uint32_t bbytes = 4u * (uint32_t)Npad * 16u;
+  const uint32_t stage_bytes = ((uint32_t)KPS * (PT_ASTAGE + bbytes) + 127u) & ~127u;
+  const uint32_t b_off = (uint32_t)KPS * PT_ASTAGE;               // B blocks follow the A blocks of a stage
+  const uint32_t raw_bytes = 128u * 32u * (uint32_t)KPS;          // [128 items][8*KPS floats]
+  const int spt = (nks + KPS - 1) / KPS;                         // stages per tile
+  unsigned char* ring = smem;
+  unsigned char* raw = smem + (size_t)NST * stage_bytes;
+  float* scs = (float*)(raw + (size_t)RS * raw_bytes);
+  float* bis = scs + Npad;
+  uint64_t* full = (uint64_t*)(bis + Npad);
+  uint64_t* empty = full + NST;
+  uint64_t* rfull = empty + NST;
+  uint64_t* rempty = rfull + RS;
+  uint64_t* tfull = rempty + RS;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int NH = A.nh, NACC = NH + 1, NBUF = A.nbuf;
+  const int acc_cols = NACC * Npad;
+  uint32_t ncols = 32;
+  while ((int)ncols < NBUF * acc_cols) ncols <<= 1;
+  if (warp == 12) {
+    if (lane == 0) {
+      for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 256u + 1u); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < RS; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 256u); }
+      mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+      mbar_init(&tempty[0], 128); mbar_init(&tempty[1], 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, ncols);
+  }
+  for (int i = tid; i < Npad; i += PT_THREADS) {
+    scs[i] = (A.scaler && i < A.N) ? A.scaler[i] : 1.0f;
+    bis[i] = (A.bias && i < A.N) ? A.bias[i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int my_tiles = first < A.tiles ? (int)((A.tiles - first + stride - 1) / stride) : 0;
+
+  if (warp == 12) {
+    if (elect_one()) {
+      // 32-bit descriptor words: only the start-address field moves (by constants inside a stage)
+      const uint32_t idesc = make_idesc_tf32(128, (uint32_t)Npad);
+      const uint32_t hiw = desc_hi_word(128u);
+      const uint32_t ring_u = smem_u32(ring);
+      const uint32_t a_w0 = desc_lo_word(ring_u, PT_APLANE);                       // A hi plane of K-step 0, stage 0
+      const uint32_t b_w0 = desc_lo_word(ring_u + b_off, (uint32_t)Npad * 16u);     // B hi plane of K-step 0, stage 0
+      const uint32_t a_lo_d = (2u * PT_APLANE) >> 4, b_lo_d = 2u * (uint32_t)Npad; // hi -> lo plane
+      const uint32_t b_step4 = bbytes >> 4, st4 = stage_bytes >> 4;
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int buf = t % NBUF;
+        mbar_wait(&tempty[buf], ((uint32_t)(t / NBUF) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * acc_cols);
+        const uint32_t d_lo = d_base + (uint32_t)(NH * Npad);
+        uint32_t d_hi = d_base; int h = 0;                          // hi*hi accumulator of the K-step (rotates over NH)
+        uint32_t seen = 0;                                          // K-steps issued so far (saturating at NH)
+        for (int s = 0; s < spt; ++s) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const int nv = (nks - s * KPS) < KPS ? (nks - s * KPS) : KPS;
+          uint32_t aw = a_w0 + (uint32_t)stage * st4, bw = b_w0 + (uint32_t)stage * st4;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] += part[j];
+          for (int j = 0; j < 4; ++j) {
+            if (j < nv) {
+              mma_tf32_w(d_lo, aw + a_lo_d, hiw, bw, hiw, idesc, seen ? 1u : 0u);
+              mma_tf32_w(d_lo, aw, hiw, bw + b_lo_d, hiw, idesc, 1u);
+              mma_tf32_w(d_hi, aw, hiw, bw, hiw, idesc, seen >= (uint32_t)NH ? 1u : 0u);
+              aw += PT_ASTAGE >> 4; bw += b_step4;
+              if (seen < (uint32_t)NH) ++seen;
+              d_hi += (uint32_t)Npad;
+              if (++h == NH) { h = 0; d_hi = d_base; }
+            }
+          }
+          mma_commit(&empty[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
-        tmem_ld16(taddr + (uint32_t)(NH * Npad + c0), part);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += part[j];
-        if (row < A.B) {
-          float yv[16], pv[16], zv[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            zv[j] = acc[j] * A.in_scale;
-            pv[j] = fmaf(zv[j], scs[c0 + j], bis[c0 + j]);
-            yv[j] = apply_act(pv[j], A.act);
-          }
-          float* yr = A.y + row * A.ldy + c0;
-          if (vec && c0 + 16 <= A.N) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) *(float4*)(yr + j) = make_float4(yv[j], yv[j + 1], yv[j + 2], yv[j + 3]);
-            if (A.pre) {
-              float* pr = A.pre + row * A.ldy + c0;
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) *(float4*)(pr + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
-            }
-            if (A.z) {
-              float* zr = A.z + row * A.ldy + c0;
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) *(float4*)(zr + j) = make_float4(zv[j], zv[j + 1], zv[j + 2], zv[j + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (c0 + j < A.N) {
-                yr[j] = yv[j];
-                if (A.pre) A.pre[row * A.ldy + c0 + j] = pv[j];
-                if (A.z) A.z[row * A.ldy + c0 + j] = zv[j];
-              }
-            }
-          }
+        mma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp == 13) {
+    if (elect_one()) {                                            // weight image: one bulk copy per stage
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int s = 0; s < spt; ++s) {
+          const int nv = (nks - s * KPS) < KPS ? (nks - s * KPS) : KPS;
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)nv * bbytes);
+          bulk_g2s(ring + stage * stage_bytes + b_off, A.vimg + (size_t)s * KPS * bbytes, (uint32_t)nv * bbytes, &full[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[buf]);
     }
+  } else if (warp == 14) {
+    if (elect_one()) {                                            // raw x tiles: one tensor box per stage
+      tma_prefetch_desc(&A.tmx);
+      int rs = 0; uint32_t rph = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int row0 = (int)((first + (int64_t)t * stride) * 128);
+        for (int s = 0; s < spt; ++s) {
+          mbar_wait(&rempty[rs], rph ^ 1u);
+          mbar_arrive_expect_tx(&rfull[rs], raw_bytes);
+          tma_load_2d(raw + (size_t)rs * raw_bytes, &A.tmx, s * KPS * 8, row0, &rfull[rs]);
+          if (++rs == RS) { rs = 0; rph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------- producers: re-lay the raw tile ----------------------------------
+    const int pt = tid - 128, w = pt >> 5;
+    const int cpr = 2 * KPS;                                      // 16-byte chunks per item row of the raw tile
+    uint32_t rd[4], st[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = (i * 8 + w) * 32 + lane;                      // a warp reads 512 contiguous bytes per step
+      const int row = c / cpr, kc = c % cpr;
+      rd[i] = (uint32_t)c * 16u;
+      st[i] = (uint32_t)(kc >> 1) * PT_ASTAGE + (uint32_t)(kc & 1) * PT_APLANE + (uint32_t)row * 16u;
+    }
+    int rs = 0; uint32_t rph = 0;
+    int stage = 0; uint32_t phase = 0;
+    const int total = my_tiles * spt;
+    for (int it = 0; it < total; ++it) {
+      mbar_wait(&rfull[rs], rph);
+      const unsigned char* src = raw + (size_t)rs * raw_bytes;
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < KPS) v[i] = *(const float4*)(src + rd[i]);
+      mbar_wait(&empty[stage], phase ^ 1u);
+      unsigned char* dst = ring + (size_t)stage * stage_bytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < KPS) {
+          float4 hi, lo;
+          split_tf32x4_fast(v[i], hi, lo);
+          *(float4*)(dst + st[i]) = hi;
+          *(float4*)(dst + st[i] + 2u * PT_APLANE) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[stage]);
+      mbar_arrive(&rempty[rs]);
+      if (++rs == RS) { rs = 0; rph ^= 1u; }
+      if (++stage == NST) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    project_epilogue(A, warp, lane, my_tiles, first, stride, tmem_base, tfull, tempty, scs, bis, NH, NBUF, acc_cols, nks);
   }
   tc_fence_before();
   __syncthreads();
@@ -408,6 +596,33 @@ int project_fwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float*
   a.scaler = scaler; a.bias = bias; a.in_scale = in_scale; a.act = act;
   a.y = y; a.ldy = ldy; a.pre = pre; a.z = z;
   a.tiles = (B + 127) / 128;
+  a.rs = 0;
+  // x staged by the TMA engine when its tensor map can be built (aligned base, ldx % 4 == 0): two operand stages
+  // (the producers only re-lay shared memory) and as many raw tiles in flight as fit
+  // Stage = 4 K-steps (12 MMAs per barrier round trip) with two operand stages while the weight blocks leave room for
+  // them, else 2 K-steps with three stages (two were measured slower than the register-prefetch kernel at N_out >= 80:
+  // the MMA of a short stage ends before the next one is re-laid).
+  const int kps_t = Npad <= 128 ? 4 : 2;
+  if (!getenv("CFL_PROJECT_NO_TMA") && B < ((int64_t)1 << 31) - 128 &&
+      make_tmap_2d_f32(&a.tmx, x, (uint64_t)F, (uint64_t)B, (uint64_t)ldx, (uint32_t)(8 * kps_t), 128)) {
+    const int kps_keep = a.kps;
+    a.kps = kps_t;
+    const size_t stage = align_up((size_t)a.kps * (PT_ASTAGE + 64u * (size_t)Npad), 128);
+    const size_t rawb = (size_t)128 * 32 * a.kps;
+    a.nst = kps_t == 4 ? 2 : 3;
+    int rs = (int)((200 * 1024 - a.nst * stage) / rawb);
+    a.rs = rs > 8 ? 8 : rs;
+    if (a.rs >= 2) {
+      const size_t smem_t = a.nst * stage + a.rs * rawb + (size_t)Npad * 8 + (2u * a.nst + 2u * a.rs + 4u) * 8 + 64 + 1024;
+      CFL_CUDA(cudaFuncSetAttribute(project_umma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      int grid_t = (int)(a.tiles < sm_count() ? a.tiles : sm_count());
+      project_umma_tma_kernel<<<grid_t, PT_THREADS, smem_t, st>>>(a);
+      CFL_LAUNCH_CHECK();
+      return CFL_OK;
+    }
+    a.nst = pu_stages(Npad);
+    a.kps = kps_keep;
+  }
   const size_t smem = (size_t)a.nst * a.kps * (PU_ASTAGE + 64u * (size_t)Npad) + (size_t)Npad * 8 + (2u * a.nst + 4u) * 8 + 64 + 1024;
   CFL_CUDA(cudaFuncSetAttribute(project_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)(a.tiles < sm_count() ? a.tiles : sm_count());

@@ -211,6 +211,26 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the descriptors as (low word, high word): between the MMAs of a kernel only the 14-bit start-address field
+// of the low word changes, so an issue loop advances one 32-bit value per operand instead of rebuilding 64-bit
+// descriptors (the issuing thread is bound by the latency of its own instruction stream, profiles/r2_02).
+__device__ __forceinline__ void mma_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// words of a SWIZZLE_NONE K-major descriptor: low = start >> 4 | (LBO >> 4) << 16, high = SBO >> 4 | version 1 << 14
+__device__ __forceinline__ uint32_t desc_lo_word(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi_word(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
+
 // all previously issued MMAs of this thread arrive on the mbarrier when complete
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
