@@ -567,14 +567,14 @@ __device__ __forceinline__ uint32_t radix_select(const uint32_t* __restrict__ sv
                                                  const int* __restrict__ s_pref, int parts, int64_t Q, int64_t q,
                                                  int total, bool in_smem, int rank, int* hist, int* s_sel) {
   // rank is 1-based; returns the ordered-uint value of the rank-th smallest
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, nt = blockDim.x;
   uint32_t prefix = 0, mask = 0;
   int want = rank;
   for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = t; i < 256; i += SEL_THREADS) hist[i] = 0;
+    for (int i = t; i < 256; i += nt) hist[i] = 0;
     __syncthreads();
     if (in_smem) {
-      for (int i = t; i < total; i += SEL_THREADS) {
+      for (int i = t; i < total; i += nt) {
         const uint32_t v = sv[i];
         if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1);
       }
@@ -582,7 +582,7 @@ __device__ __forceinline__ uint32_t radix_select(const uint32_t* __restrict__ sv
       for (int p = 0; p < parts; ++p) {
         const int c = s_pref[p + 1] - s_pref[p];
         const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
-        for (int i = t; i < c; i += SEL_THREADS) {
+        for (int i = t; i < c; i += nt) {
           const uint32_t v = (uint32_t)(src[i] >> 32);
           if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1);
         }
@@ -617,10 +617,10 @@ __device__ __forceinline__ uint32_t radix_select(const uint32_t* __restrict__ sv
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ counts, int parts,
-                        int64_t Q, int kk, float* __restrict__ tau, float* __restrict__ tau_opt, int r_opt) {
+                        int64_t Q, int kk, float* __restrict__ tau, float* __restrict__ tau_opt, int r_opt, int smem_keys) {
   extern __shared__ uint32_t s_sel_dyn[];
   int* s_pref = (int*)s_sel_dyn;                             // [parts + 1]
-  uint32_t* sv = s_sel_dyn + parts + 1;                      // [SEL_SMEM_KEYS]
+  uint32_t* sv = s_sel_dyn + parts + 1;                      // [smem_keys]
   __shared__ int hist[256];
   __shared__ int s_sel[2];
   const int t = threadIdx.x;
@@ -641,12 +641,12 @@ select_threshold_kernel(const tkey_t* __restrict__ keys, const int* __restrict__
     if (t == 0) { tau[q] = INF; if (tau_opt) tau_opt[q] = INF; }
     return;
   }
-  const bool in_smem = total <= SEL_SMEM_KEYS;
+  const bool in_smem = total <= smem_keys;
   if (in_smem) {
     for (int p = 0; p < parts; ++p) {
       const int c = s_pref[p + 1] - s_pref[p];
       const tkey_t* src = keys + ((int64_t)p * Q + q) * TOPK_STRIDE;
-      for (int i = t; i < c; i += SEL_THREADS) sv[s_pref[p] + i] = (uint32_t)(src[i] >> 32);
+      for (int i = t; i < c; i += blockDim.x) sv[s_pref[p] + i] = (uint32_t)(src[i] >> 32);
     }
     __syncthreads();
   }
@@ -882,9 +882,15 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       const bool two_pass = score_two_pass(kn, plan, dist_out != nullptr);
       float* tau = (float*)(base + align_up(o_cimg + ((image == (const void*)(base + o_cimg)) ? catalog_image_bytes(N, d) : 0), 1024));
       if (!two_pass) timer_record(0, cs);
-      const size_t sel_smem = ((size_t)plan.parts + 1 + SEL_SMEM_KEYS) * sizeof(uint32_t);
+      // Threshold selection: one block per query.  Many queries -> narrow blocks with 32 KB of staged keys each (a whole
+      // wave of them is resident; a query with more keys selects from global memory); few queries -> wide blocks that
+      // stage up to 148 parts x kk keys.
+      const int sel_threads = Q >= 2 * (int64_t)sm_count() ? 256 : SEL_THREADS;
+      const int sel_cap = Q >= 2 * (int64_t)sm_count() ? 8192 : SEL_SMEM_KEYS;
+      auto sel_keys = [&](int64_t bound) { return (int)(bound < sel_cap ? (bound < 1024 ? 1024 : bound) : sel_cap); };
       if (two_pass) {
-        CFL_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+        CFL_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(((size_t)plan.parts + 1 + SEL_SMEM_KEYS) * sizeof(uint32_t))));
         // Sample = every sstride-th tile of each part.  When a few collect-everything tiles per
         // part already give a bound tau_a under which the sample yields <= ~384 keys per buffer,
         // the sample itself is scored in filter mode (no barriers); otherwise it runs adaptively.
@@ -906,7 +912,11 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
           while ((tpp + 1 + a.tile_stride - 1) / a.tile_stride > 7) ++a.tile_stride;
           st = score_umma_launch(a, cs);
           if (st != CFL_OK) return st;
-          select_threshold_kernel<<<(unsigned)Q, SEL_THREADS, sel_smem, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau, nullptr, 0);
+          {
+            const int nk = sel_keys((int64_t)plan.parts * 7 * 128);   // pass A: at most 7 tiles of 128 rows per part
+            select_threshold_kernel<<<(unsigned)Q, sel_threads, ((size_t)plan.parts + 1 + nk) * sizeof(uint32_t), cs>>>(
+                a.keys, a.counts, plan.parts, Q, plan.kk, tau, nullptr, 0, nk);
+          }
           CFL_LAUNCH_CHECK();
           a.phase = 2; a.tile_stride = sstride; a.thr_init = tau;
           st = score_umma_launch(a, cs);
@@ -929,8 +939,11 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         CFL_CUDA(cudaMemsetAsync(stats, 0, CFL_SCORE_NSTATS * sizeof(unsigned long long), cs));
         int r_opt = (int)((kn.opt_mult * (int64_t)plan.kk + sstride - 1) / sstride);
         if (kn.no_optimistic) r_opt = 0;
-        select_threshold_kernel<<<(unsigned)Q, SEL_THREADS, sel_smem, cs>>>(a.keys, a.counts, plan.parts, Q, plan.kk, tau,
-                                                                            tau_opt, r_opt);
+        {
+          const int nk = sel_keys((int64_t)plan.parts * TOPK_STRIDE);
+          select_threshold_kernel<<<(unsigned)Q, sel_threads, ((size_t)plan.parts + 1 + nk) * sizeof(uint32_t), cs>>>(
+              a.keys, a.counts, plan.parts, Q, plan.kk, tau, tau_opt, r_opt, nk);
+        }
         CFL_LAUNCH_CHECK();
         CFL_CUDA(cudaMemsetAsync(redo_tile, 0, (size_t)plan.nqt * sizeof(int), cs));
         a.phase = 2; a.tile_stride = 1; a.thr_init = tau_opt;
