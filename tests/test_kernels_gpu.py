@@ -291,10 +291,12 @@ def test_score_topk_deterministic(nat):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
-def test_topk_merge_equals_single_list(nat):
-    """Catalog sharding: merging per-shard top-k == top-k of the whole catalog, bit for bit."""
+@pytest.mark.parametrize("R,N", [(4, 8000), (8, 8000), (8, 1200003), (3, 301)])
+def test_topk_merge_equals_single_list(nat, R, N):
+    """Catalog sharding: merging per-shard top-k == top-k of the whole catalog, bit for bit -- for 8 shards too (what
+    an 8-rank run exchanges), on a catalog long enough for the sampled cascade per shard, and with ragged shards."""
     rng = np.random.default_rng(6)
-    N, d, Q, K, k, R = 8000, 20, 24, 4, 100, 4
+    d, Q, K, k = 20, 24, 4, 100
     E = dev(rng.normal(size=(N, d)).astype(np.float32))
     Pq = dev(rng.normal(size=(Q, K, d)).astype(np.float32))
     mu = nat.col_mean(E)
