@@ -316,14 +316,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     inflight = []
+    INFLIGHT = int(os.environ.get("CFL_BENCH_INFLIGHT", "4"))
 
     def step_device(i):
         # independent query batches: with several ranks the exchange (all-gather + merge) of batch i runs on a side
-        # stream under the scoring of batch i+1; at most two results are outstanding, every one is waited for inside
-        # the timed region (the loop's closing drain)
+        # stream under the scoring of the following batches; at most INFLIGHT results are outstanding (the survivor
+        # counts, hence the step times, differ from rank to rank and batch to batch: a deeper queue keeps a rank that
+        # waits for a slower peer's all-gather fed), every one is waited for inside the timed region (the closing drain)
         if world == 1:
             return index.rank(xq_dev[i % nb], TOPK)
-        if len(inflight) >= 2:
+        if len(inflight) >= INFLIGHT:
             inflight.pop(0)[2].synchronize()
         inflight.append(index.rank_async(xq_dev[i % nb], TOPK))
 

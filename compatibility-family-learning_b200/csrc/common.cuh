@@ -32,6 +32,21 @@ void timer_record(int which, cudaStream_t st);  // api.cu: 0 = start, 1 = stop (
 
 #define CFL_LAUNCH_CHECK() CFL_CUDA(cudaGetLastError())
 
+// Raises a kernel's dynamic shared-memory limit.  cudaFuncSetAttribute costs tens of microseconds of host time, and a
+// ranking step would issue ten of them: remember the limit set per call site (= per kernel instantiation) and device,
+// call the runtime only when the request grows.  (A race between host threads only repeats the call.)
+#define CFL_SMEM_LIMIT(kern, bytes)                                                                     \
+  do {                                                                                                  \
+    static int _cfl_lim[16];                                                                            \
+    int _cfl_dev = 0;                                                                                   \
+    CFL_CUDA(cudaGetDevice(&_cfl_dev));                                                                 \
+    const int _cfl_want = (int)(bytes);                                                                 \
+    if (_cfl_want >= _cfl_lim[_cfl_dev & 15]) {                                                         \
+      CFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, _cfl_want));     \
+      _cfl_lim[_cfl_dev & 15] = _cfl_want + 1;                                                          \
+    }                                                                                                   \
+  } while (0)
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace.

@@ -553,10 +553,10 @@ static int pt_launch(PbArgs a, int grid, cudaStream_t st) {
   a.rs = rs > 12 ? 12 : rs;
   const size_t smem = a.nst * stage + a.rs * rawb + (2u * a.nst + 2u * a.rs + 2u) * 8 + 64 + 1024;
   if (needy) {
-    CFL_CUDA(cudaFuncSetAttribute(project_bwd_umma_tma_kernel<NBI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFL_SMEM_LIMIT((project_bwd_umma_tma_kernel<NBI, true>), smem);
     project_bwd_umma_tma_kernel<NBI, true><<<grid, PT_THREADS, smem, st>>>(a);
   } else {
-    CFL_CUDA(cudaFuncSetAttribute(project_bwd_umma_tma_kernel<NBI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFL_SMEM_LIMIT((project_bwd_umma_tma_kernel<NBI, false>), smem);
     project_bwd_umma_tma_kernel<NBI, false><<<grid, PT_THREADS, smem, st>>>(a);
   }
   CFL_LAUNCH_CHECK();
@@ -566,10 +566,10 @@ static int pt_launch(PbArgs a, int grid, cudaStream_t st) {
 template <int NBI>
 static int pb_launch(const PbArgs& a, size_t smem, int grid, cudaStream_t st) {
   if (a.act != CFL_ACT_LINEAR) {
-    CFL_CUDA(cudaFuncSetAttribute(project_bwd_umma_kernel<NBI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFL_SMEM_LIMIT((project_bwd_umma_kernel<NBI, true>), smem);
     project_bwd_umma_kernel<NBI, true><<<grid, PB_THREADS, smem, st>>>(a);
   } else {
-    CFL_CUDA(cudaFuncSetAttribute(project_bwd_umma_kernel<NBI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFL_SMEM_LIMIT((project_bwd_umma_kernel<NBI, false>), smem);
     project_bwd_umma_kernel<NBI, false><<<grid, PB_THREADS, smem, st>>>(a);
   }
   CFL_LAUNCH_CHECK();

@@ -614,7 +614,7 @@ int project_fwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float*
     a.rs = rs > 8 ? 8 : rs;
     if (a.rs >= 2) {
       const size_t smem_t = a.nst * stage + a.rs * rawb + (size_t)Npad * 8 + (2u * a.nst + 2u * a.rs + 4u) * 8 + 64 + 1024;
-      CFL_CUDA(cudaFuncSetAttribute(project_umma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      CFL_SMEM_LIMIT(project_umma_tma_kernel, smem_t);
       int grid_t = (int)(a.tiles < sm_count() ? a.tiles : sm_count());
       project_umma_tma_kernel<<<grid_t, PT_THREADS, smem_t, st>>>(a);
       CFL_LAUNCH_CHECK();
@@ -624,7 +624,7 @@ int project_fwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float*
     a.kps = kps_keep;
   }
   const size_t smem = (size_t)a.nst * a.kps * (PU_ASTAGE + 64u * (size_t)Npad) + (size_t)Npad * 8 + (2u * a.nst + 4u) * 8 + 64 + 1024;
-  CFL_CUDA(cudaFuncSetAttribute(project_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CFL_SMEM_LIMIT(project_umma_kernel, smem);
   int grid = (int)(a.tiles < sm_count() ? a.tiles : sm_count());
   project_umma_kernel<<<grid, PU_THREADS, smem, st>>>(a);
   CFL_LAUNCH_CHECK();
@@ -645,7 +645,7 @@ extern "C" int cfl_selftest_umma(const float* A, const float* Bm, float* D, int 
   size_t smem = (size_t)nks * (4 * 128 * 16 + 4 * (size_t)N * 16);
   const char* v = getenv("CFL_UMMA_VARIANT");
   int variant = v ? atoi(v) : 0;
-  CFL_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CFL_SMEM_LIMIT(umma_selftest_kernel, smem);
   umma_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, Bm, D, N, Kd, variant);
   CFL_LAUNCH_CHECK();
   return CFL_OK;

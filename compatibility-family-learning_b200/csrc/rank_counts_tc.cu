@@ -484,12 +484,12 @@ static int rank_tc_launch(const RtArgs& a, const float* Pq, int64_t ldq, const f
                           unsigned long long* stats, cudaStream_t cs) {
   const RtLayout L = rt_layout(K, a.qt, a.dpad);
   const size_t smem = L.total + 1024;
-  CFL_CUDA(cudaFuncSetAttribute(rank_count_umma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CFL_SMEM_LIMIT(rank_count_umma_kernel<K>, smem);
   dim3 grid((unsigned)a.parts, (unsigned)a.nqt);
   rank_count_umma_kernel<K><<<grid, RT_THREADS, smem, cs>>>(a);
   CFL_LAUNCH_CHECK();
   const size_t fx_smem = ((size_t)a.qt * (K * a.d + 1) + (size_t)FX_THREADS * (a.d + 1)) * sizeof(float);
-  CFL_CUDA(cudaFuncSetAttribute(rank_fix_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fx_smem));
+  CFL_SMEM_LIMIT(rank_fix_kernel<K>, fx_smem);
   rank_fix_kernel<K><<<dim3(FX_BLOCKS, (unsigned)(a.parts * a.nqt)), FX_THREADS, fx_smem, cs>>>(
       a.recs, a.rec_n, a.rec_slice, Pq, ldq, E, lde, a.N, a.Q, a.d, a.qt, a.parts, a.thr, a.J, a.j0, a.only, a.counts, stats);
   CFL_LAUNCH_CHECK();

@@ -889,8 +889,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
       const int sel_cap = Q >= 2 * (int64_t)sm_count() ? 8192 : SEL_SMEM_KEYS;
       auto sel_keys = [&](int64_t bound) { return (int)(bound < sel_cap ? (bound < 1024 ? 1024 : bound) : sel_cap); };
       if (two_pass) {
-        CFL_CUDA(cudaFuncSetAttribute(select_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(((size_t)plan.parts + 1 + SEL_SMEM_KEYS) * sizeof(uint32_t))));
+        CFL_SMEM_LIMIT(select_threshold_kernel, ((size_t)plan.parts + 1 + SEL_SMEM_KEYS) * sizeof(uint32_t));
         // Sample = every sstride-th tile of each part.  When a few collect-everything tiles per
         // part already give a bound tau_a under which the sample yields <= ~384 keys per buffer,
         // the sample itself is scored in filter mode (no barriers); otherwise it runs adaptively.
@@ -985,8 +984,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
           const size_t rs_smem = ((size_t)K * dp + (size_t)(MRG_THREADS / 32) * 32 * RSC_LD + a.lb.parts + 2 + 4) * sizeof(float);
 #define CFL_RSC_CASE(KK)                                                                                        \
   case KK:                                                                                                      \
-    CFL_CUDA(cudaFuncSetAttribute(rescore_merge_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                  (int)rs_smem));                                                               \
+    CFL_SMEM_LIMIT(rescore_merge_kernel<KK>, rs_smem);                                                           \
     rescore_merge_kernel<KK><<<(unsigned)Q, MRG_THREADS, rs_smem, cs>>>(                                        \
         a.keys, a.counts, a.lb.parts, Q, plan.kk, k, Pq, ldq, d, E, lde, idx_base, top_val, top_idx, tau,       \
         tau_opt, plan.qt, thr_redo, redo_tile, stats, a.spill, a.spill_cnt);                                    \

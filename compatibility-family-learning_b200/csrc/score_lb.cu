@@ -543,7 +543,7 @@ template <int K>
 static int launch_lb(const ScoreArgs& a, cudaStream_t st) {
   const LbLayout L = lb_layout(K, a.lb.qt, a.lb.sub, (a.plan.dpad + 15) / 16);
   const size_t smem = L.total + 1024;                          // slack for the alignment of the dynamic segment
-  CFL_CUDA(cudaFuncSetAttribute(score_lb_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CFL_SMEM_LIMIT(score_lb_kernel<K>, smem);
   dim3 grid(a.lb.parts, a.lb.nqt);
   score_lb_kernel<K><<<grid, LB_THREADS, smem, st>>>(a);
   CFL_LAUNCH_CHECK();
@@ -638,7 +638,7 @@ extern "C" int cfl_selftest_umma_f16(const float* A, const float* Bm, float* D, 
   CFL_REQUIRE(Kd >= 1 && Kd <= 128, CFL_ERR_INVALID, "selftest_umma_f16: Kd must be in [1,128]");
   const int nks = (Kd + 15) / 16;
   const size_t smem = (size_t)nks * (2 * 128 * 16 + 2 * (size_t)N * 16) + 1024;
-  CFL_CUDA(cudaFuncSetAttribute(lb_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CFL_SMEM_LIMIT(lb_selftest_kernel, smem);
   lb_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, Bm, D, N, Kd);
   CFL_LAUNCH_CHECK();
   return CFL_OK;

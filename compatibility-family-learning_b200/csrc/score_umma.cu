@@ -529,7 +529,7 @@ template <int K>
 static int launch_umma(const ScoreArgs& a, cudaStream_t st) {
   SuLayout L = su_layout(K, a.plan.qt, a.plan.dpad);
   size_t smem = L.total + 1024;      // slack for the alignment of the dynamic segment
-  CFL_CUDA(cudaFuncSetAttribute(score_umma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CFL_SMEM_LIMIT(score_umma_kernel<K>, smem);
   dim3 grid(a.plan.parts, a.plan.nqt);
   score_umma_kernel<K><<<grid, SU_THREADS, smem, st>>>(a);
   CFL_LAUNCH_CHECK();
