@@ -253,12 +253,16 @@ def dist_eval_sharded(sess, model, batch_size, data, rank=None, world=None, grou
     for b, batches in enumerate(data.whole_neg_batches(batch_size)):
         if b % world == rank:
             neg.append(model.predict(*_pair_batches(batches, model)).reshape(-1))
-    dev = getattr(model, "device", None) or (pos[0].device if pos else neg[0].device if neg else "cpu")
+    # a rank that received no batch still takes part in the collectives: its empty tensors must live on the GPU
+    from . import variables as vs
+    dev = getattr(model, "device", None) or (pos[0].device if pos else neg[0].device if neg else vs.default_device())
     pos = torch.cat(pos) if pos else torch.empty(0, device=dev)
     neg = torch.cat(neg) if neg else torch.empty(0, device=dev)
     two_u, n_pos, n_neg, correct = sharded_auc_counts(pos, neg, group)
     total = n_pos + n_neg
     auc = two_u / (2.0 * n_pos * n_neg) if n_pos and n_neg else float("nan")
+    if total == 0:                                           # no labelled pairs at all
+        return Namespace(error=float("nan"), accuracy=float("nan"), auc=auc, roc=None, two_u=0, n_pos=0, n_neg=0)
     return Namespace(error=(total - correct) / total, accuracy=correct / total, auc=auc, roc=None,
                      two_u=two_u, n_pos=n_pos, n_neg=n_neg)
 
