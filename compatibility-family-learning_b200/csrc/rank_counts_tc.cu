@@ -53,6 +53,7 @@ struct RtArgs {
   int qt, nqt, parts, dpad;
   int64_t tiles;
   const float* qpar;
+  const float* qplane;            // per query: affine-hull bound block (score.cuh)
   const void* qimg;
   const void* cimg;
   const float* e2;
@@ -65,15 +66,17 @@ struct RtArgs {
   float rel1, rel2;
 };
 
-struct RtLayout { uint32_t b_img, a_ring, qpar, thr, qm, cs, rcn, bars, tmem_slot, total; };
+struct RtLayout { uint32_t b_img, a_ring, qpar, qpl, thr, qm, skp, cs, rcn, bars, tmem_slot, total; };
 __host__ __device__ inline RtLayout rt_layout(int K, int qt, int dpad) {
   RtLayout L;
   uint32_t off = 0;
   L.b_img = off;   off += (uint32_t)dpad * 8u * (uint32_t)(K * qt);  off = (off + 1023u) & ~1023u;
   L.a_ring = off;  off += RT_NSTAGE * 2u * RT_ASTAGE;
   L.qpar = off;    off += (uint32_t)qt * (uint32_t)qpar_stride(K) * 4u;  off = (off + 15u) & ~15u;
+  L.qpl = off;     off += (uint32_t)qt * (uint32_t)qplane_stride(K) * 4u; off = (off + 15u) & ~15u;
   L.thr = off;     off += (uint32_t)qt * RT_JC * 4u;
   L.qm = off;      off += (uint32_t)qt * 4u;                           off = (off + 15u) & ~15u;
+  L.skp = off;     off += (uint32_t)qt * 16u;                          // per query: (tmax, kappa0, kappa1, -)
   L.cs = off;      off += (uint32_t)qt * RT_JC * 4u;
   L.rcn = off;     off += 16u;
   L.bars = off;    off += (2u * RT_NSTAGE + 5u) * 8u;
@@ -97,7 +100,7 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(RT_THREADS, 1)
+__global__ void __launch_bounds__(RT_THREADS, 1)     // 18 warps = 5 on one sub-partition: 5 x 32 x 96 registers is its whole file
 rank_count_umma_kernel(RtArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int GQ = K <= 2 ? 16 : (K <= 4 ? 8 : 4);     // queries per epilogue group
@@ -113,6 +116,8 @@ rank_count_umma_kernel(RtArgs A) {
   float* qpar = (float*)(smem + L.qpar);
   float* thr = (float*)(smem + L.thr);
   float* qm = (float*)(smem + L.qm);
+  float* qpl = (float*)(smem + L.qpl);
+  float4* skp = (float4*)(smem + L.skp);
   unsigned int* cs = (unsigned int*)(smem + L.cs);
   unsigned int* rcn = (unsigned int*)(smem + L.rcn);
   uint64_t* full = (uint64_t*)(smem + L.bars);
@@ -168,6 +173,36 @@ rank_count_umma_kernel(RtArgs A) {
     if (ql < nq)
       for (int k = 0; k < K; ++k) pm = fmaxf(pm, A.qpar[(q0 + ql) * QPS + k]);      // log2(e) |p_k|^2
     qm[ql] = pm * CFL_LN2;                                    // max_k |p_k|^2
+  }
+  {
+    constexpr int PBS0 = qplane_stride(K);                     // pair interleave, as the soft-min blocks
+    for (int i = tid; i < QT * PBS0; i += RT_THREADS) {
+      const int ql = i / PBS0, j = i % PBS0;
+      qpl[((ql >> 1) * PBS0 + j) * 2 + (ql & 1)] = (ql < nq) ? A.qplane[(q0 + ql) * PBS0 + j] : 0.0f;
+    }
+  }
+  // Skip test of a whole query group (epilogue): with LB <= D~ the affine-hull lower bound and Vq >= V,
+  //   D~ - m(D~) >= LB - S (rel1 + rel2 sqrt(LB Vq)) >= LB (1 - S k1) - S k0   (AM-GM with c = sqrt(Vq / tmax)),
+  // k0 = rel1 + rel2 Vq / (2c), k1 = rel2 c / 2: when that exceeds the query's largest threshold the pair is farther than
+  // every threshold and outside every band -- nothing to count, nothing to record.
+  for (int ql = tid; ql < QT; ql += RT_THREADS) {
+    float tmax = __int_as_float(0xff800000);
+    float k0 = A.rel1, k1 = 0.0f;
+    if (ql < nq) {
+      for (int j = 0; j < jn; ++j) {
+        const float v = A.thr[(q0 + ql) * A.J + A.j0 + j];
+        if (v == v) tmax = fmaxf(tmax, fminf(v, 3.4028234e38f));
+      }
+      if (K > 1) {
+        const float cq = A.qpar[(q0 + ql) * QPS + K + qpar_tri(K)];       // >= (1 - 1/K) / 2 * max_kl |p_k - p_l|^2
+        const float vq = cq / (0.5f * (1.0f - 1.0f / (float)K));          // >= the prototypes' spread under any weights
+        const float c = sqrtf(vq / fmaxf(tmax, 1.0e-30f));
+        k0 = A.rel1 + 0.5f * A.rel2 * vq / fmaxf(c, 1.0e-30f);
+        k1 = 0.5f * A.rel2 * c;
+        if (!(c == c) || !(k0 == k0) || !(k1 == k1) || k1 > 1.0e30f) { k0 = __int_as_float(0x7f800000); k1 = 0.0f; }   // never skip
+      }
+    }
+    skp[ql] = make_float4(tmax, k0 * 1.0001f, k1 * 1.0001f, 0.0f);
   }
   if (tid == 0) *rcn = 0u;
   const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
@@ -261,6 +296,10 @@ rank_count_umma_kernel(RtArgs A) {
     };
 
     int since_flush = 0;
+    // the skip test pays when most groups are far from every threshold (labelled positives near the top of the ranking:
+    // the usual evaluation); each warp measures its hit rate over the first 16 tiles and switches the test off otherwise
+    bool bound_on = true;
+    int grp_seen = 0, grp_skipped = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const int64_t row = (t0 + t) * 128 + lrow;
@@ -281,6 +320,31 @@ rank_count_umma_kernel(RtArgs A) {
           else                        tmem_ld4(taddr + (uint32_t)(k * QT + g * GQ), gk[k]);
         }
         tmem_ld_wait();
+        if (bound_on) {
+          constexpr int PBS = qplane_stride(K);
+          const float e2s = e2 * (1.0f - CFL_PLANE_REL);
+          const f2_t e2sp = pk2(e2s, e2s);
+          bool need = false;
+#pragma unroll
+          for (int pi = 0; pi < GQ / 2; ++pi) {
+            f2_t pv[PBS];
+            const ulonglong2* src = (const ulonglong2*)(qpl + (g * (GQ / 2) + pi) * PBS * 2);
+#pragma unroll
+            for (int j = 0; j < PBS; j += 2) { const ulonglong2 u = src[j >> 1]; pv[j] = u.x; pv[j + 1] = u.y; }
+            float gA[K], gB[K], lbA, lbB;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { gA[k] = gk[k][2 * pi]; gB[k] = gk[k][2 * pi + 1]; }
+            plane_bound_pair<K>(gA, gB, e2sp, pv, lbA, lbB);
+            const int ql = g * GQ + 2 * pi;
+            const float4 sa = skp[ql], sb = skp[ql + 1];
+            const float SA = e2 + qm[ql], SB = e2 + qm[ql + 1];
+            const float va = fmaf(lbA, fmaf(-SA, sa.z, 1.0f), -SA * sa.y);
+            const float vb = fmaf(lbB, fmaf(-SB, sb.z, 1.0f), -SB * sb.y);
+            need |= !(va > sa.x) | !(vb > sb.x);
+          }
+          ++grp_seen;
+          if (!__any_sync(0xffffffffu, need && valid)) { ++grp_skipped; continue; }
+        }
         const float* qg = qpar + g * GQ * QPS;
         float dist[GQ], var[GQ];
 #pragma unroll
@@ -341,6 +405,7 @@ rank_count_umma_kernel(RtArgs A) {
           }
         }
       }
+      if (t == 15 && grp_skipped * 2 < grp_seen) bound_on = false;
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
       if (++since_flush == 15) { flush(); since_flush = 0; }
@@ -554,7 +619,7 @@ int cfl_rank_counts_packed(int mode, const float* Pq, int64_t Q, int K, int d, i
   if (parts < 1) parts = 1;
   if (parts > a.tiles) parts = a.tiles;
   a.parts = (int)parts;
-  a.qpar = qpar; a.qimg = base + w.qimg; a.cimg = image;
+  a.qpar = qpar; a.qplane = qplane; a.qimg = base + w.qimg; a.cimg = image;
   a.e2 = (const float*)((const char*)image + (size_t)a.tiles * (a.dpad / 8) * 8192);
   a.thr = pos_dist; a.counts = (unsigned long long*)counts;
   CFL_REQUIRE((int64_t)a.parts * a.nqt <= 4096, CFL_ERR_UNSUPPORTED, "rank_counts_packed: Q=%lld needs more than 4096 CTAs",

@@ -38,6 +38,10 @@ def test_workspace_queries_do_not_need_a_gpu():
     assert lib.cfl_score_topk_workspace_bytes(1024, 3, 64, 1 << 20, 100) > 0
     mono = lib.cfl_score_topk_monomer_workspace_bytes(1024, 4, 20, 1 << 20, 100)
     assert 1024 * 512 * 8 <= mono <= 256 << 20         # >= one 512-key buffer per query, one wave of parts at most
+    # fused rank counts: query blocks + image + a record list of max(2^20, Q*N/256) 16-byte records
+    rc = lib.cfl_rank_counts_packed_workspace_bytes(1024, 3, 64, 1 << 20)
+    assert (1 << 22) * 16 <= rc <= (1 << 22) * 16 + (64 << 20)
+    assert lib.cfl_rank_counts_packed_workspace_bytes(4, 2, 16, 1000) >= (1 << 20) * 16
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -54,11 +58,14 @@ def test_compute_calls_fail_loudly_without_a_gpu():
     assert lib.cfl_pair_dist_rows(0, None, 1, 2, 4, 8, None, None, 8, 4, None, 1, None, None) == -5
     assert lib.cfl_rank_counts(0, None, 1, 2, 4, 8, None, None, 8, 4, None, 1, None, None) == -5
     assert lib.cfl_dense_rank_counts(None, 1, 8, 8, None, 1, None, None) == -5
+    assert lib.cfl_rank_counts_packed(0, None, 1, 2, 4, 8, None, None, 8, 4, None, None, 1, None, None, 0, None) == -5
     a, w, P = torch.zeros(2, 4), torch.full((2, 3), 1 / 3), torch.zeros(5, 3, 4)
     for call in (lambda: _native.score_topk_monomer(a, w, P, 2),
                  lambda: _native.pair_dist_rows("monomer", a, P, torch.zeros(2, 1, dtype=torch.int64), w=w),
                  lambda: _native.rank_counts("pcd", torch.zeros(2, 3, 4), torch.zeros(5, 4), torch.zeros(2, 1)),
-                 lambda: _native.dense_rank_counts(torch.zeros(2, 5), torch.zeros(2, 1))):
+                 lambda: _native.dense_rank_counts(torch.zeros(2, 5), torch.zeros(2, 1)),
+                 lambda: _native.rank_counts_packed(torch.zeros(2, 3, 4), torch.zeros(5, 4), torch.zeros(64), None,
+                                                    torch.zeros(2, 1))):
         with pytest.raises(_native.CflNativeError):
             call()
     from cfl import ranking
