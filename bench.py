@@ -17,6 +17,7 @@ streams it from HBM/L2 afresh (no explicit L2 flush needed; stated in config).
 Besides the headline line (C3, weak scaling) the same JSON line carries, measured in the same run:
   "c5"       BASELINE configs[4]: 10 M catalog rows in TOTAL (strong scaling: 10 M / N rows per rank), K = 4,
              d in {64, 128}, Q = 2048 queries per step, embeddings generated directly (SURVEY 8d C5);
+  "c4"       the ranking shape of BASELINE configs[3]: K = 4, d = 20, 2 M target rows in total (strong scaling), Q = 1024;
   "small_q"  Q = 16 queries against the C3 catalog: the HBM-bound regime (catalog GB/s against the measured copy peak);
   "filter"   survivors per query of the full filter pass and the queries that spilled / were redone (a regression to
              the slow paths shows up here);
@@ -133,11 +134,12 @@ def synth_features(n, device, seed):
     return out
 
 
-def c5_line(d, world, rank, device, steps=8):
+def c5_line(d, world, rank, device, steps=8, K5=4, Q5=2048, N5=10_000_000, label="C5"):
     """C5: N = 10 M rows in total, e ~ N(0,1)^d, p_k = e_anchor + 0.5 N(0,1), K = 4, Q = 2048, top-100.
-    Strong scaling: rank r holds rows [r N/R, (r+1) N/R).  Scoring call only (the embeddings ARE the input)."""
+    Strong scaling: rank r holds rows [r N/R, (r+1) N/R).  Scoring call only (the embeddings ARE the input).
+    Also used for the C4 ranking shape (K = 4, d = 20, 2 M target rows in total, Q = 1024: BASELINE configs[3] /
+    experiments/polyvore/run.sh -- its embeddings generated directly, the F = 2048 projection is stage 1's job)."""
     from cfl import _native as nat
-    K5, Q5, N5 = 4, 2048, 10_000_000
     lo, hi = N5 * rank // world, N5 * (rank + 1) // world
     g = torch.Generator(device=device).manual_seed(SEED + 50 + d + 1000 * rank)
     E = torch.empty(hi - lo, d, dtype=torch.float32, device=device)
@@ -186,7 +188,7 @@ def c5_line(d, world, rank, device, steps=8):
     flops = 2.0 * K5 * d * Q5 * (hi - lo)
     del E, img
     torch.cuda.empty_cache()
-    return {"workload": f"C5: 10M-item catalog in total, K=4 d={d}, Q=2048 queries/step, top-100", "scaling": "strong",
+    return {"workload": f"{label}: {N5 // 1_000_000}M-item catalog in total, K={K5} d={d}, Q={Q5} queries/step, top-100", "scaling": "strong",
             "catalog_total": N5, "catalog_per_gpu": hi - lo, "value": Q5 * float(N5) / (ms / 1e3), "unit": "scores/s",
             "ms_per_step": ms, "filter_kernel_ms": kms, "filter_kernel_tflops": flops / (kms / 1e3) / 1e12,
             "filter_kernel_frac_of_bf16_burst": flops / (kms / 1e3) / 1e12 / pk["bf16"],
@@ -453,6 +455,7 @@ def run_ours(args):
     del index, E
     torch.cuda.empty_cache()
     c5 = None if args.quick else [c5_line(64, world, rank, device), c5_line(128, world, rank, device)]
+    c4 = None if args.quick else c5_line(20, world, rank, device, steps=20, K5=4, Q5=1024, N5=2_000_000, label="C4")
     line = None
     if rank == 0:
         # the CPU arms are timed on rank 0 at N=1 only (torchrun pins OMP threads and the other ranks spin)
@@ -473,7 +476,7 @@ def run_ours(args):
             "filter": {"survivors_per_query": filt["survivors"] / Q, "redo_queries": filt["redo_queries"],
                        "spill_queries": filt["spill_queries"], "probe_dropped_queries": filt["probe_dropped_queries"],
                        "lower_bound_pass": filt["lower_bound_pass"]},
-            "per_rank": per_rank, "small_q": small_q, "auc": auc, "c5": c5,
+            "per_rank": per_rank, "small_q": small_q, "auc": auc, "c5": c5, "c4": c4,
             "catalog_projection": proj,
             "setup_s": setup_s,
         }

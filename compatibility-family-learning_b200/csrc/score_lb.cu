@@ -1,6 +1,7 @@
 // Lower-bound filter pass of the all-pairs scoring (phase 3 of cfl_score_topk on long catalogs): its own tiling,
 // its own query image, its own kernel.  See score_umma.cu for the exact 3xTF32 kernel and score.cu for the host side.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "score.cuh"
 #include "umma.cuh"
 
@@ -82,7 +83,12 @@ LbPlan make_lb_plan(int64_t Q, int K, int d, int64_t tiles) {
   const double l2_clk = nkm * 4096.0 / 20.0;
   LbPlan best{qt, 1, (int)((Q + qt - 1) / qt), 1, nbuf};
   double best_cost = 1e30;
-  for (int sub = 1; sub <= 4; ++sub) {
+  int sub_lo = 1, sub_hi = 4;
+  {                                                            // experiments: force the number of query images per CTA
+    const char* e = getenv("CFL_EXPERIMENTS");
+    if (e && atoi(e) != 0 && (e = getenv("CFL_LB_SUB")) && atoi(e) >= 1 && atoi(e) <= 4) sub_lo = sub_hi = atoi(e);
+  }
+  for (int sub = sub_lo; sub <= sub_hi; ++sub) {
     const size_t smem = (size_t)sub * nkm * 2 * nc * 16 + (size_t)LB_NSTAGE * LB_STAGE + 8192;
     if (smem > 200 * 1024) break;
     const int64_t nqt = (Q + (int64_t)qt * sub - 1) / ((int64_t)qt * sub);
