@@ -192,7 +192,8 @@ def c5_line(d, world, rank, device, steps=8, K5=4, Q5=2048, N5=10_000_000, label
             "catalog_total": N5, "catalog_per_gpu": hi - lo, "value": Q5 * float(N5) / (ms / 1e3), "unit": "scores/s",
             "ms_per_step": ms, "filter_kernel_ms": kms, "filter_kernel_tflops": flops / (kms / 1e3) / 1e12,
             "filter_kernel_frac_of_bf16_burst": flops / (kms / 1e3) / 1e12 / pk["bf16"],
-            "survivors_per_query": st["survivors"] / Q5, "redo_queries": st["redo_queries"]}
+            "survivors_per_query": st["survivors"] / Q5, "redo_queries": st["redo_queries"],
+            "exact_redo_queries": st["exact_redo_queries"]}
 
 
 def small_q_line(index, device, q=16, steps=50):
@@ -474,6 +475,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step(world) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_gram": cpu_gram, "clocks": clocks,
             "filter": {"survivors_per_query": filt["survivors"] / Q, "redo_queries": filt["redo_queries"],
+                       "exact_redo_queries": filt["exact_redo_queries"],
                        "spill_queries": filt["spill_queries"], "probe_dropped_queries": filt["probe_dropped_queries"],
                        "lower_bound_pass": filt["lower_bound_pass"]},
             "per_rank": per_rank, "small_q": small_q, "auc": auc, "c5": c5, "c4": c4,
@@ -489,10 +491,11 @@ def run_ours(args):
 
 def launches_per_step(world):
     # colnorm, pack_weights, project_umma, prep_queries, pack_queries, score_umma x2 (passes A/B), select_threshold x2,
-    # prep_lb, score_lb (probe) + probe_classify, score_lb (pass C), rescore_merge, score_umma (redo, exits when
-    # nothing failed verification), merge_rescore (redone queries only)
+    # prep_lb, score_lb (probe) + probe_classify, score_lb (pass C), rescore_merge, score_lb + rescore_merge (second
+    # round under the safe threshold: both leave at once when every query was verified), score_umma (exact redo, exits
+    # when nothing is left to redo), merge_rescore (redone queries only)
     # (+ topk_merge after the all-gather for N>1)
-    return 16 + (1 if world > 1 else 0)
+    return 18 + (1 if world > 1 else 0)
 
 
 # ------------------------------------------------------------------------------------------

@@ -335,7 +335,8 @@ def score_topk(Pq, E, k, mu=None, mode="pcd", idx_base=0, want_dense=False, imag
 
 
 SCORE_NSTATS = 8
-SCORE_STAT_NAMES = ("survivors", "spill_queries", "probe_dropped_queries", "redo_queries", "lower_bound_pass")
+SCORE_STAT_NAMES = ("survivors", "spill_queries", "probe_dropped_queries", "redo_queries", "lower_bound_pass",
+                    "exact_redo_queries")
 
 
 def score_topk_monomer(a, w, P, k, idx_base=0, want_dense=False):

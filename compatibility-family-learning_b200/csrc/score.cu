@@ -348,8 +348,21 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
                      float* __restrict__ top_val, int64_t* __restrict__ top_idx,
                      const float* __restrict__ tau, const float* __restrict__ tau_opt, int qt,
                      float* __restrict__ thr_redo, int* __restrict__ redo_tile, unsigned long long* __restrict__ dbg,
-                     const tkey_t* __restrict__ spill, const int* __restrict__ spill_cnt) {
+                     const tkey_t* __restrict__ spill, const int* __restrict__ spill_cnt,
+                     const float* __restrict__ only_redo, const float* __restrict__ prev_redo,
+                     float* __restrict__ second_round) {
   extern __shared__ __align__(16) float s_dyn[];
+  // Second round (only_redo != NULL): only the queries whose optimistic threshold was not confirmed, filtered again
+  // under the safe threshold (the caller passes tau as tau_opt).  Every other query keeps the first round's verdict
+  // (prev_redo: -inf = done, else the threshold of its exact redo).
+  if (only_redo != nullptr && !(only_redo[blockIdx.x] > __int_as_float(0xff800000))) {
+    if (threadIdx.x == 0) {
+      const float pr = prev_redo[blockIdx.x];
+      thr_redo[blockIdx.x] = pr;
+      if (pr > __int_as_float(0xff800000)) { redo_tile[blockIdx.x / qt] = 1; if (dbg) atomicAdd(&dbg[5], 1ull); }
+    }
+    return;
+  }
   const int dp = (d + RSC_CH - 1) / RSC_CH * RSC_CH;        // d padded to whole chunks
   float* s_pq = s_dyn;                                       // [K][dp], zero padded
   float* s_rows = s_pq + K * dp;                             // [warps][32][RSC_LD]
@@ -474,7 +487,12 @@ rescore_merge_kernel(const tkey_t* __restrict__ keys, const int* __restrict__ co
     s_redo = redo;
     thr_redo[q] = redo ? tau[q] : __int_as_float(0xff800000);
     if (redo) redo_tile[q / qt] = 1;
-    if (dbg) {                                               // statistics of the call (cfl_score_topk_stats)
+    // a second lower-bound round can help only when the optimistic threshold was the problem: not for overflowing
+    // buffers, raised range flags or queries the probe took out (tau_opt = -inf)
+    if (second_round)
+      second_round[q] = (redo && !s_over && tau_opt[q] > __int_as_float(0xff800000)) ? tau[q] : __int_as_float(0xff800000);
+    if (dbg && only_redo != nullptr && redo) atomicAdd(&dbg[5], 1ull);
+    if (dbg && only_redo == nullptr) {                       // statistics of the call (cfl_score_topk_stats)
       atomicAdd(&dbg[0], (unsigned long long)total);
       if (spill_cnt[q] > 0) atomicAdd(&dbg[1], 1ull);
       if (!(tau_opt[q] > __int_as_float(0xff800000))) atomicAdd(&dbg[2], 1ull);
@@ -787,8 +805,9 @@ static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePla
   *o_keys = off; off = align_up(off + (size_t)kparts * Q * TOPK_STRIDE * sizeof(tkey_t), 256);
   *o_cnt = off;  off = align_up(off + (size_t)kparts * Q * sizeof(int), 1024);
   *o_cimg = off; off = align_up(off + ((p.impl && own_image) ? catalog_image_bytes(N, d) : 0), 1024);
-  // tau[Q], tau_opt[Q], thr_redo[Q], redo flags per query tile: live right after (see `tau` below)
-  off = align_up(off + (size_t)(3 * Q + p.nqt + 4) * sizeof(float), 256);
+  // tau[Q], tau_opt[Q], thr_redo[Q], redo flags per query tile, then the second round's thr_redo2[Q] and tile flags:
+  // live right after (see `tau` below)
+  off = align_up(off + (size_t)(5 * Q + 2 * p.nqt + 12) * sizeof(float), 256);
   // lower-bound pass: per-query spill list for keys that do not fit their (part, query) buffer + counters
   if (p.impl) off = align_up(off + (size_t)Q * LB_SPILL * sizeof(tkey_t) + (size_t)Q * sizeof(int), 256);
   // statistics of the call (cfl_score_topk_stats): CFL_SCORE_NSTATS 64-bit counters
@@ -849,6 +868,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   a.cimg16 = nullptr; a.qimg16 = nullptr; a.cflag16 = nullptr; a.qflag16 = nullptr; a.lbrow = nullptr; a.lbq = nullptr;
   bool lb_pass = false;
   const float* redo_only = nullptr;
+  int redo_parts = 0;                                        // parts of the exact redo launch when it differs from the plan's
   const ScoreKnobs kn = read_knobs();
   a.dbg_mode = kn.dbg_mode;
   a.plan = plan;
@@ -932,7 +952,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         float* tau_opt = tau + Q;
         float* thr_redo = tau + 2 * Q;
         int* redo_tile = (int*)(tau + 3 * Q);
-        a.spill = (tkey_t*)((char*)tau + align_up((size_t)(3 * Q + plan.nqt + 4) * sizeof(float), 256));
+        a.spill = (tkey_t*)((char*)tau + align_up((size_t)(5 * Q + 2 * plan.nqt + 12) * sizeof(float), 256));
         a.spill_cnt = (int*)(a.spill + (size_t)Q * LB_SPILL);
         unsigned long long* stats = (unsigned long long*)((char*)a.spill + align_up((size_t)Q * LB_SPILL * sizeof(tkey_t) + (size_t)Q * sizeof(int), 256));
         CFL_CUDA(cudaMemsetAsync(stats, 0, CFL_SCORE_NSTATS * sizeof(unsigned long long), cs));
@@ -987,12 +1007,38 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
     CFL_SMEM_LIMIT(rescore_merge_kernel<KK>, rs_smem);                                                           \
     rescore_merge_kernel<KK><<<(unsigned)Q, MRG_THREADS, rs_smem, cs>>>(                                        \
         a.keys, a.counts, a.lb.parts, Q, plan.kk, k, Pq, ldq, d, E, lde, idx_base, top_val, top_idx, tau,       \
-        tau_opt, plan.qt, thr_redo, redo_tile, stats, a.spill, a.spill_cnt);                                    \
+        rs_tau_opt, plan.qt, rs_thr_out, rs_tile_out, stats, a.spill, a.spill_cnt, rs_only, rs_prev, rs_second); \
     break;
-          switch (K) {
-            CFL_RSC_CASE(1) CFL_RSC_CASE(2) CFL_RSC_CASE(3) CFL_RSC_CASE(4)
-            CFL_RSC_CASE(5) CFL_RSC_CASE(6) CFL_RSC_CASE(7) CFL_RSC_CASE(8)
-          }
+#define CFL_RSC_LAUNCH()                                                                                        \
+  switch (K) {                                                                                                  \
+    CFL_RSC_CASE(1) CFL_RSC_CASE(2) CFL_RSC_CASE(3) CFL_RSC_CASE(4)                                             \
+    CFL_RSC_CASE(5) CFL_RSC_CASE(6) CFL_RSC_CASE(7) CFL_RSC_CASE(8)                                             \
+  }
+          const float* rs_tau_opt = tau_opt;
+          float* rs_thr_out = thr_redo;
+          int* rs_tile_out = redo_tile;
+          const float* rs_only = nullptr;
+          const float* rs_prev = nullptr;
+          float* lb2 = tau + 4 * Q + 2 * plan.nqt + 8;         // per query: threshold of the second round, -inf = none
+          float* rs_second = lb2;
+          CFL_RSC_LAUNCH()
+          CFL_LAUNCH_CHECK();
+          // Second chance for the queries whose optimistic threshold was not confirmed (fewer than kk survivors under
+          // it): the lower-bound pass again, under the SAFE threshold and only for them -- query tiles without such a
+          // query leave at once -- then the exact rescoring of THEIR survivors.  Bounded by one more filter pass; the
+          // exact 3xTF32 redo below (a few CTAs per query tile walk the whole catalog) remains for overflowing buffers,
+          // raised range flags and the queries the probe took out.
+          float* thr_redo2 = tau + 3 * Q + plan.nqt + 4;
+          int* redo_tile2 = (int*)(thr_redo2 + Q);
+          CFL_CUDA(cudaMemsetAsync(redo_tile2, 0, (size_t)plan.nqt * sizeof(int), cs));
+          CFL_CUDA(cudaMemsetAsync(a.spill_cnt, 0, (size_t)Q * sizeof(int), cs));
+          a.thr_init = lb2;
+          a.phase = 3; st = score_lb_launch(a, cs); a.phase = 2;
+          if (st != CFL_OK) return st;
+          rs_tau_opt = tau; rs_thr_out = thr_redo2; rs_tile_out = redo_tile2; rs_only = lb2; rs_prev = thr_redo; rs_second = nullptr;
+          CFL_RSC_LAUNCH()
+          thr_redo = thr_redo2; redo_tile = redo_tile2;
+#undef CFL_RSC_LAUNCH
 #undef CFL_RSC_CASE
         } else {
           verify_counts_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, cs>>>(a.counts, plan.parts, Q, plan.kk, plan.qt,
@@ -1000,7 +1046,17 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
         }
         CFL_LAUNCH_CHECK();
         a.thr_init = thr_redo; a.redo_tile = redo_tile;
-        st = score_umma_launch(a, cs);
+        if (lb_pass && a.lb.parts > plan.parts) {
+          // After a lower-bound pass only the redone queries use the exact kernel's key buffers, and the buffers exist
+          // for the lower-bound tiling's (more numerous) catalog parts: cut the catalog that finely, so that the few
+          // query tiles with something to redo are spread over more SMs (the others leave at once).
+          ScoreArgs r = a;
+          r.plan.parts = a.lb.parts;
+          st = score_umma_launch(r, cs);
+          redo_parts = a.lb.parts;
+        } else {
+          st = score_umma_launch(a, cs);
+        }
         a.redo_tile = nullptr;
         redo_only = lb_pass ? thr_redo : nullptr;
       } else {
@@ -1026,7 +1082,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
     }
   }
   // after a lower-bound pass the verified queries are already written; only the redone ones remain
-  merge_rescore_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(mode, a.keys, a.counts, plan.parts, Q, plan.kk, k,
+  merge_rescore_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(mode, a.keys, a.counts, redo_parts ? redo_parts : plan.parts, Q, plan.kk, k,
                                                   Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx, redo_only);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
@@ -1092,7 +1148,7 @@ int cfl_score_topk_stats(int64_t Q, int K, int d, int64_t N, int k, int packed, 
   const size_t need = score_ws_layout(Q, K, d, N, plan, packed == 0, &o_pc, &o_qpar, &o_qimg, &o_keys, &o_cnt, &o_cimg);
   CFL_REQUIRE(ws_bytes >= need, CFL_ERR_WORKSPACE, "score_topk_stats: workspace too small (%zu < %zu)", ws_bytes, need);
   const char* tau = (const char*)ws + align_up(o_cimg + (packed == 0 ? catalog_image_bytes(N, d) : 0), 1024);
-  const char* spill = tau + align_up((size_t)(3 * Q + plan.nqt + 4) * sizeof(float), 256);
+  const char* spill = tau + align_up((size_t)(5 * Q + 2 * plan.nqt + 12) * sizeof(float), 256);
   const char* stats = spill + align_up((size_t)Q * LB_SPILL * sizeof(tkey_t) + (size_t)Q * sizeof(int), 256);
   CFL_CUDA(cudaMemcpyAsync(stats_out, stats, CFL_SCORE_NSTATS * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, cs));
   if (thr_out) CFL_CUDA(cudaMemcpyAsync(thr_out, tau, (size_t)3 * Q * sizeof(float), cudaMemcpyDeviceToDevice, cs));

@@ -156,7 +156,8 @@ int cfl_score_topk_packed(int mode, const float* Pq, int64_t Q, int K, int d, in
  * (packed = 1 for the _packed entry point): CFL_SCORE_NSTATS unsigned 64-bit counters copied to device memory
  * `stats_out` on `stream`: [0] keys that survived the full filter pass, summed over queries (each is rescored
  * exactly), [1] queries that used their spill list, [2] queries the probe took out of the lower-bound pass,
- * [3] queries redone by the exact kernel under the safe threshold, [4] 1 when the lower-bound pass ran.  All zero
+ * [3] queries that failed the first verification (second lower-bound round under the safe threshold, or the exact
+ * redo), [4] 1 when the lower-bound pass ran, [5] queries redone by the exact kernel under the safe threshold.  All zero
  * for catalogs short enough for the single adaptive pass.  thr_out (optional, device, 3*Q floats): the per-query
  * thresholds of that call -- safe threshold tau, optimistic threshold tau_opt, redo threshold (-inf = not redone).
  * (bench.py prints the counters so that a regression to the slow paths is visible; no reference call site.) */

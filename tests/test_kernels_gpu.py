@@ -508,6 +508,30 @@ def test_large_catalog_cascade_matches_oracle(nat, monkeypatch, K, d):
             assert abs(D[r, c_] - wv[r, -1]) <= 1e-5 * max(wv[r, -1], 1.0) + 1e-7
 
 
+@pytest.mark.parametrize("K,d", [(3, 64), (4, 20), (1, 32)])
+def test_unconfirmed_optimistic_threshold_takes_the_second_lower_bound_round(nat, monkeypatch, K, d):
+    """An optimistic threshold that is too tight (CFL_SCORE_OPT_MULT = 1: about kk rows expected under it, so every
+    other query finds fewer) is not an error: those queries are filtered again under the SAFE threshold by the
+    lower-bound kernel and rescored, without the exact redo pass -- and the result is the single adaptive pass's,
+    bit for bit."""
+    rng = np.random.default_rng(7 * K + d)
+    N, Q = 150_000, 200
+    E = rng.normal(size=(N, d)).astype(np.float32)
+    Pq = (E[rng.integers(0, N, Q)][:, None, :] + 0.5 * rng.normal(size=(Q, K, d))).astype(np.float32)
+    E, Pq = dev(E), dev(Pq)
+    mu = nat.col_mean(E)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "100000000")
+    a = nat.score_topk(Pq, E, 100, mu=mu)
+    monkeypatch.setenv("CFL_SCORE_MIN_TILES", "2")
+    monkeypatch.setenv("CFL_SCORE_SAMPLE_STRIDE", "8")
+    monkeypatch.setenv("CFL_SCORE_OPT_MULT", "1")
+    tv, ti, st = nat.score_topk(Pq, E, 100, mu=mu, want_stats=True)
+    stats = dict(zip(nat.SCORE_STAT_NAMES, st.tolist()))
+    assert torch.equal(a[1], ti) and torch.equal(a[0], tv)
+    assert stats["lower_bound_pass"] == 1 and stats["redo_queries"] >= Q // 10, stats
+    assert stats["exact_redo_queries"] == 0, stats
+
+
 def test_clustered_catalog_cascade_matches_oracle(nat, monkeypatch):
     """Adversarial catalog for the threshold cascade: 40 tight clusters (sigma 0.02), queries sitting on cluster
     centres, so that thousands of rows lie within a hair of every threshold, the samples see only a few clusters per
