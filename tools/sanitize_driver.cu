@@ -1,6 +1,7 @@
 // Standalone driver of the C ABI for compute-sanitizer (python + torch do not survive under the sanitizer on this image):
 // projection -> catalog image -> all-pairs scoring through the sampled two-pass path (exact 3xTF32 kernel, lower-bound
-// tensor-core pass, rescoring, redo) -> monomer tensor-core path -> paired loss forward / backward -> AUC.
+// tensor-core pass, rescoring, second round, redo) -> monomer tensor-core path -> fused per-query rank counts (against the
+// CUDA-core route) -> projection forward (TMA-staged) and weight gradient (tensor-map TMA + transposing producers).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I include tools/sanitize_driver.cu \
 //        -o compatibility-family-learning_b200/build/sanitize_driver -L compatibility-family-learning_b200/cfl/_lib -lcfl_b200 \
 //        -Xlinker -rpath -Xlinker '$ORIGIN/../cfl/_lib'
@@ -74,6 +75,53 @@ int main() {
   CK(cudaMemcpy(hs, st, sizeof(hs), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(hv.data(), tv, hv.size() * 4, cudaMemcpyDeviceToHost));
   printf("monomer: survivors %llu, redo %llu, best dist of query 0 = %g\n", hs[0], hs[3], hv[0]);
+  // ---- round-2 kernels: fused rank counts, TMA-staged projection forward, dV GEMM (tensor-map TMA) ----
+  {
+    const int J = 9;                                             // two threshold chunks
+    std::vector<long long> hpos((size_t)Q * J);
+    for (auto& x : hpos) x = rand() % N;
+    long long* pos; CK(cudaMalloc(&pos, hpos.size() * 8)); CK(cudaMemcpy(pos, hpos.data(), hpos.size() * 8, cudaMemcpyHostToDevice));
+    float* tpos = dalloc<float>((size_t)Q * J);
+    CF(cfl_pair_dist_rows(CFL_PCD, Pq, Q, K, d, (int64_t)K * d, nullptr, E, N, d, (const int64_t*)pos, J, tpos, nullptr));
+    int64_t *cf = dalloc<int64_t>((size_t)Q * J * 2), *cd = dalloc<int64_t>((size_t)Q * J * 2);
+    const size_t rwb = cfl_rank_counts_packed_workspace_bytes(Q, K, d, N);
+    void* rws = aligned(rwb);
+    CF(cfl_rank_counts_packed(CFL_PCD, Pq, Q, K, d, (int64_t)K * d, E, img, N, d, mu, tpos, J, cf, rws, rwb, nullptr));
+    CF(cfl_rank_counts(CFL_PCD, Pq, Q, K, d, (int64_t)K * d, nullptr, E, N, d, tpos, J, cd, nullptr));
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> hcf((size_t)Q * J * 2), hcd((size_t)Q * J * 2);
+    CK(cudaMemcpy(hcf.data(), cf, hcf.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hcd.data(), cd, hcd.size() * 8, cudaMemcpyDeviceToHost));
+    int diff = 0;
+    for (size_t i = 0; i < hcf.size(); ++i) diff += hcf[i] != hcd[i];
+    int64_t rst[CFL_RANK_NSTATS];
+    CF(cfl_rank_counts_packed_stats(Q, K, d, N, rws, rwb, rst, nullptr));
+    printf("rank counts: fused vs direct differences %d, ambiguous records %lld\n", diff, (long long)rst[0]);
+    bad += diff;
+  }
+  {
+    const int64_t B = 2500; const int F = 512, No = 80;          // ragged last tile, two batch slabs of the dV kernel
+    std::vector<float> hx((size_t)B * F), hV((size_t)F * No), hdy((size_t)B * No), hg(No, 1.0f), hb(No, 0.1f);
+    for (auto& x : hx) x = fabsf(frand());
+    for (auto& x : hV) x = 0.05f * frand();
+    for (auto& x : hdy) x = frand();
+    float *x = upload(hx), *V = upload(hV), *dy = upload(hdy), *g = upload(hg), *bb = upload(hb);
+    float *y = dalloc<float>((size_t)B * No), *z = dalloc<float>((size_t)B * No);
+    float *dV = dalloc<float>((size_t)F * No), *dg = dalloc<float>(No), *db = dalloc<float>(No);
+    const size_t fw = cfl_project_fwd_workspace_bytes(B, F, No), bw = cfl_project_bwd_workspace_bytes(B, F, No);
+    void *fws = aligned(fw), *bws = aligned(bw);
+    CF(cfl_project_fwd(x, B, F, F, V, No, No, g, bb, 1, 0.5f, CFL_ACT_TANH, y, No, nullptr, z, fws, fw, nullptr));
+    CF(cfl_project_bwd(x, B, F, F, V, No, No, g, bb, 1, 0.5f, CFL_ACT_TANH, y, No, z, dy, No, dV, dg, db, 0, 0.0f, bws, bw, nullptr));
+    CK(cudaDeviceSynchronize());
+    std::vector<float> hy((size_t)B * No), hdV((size_t)F * No);
+    CK(cudaMemcpy(hy.data(), y, hy.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hdV.data(), dV, hdV.size() * 4, cudaMemcpyDeviceToHost));
+    double sy = 0, sv = 0; int nan = 0;
+    for (float v : hy) { sy += v; nan += !(v == v); }
+    for (float v : hdV) { sv += v; nan += !(v == v); }
+    printf("projection: sum y %.6g, sum dV %.6g, NaNs %d\n", sy, sv, nan);
+    bad += nan;
+  }
   printf("sanitize_driver done\n");
   return bad ? 1 : 0;
 }
