@@ -470,7 +470,8 @@ def rank_counts(mode, query, catalog, pos_dist, w=None):
 def rank_counts_packed(query, catalog, image, mu, pos_dist, want_stats=False):
     """``rank_counts("pcd", ...)`` on the tensor cores: the counts are taken inside the fused scoring kernel's epilogue
     over the packed catalog ``image`` (``catalog_pack`` of the same catalog / ``mu``), near-ties re-evaluated in the
-    direct form -> the same int64 [Q,J,2] as ``rank_counts``.  want_stats: also a dict of the call's statistics."""
+    direct form -> the same int64 [Q,J,2] as ``rank_counts``.  want_stats: also a dict of the call's statistics.
+    Query batches beyond 65536 go through the C entry point in chunks (one call holds at most 4096 scoring CTAs)."""
     q2, Q, K, d, ldq, _, E2, N, lde = _rank_operands("pcd", query, catalog, None)
     pos_dist = _f32c(pos_dist, "pos_dist").contiguous()
     if pos_dist.dim() != 2 or pos_dist.shape[0] != Q:
@@ -478,19 +479,23 @@ def rank_counts_packed(query, catalog, image, mu, pos_dist, want_stats=False):
     J = pos_dist.shape[1]
     out = torch.empty(Q, J, 2, dtype=torch.int64, device=E2.device)
     mode = MODES["siamese"] if K == 1 else MODES["pcd"]
-    need = lib().cfl_rank_counts_packed_workspace_bytes(Q, K, d, N)
-    ws = _ws.get(need, E2.device)
     mu = None if mu is None else _f32c(mu, "mu").contiguous()
-    _check(lib().cfl_rank_counts_packed(mode, _ptr(q2), Q, K, d, ldq, _ptr(E2), _ptr(image), N, lde, _ptr(mu),
-                                        _ptr(pos_dist), J, _ptr(out), _ptr(ws), ws.numel(), _stream()),
-           "cfl_rank_counts_packed")
-    if not want_stats:
-        return out
-    raw = (C.c_int64 * 4)()
-    _check(lib().cfl_rank_counts_packed_stats(Q, K, d, N, _ptr(ws), ws.numel(), raw, _stream()),
-           "cfl_rank_counts_packed_stats")
-    return out, dict(records=int(raw[0]), worst_ratio=raw[1] / 1048576.0, beyond_half_band=int(raw[2]),
-                     recounted_queries=int(raw[3]))
+    chunk = 65536
+    tot = dict(records=0, worst_ratio=0.0, beyond_half_band=0, recounted_queries=0)
+    for lo in range(0, max(Q, 1), chunk):
+        hi = min(Q, lo + chunk)
+        need = lib().cfl_rank_counts_packed_workspace_bytes(hi - lo, K, d, N)
+        ws = _ws.get(need, E2.device)
+        _check(lib().cfl_rank_counts_packed(mode, _ptr(q2[lo:hi]), hi - lo, K, d, ldq, _ptr(E2), _ptr(image), N, lde,
+                                            _ptr(mu), _ptr(pos_dist[lo:hi]), J, _ptr(out[lo:hi]), _ptr(ws), ws.numel(),
+                                            _stream()), "cfl_rank_counts_packed")
+        if want_stats:
+            raw = (C.c_int64 * 4)()
+            _check(lib().cfl_rank_counts_packed_stats(hi - lo, K, d, N, _ptr(ws), ws.numel(), raw, _stream()),
+                   "cfl_rank_counts_packed_stats")
+            tot["records"] += int(raw[0]); tot["worst_ratio"] = max(tot["worst_ratio"], raw[1] / 1048576.0)
+            tot["beyond_half_band"] += int(raw[2]); tot["recounted_queries"] += int(raw[3])
+    return (out, tot) if want_stats else out
 
 
 def dense_rank_counts(dense, pos_dist):

@@ -254,7 +254,8 @@ int cfl_dense_rank_counts(const float* dense, int64_t Q, int64_t N, int64_t ldn,
  * image = cfl_catalog_pack of the same E / mu.  Every (row, query) Gram-form distance is classified against the
  * thresholds with a rounding band; pairs inside a band (exact ties included) are re-evaluated in the direct form of
  * cfl_pair_dist_rows, so counts == cfl_rank_counts(...) for pos_dist produced by cfl_pair_dist_rows.  pcd / siamese.
- * Replaces roc_auc_score over all candidates (cfl/utils.py:267-268); see csrc/rank_counts_tc.cu.
+ * Replaces roc_auc_score over all candidates (cfl/utils.py:267-268); see csrc/rank_counts_tc.cu.  One call takes up
+ * to 4096 scoring CTAs' worth of queries (>= 131072 queries; CFL_ERR_UNSUPPORTED beyond: split the query batch).
  * cfl_rank_counts_packed_stats (synchronises the stream): out[CFL_RANK_NSTATS] = {ambiguous records, largest
  * |Gram - direct| / band in units of 2^-20, records beyond half the band, queries recounted on the CUDA cores}. */
 #define CFL_RANK_NSTATS 4
