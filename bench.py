@@ -492,10 +492,11 @@ def run_ours(args):
 def launches_per_step(world):
     # colnorm, pack_weights, project_umma, prep_queries, pack_queries, score_umma x2 (passes A/B), select_threshold x2,
     # prep_lb, score_lb (probe) + probe_classify, score_lb (pass C), rescore_merge, score_lb + rescore_merge (second
-    # round under the safe threshold: both leave at once when every query was verified), score_umma (exact redo, exits
-    # when nothing is left to redo), merge_rescore (redone queries only)
+    # round under the safe threshold: both leave at once when every query was verified), redo_compact + score_umma
+    # (compact exact redo: what still needs the exact kernel, gathered into one query tile), score_umma (in-place exact
+    # redo of what did not fit; both exit when nothing is left to redo), merge_rescore (redone queries only)
     # (+ topk_merge after the all-gather for N>1)
-    return 18 + (1 if world > 1 else 0)
+    return 20 + (1 if world > 1 else 0)
 
 
 # ------------------------------------------------------------------------------------------

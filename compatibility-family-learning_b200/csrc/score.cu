@@ -5,6 +5,7 @@
 // both kernels share the soft-min epilogue (score.cuh) and the top-k machinery (topk.cuh).
 #include <stdlib.h>
 #include "score.cuh"
+#include "umma.cuh"
 
 namespace cfl {
 
@@ -250,15 +251,25 @@ merge_rescore_kernel(int mode, const tkey_t* __restrict__ keys, const int* __res
                      int parts, int64_t Q, int kk, int k, const float* __restrict__ Pq,
                      int64_t ldq, int K, int d, const float* __restrict__ E, int64_t lde,
                      int64_t idx_base, float* __restrict__ top_val, int64_t* __restrict__ top_idx,
-                     const float* __restrict__ only_redo = nullptr) {
+                     const float* __restrict__ only_redo = nullptr,
+                     // compact exact redo: blocks [Q, Q + cq) merge the compact tile's slots (own buffers, query map)
+                     int cq = 0, const tkey_t* __restrict__ ckeys = nullptr, const int* __restrict__ ccounts = nullptr,
+                     int cparts = 0, const float* __restrict__ cthr = nullptr, const int* __restrict__ cmap = nullptr) {
   __shared__ tkey_t s[TOPK_CAP];
   __shared__ int s_fill;
   __shared__ tkey_t s_thr;
   const int t = threadIdx.x;
-  const int64_t q = blockIdx.x;
-  // second merge after a lower-bound pass: only the queries that were redone by the exact kernel
-  if (only_redo != nullptr && !(only_redo[q] > __int_as_float(0xff800000))) return;
-  const int fill = block_merge_topkk(keys, counts, parts, Q, q, kk, s, &s_fill, &s_thr);
+  int64_t qk = blockIdx.x;                                  // position in the key buffers
+  int64_t q = qk;                                           // the query it stands for
+  if (qk >= Q) {
+    qk -= Q;
+    if (!(cthr[qk] > __int_as_float(0xff800000))) return;
+    q = cmap[qk];
+    keys = ckeys; counts = ccounts; parts = cparts; Q = cq;
+  } else if (only_redo != nullptr && !(only_redo[qk] > __int_as_float(0xff800000))) {
+    return;                                                 // second merge after a lower-bound pass: only the redone queries
+  }
+  const int fill = block_merge_topkk(keys, counts, parts, Q, qk, kk, s, &s_fill, &s_thr);
   const float* pq = Pq + q * ldq;
   if (t < fill) {
     const uint32_t idx = (uint32_t)(s[t] & 0xffffffffu);
@@ -791,6 +802,94 @@ static bool score_lb_pass(const ScoreKnobs& kn, int K) {
   return !kn.no_lb && (K <= 4 || kn.force_lb);
 }
 
+// Compact exact redo: the (rare) queries that still need the exact kernel after the lower-bound rounds are gathered
+// into ONE query tile, so that every SM works on a slice of the catalog for them -- the in-place redo below keeps a
+// query in its own tile, i.e. on a few CTAs that each walk a large part of the catalog.
+struct CerLayout { size_t idx, thr, flag, pc, qpar, qplane, qimg, total; };
+static CerLayout cer_layout(int K, int d, int qt, int dpad) {
+  CerLayout L;
+  size_t off = 0;
+  L.idx = off;    off = align_up(off + (size_t)qt * sizeof(int), 256);
+  L.thr = off;    off = align_up(off + (size_t)qt * sizeof(float), 256);
+  L.flag = off;   off = align_up(off + 16, 256);
+  L.pc = off;     off = align_up(off + (size_t)qt * K * d * sizeof(float), 256);
+  L.qpar = off;   off = align_up(off + (size_t)qt * qpar_stride(K) * sizeof(float), 256);
+  L.qplane = off; off = align_up(off + (size_t)qt * qplane_stride(K) * sizeof(float), 1024);
+  L.qimg = off;   off = align_up(off + (size_t)dpad * 8 * (size_t)(K * qt), 1024);
+  L.total = off;
+  return L;
+}
+static size_t cer_bytes(int K, int d, int qt, int dpad) { return cer_layout(K, d, qt, dpad).total; }
+
+// One block.  Takes the first `cap` flagged queries (thr[q] > -inf) in query order: idx_c / thr_c / gathered prototype
+// and parameter rows; un-flags them in thr, rebuilds the per-tile flags for what is left, flag_c = "something taken".
+__global__ void __launch_bounds__(256)
+redo_compact_kernel(float* __restrict__ thr, int64_t Q, int cap, int K, int d, int plan_qt, int nqt,
+                    const float* __restrict__ Pc, const float* __restrict__ qpar, const float* __restrict__ qplane,
+                    int* __restrict__ idx_c, float* __restrict__ thr_c, int* __restrict__ flag_c,
+                    float* __restrict__ Pc_c, float* __restrict__ qpar_c, float* __restrict__ qplane_c,
+                    int* __restrict__ redo_tile, int dpad, float* __restrict__ qimg_c) {
+  __shared__ int s_cnt[256];
+  __shared__ int s_total;
+  const int t = threadIdx.x;
+  const float NEG_INF = __int_as_float(0xff800000);
+  const int64_t per = (Q + 255) / 256;
+  const int64_t lo = (int64_t)t * per, hi = lo + per < Q ? lo + per : Q;
+  int mine = 0;
+  for (int64_t q = lo; q < hi; ++q) mine += thr[q] > NEG_INF ? 1 : 0;
+  s_cnt[t] = mine;
+  for (int i = t; i < nqt; i += 256) redo_tile[i] = 0;
+  for (int i = t; i < cap; i += 256) { idx_c[i] = 0; thr_c[i] = NEG_INF; }
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int i = 0; i < 256; ++i) { const int c = s_cnt[i]; s_cnt[i] = run; run += c; }
+    s_total = run;
+    *flag_c = run > 0 ? 1 : 0;
+  }
+  __syncthreads();
+  int pos = s_cnt[t];
+  for (int64_t q = lo; q < hi; ++q) {
+    const float v = thr[q];
+    if (!(v > NEG_INF)) continue;
+    if (pos < cap) { idx_c[pos] = (int)q; thr_c[pos] = v; thr[q] = NEG_INF; }
+    else redo_tile[q / plan_qt] = 1;                           // left to the in-place redo
+    ++pos;
+  }
+  __syncthreads();
+  const int R = s_total < cap ? s_total : cap;
+  const int qps = qpar_stride(K), pbs = qplane_stride(K), kd = K * d;
+  for (int i = t; i < R * kd; i += 256) Pc_c[i] = Pc[(int64_t)idx_c[i / kd] * kd + i % kd];
+  for (int i = t; i < R * qps; i += 256) qpar_c[i] = qpar[(int64_t)idx_c[i / qps] * qps + i % qps];
+  for (int i = t; i < R * pbs; i += 256) qplane_c[i] = qplane[(int64_t)idx_c[i / pbs] * pbs + i % pbs];
+  for (int i = R * kd + t; i < cap * kd; i += 256) Pc_c[i] = 0.0f;
+  for (int i = R * qps + t; i < cap * qps; i += 256) qpar_c[i] = 0.0f;
+  for (int i = R * pbs + t; i < cap * pbs; i += 256) qplane_c[i] = 0.0f;
+  if (R == 0) return;                                          // the exact kernel's CTAs leave on flag_c
+  __syncthreads();
+  // tcgen05 B-operand image of the compact tile (the layout of pack_queries_kernel, score_umma.cu): cap = the query tile
+  const int nc = K * cap, nks = dpad / 8;
+  for (int e = t; e < nks * 2 * nc; e += 256) {
+    const int n = e % nc, c = (e / nc) % 2, ks = e / (2 * nc);
+    const int k = n / cap, ql = n % cap;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* xp = &x.x;
+    if (ql < R) {
+      const float* src = Pc_c + ((int64_t)ql * K + k) * d;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = ks * 8 + c * 4 + i;
+        if (j < d) xp[i] = src[j];
+      }
+    }
+    float4 hi4, lo4;
+    umma::split_tf32x4(x, hi4, lo4);
+    const size_t step = (size_t)ks * 4 * nc;
+    ((float4*)qimg_c)[step + (size_t)(0 * 2 + c) * nc + n] = hi4;
+    ((float4*)qimg_c)[step + (size_t)(1 * 2 + c) * nc + n] = lo4;
+  }
+}
+
 static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePlan& p, bool own_image,
                               size_t* o_pc, size_t* o_qpar, size_t* o_qimg, size_t* o_keys, size_t* o_cnt,
                               size_t* o_cimg, size_t* o_lbimg = nullptr) {
@@ -812,6 +911,8 @@ static size_t score_ws_layout(int64_t Q, int K, int d, int64_t N, const ScorePla
   if (p.impl) off = align_up(off + (size_t)Q * LB_SPILL * sizeof(tkey_t) + (size_t)Q * sizeof(int), 256);
   // statistics of the call (cfl_score_topk_stats): CFL_SCORE_NSTATS 64-bit counters
   if (p.impl) off = align_up(off + CFL_SCORE_NSTATS * sizeof(unsigned long long), 256);
+  // compact exact redo (one query tile of gathered queries): index map, thresholds, flag, prototypes, parameter blocks, image
+  if (p.impl) off = align_up(off + cer_bytes(K, d, p.qt, p.dpad), 1024);
   return off + 1024;
 }
 
@@ -869,6 +970,7 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
   bool lb_pass = false;
   const float* redo_only = nullptr;
   int redo_parts = 0;                                        // parts of the exact redo launch when it differs from the plan's
+  int* cer_idx = nullptr; float* cer_thr = nullptr; tkey_t* cer_keys = nullptr; int* cer_counts = nullptr; int cer_parts = 0;
   const ScoreKnobs kn = read_knobs();
   a.dbg_mode = kn.dbg_mode;
   a.plan = plan;
@@ -1045,6 +1147,38 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
                                                                            tau, tau_opt, thr_redo, redo_tile, stats);
         }
         CFL_LAUNCH_CHECK();
+        if (lb_pass && plan.nqt > 1) {
+          // compact exact redo: up to one query tile of flagged queries, every SM on a slice of the catalog.  Its key
+          // buffers live in the spill lists (free once the rescoring rounds are done): [parts][qt][TOPK_STRIDE] + counts.
+          int sms_c = sm_count();
+          if (sms_c <= 0) sms_c = 148;
+          int64_t pc_parts = ((int64_t)Q * LB_SPILL) / ((int64_t)plan.qt * (TOPK_STRIDE + 1));
+          if (pc_parts > sms_c) pc_parts = sms_c;
+          if (pc_parts > plan.tiles) pc_parts = plan.tiles;
+          if (pc_parts >= 1) {
+            const CerLayout CL = cer_layout(K, d, plan.qt, plan.dpad);
+            char* cer = (char*)stats + align_up(CFL_SCORE_NSTATS * sizeof(unsigned long long), 256);
+            cer = (char*)align_up((size_t)(uintptr_t)cer, 1024);
+            cer_idx = (int*)(cer + CL.idx);
+            cer_thr = (float*)(cer + CL.thr);
+            int* flag_c = (int*)(cer + CL.flag);
+            cer_keys = a.spill;
+            cer_counts = (int*)(a.spill + (size_t)pc_parts * plan.qt * TOPK_STRIDE);
+            cer_parts = (int)pc_parts;
+            redo_compact_kernel<<<1, 256, 0, cs>>>(thr_redo, Q, plan.qt, K, d, plan.qt, plan.nqt, a.Pc, a.qpar, a.qplane, cer_idx,
+                                                  cer_thr, flag_c, (float*)(cer + CL.pc), (float*)(cer + CL.qpar),
+                                                  (float*)(cer + CL.qplane), redo_tile, plan.dpad, (float*)(cer + CL.qimg));
+            CFL_LAUNCH_CHECK();
+            ScoreArgs b = a;
+            b.Q = plan.qt; b.Pc = (const float*)(cer + CL.pc); b.qpar = (const float*)(cer + CL.qpar);
+            b.qplane = (const float*)(cer + CL.qplane); b.qimg = cer + CL.qimg;
+            b.keys = cer_keys; b.counts = cer_counts;
+            b.thr_init = cer_thr; b.redo_tile = flag_c; b.phase = 2; b.tile_stride = 1; b.dist_out = nullptr;
+            b.plan.nqt = 1; b.plan.parts = cer_parts;
+            st = score_umma_launch(b, cs);
+            if (st != CFL_OK) return st;
+          }
+        }
         a.thr_init = thr_redo; a.redo_tile = redo_tile;
         if (lb_pass && a.lb.parts > plan.parts) {
           // After a lower-bound pass only the redone queries use the exact kernel's key buffers, and the buffers exist
@@ -1082,8 +1216,9 @@ static int score_topk_impl(int mode, const float* Pq, int64_t Q, int K, int d, i
     }
   }
   // after a lower-bound pass the verified queries are already written; only the redone ones remain
-  merge_rescore_kernel<<<(unsigned)Q, MRG_THREADS, 0, cs>>>(mode, a.keys, a.counts, redo_parts ? redo_parts : plan.parts, Q, plan.kk, k,
-                                                  Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx, redo_only);
+  merge_rescore_kernel<<<(unsigned)(Q + (cer_parts ? plan.qt : 0)), MRG_THREADS, 0, cs>>>(
+      mode, a.keys, a.counts, redo_parts ? redo_parts : plan.parts, Q, plan.kk, k, Pq, ldq, K, d, E, lde, idx_base, top_val, top_idx,
+      redo_only, plan.qt, cer_keys, cer_counts, cer_parts, cer_thr, cer_idx);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
 }
