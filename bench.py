@@ -490,7 +490,7 @@ def run_ours(args):
 
 
 def launches_per_step(world):
-    # colnorm, pack_weights, project_umma, prep_queries, pack_queries, score_umma x2 (passes A/B), select_threshold x2,
+    # colnorm, project_fwd_splitk + its finalize (1024 queries = 8 tcgen05 tiles: split-F CUDA-core kernel), prep_queries, pack_queries, score_umma x2 (passes A/B), select_threshold x2,
     # prep_lb, score_lb (probe) + probe_classify, score_lb (pass C), rescore_merge, score_lb + rescore_merge (second
     # round under the safe threshold: both leave at once when every query was verified), redo_compact + score_umma
     # (compact exact redo: what still needs the exact kernel, gathered into one query tile), score_umma (in-place exact

@@ -174,7 +174,7 @@ static int splitk_slices(int64_t B, int F, int N, int* fslice) {
   *fslice = fs;
   return (int)((F + fs - 1) / fs);
 }
-static bool use_splitk(int64_t B) { return B <= 512; }
+static bool use_splitk(int64_t B) { return B <= 1024; }   // <= 8 tcgen05 tiles would leave 140 SMs idle: split F over ~2 CTAs per SM instead
 
 // ---- backward ----------------------------------------------------------------------------
 __device__ __forceinline__ float dpre_of(const float* __restrict__ dy, int64_t lddy,
