@@ -338,9 +338,10 @@ rank_count_umma_kernel(RtArgs A) {
             const int ql = g * GQ + 2 * pi;
             const float4 sa = skp[ql], sb = skp[ql + 1];
             const float SA = e2 + qm[ql], SB = e2 + qm[ql + 1];
-            const float va = fmaf(lbA, fmaf(-SA, sa.z, 1.0f), -SA * sa.y);
-            const float vb = fmaf(lbB, fmaf(-SB, sb.z, 1.0f), -SB * sb.y);
-            need |= !(va > sa.x) | !(vb > sb.x);
+            const float fa = fmaf(-SA, sa.z, 1.0f), fb = fmaf(-SB, sb.z, 1.0f);     // 1 - S k1: must stay positive
+            const float va = fmaf(lbA, fa, -SA * sa.y);
+            const float vb = fmaf(lbB, fb, -SB * sb.y);
+            need |= !(va > sa.x) | !(vb > sb.x) | !(fminf(fa, fb) > 0.0f);
           }
           ++grp_seen;
           if (!__any_sync(0xffffffffu, need && valid)) { ++grp_skipped; continue; }

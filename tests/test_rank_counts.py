@@ -324,7 +324,14 @@ def _fused_case(rng, K, d, Q, N, J, kind):
             Pq += 10.0
         if kind == "far":                       # prototypes far apart: one-hot soft-min
             Pq *= 4.0
+        if kind == "degenerate" and K > 1:      # coinciding prototypes: no affine-hull bound for those queries
+            Pq[::2, 1] = Pq[::2, 0]
     pos = _planted(rng, Q, N, J, pad=Q > 4)
+    if kind in ("top", "degenerate"):           # positives among the query's best rows: the group-skip regime
+        D = O.all_pairs_dist(Pq.astype(np.float64), E.astype(np.float64))
+        best = np.argsort(D, axis=1)[:, :4 * J]
+        pos = np.stack([rng.permutation(best[q])[:J] for q in range(Q)]).astype(np.int64)
+        pos[::3, -1] = -1
     return E, Pq, pos
 
 
@@ -333,7 +340,9 @@ def _fused_case(rng, K, d, Q, N, J, kind):
     (3, 64, 70, 30000, 8, "normal"), (1, 20, 5, 5000, 3, "normal"), (2, 16, 33, 20000, 9, "normal"),
     (4, 20, 64, 25000, 8, "offset"), (8, 20, 10, 9000, 8, "normal"), (5, 32, 50, 12000, 8, "normal"),
     (3, 128, 40, 10000, 20, "normal"), (4, 128, 9, 7000, 32, "far"), (2, 8, 20, 3000, 4, "integer"),
-    (3, 12, 130, 129, 2, "integer"), (1, 64, 3, 1, 1, "normal"), (6, 10, 65, 40000, 8, "offset")])
+    (3, 12, 130, 129, 2, "integer"), (1, 64, 3, 1, 1, "normal"), (6, 10, 65, 40000, 8, "offset"),
+    (3, 64, 70, 30000, 8, "top"), (4, 20, 40, 25000, 8, "top"), (1, 32, 33, 20000, 5, "top"),
+    (3, 16, 50, 20000, 8, "degenerate")])
 def test_rank_counts_packed_equals_direct(nat, K, d, Q, N, J, kind):
     """cfl_rank_counts_packed == cfl_rank_counts, integer for integer (ties, padded slots, ragged tiles, J > 8 in
     several threshold chunks), and the rounding band has headroom: no ambiguous pair deviated by half of it."""
