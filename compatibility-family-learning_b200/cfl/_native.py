@@ -62,6 +62,9 @@ SIGNATURES = {
     "cfl_score_topk_monomer_packed": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _vp, _i64, _i64, _vp, _int, _i64,
                                              _vp, _vp, _vp, _vp, _sz, _vp]),
     "cfl_topk_merge": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
+    "cfl_topk_record_bytes": (_sz, [_i64, _int]),
+    "cfl_topk_pack_records": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
+    "cfl_topk_merge_records": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp]),
     "cfl_col_mean_workspace_bytes": (_sz, [_i64, _int]),
     "cfl_col_mean": (_int, [_vp, _i64, _int, _i64, _vp, _vp, _sz, _vp]),
     "cfl_pair_dist_rows": (_int, [_int, _vp, _i64, _int, _int, _i64, _vp, _vp, _i64, _i64, _vp, _int, _vp, _vp]),
@@ -415,6 +418,25 @@ def topk_merge(vals, idx):
     ti = torch.empty(Q, k, dtype=torch.int64, device=vals.device)
     _check(lib().cfl_topk_merge(_ptr(vals), _ptr(idx), R, Q, k, _ptr(tv), _ptr(ti), _stream()),
            "cfl_topk_merge")
+    return tv, ti
+
+
+def topk_record_bytes(Q, k):
+    return int(lib().cfl_topk_record_bytes(Q, k))
+
+
+def topk_pack_records(vals, idx, rec):
+    """[Q,k] lists of this rank -> its exchange record (uint8 buffer of topk_record_bytes(Q,k))."""
+    Q, k = vals.shape
+    _check(lib().cfl_topk_pack_records(_ptr(vals), _ptr(idx), Q, k, _ptr(rec), _stream()), "cfl_topk_pack_records")
+    return rec
+
+
+def topk_merge_records(recs, R, Q, k):
+    """Gathered records of R ranks (uint8, R * topk_record_bytes(Q,k)) -> merged (dist [Q,k], index [Q,k])."""
+    tv = torch.empty(Q, k, dtype=torch.float32, device=recs.device)
+    ti = torch.empty(Q, k, dtype=torch.int64, device=recs.device)
+    _check(lib().cfl_topk_merge_records(_ptr(recs), R, Q, k, _ptr(tv), _ptr(ti), _stream()), "cfl_topk_merge_records")
     return tv, ti
 
 

@@ -278,21 +278,39 @@ def _auc_per_query(mode, query, catalog, gate, pos_idx, idx_base, n_total, group
     return SimpleNamespace(auc=auc, two_u=two_u, n_pos=n_pos, n_neg=n_neg, counts=counts, pos_dist=pos_dist)
 
 
+_XCHG_BUFS = {}
+
+
 def _gather_merge(tv, ti, group, world):
-    """The one exchange step of the sharded ranking: ONE all-gather of the per-rank [Q,k] lists -- indices and values
-    packed into a single 12-byte-per-entry record buffer, so the latency-bound collective is paid once, not twice --
-    then the merge kernel."""
+    """The one exchange step of the sharded ranking: every rank packs its [Q,k] lists into one record (one kernel), ONE
+    all-gather of the records -- the latency-bound collective is paid once -- and the merge kernel reads the gathered
+    records in place.  The buffers are kept per (device, stream, shape) in a ring of four (the exchange of batch i runs
+    while batches i+1.. are scored), so a step allocates nothing but its two result tensors: the host time to enqueue
+    a step is what limits the sharded throughput."""
     Q, k = tv.shape
-    n = Q * k
-    rec = torch.empty(12 * n, dtype=torch.uint8, device=tv.device)
-    rec[:8 * n].view(torch.int64).copy_(ti.reshape(-1))
-    rec[8 * n:].view(torch.float32).copy_(tv.reshape(-1))
-    out = torch.empty(world * 12 * n, dtype=torch.uint8, device=tv.device)
+    if not tv.is_cuda:                                         # CPU tensors (gloo tests of the host logic)
+        n = Q * k
+        rec = torch.empty(12 * n, dtype=torch.uint8)
+        rec[:8 * n].view(torch.int64).copy_(ti.reshape(-1))
+        rec[8 * n:].view(torch.float32).copy_(tv.reshape(-1))
+        out = torch.empty(world * 12 * n, dtype=torch.uint8)
+        torch.distributed.all_gather_into_tensor(out, rec, group=group)
+        out = out.view(world, 12 * n)
+        gi = out[:, :8 * n].contiguous().view(torch.int64).view(world, Q, k)
+        gv = out[:, 8 * n:].contiguous().view(torch.float32).view(world, Q, k)
+        return nat.topk_merge(gv, gi)
+    rb = nat.topk_record_bytes(Q, k)
+    key = (tv.device.index, torch.cuda.current_stream(tv.device).cuda_stream, Q, k, world)
+    ring = _XCHG_BUFS.get(key)
+    if ring is None:
+        ring = [[torch.empty(rb, dtype=torch.uint8, device=tv.device),
+                 torch.empty(world * rb, dtype=torch.uint8, device=tv.device)] for _ in range(4)] + [0]
+        _XCHG_BUFS[key] = ring
+    rec, out = ring[ring[4]]
+    ring[4] = (ring[4] + 1) % 4
+    nat.topk_pack_records(tv.contiguous(), ti.contiguous(), rec)
     torch.distributed.all_gather_into_tensor(out, rec, group=group)
-    out = out.view(world, 12 * n)
-    gi = out[:, :8 * n].contiguous().view(torch.int64).view(world, Q, k)
-    gv = out[:, 8 * n:].contiguous().view(torch.float32).view(world, Q, k)
-    return nat.topk_merge(gv, gi)
+    return nat.topk_merge_records(out, world, Q, k)
 
 
 class MonomerCatalogIndex:

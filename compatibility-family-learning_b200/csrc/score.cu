@@ -735,19 +735,31 @@ __device__ __forceinline__ bool lex_less(float va, int64_t ia, float vb, int64_t
   return va < vb || (va == vb && (uint64_t)ia < (uint64_t)ib);
 }
 
+// vals / idx of rank r start rs_v / rs_i BYTES after those of rank r - 1 (contiguous [R,Q,k] arrays, or the gathered
+// exchange records [R][idx | val] of cfl_topk_pack_records).
+// exchange record of one rank: [idx: n int64][val: n float][pad to 16 bytes], n = Q * k
+__host__ __device__ inline size_t topk_record_bytes(int64_t n) { return ((size_t)n * 12 + 15) / 16 * 16; }
+__global__ void topk_pack_records_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx, int64_t n,
+                                         char* __restrict__ rec) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ((int64_t*)rec)[i] = idx[i];
+  ((float*)(rec + (size_t)n * 8))[i] = vals[i];
+}
+
 __global__ void __launch_bounds__(128)
-topk_merge_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx, int R,
+topk_merge_kernel(const char* __restrict__ vals_b, const char* __restrict__ idx_b, size_t rs_v, size_t rs_i, int R,
                   int64_t Q, int k, float* __restrict__ top_val, int64_t* __restrict__ top_idx) {
   const int64_t q = blockIdx.x;
   for (int e = threadIdx.x; e < R * k; e += blockDim.x) {
     int r = e / k, j = e % k;
-    float v = vals[((int64_t)r * Q + q) * k + j];
-    int64_t id = idx[((int64_t)r * Q + q) * k + j];
+    float v = ((const float*)(vals_b + (size_t)r * rs_v))[q * k + j];
+    int64_t id = ((const int64_t*)(idx_b + (size_t)r * rs_i))[q * k + j];
     int rank = j;
     for (int r2 = 0; r2 < R; ++r2) {
       if (r2 == r) continue;
-      const float* lv = vals + ((int64_t)r2 * Q + q) * k;
-      const int64_t* li = idx + ((int64_t)r2 * Q + q) * k;
+      const float* lv = (const float*)(vals_b + (size_t)r2 * rs_v) + q * k;
+      const int64_t* li = (const int64_t*)(idx_b + (size_t)r2 * rs_i) + q * k;
       // r2 < r: count elements <= e ; r2 > r: count elements < e   (stable merge rank)
       int lo = 0, hi = k;
       while (lo < hi) {
@@ -1297,7 +1309,34 @@ int cfl_topk_merge(const float* vals, const int64_t* idx, int R, int64_t Q, int 
   CFL_REQUIRE(vals && idx && top_val && top_idx && R >= 1 && Q >= 0 && k >= 1, CFL_ERR_INVALID,
               "topk_merge: bad arguments");
   if (Q == 0) return CFL_OK;
-  topk_merge_kernel<<<(unsigned)Q, 128, 0, (cudaStream_t)stream>>>(vals, idx, R, Q, k, top_val, top_idx);
+  topk_merge_kernel<<<(unsigned)Q, 128, 0, (cudaStream_t)stream>>>((const char*)vals, (const char*)idx, (size_t)Q * k * sizeof(float),
+                                                                   (size_t)Q * k * sizeof(int64_t), R, Q, k, top_val, top_idx);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+size_t cfl_topk_record_bytes(int64_t Q, int k) { return topk_record_bytes(Q * (int64_t)k); }
+
+int cfl_topk_pack_records(const float* vals, const int64_t* idx, int64_t Q, int k, void* rec, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(Q >= 0 && k >= 1 && (Q == 0 || (vals && idx && rec)), CFL_ERR_INVALID, "topk_pack_records: bad arguments");
+  const int64_t n = Q * (int64_t)k;
+  if (n == 0) return CFL_OK;
+  topk_pack_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vals, idx, n, (char*)rec);
+  CFL_LAUNCH_CHECK();
+  return CFL_OK;
+}
+
+int cfl_topk_merge_records(const void* recs, int R, int64_t Q, int k, float* top_val, int64_t* top_idx, void* stream) {
+  int st = device_check();
+  if (st != CFL_OK) return st;
+  CFL_REQUIRE(recs && top_val && top_idx && R >= 1 && Q >= 0 && k >= 1, CFL_ERR_INVALID, "topk_merge_records: bad arguments");
+  if (Q == 0) return CFL_OK;
+  const int64_t n = Q * (int64_t)k;
+  const size_t rb = topk_record_bytes(n);
+  topk_merge_kernel<<<(unsigned)Q, 128, 0, (cudaStream_t)stream>>>((const char*)recs + (size_t)n * 8, (const char*)recs, rb, rb, R, Q, k,
+                                                                   top_val, top_idx);
   CFL_LAUNCH_CHECK();
   return CFL_OK;
 }

@@ -202,6 +202,14 @@ int cfl_score_topk_monomer_packed(const float* Aq, int64_t lda, const float* Wq,
 int cfl_topk_merge(const float* vals, const int64_t* idx, int R, int64_t Q, int k,
                    float* top_val, int64_t* top_idx, void* stream);
 
+/* The same merge straight from the exchange buffer of the sharded ranking: every rank packs its [Q,k] lists into ONE
+ * record (cfl_topk_pack_records: [idx: Q*k int64][val: Q*k float], cfl_topk_record_bytes(Q,k) bytes, a multiple of 16),
+ * one all-gather of the records, cfl_topk_merge_records over the R gathered records -- no repacking copies on either
+ * side of the collective (the exchange is latency-bound: host time per step matters). */
+size_t cfl_topk_record_bytes(int64_t Q, int k);
+int cfl_topk_pack_records(const float* vals, const int64_t* idx, int64_t Q, int k, void* rec, void* stream);
+int cfl_topk_merge_records(const void* recs, int R, int64_t Q, int k, float* top_val, int64_t* top_idx, void* stream);
+
 /* Column mean of a catalog E[N,d] (the centring vector mu). */
 int cfl_col_mean(const float* E, int64_t N, int d, int64_t lde, float* mu,
                  void* ws, size_t ws_bytes, void* stream);

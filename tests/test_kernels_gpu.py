@@ -308,6 +308,14 @@ def test_topk_merge_equals_single_list(nat, R, N):
         vs.append(v); is_.append(i)
     mv, mi = nat.topk_merge(torch.stack(vs), torch.stack(is_))
     assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
+    # the same merge straight from the exchange records (what the all-gather of the sharded ranking delivers)
+    rb = nat.topk_record_bytes(Q, k)
+    assert rb % 16 == 0 and rb >= 12 * Q * k
+    recs = torch.empty(R * rb, dtype=torch.uint8, device="cuda")
+    for r in range(R):
+        nat.topk_pack_records(vs[r], is_[r], recs[r * rb:(r + 1) * rb])
+    rv, ri = nat.topk_merge_records(recs, R, Q, k)
+    assert torch.equal(ri, full_i) and torch.equal(rv, full_v)
 
 
 # ---------------------------------------------------------------------------- AUC / Adam
