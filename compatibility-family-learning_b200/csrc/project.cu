@@ -25,21 +25,32 @@ int project_bwd_umma(const float* x, int64_t B, int F, int64_t ldx, const float*
                      int64_t ldy, int act, int N, float* Cpart, cudaStream_t st);
 
 // ---- column scaler s_j = g_j / |V_:j| ----------------------------------------------------
-// one block per 32 columns, 8 row slices per block, fixed-order reduction over the slices.
-__global__ void colnorm_kernel(const float* __restrict__ V, int F, int N, int64_t ldV,
-                               const float* __restrict__ g, float* __restrict__ scaler,
-                               float* __restrict__ norm_out) {
-  __shared__ float sm[8][33];
+// one block per 32 columns, 32 row slices per block (four independent accumulators per thread keep four loads in
+// flight: the 8-slice version walked F / 8 dependent loads per thread, 16 us at F = 1024 on a handful of CTAs),
+// fixed-order reduction over the slices.
+constexpr int CN_SLICES = 32;
+__global__ void __launch_bounds__(32 * CN_SLICES)
+colnorm_kernel(const float* __restrict__ V, int F, int N, int64_t ldV,
+               const float* __restrict__ g, float* __restrict__ scaler,
+               float* __restrict__ norm_out) {
+  __shared__ float sm[CN_SLICES][33];
   int j = blockIdx.x * 32 + threadIdx.x;
-  float acc = 0.0f;
-  if (j < N)
-    for (int i = threadIdx.y; i < F; i += 8) { float v = V[(int64_t)i * ldV + j]; acc = fmaf(v, v, acc); }
-  sm[threadIdx.y][threadIdx.x] = acc;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  if (j < N) {
+    int i = threadIdx.y;
+    for (; i + 3 * CN_SLICES < F; i += 4 * CN_SLICES) {
+      const float v0 = V[(int64_t)i * ldV + j], v1 = V[(int64_t)(i + CN_SLICES) * ldV + j];
+      const float v2 = V[(int64_t)(i + 2 * CN_SLICES) * ldV + j], v3 = V[(int64_t)(i + 3 * CN_SLICES) * ldV + j];
+      a0 = fmaf(v0, v0, a0); a1 = fmaf(v1, v1, a1); a2 = fmaf(v2, v2, a2); a3 = fmaf(v3, v3, a3);
+    }
+    for (; i < F; i += CN_SLICES) { const float v = V[(int64_t)i * ldV + j]; a0 = fmaf(v, v, a0); }
+  }
+  sm[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (threadIdx.y == 0 && j < N) {
     float t = 0.0f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += sm[r][threadIdx.x];
+    for (int r = 0; r < CN_SLICES; ++r) t += sm[r][threadIdx.x];
     float n = sqrtf(t);                                   // no epsilon: layers.py:81
     if (norm_out) norm_out[j] = n;
     scaler[j] = (g ? g[j] : 1.0f) / n;
@@ -334,7 +345,7 @@ int cfl_project_fwd(const float* x, int64_t B, int F, int64_t ldx, const float* 
   float* scaler = nullptr;
   if (weight_norm) {
     scaler = W.take<float>(N);
-    colnorm_kernel<<<(N + 31) / 32, dim3(32, 8), 0, cs>>>(V, F, N, ldV, g, scaler, nullptr);
+    colnorm_kernel<<<(N + 31) / 32, dim3(32, CN_SLICES), 0, cs>>>(V, F, N, ldV, g, scaler, nullptr);
     CFL_LAUNCH_CHECK();
   }
   if (use_splitk(B)) {
@@ -400,7 +411,7 @@ int cfl_project_bwd(const float* x, int64_t B, int F, int64_t ldx, const float* 
   rps = (rps + TK - 1) / TK * TK;
   if (rps < TK) rps = TK;
   if (weight_norm) {
-    colnorm_kernel<<<(N + 31) / 32, dim3(32, 8), 0, cs>>>(V, F, N, ldV, g, scaler, norm);
+    colnorm_kernel<<<(N + 31) / 32, dim3(32, CN_SLICES), 0, cs>>>(V, F, N, ldV, g, scaler, norm);
     CFL_LAUNCH_CHECK();
   }
   colstats_kernel<<<dim3((N + 31) / 32, slabs), dim3(32, 8), 0, cs>>>(
