@@ -15,8 +15,12 @@ table*, which follow LevelDB's table format):
     key ``<variable name>`` -> ``BundleEntryProto`` {1: dtype, 2: shape {2: dim {1: size}}, 3: shard_id,
     4: offset, 5: size, 6: fixed32 masked crc32c of the bytes}.
   * ``.data-00000-of-00001`` holds the raw little-endian tensor bytes at those offsets.
-TensorFlow is not installable in the build container, so this is validated against the format
-description (known-answer CRC32C / varint vectors) and by round trips, not against TF-written files.
+TensorFlow is not installable in the build container, so no TF-written file has been read.  What the
+tests establish instead (tests/test_tf_checkpoint.py): known-answer CRC32C / varint vectors; the masked
+CRC against the implementation in tensorboard's TensorFlow stub; the bundle protos in both directions
+against Google's protobuf runtime over TensorFlow's own compiled DataType / TensorShapeProto / VersionDef
+descriptors (shipped with tensorboard); round trips, multi-block tables and corruption detection for the
+table layer, which has no independent implementation in this image.
 """
 from __future__ import annotations
 
