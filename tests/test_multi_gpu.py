@@ -62,6 +62,44 @@ def test_sharded_ranking_two_gpus_equals_one(tmp_path):
     assert torch.equal(ti.cpu(), got["ti"]) and torch.equal(tv.cpu(), got["tv"])
 
 
+def _pipelined_worker(rank, world, port, out):
+    """rank_async / rank_host (exchange on the side stream over the ring of record buffers, batches in flight beyond
+    the ring's depth) must return what the blocking rank() returns for the same batches."""
+    _setup(rank, world, port)
+    from cfl import ranking
+    X, V0, Vp, K, d, Q = _data()
+    c = lambda a: torch.as_tensor(a).cuda()
+    w = ranking.EncoderWeights(V0=c(V0), Vp=c(Vp), g0=torch.ones(d).cuda(), gp=torch.ones(K * d).cuda(),
+                               b0=torch.zeros(d).cuda(), bp=torch.zeros(K * d).cuda())
+    lo, hi = ranking.shard_bounds(len(X), world, rank)
+    idx = ranking.CatalogIndex.from_features(w, c(X[lo:hi]), idx_base=lo, n_total=len(X))
+    k, nb = 100, 6
+    xs_host = [torch.as_tensor(X[i * Q:(i + 1) * Q]).pin_memory() for i in range(nb)]
+    xs = [x.cuda() for x in xs_host]
+    want = [idx.rank(x, k) for x in xs]
+    torch.cuda.synchronize()
+    got = [idx.rank_async(x, k) for x in xs]                      # six exchanges queued over a ring of four
+    for (wv, wi), (gv, gi, ev) in zip(want, got):
+        ev.synchronize()
+        assert torch.equal(gv, wv) and torch.equal(gi, wi)
+    outs = [(torch.empty(Q, k).pin_memory(), torch.empty(Q, k, dtype=torch.int64).pin_memory()) for _ in range(nb)]
+    evs = [idx.rank_host(x, k, ov, oi) for x, (ov, oi) in zip(xs_host, outs)]
+    for (wv, wi), (ov, oi), ev in zip(want, outs, evs):
+        ev.synchronize()
+        assert torch.equal(ov, wv.cpu()) and torch.equal(oi, wi.cpu())
+    if rank == 0:
+        torch.save(dict(ok=True, ti=want[-1][1].cpu()), out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_pipelined_ranking_entry_points_two_gpus(tmp_path):
+    out = str(tmp_path / "p.pt")
+    mp.spawn(_pipelined_worker, args=(2, 29700 + os.getpid() % 1000, out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert got["ok"] and int(got["ti"].max()) >= 30_000            # global indices reach into the second shard
+
+
 def _train_worker(rank, world, port, out):
     _setup(rank, world, port)
     from cfl import ops, variables as vs
