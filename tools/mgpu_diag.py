@@ -41,7 +41,6 @@ for it in range(steps):
 cpu_issue = (time.time() - t0) / steps * 1e3
 torch.cuda.synchronize()
 wall = (time.time() - t0) / steps * 1e3
-os.environ["CFL_SCORE_DEBUG"] = "1"
 index.rank(xq, 100); torch.cuda.synchronize()
 print(f"rank {rank}: sampled steps local {T['local']/4:.3f} ms gather {T['gather']/4:.3f} ms merge {T['merge']/4:.3f} ms | cpu issue {cpu_issue:.3f} ms/step, wall {wall:.3f} ms/step", flush=True)
 torch.distributed.destroy_process_group()

@@ -18,5 +18,4 @@ e0.record()
 for _ in range(5): nat.score_topk(Pq, E, k, mu=mu, image=img)
 e1.record(); torch.cuda.synchronize()
 print(json.dumps(dict(K=K, d=d, env={k_: v for k_, v in os.environ.items() if k_.startswith("CFL_")}, ms=round(e0.elapsed_time(e1) / 5, 3))), flush=True)
-os.environ["CFL_SCORE_DEBUG"] = "1"
 nat.score_topk(Pq, E, k, mu=mu, image=img); torch.cuda.synchronize()
