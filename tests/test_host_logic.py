@@ -127,7 +127,7 @@ def _rank_worker(rank, world, port, out_dir):
     _doubles()
     ranking.CatalogIndex.__init__.__globals__["nat"].CflNativeError = RuntimeError
     rng = np.random.default_rng(0)
-    N, F, K, d, Q, k = 400, 12, 3, 6, 9, 20
+    N, F, K, d, Q, k = 401, 12, 3, 6, 9, 20                       # 401 rows: ragged shards at every world size
     X = rng.normal(size=(N, F)).astype(np.float32)
     w = ranking.EncoderWeights(V0=torch.as_tensor(O.xavier_uniform(rng, F, d)), Vp=torch.as_tensor(O.xavier_uniform(rng, F, K * d)),
                                g0=torch.ones(d), gp=torch.ones(K * d), b0=torch.zeros(d), bp=torch.zeros(K * d))
@@ -142,13 +142,15 @@ def _rank_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_sharded_ranking_world2_gloo_matches_single_process(tmp_path):
-    """Catalog rows sharded over 2 ranks + all_gather + merge == ranking the whole catalog."""
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_rank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_ranking_world2_gloo_matches_single_process(tmp_path, world):
+    """Catalog rows sharded over 2 / 4 ranks (ragged shards) + one all_gather of the records + merge == ranking the
+    whole catalog: the result does not depend on the number of ranks."""
+    port = 29500 + os.getpid() % 2000 + world
+    mp.spawn(_rank_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     got = np.load(tmp_path / "r.npz")
     rng = np.random.default_rng(0)
-    N, F, K, d, Q, k = 400, 12, 3, 6, 9, 20
+    N, F, K, d, Q, k = 401, 12, 3, 6, 9, 20
     X = rng.normal(size=(N, F)).astype(np.float32)
     V0, Vp = O.xavier_uniform(rng, F, d), O.xavier_uniform(rng, F, K * d)
     E = O.fc_weight_norm(X.astype(np.float64), V0.astype(np.float64), np.ones(d), np.zeros(d)).astype(np.float32)
