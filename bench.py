@@ -278,7 +278,19 @@ def auc_line(index, device, j=8, steps=10):
     return out
 
 
+def _ensure_library():
+    """The in-tree C-ABI library, built by nvcc when it is missing or older than its sources (a no-op on a snapshot that
+    carries the prebuilt .so; ranks of one job take turns on a file lock).  There is no fallback: without nvcc and
+    without the library this raises."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("cfl_build", os.path.join(PKG, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
+
+
 def run_ours(args):
+    _ensure_library()
     from cfl import _native as nat
     from cfl.ranking import CatalogIndex
 

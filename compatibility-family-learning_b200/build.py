@@ -62,16 +62,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "libcfl_b200.sha256")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    def fresh() -> bool:
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig
+
+    if not force and fresh():
         return LIB
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as fh:
-        fh.write(dig)
+    # one builder at a time (several ranks of one torchrun job may get here together): the others wait on the lock
+    # and find the library fresh when they get it
+    import fcntl
+    with open(os.path.join(OBJ, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return LIB
+            with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+                objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+            tmp = LIB + ".tmp%d" % os.getpid()
+            cmd = [_nvcc(), "-shared", "-o", tmp, *objs, "-lcudart"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+            os.replace(tmp, LIB)                                   # a process that has the old library mapped keeps it
+            with open(stamp, "w") as fh:
+                fh.write(dig)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
