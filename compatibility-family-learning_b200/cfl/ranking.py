@@ -305,6 +305,8 @@ def _gather_merge(tv, ti, group, world):
     if ring is None:
         ring = [[torch.empty(rb, dtype=torch.uint8, device=tv.device),
                  torch.empty(world * rb, dtype=torch.uint8, device=tv.device)] for _ in range(4)] + [0]
+        if len(_XCHG_BUFS) >= 8:                               # ragged batch sizes: keep the eight most recent shapes (the
+            _XCHG_BUFS.pop(next(iter(_XCHG_BUFS)))             # freed blocks go back to this stream's pool, in stream order)
         _XCHG_BUFS[key] = ring
     rec, out = ring[ring[4]]
     ring[4] = (ring[4] + 1) % 4
