@@ -61,7 +61,7 @@ def test_variable_scope_reuse_semantics():
                 vs.get_variable("missing", [1], vs.zeros_initializer())
         with vs.variable_scope(sc), vs.variable_scope("t"):           # re-enter a captured scope
             vs.get_variable("threshold", [], vs.constant_initializer(1e-6))
-        assert float(vs.all_variables()["enc/t/threshold"]) == pytest.approx(1e-6)
+        assert float(vs.all_variables()["enc/t/threshold"].detach()) == pytest.approx(1e-6)
     finally:
         vs.set_default_device(None)
         vs.reset_default_graph()
