@@ -29,6 +29,16 @@ def test_library_exports_every_declared_symbol():
     assert lib.cfl_version() >= 100
 
 
+def test_every_declared_symbol_is_documented_for_the_integrator():
+    """INTEGRATION.md names every entry point of the header (its section 5 maps each to the reference site it serves), and
+    every compute entry point cites a reference file:line or says that it is an extension in the header itself."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for n in _declared():
+        assert re.search(r"`%s`" % n, doc), f"{n} is not mentioned in INTEGRATION.md"
+    header = open(HEADER).read()
+    assert len(re.findall(r"cfl/[a-z_/]+\.py:\d+", header)) >= 20          # reference file:line citations
+
+
 def test_workspace_queries_do_not_need_a_gpu():
     from cfl import _native
     lib = _native.lib()
