@@ -40,7 +40,9 @@ def _digest() -> str:
         p = f if os.path.isabs(f) else os.path.join(CSRC, f)
         with open(p, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # flags with the checkout's location factored out: the library built here must count as fresh in a copy of the tree
+    # under another path (the GPU box runs a snapshot from a scratch directory)
+    h.update(" ".join(f.replace(ROOT, "<root>") for f in NVCC_FLAGS).encode())
     return h.hexdigest()
 
 

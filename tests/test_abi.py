@@ -39,6 +39,30 @@ def test_every_declared_symbol_is_documented_for_the_integrator():
     assert len(re.findall(r"cfl/[a-z_/]+\.py:\d+", header)) >= 20          # reference file:line citations
 
 
+def test_build_digest_does_not_depend_on_the_checkout_location(tmp_path):
+    """The prebuilt library travels with a snapshot of the tree to the GPU box, where the tree sits under another path:
+    the freshness stamp must still match there (otherwise every process would rebuild the library on the box)."""
+    import importlib.util
+    import shutil
+
+    def load(build_py):
+        spec = importlib.util.spec_from_file_location("cfl_build_%d" % abs(hash(build_py)), build_py)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    pkg = os.path.join(ROOT, "compatibility-family-learning_b200")
+    here = load(os.path.join(pkg, "build.py"))
+    copy = tmp_path / "elsewhere"
+    shutil.copytree(os.path.join(ROOT, "include"), copy / "include")
+    shutil.copytree(os.path.join(pkg, "csrc"), copy / "compatibility-family-learning_b200" / "csrc")
+    shutil.copy(os.path.join(pkg, "build.py"), copy / "compatibility-family-learning_b200" / "build.py")
+    there = load(str(copy / "compatibility-family-learning_b200" / "build.py"))
+    assert there.ROOT != here.ROOT and there._digest() == here._digest()
+    stamp = os.path.join(here.LIBDIR, "libcfl_b200.sha256")
+    assert open(stamp).read() == here._digest()                     # the library on disk is the one built from these sources
+
+
 def test_workspace_queries_do_not_need_a_gpu():
     from cfl import _native
     lib = _native.lib()
